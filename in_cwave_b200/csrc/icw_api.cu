@@ -1,0 +1,769 @@
+// icw_api.cu -- the C ABI declared in include/icw_b200.h: spec validation and folding, sessions,
+// stream state, and the per-call launch sequence.  Host side only; kernels live in icw_kernels.cu.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "icw_internal.h"
+#include "icw_kernels.h"
+#include "icw_mt.h"
+#include "icw_hb_tables.inc"
+
+using namespace icw;
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ICW_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char *icw_last_error(void) { return g_err.c_str(); }
+extern "C" int icw_abi_version(void) { return ICW_ABI_VERSION; }
+
+// ---------------------------------------------------------------------------------------------
+// objects
+// ---------------------------------------------------------------------------------------------
+struct Scratch {
+    void  *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t n)
+    {
+        if (n <= cap) return ICW_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 256;
+        if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return fail(ICW_E_NOMEM, "cudaMalloc(%zu) failed", want); }
+        cap = want;
+        return ICW_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct icw_engine {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    Scratch analytic, mtw[2], ckpt, io_in, io_out, leaf;
+    MtJump mt;                          // MT19937 checkpoint service (icw_mt.cu)
+};
+
+struct icw_session {
+    icw_engine *e = nullptr;
+    icw_chain_spec spec;
+    DevChain ch;
+    HbCoef coef;
+    int n_streams = 0;
+    DevStream *d_streams = nullptr;
+    // host mirror of the generator identity per stream (closed form: never needs a device read)
+    std::vector<uint32_t> mt_seed[2];
+    std::vector<uint64_t> mt_drawn[2];
+    uint64_t launches = 0;
+    double *d_tap_bus = nullptr;        // test taps, set through icw_session_set_taps
+    double *d_tap_lr = nullptr;
+    // measurement: event pairs around each kernel class (icw_session_profile)
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;
+    struct Span { int k; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    double prof_ms[ICW_K_COUNT] = { 0, 0, 0, 0 };
+    uint64_t prof_n[ICW_K_COUNT] = { 0, 0, 0, 0 };
+};
+
+// RAII: records an event pair around a group of launches of one kernel class
+struct ProfSpan {
+    icw_session *s; cudaStream_t st; int k; cudaEvent_t a = nullptr, b = nullptr;
+    static cudaEvent_t take(icw_session *s)
+    {
+        cudaEvent_t e = nullptr;
+        if (!s->ev_pool.empty()) { e = s->ev_pool.back(); s->ev_pool.pop_back(); }
+        else cudaEventCreate(&e);
+        return e;
+    }
+    ProfSpan(icw_session *s_, cudaStream_t st_, int k_) : s(s_), st(st_), k(k_)
+    {
+        if (!s->profiling) return;
+        a = take(s); b = take(s);
+        cudaEventRecord(a, st);
+    }
+    ~ProfSpan()
+    {
+        if (!a) return;
+        cudaEventRecord(b, st);
+        s->spans.push_back({ k, a, b });
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// defaults and small queries
+// ---------------------------------------------------------------------------------------------
+static int chan_bytes_of(int fmt)
+{
+    switch (fmt) {
+    case ICW_FMT_WAV_U8: return 1;
+    case ICW_FMT_WAV_I16: return 2;
+    case ICW_FMT_WAV_I24: return 3;
+    case ICW_FMT_WAV_I32: return 4;
+    case ICW_FMT_WAV_F32: return 4;
+    case ICW_FMT_CW_F64: return 16;
+    case ICW_FMT_CW_I16: return 4;
+    case ICW_FMT_CW_I16F32: return 6;
+    case ICW_FMT_CW_F32: return 8;
+    default: return -1;
+    }
+}
+
+extern "C" void icw_default_spec(icw_chain_spec *sp)
+{
+    memset(sp, 0, sizeof *sp);
+    sp->fmt = ICW_FMT_WAV_F32;
+    sp->n_channels = 2;
+    sp->sample_rate = 48000;
+    sp->filter_no = 1;              // IIR_HBLPF_IX   (reference src/config.c:158)
+    sp->is_kahan = 1;               // IIR_SUM_KAHAN  (:161)
+    sp->is_subnorm_reject = 1;      // IIR_SUBN_ZERO  (:164)
+    sp->hilbert_mode = ICW_HILBERT_EXACT;
+    sp->is_frmod_scaled = 1;        // FRMOD_SCALED   (:154)
+    sp->need24bits = 1;             // NEED24BITS     (:183)
+    sp->dth_bits = 1.0;
+    sp->quantz_type = 1;            // mid riser      (:190)
+    sp->render_type = ICW_RENDER_ROUND;
+    sp->nshape_type = 0;
+    sp->sign_bits16 = 16;
+    sp->sign_bits24 = 24;
+    sp->n_nodes = 1;                // the lone master (reference src/adv_modulator.c:112-118)
+    sp->nodes[0].mode = ICW_MODE_MASTER;
+    sp->nodes[0].inputs_mask = 1u;
+    sp->nodes[0].l_gain = sp->nodes[0].r_gain = 0.8;
+    sp->nodes[0].l_tout = sp->nodes[0].r_tout = ICW_OUT_ADD_REIM;
+}
+
+extern "C" void icw_default_state(icw_stream_state *st)
+{
+    memset(st, 0, sizeof *st);
+    st->mt_seed[0] = 0x13579BDFu;   // reference src/in_cwave.c:69
+    st->mt_seed[1] = 0x479B22ABu;   // reference src/in_cwave.c:70
+}
+
+extern "C" int icw_frame_bytes(const icw_chain_spec *sp)
+{
+    int cb = chan_bytes_of(sp->fmt);
+    return (cb < 0 || sp->n_channels < 1 || sp->n_channels > 2) ? -1 : cb * sp->n_channels;
+}
+extern "C" int icw_out_frame_bytes(const icw_chain_spec *sp) { return sp->need24bits ? 6 : 4; }
+extern "C" double icw_peak_db(double lin) { return lin ? 20.0 * log10(lin) : ICW_SILENCE_DB; }
+
+// ---------------------------------------------------------------------------------------------
+// spec -> device form
+// ---------------------------------------------------------------------------------------------
+static double word_as_double(unsigned long long w) { double d; memcpy(&d, &w, 8); return d; }
+
+static double scaled_freq(double f, int scaled)
+{
+    // reference src/adv_modulator.c:36-38
+    return scaled ? (double)(unsigned)(f * (double)ICW_HZ_SCALE + 0.5) : f;
+}
+
+static int fold_spec(const icw_chain_spec &sp, DevChain &ch, HbCoef &coef)
+{
+    memset(&ch, 0, sizeof ch);
+    memset(&coef, 0, sizeof coef);
+    int cb = chan_bytes_of(sp.fmt);
+    if (cb < 0) return fail(ICW_E_ARG, "unknown sample format %d", sp.fmt);
+    if (sp.n_channels < 1 || sp.n_channels > 2) return fail(ICW_E_ARG, "n_channels must be 1 or 2");
+    if (sp.sample_rate == 0 || sp.sample_rate > 2000000u) return fail(ICW_E_ARG, "sample_rate out of range");
+    if (sp.filter_no < 0 || sp.filter_no >= ICW_HB_NTYPES) return fail(ICW_E_ARG, "filter_no must be 0..5");
+    if (sp.n_nodes < 1 || sp.n_nodes > ICW_MAX_NODES) return fail(ICW_E_ARG, "n_nodes out of range");
+    if (sp.nodes[sp.n_nodes - 1].mode != ICW_MODE_MASTER) return fail(ICW_E_ARG, "the last node must be the master");
+    if (sp.render_type > ICW_RENDER_GAUSS) return fail(ICW_E_ARG, "render_type out of range");
+    if (sp.quantz_type > 1) return fail(ICW_E_ARG, "quantz_type out of range");
+    if (sp.nshape_type != 0)
+        return fail(ICW_E_UNSUPPORTED, "noise shaping %u: error feedback through the quantiser is serial per channel; "
+                                       "only FLAT runs on the GPU (SURVEY.md 8f N3)", sp.nshape_type);
+    if (sp.sign_bits16 < 2 || sp.sign_bits16 > 16 || sp.sign_bits24 < 2 || sp.sign_bits24 > 24)
+        return fail(ICW_E_ARG, "significant bits out of range");
+    if (sp.n_fade_in < 0 || sp.n_fade_out < 0) return fail(ICW_E_ARG, "negative fade length");
+
+    ch.fmt = sp.fmt;
+    ch.n_channels = sp.n_channels;
+    ch.chan_bytes = cb;
+    ch.frame_bytes = cb * sp.n_channels;
+    ch.out_frame_bytes = sp.need24bits ? 6 : 4;
+    ch.is_complex = sp.fmt >= ICW_FMT_CW_F64;
+    ch.is_frmod_scaled = sp.is_frmod_scaled != 0;
+    ch.bypass = sp.bypass != 0;
+    ch.n_nodes = sp.n_nodes;
+    ch.n_samples = sp.n_samples;
+    ch.n_fade_in = sp.n_fade_in;
+    ch.n_fade_out = sp.n_fade_out;
+    if (ch.is_frmod_scaled) {
+        // reference src/adv_modulator.c:614: unsigned scale_sr = sample_rate * HZ_SCALE
+        unsigned scale = sp.sample_rate * ICW_HZ_SCALE;
+        ch.scale_sr = scale;
+        ch.osc_div = (double)scale;
+    } else {
+        ch.scale_sr = 0;
+        ch.osc_div = (double)sp.sample_rate;
+    }
+    ch.osc_rdiv = 1.0 / ch.osc_div;
+
+    // half-band design (reference src/hblpf.c:849-856)
+    ch.filter_no = sp.filter_no;
+    ch.hb_ord = ICW_HB_ORDER[sp.filter_no];
+    ch.is_kahan = sp.is_kahan != 0;
+    ch.reject_flag = sp.is_subnorm_reject;
+    {
+        double a0 = word_as_double(ICW_HB_A[sp.filter_no][0]);
+        coef.d0 = word_as_double(ICW_HB_B[sp.filter_no][0]) / a0;
+        for (int i = 0; i < ch.hb_ord; ++i) {
+            coef.fb[i] = -word_as_double(ICW_HB_A[sp.filter_no][i + 1]) / a0;
+            coef.ff[i] = word_as_double(ICW_HB_B[sp.filter_no][i + 1]) / a0;
+        }
+        memcpy(ch.hb_fb, coef.fb, sizeof coef.fb);
+        memcpy(ch.hb_ff, coef.ff, sizeof coef.ff);
+        ch.hb_d0 = coef.d0;
+    }
+
+    // quantiser (reference src/sound_render.c:499-551)
+    DevRender &q = ch.render;
+    q.dth_mul = pow(2.0, sp.dth_bits) - 1.0;
+    if (sp.quantz_type == 0) { q.round_off = 0.5; q.neg_delta = 0; }
+    else                     { q.round_off = 0.0; q.neg_delta = -1; }
+    long long top;
+    if (sp.need24bits) {
+        q.bytes = 3;
+        q.shift = 24 - (int)sp.sign_bits24;
+        top = 0x800000LL >> q.shift;
+        q.norm_mul = q.shift < 8 ? (double)(0x100 >> q.shift) : 1.0 / (double)(1ULL << (q.shift - 8));
+    } else {
+        q.bytes = 2;
+        q.shift = 16 - (int)sp.sign_bits16;
+        top = 0x8000LL >> q.shift;
+        q.norm_mul = 1.0 / (double)(1ULL << q.shift);
+    }
+    q.hi = (double)top;
+    q.lo = -(double)(top + 1 + q.neg_delta);
+    q.lo -= (double)q.neg_delta;
+    q.inv_hi = 1.0 / q.hi;
+    q.render_type = (int)sp.render_type;
+    static const int wps[5] = { 0, 2, 4, 2, 24 };       // reference src/sound_render.c:711-751
+    q.words_per_sample = wps[sp.render_type];
+
+    // DSP list
+    uint32_t written = 1u;                                // plug 0 is written by the unpacker
+    for (int i = 0; i < sp.n_nodes; ++i) {
+        const icw_node &s = sp.nodes[i];
+        DevNode &d = ch.nodes[i];
+        if (s.mode < ICW_MODE_MASTER || s.mode > ICW_MODE_MIX) return fail(ICW_E_ARG, "node %d: bad mode %d", i, s.mode);
+        if (s.mode == ICW_MODE_MASTER && i != sp.n_nodes - 1) return fail(ICW_E_ARG, "node %d: a second master", i);
+        if (s.inputs_mask >> ICW_N_PLUGS) return fail(ICW_E_ARG, "node %d: input plug out of range", i);
+        if (s.mode != ICW_MODE_MASTER && (s.n_out < 1 || s.n_out >= ICW_N_PLUGS))
+            return fail(ICW_E_ARG, "node %d: output plug %d out of range", i, s.n_out);
+        if (!sp.bypass) {
+            // a plug read before its writer in the same frame carries the PREVIOUS frame's value
+            // (reference src/adv_modulator.c:634-751): a one-frame feedback loop, serial in time
+            uint32_t later = 0;
+            for (int j = i; j < sp.n_nodes; ++j)
+                if (sp.nodes[j].mode != ICW_MODE_MASTER) later |= 1u << sp.nodes[j].n_out;
+            if (s.inputs_mask & later & ~written)
+                return fail(ICW_E_UNSUPPORTED, "node %d reads a plug that is written later in the list: feedback "
+                                               "graphs are serial in time and are not run on the GPU", i);
+        }
+        d.mode = s.mode;
+        d.inputs_mask = s.inputs_mask;
+        d.xch_mode = s.xch_mode;
+        d.l_iq_invert = s.l_iq_invert != 0;
+        d.r_iq_invert = s.r_iq_invert != 0;
+        d.n_out = s.n_out;
+        d.l_tout = s.l_tout; d.r_tout = s.r_tout;
+        d.l_on = s.l_on != 0; d.r_on = s.r_on != 0;
+        d.l_gain = s.l_gain; d.r_gain = s.r_gain;
+        if (s.mode == ICW_MODE_SHIFT) {
+            d.l_neg = s.l_p[0] < 0.0; d.r_neg = s.r_p[0] < 0.0;
+            d.l_f = scaled_freq(d.l_neg ? -s.l_p[0] : s.l_p[0], ch.is_frmod_scaled);
+            d.r_f = scaled_freq(d.r_neg ? -s.r_p[0] : s.r_p[0], ch.is_frmod_scaled);
+        } else if (s.mode == ICW_MODE_PM) {
+            d.l_f = scaled_freq(s.l_p[0], ch.is_frmod_scaled);
+            d.r_f = scaled_freq(s.r_p[0], ch.is_frmod_scaled);
+            d.l_ph0 = s.l_p[1] * ICW_PI;    d.r_ph0 = s.r_p[1] * ICW_PI;
+            d.l_lvlpi = s.l_p[2] * ICW_PI;  d.r_lvlpi = s.r_p[2] * ICW_PI;
+            d.l_angle = s.l_p[3];           d.r_angle = s.r_p[3];
+        }
+        if (s.mode != ICW_MODE_MASTER) written |= 1u << s.n_out;
+    }
+    if (!ch.is_complex && sp.hilbert_mode != ICW_HILBERT_EXACT && sp.hilbert_mode != ICW_HILBERT_SCAN)
+        return fail(ICW_E_ARG, "hilbert_mode out of range");
+    return ICW_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// engine
+// ---------------------------------------------------------------------------------------------
+extern "C" int icw_engine_create(int device, icw_engine **out)
+{
+    if (!out) return fail(ICW_E_ARG, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    CK(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) return fail(ICW_E_ARG, "device %d of %d", device, n);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(ICW_E_CUDA, "this library is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+    icw_engine *e = new icw_engine;
+    e->device = device;
+    e->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    *out = e;
+    return ICW_OK;
+}
+
+extern "C" void icw_engine_destroy(icw_engine *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    e->analytic.release(); e->mtw[0].release(); e->mtw[1].release(); e->ckpt.release();
+    e->io_in.release(); e->io_out.release(); e->leaf.release();
+    e->mt.release();
+    cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sessions and state
+// ---------------------------------------------------------------------------------------------
+static void to_dev(const icw_stream_state &s, DevStream &d)
+{
+    memset(&d, 0, sizeof d);
+    d.n_frame = s.n_frame;
+    d.pos = s.pos;
+    memcpy(d.hb, s.hb, sizeof d.hb);
+    for (int c = 0; c < 2; ++c) {
+        for (int f = 0; f < 2; ++f) d.hb_rejects[c][f] = s.hb_rejects[c][f];
+        d.quad[c] = s.quad[c] & 3u;
+        d.mt_seed[c] = s.mt_seed[c];
+        d.mt_drawn[c] = s.mt_drawn[c];
+        d.prev_rnd[c] = s.prev_rnd[c];
+        d.clips[c] = s.clips[c];
+        d.peak[c] = s.peak[c];
+    }
+    memcpy(d.bus, s.bus, sizeof d.bus);
+}
+
+static void from_dev(const DevStream &d, icw_stream_state &s)
+{
+    memset(&s, 0, sizeof s);
+    s.n_frame = d.n_frame;
+    s.pos = d.pos;
+    memcpy(s.hb, d.hb, sizeof s.hb);
+    for (int c = 0; c < 2; ++c) {
+        for (int f = 0; f < 2; ++f) s.hb_rejects[c][f] = d.hb_rejects[c][f];
+        s.quad[c] = d.quad[c];
+        s.mt_seed[c] = d.mt_seed[c];
+        s.mt_drawn[c] = d.mt_drawn[c];
+        s.prev_rnd[c] = d.prev_rnd[c];
+        s.clips[c] = d.clips[c];
+        s.peak[c] = d.peak[c];
+    }
+    memcpy(s.bus, d.bus, sizeof s.bus);
+}
+
+extern "C" int icw_session_create(icw_engine *e, const icw_chain_spec *spec, int n_streams, icw_session **out)
+{
+    if (!e || !spec || !out) return fail(ICW_E_ARG, "NULL argument");
+    *out = nullptr;
+    if (n_streams < 1) return fail(ICW_E_ARG, "n_streams must be >= 1");
+    icw_session *s = new icw_session;
+    s->e = e;
+    s->spec = *spec;
+    int rc = fold_spec(*spec, s->ch, s->coef);
+    if (rc) { delete s; return rc; }
+    s->n_streams = n_streams;
+    CK(cudaSetDevice(e->device));
+    if (cudaMalloc(&s->d_streams, sizeof(DevStream) * (size_t)n_streams) != cudaSuccess) {
+        cudaGetLastError();
+        delete s;
+        return fail(ICW_E_NOMEM, "cudaMalloc of %d stream states failed", n_streams);
+    }
+    icw_stream_state fresh;
+    icw_default_state(&fresh);
+    DevStream d;
+    to_dev(fresh, d);
+    std::vector<DevStream> all((size_t)n_streams, d);
+    CK(cudaMemcpyAsync(s->d_streams, all.data(), sizeof(DevStream) * all.size(), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    for (int c = 0; c < 2; ++c) {
+        s->mt_seed[c].assign((size_t)n_streams, fresh.mt_seed[c]);
+        s->mt_drawn[c].assign((size_t)n_streams, 0);
+    }
+    *out = s;
+    return ICW_OK;
+}
+
+extern "C" void icw_session_destroy(icw_session *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->e->device);
+    cudaStreamSynchronize(s->e->stream);
+    if (s->d_streams) cudaFree(s->d_streams);
+    for (auto &sp : s->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (auto ev : s->ev_pool) cudaEventDestroy(ev);
+    delete s;
+}
+
+extern "C" int icw_session_sync(icw_session *s)
+{
+    if (!s) return fail(ICW_E_ARG, "NULL session");
+    CK(cudaStreamSynchronize(s->e->stream));
+    return ICW_OK;
+}
+
+extern "C" int icw_session_get_state(icw_session *s, int k, icw_stream_state *out)
+{
+    if (!s || !out || k < 0 || k >= s->n_streams) return fail(ICW_E_ARG, "bad stream index");
+    DevStream d;
+    CK(cudaStreamSynchronize(s->e->stream));
+    CK(cudaMemcpy(&d, s->d_streams + k, sizeof d, cudaMemcpyDeviceToHost));
+    from_dev(d, *out);
+    return ICW_OK;
+}
+
+extern "C" int icw_session_set_state(icw_session *s, int k, const icw_stream_state *in)
+{
+    if (!s || !in || k < 0 || k >= s->n_streams) return fail(ICW_E_ARG, "bad stream index");
+    DevStream d;
+    to_dev(*in, d);
+    CK(cudaStreamSynchronize(s->e->stream));
+    CK(cudaMemcpy(s->d_streams + k, &d, sizeof d, cudaMemcpyHostToDevice));
+    for (int c = 0; c < 2; ++c) { s->mt_seed[c][k] = in->mt_seed[c]; s->mt_drawn[c][k] = in->mt_drawn[c]; }
+    return ICW_OK;
+}
+
+static int rewrite_states(icw_session *s, void (*fn)(DevStream &, void *), void *arg)
+{
+    std::vector<DevStream> all((size_t)s->n_streams);
+    CK(cudaStreamSynchronize(s->e->stream));
+    CK(cudaMemcpy(all.data(), s->d_streams, sizeof(DevStream) * all.size(), cudaMemcpyDeviceToHost));
+    for (auto &d : all) fn(d, arg);
+    CK(cudaMemcpy(s->d_streams, all.data(), sizeof(DevStream) * all.size(), cudaMemcpyHostToDevice));
+    return ICW_OK;
+}
+
+extern "C" int icw_session_reset(icw_session *s, unsigned what)
+{
+    if (!s) return fail(ICW_E_ARG, "NULL session");
+    return rewrite_states(s, [](DevStream &d, void *a) {
+        unsigned w = *(unsigned *)a;
+        if (w & ICW_RESET_HILBERT) {            // hq_rp_reset, reference src/lpf_hilbert_quad.c:160-165
+            memset(d.hb, 0, sizeof d.hb);
+            memset(d.hb_rejects, 0, sizeof d.hb_rejects);
+            d.quad[0] = d.quad[1] = 0;
+        }
+        if (w & ICW_RESET_FRAMECNT) d.n_frame = 0;
+        if (w & ICW_RESET_COUNTERS) { d.clips[0] = d.clips[1] = 0; d.peak[0] = d.peak[1] = 0.0; }
+        if (w & ICW_RESET_FILEPOS) d.pos = 0;
+    }, &what);
+}
+
+extern "C" int icw_session_set_spec(icw_session *s, const icw_chain_spec *spec)
+{
+    if (!s || !spec) return fail(ICW_E_ARG, "NULL argument");
+    DevChain ch;
+    HbCoef coef;
+    int rc = fold_spec(*spec, ch, coef);
+    if (rc) return rc;
+    unsigned flags = 0;
+    // a different half-band design replaces the converters (reference src/in_cwave.c:135-150,177-191)
+    if (spec->filter_no != s->spec.filter_no) flags |= 1;
+    // any sound_render_setup / set_outbits clears prev_rnd (reference src/sound_render.c:509)
+    if (memcmp(&ch.render, &s->ch.render, sizeof ch.render) != 0) flags |= 2;
+    // iir_rp_setcfg clears the reject counters (reference src/hblpf.c:1114-1125)
+    if (spec->is_kahan != s->spec.is_kahan || spec->is_subnorm_reject != s->spec.is_subnorm_reject) flags |= 4;
+    if (flags) {
+        rc = rewrite_states(s, [](DevStream &d, void *a) {
+            unsigned f = *(unsigned *)a;
+            if (f & 1) { memset(d.hb, 0, sizeof d.hb); d.quad[0] = d.quad[1] = 0; }
+            if (f & (1 | 4)) memset(d.hb_rejects, 0, sizeof d.hb_rejects);
+            if (f & 2) d.prev_rnd[0] = d.prev_rnd[1] = 0.0;
+        }, &flags);
+        if (rc) return rc;
+    }
+    s->spec = *spec;
+    s->ch = ch;
+    s->coef = coef;
+    return ICW_OK;
+}
+
+// test-only taps: device buffers that receive the whole bus and the master output per frame
+extern "C" int icw_session_set_taps(icw_session *s, double *d_tap_bus, double *d_tap_lr)
+{
+    if (!s) return fail(ICW_E_ARG, "NULL session");
+    s->d_tap_bus = d_tap_bus;
+    s->d_tap_lr = d_tap_lr;
+    return ICW_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the hot call
+// ---------------------------------------------------------------------------------------------
+static int make_dither_words(icw_session *s, int64_t n_frames, cudaStream_t st, int &mt_shared,
+                             const uint32_t *&wl, const uint32_t *&wr)
+{
+    icw_engine *e = s->e;
+    const int wps = s->ch.render.words_per_sample;
+    wl = wr = nullptr;
+    mt_shared = 1;
+    if (!wps) return ICW_OK;
+    const int K = s->n_streams;
+    for (int c = 0; c < 2; ++c)
+        for (int k = 1; k < K; ++k)
+            if (s->mt_seed[c][k] != s->mt_seed[c][0] || s->mt_drawn[c][k] != s->mt_drawn[c][0]) mt_shared = 0;
+    for (int c = 0; c < 2; ++c)
+        for (int k = 0; k < K; ++k)
+            if (s->mt_drawn[c][k] % (uint64_t)wps)
+                return fail(ICW_E_UNSUPPORTED, "stream %d channel %d: generator offset %llu is not a multiple of the %d words "
+                                               "one sample draws (left by another dither type or a rejected draw)", k, c,
+                            (unsigned long long)s->mt_drawn[c][k], wps);
+    const int64_t words = n_frames * wps;
+    const int groups = mt_shared ? 1 : K;
+    for (int c = 0; c < 2; ++c) {
+        int rc = e->mtw[c].reserve((size_t)groups * (size_t)words * sizeof(uint32_t));
+        if (rc) return rc;
+        for (int g = 0; g < groups; ++g) {
+            uint32_t *dst = (uint32_t *)e->mtw[c].p + (size_t)g * (size_t)words;
+            rc = e->mt.generate(s->mt_seed[c][g], s->mt_drawn[c][g], words, dst, e->sm_count, st, &s->launches);
+            if (rc) return fail(rc, "%s", e->mt.error());
+        }
+    }
+    wl = (const uint32_t *)e->mtw[0].p;
+    wr = (const uint32_t *)e->mtw[1].p;
+    return ICW_OK;
+}
+
+extern "C" int icw_session_process_device(icw_session *s, int64_t n_frames, const void *d_in, size_t in_stride,
+                                          void *d_out, size_t out_stride, void *cuda_stream)
+{
+    if (!s || !d_in || !d_out) return fail(ICW_E_ARG, "NULL argument");
+    if (n_frames < 0) return fail(ICW_E_ARG, "negative frame count");
+    if (n_frames == 0) return ICW_OK;
+    icw_engine *e = s->e;
+    const DevChain &ch = s->ch;
+    const int K = s->n_streams;
+    if (K > 1 && (in_stride < (size_t)n_frames * ch.frame_bytes || out_stride < (size_t)n_frames * ch.out_frame_bytes))
+        return fail(ICW_E_ARG, "stream strides are shorter than one stream's data");
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
+
+    const uint8_t *src = (const uint8_t *)d_in;
+    size_t src_stride = in_stride;
+    int from_analytic = 0;
+    if (!ch.is_complex) {
+        if (s->spec.hilbert_mode != ICW_HILBERT_EXACT)
+            return fail(ICW_E_UNSUPPORTED, "hilbert_mode %d is not available in this build", s->spec.hilbert_mode);
+        size_t per = (size_t)n_frames * 4 * sizeof(double);
+        int rc = e->analytic.reserve(per * (size_t)K);
+        if (rc) return rc;
+        {
+            ProfSpan ps(s, st, ICW_K_HILBERT);
+            CK(launch_hb_exact(s->coef, ch, s->d_streams, K, n_frames, src, in_stride, (double *)e->analytic.p, st));
+        }
+        s->launches++;
+        src = (const uint8_t *)e->analytic.p;
+        src_stride = per;
+        from_analytic = 1;
+    }
+    int mt_shared;
+    const uint32_t *wl, *wr;
+    int rc;
+    {
+        ProfSpan ps(s, st, ICW_K_MT);
+        rc = make_dither_words(s, n_frames, st, mt_shared, wl, wr);
+    }
+    if (rc) return rc;
+    {
+        ProfSpan ps(s, st, ICW_K_CHAIN);
+        CK(launch_chain(ch, s->d_streams, K, n_frames, src, src_stride, from_analytic, wl, wr, mt_shared,
+                        (uint8_t *)d_out, out_stride, s->d_tap_bus, s->d_tap_lr, e->sm_count, st));
+    }
+    {
+        ProfSpan ps(s, st, ICW_K_MISC);
+        CK(launch_advance(ch, s->d_streams, K, n_frames, !ch.is_complex, st));
+    }
+    s->launches += 2;
+    const uint64_t words = (uint64_t)n_frames * (uint64_t)ch.render.words_per_sample;
+    for (int c = 0; c < 2; ++c)
+        for (int k = 0; k < K; ++k) s->mt_drawn[c][k] += words;
+    return ICW_OK;
+}
+
+extern "C" int icw_session_process_host(icw_session *s, int64_t n_frames, const void *in, size_t in_stride,
+                                        void *out, size_t out_stride)
+{
+    if (!s || !in || !out) return fail(ICW_E_ARG, "NULL argument");
+    if (n_frames <= 0) return n_frames ? fail(ICW_E_ARG, "negative frame count") : ICW_OK;
+    icw_engine *e = s->e;
+    const int K = s->n_streams;
+    const size_t in_row = (size_t)n_frames * s->ch.frame_bytes, out_row = (size_t)n_frames * s->ch.out_frame_bytes;
+    if (K > 1 && (in_stride < in_row || out_stride < out_row)) return fail(ICW_E_ARG, "stream strides too short");
+    // device rows are padded to 16 bytes so every stream starts on a vector boundary
+    const size_t din_stride = (in_row + 15) & ~(size_t)15, dout_stride = (out_row + 15) & ~(size_t)15;
+    CK(cudaSetDevice(e->device));
+    int rc = e->io_in.reserve(din_stride * K);
+    if (rc) return rc;
+    rc = e->io_out.reserve(dout_stride * K);
+    if (rc) return rc;
+    CK(cudaMemcpy2DAsync(e->io_in.p, din_stride, in, K > 1 ? in_stride : in_row, in_row, K, cudaMemcpyHostToDevice, e->stream));
+    rc = icw_session_process_device(s, n_frames, e->io_in.p, din_stride, e->io_out.p, dout_stride, e->stream);
+    if (rc) return rc;
+    CK(cudaMemcpy2DAsync(out, K > 1 ? out_stride : out_row, e->io_out.p, dout_stride, out_row, K, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return ICW_OK;
+}
+
+extern "C" int icw_session_profile(icw_session *s, int on)
+{
+    if (!s) return fail(ICW_E_ARG, "NULL session");
+    s->profiling = on != 0;
+    return ICW_OK;
+}
+
+extern "C" int icw_session_profile_read(icw_session *s, icw_profile *out, int reset)
+{
+    if (!s || !out) return fail(ICW_E_ARG, "NULL argument");
+    CK(cudaDeviceSynchronize());
+    for (auto &sp : s->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) { s->prof_ms[sp.k] += ms; s->prof_n[sp.k]++; }
+        else cudaGetLastError();
+        s->ev_pool.push_back(sp.a);
+        s->ev_pool.push_back(sp.b);
+    }
+    s->spans.clear();
+    for (int k = 0; k < ICW_K_COUNT; ++k) { out->ms[k] = s->prof_ms[k]; out->launches[k] = s->prof_n[k]; }
+    if (reset) for (int k = 0; k < ICW_K_COUNT; ++k) { s->prof_ms[k] = 0; s->prof_n[k] = 0; }
+    return ICW_OK;
+}
+
+extern "C" const char *icw_kernel_class_name(int k)
+{
+    static const char *names[ICW_K_COUNT] = { "hilbert", "chain", "mt", "misc" };
+    return (k >= 0 && k < ICW_K_COUNT) ? names[k] : "?";
+}
+
+extern "C" int icw_session_stats(icw_session *s, icw_stats *out)
+{
+    if (!s || !out) return fail(ICW_E_ARG, "NULL argument");
+    std::vector<DevStream> all((size_t)s->n_streams);
+    CK(cudaStreamSynchronize(s->e->stream));
+    CK(cudaMemcpy(all.data(), s->d_streams, sizeof(DevStream) * all.size(), cudaMemcpyDeviceToHost));
+    memset(out, 0, sizeof *out);
+    double pk[2] = { 0.0, 0.0 };
+    for (const auto &d : all) {
+        for (int c = 0; c < 2; ++c) {
+            out->clips[c] += d.clips[c];
+            pk[c] = std::max(pk[c], d.peak[c]);
+            out->hb_rejects += d.hb_rejects[c][0] + d.hb_rejects[c][1];
+        }
+        out->mt_redraws += d.mt_redraws;
+    }
+    out->peak_db[0] = icw_peak_db(pk[0]);
+    out->peak_db[1] = icw_peak_db(pk[1]);
+    out->kernel_launches = s->launches;
+    return ICW_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// leaves
+// ---------------------------------------------------------------------------------------------
+extern "C" int icw_hilbert_device(icw_engine *e, int filter_no, int is_kahan, int is_reject, int mode,
+                                  int n_chan, int64_t n, const double *d_x, double *d_out_iq,
+                                  icw_stream_state *chan_state)
+{
+    if (!e || !d_x || !d_out_iq || !chan_state || n_chan < 1 || n < 0) return fail(ICW_E_ARG, "bad argument");
+    if (filter_no < 0 || filter_no >= ICW_HB_NTYPES) return fail(ICW_E_ARG, "filter_no must be 0..5");
+    if (mode != ICW_HILBERT_EXACT) return fail(ICW_E_UNSUPPORTED, "hilbert_mode %d is not available in this build", mode);
+    CK(cudaSetDevice(e->device));
+    HbCoef coef;
+    memset(&coef, 0, sizeof coef);
+    const int ord = ICW_HB_ORDER[filter_no];
+    double a0 = word_as_double(ICW_HB_A[filter_no][0]);
+    coef.d0 = word_as_double(ICW_HB_B[filter_no][0]) / a0;
+    for (int i = 0; i < ord; ++i) {
+        coef.fb[i] = -word_as_double(ICW_HB_A[filter_no][i + 1]) / a0;
+        coef.ff[i] = word_as_double(ICW_HB_B[filter_no][i + 1]) / a0;
+    }
+    std::vector<HbLeafState> hs((size_t)n_chan);
+    for (int c = 0; c < n_chan; ++c) {
+        memcpy(hs[c].z, chan_state[c].hb[0], sizeof hs[c].z);
+        hs[c].rejects[0] = chan_state[c].hb_rejects[0][0];
+        hs[c].rejects[1] = chan_state[c].hb_rejects[0][1];
+        hs[c].quad = chan_state[c].quad[0] & 3u;
+        hs[c].pad = 0;
+    }
+    int rc = e->leaf.reserve(sizeof(HbLeafState) * hs.size());
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(e->leaf.p, hs.data(), sizeof(HbLeafState) * hs.size(), cudaMemcpyHostToDevice, e->stream));
+    if (n) CK(launch_hb_leaf(coef, ord, is_kahan != 0, is_reject, n_chan, n, d_x, d_out_iq, (HbLeafState *)e->leaf.p, e->stream));
+    CK(cudaMemcpyAsync(hs.data(), e->leaf.p, sizeof(HbLeafState) * hs.size(), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    for (int c = 0; c < n_chan; ++c) {
+        memcpy(chan_state[c].hb[0], hs[c].z, sizeof hs[c].z);
+        chan_state[c].hb_rejects[0][0] = hs[c].rejects[0];
+        chan_state[c].hb_rejects[0][1] = hs[c].rejects[1];
+        chan_state[c].quad[0] = hs[c].quad;
+    }
+    return ICW_OK;
+}
+
+extern "C" int icw_mt_words_device(icw_engine *e, uint32_t seed, uint64_t skip, int64_t n, uint32_t *d_out)
+{
+    if (!e || !d_out || n < 0) return fail(ICW_E_ARG, "bad argument");
+    if (!n) return ICW_OK;
+    CK(cudaSetDevice(e->device));
+    uint64_t launches = 0;
+    int rc = e->mt.generate(seed, skip, n, d_out, e->sm_count, e->stream, &launches);
+    if (rc) return fail(rc, "%s", e->mt.error());
+    CK(cudaStreamSynchronize(e->stream));
+    return ICW_OK;
+}
+
+// parity leaf for the oscillator: omega and fmod(omega*f, 2pi) for frames n0 .. n0+n-1 of a spec
+extern "C" int icw_debug_phase_device(icw_engine *e, const icw_chain_spec *spec, uint64_t n0, int64_t n,
+                                      double freq_hz, double *d_out)
+{
+    if (!e || !spec || !d_out || n < 0) return fail(ICW_E_ARG, "bad argument");
+    DevChain ch;
+    HbCoef coef;
+    int rc = fold_spec(*spec, ch, coef);
+    if (rc) return rc;
+    if (!n) return ICW_OK;
+    CK(cudaSetDevice(e->device));
+    CK(launch_phase_leaf(ch, n0, n, scaled_freq(fabs(freq_hz), ch.is_frmod_scaled), d_out, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return ICW_OK;
+}

@@ -1,0 +1,77 @@
+// icw_internal.h -- structures shared by the host side (icw_api.cu) and the kernels.
+#pragma once
+#include <cstdint>
+#include "../../include/icw_b200.h"
+
+#define ICW_PI          3.1415926535897932384626433832795029   // reference src/in_cwave.h:148
+#define ICW_TWO_PI      (2.0 * ICW_PI)
+#define ICW_INV_TWO_PI  (1.0 / ICW_TWO_PI)
+#define ICW_SQRT2       1.4142135623730950488016887242097       // reference src/adv_modulator.c:43
+#define ICW_RSQRT2      (1.0 / ICW_SQRT2)
+#define ICW_SQRT6       2.4494897427831780981972840747059       // reference src/sound_render.c:50
+#define ICW_HZ_SCALE    1000u                                   // reference src/in_cwave.h:162
+#define ICW_SILENCE_DB  (-555.0)                                // reference src/sound_render.h:103
+#define ICW_MT_N        624
+#define ICW_MT_M        397
+
+namespace icw {
+
+// a DSP-list node with everything the host can fold ahead of time already folded, using the
+// same IEEE operations the reference would perform per frame (so the folding is invisible)
+struct DevNode {
+    int32_t  mode;
+    uint32_t inputs_mask;
+    int32_t  xch_mode;
+    int32_t  l_iq_invert, r_iq_invert;
+    int32_t  n_out;
+    int32_t  l_tout, r_tout;
+    int32_t  l_on, r_on;
+    int32_t  l_neg, r_neg;          // shift: fr_shift < 0 (adv_modulator.c:528-541)
+    double   l_gain, r_gain;
+    double   l_f, r_f;              // |frequency|, scaled to mHz grid when is_frmod_scaled (:36-38)
+    double   l_ph0, r_ph0;          // pm: phase * PI          (:572)
+    double   l_lvlpi, r_lvlpi;      // pm: level * PI          (:572)
+    double   l_angle, r_angle;      // pm: angle
+};
+
+// quantiser constants (reference sound_render_recalc, src/sound_render.c:499-551)
+struct DevRender {
+    double  dth_mul, hi, lo, inv_hi, norm_mul, round_off;
+    int32_t neg_delta, shift, bytes;    // bytes per channel sample: 2 or 3
+    int32_t render_type;
+    int32_t words_per_sample;           // MT words per channel sample: 0/2/4/2/24
+};
+
+struct DevChain {
+    int32_t  fmt, n_channels, chan_bytes, frame_bytes, out_frame_bytes;
+    int32_t  is_complex;
+    int32_t  is_frmod_scaled;
+    int32_t  bypass, n_nodes;
+    int32_t  filter_no, hb_ord, is_kahan, reject_flag;
+    int64_t  n_samples, n_fade_in, n_fade_out;
+    uint64_t scale_sr;                  // sample_rate * 1000 (scaled) or 0
+    double   osc_div, osc_rdiv;         // divisor of the oscillator phase and RN(1/divisor)
+    double   hb_fb[ICW_MAX_ORD];        // -a[j+1]/a0        (src/hblpf.c:853)
+    double   hb_ff[ICW_MAX_ORD];        //  b[j+1]/a0        (src/hblpf.c:854)
+    double   hb_d0;                     //  b0/a0            (src/hblpf.c:850)
+    DevRender render;
+    DevNode  nodes[ICW_MAX_NODES];
+};
+
+// device-resident per-stream state: icw_stream_state plus what only the kernels need
+struct DevStream {
+    uint64_t n_frame;
+    int64_t  pos;
+    double   hb[2][2][ICW_MAX_ORD];
+    unsigned long long hb_rejects[2][2];
+    uint32_t quad[2];
+    uint32_t mt_seed[2];
+    uint64_t mt_drawn[2];
+    double   prev_rnd[2];
+    uint32_t clips[2];
+    double   peak[2];
+    double   bus[ICW_N_PLUGS][4];
+    unsigned long long mt_redraws;
+};
+
+}  // namespace icw

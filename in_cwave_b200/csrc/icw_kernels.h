@@ -1,0 +1,41 @@
+// icw_kernels.h -- launch wrappers exported by icw_kernels.cu to the host side (icw_api.cu).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "icw_internal.h"
+
+namespace icw {
+
+// half-band design in the form the recurrence consumes; passed as a __grid_constant__ kernel
+// parameter so every coefficient is a constant-bank operand of its DMUL (no registers spent)
+struct HbCoef {
+    double fb[ICW_MAX_ORD];
+    double ff[ICW_MAX_ORD];
+    double d0;
+};
+
+struct HbLeafState {
+    double   z[2][ICW_MAX_ORD];     // [0 = I, 1 = Q][newest first]
+    unsigned long long rejects[2];
+    unsigned quad;
+    unsigned pad;
+};
+
+cudaError_t launch_hb_exact(const HbCoef &coef, const DevChain &ch, DevStream *streams, int n_streams,
+                            int64_t n_frames, const uint8_t *in, size_t in_stride, double *analytic,
+                            cudaStream_t s);
+cudaError_t launch_hb_leaf(const HbCoef &coef, int ord, bool kahan, int reject, int n_chan, int64_t n,
+                           const double *x, double *out, HbLeafState *st, cudaStream_t s);
+cudaError_t launch_mt_words(const uint32_t *ckpt, int n_cta, int blocks_per_cta, int64_t first_word,
+                            int64_t want_lo, int64_t want_hi, uint32_t *out, cudaStream_t s);
+cudaError_t launch_chain(const DevChain &ch, DevStream *streams, int n_streams, int64_t n_frames,
+                         const uint8_t *in, size_t in_stride, int from_analytic,
+                         const uint32_t *mtw_l, const uint32_t *mtw_r, int mt_shared,
+                         uint8_t *out, size_t out_stride, double *tap_bus, double *tap_lr,
+                         int sm_count, cudaStream_t s);
+cudaError_t launch_advance(const DevChain &ch, DevStream *streams, int n_streams, int64_t n_frames,
+                           int advance_quad, cudaStream_t s);
+cudaError_t launch_phase_leaf(const DevChain &ch, uint64_t n0, int64_t n, double f, double *out, cudaStream_t s);
+
+}  // namespace icw

@@ -1,0 +1,395 @@
+// icw_mt.cu -- MT19937 jump-ahead: GF(2) polynomial arithmetic on the host, application on the GPU.
+// See icw_mt.h for the identity this relies on.  Stream facts follow the reference generator,
+// src/mersene_twister/mt_jrnd.c:28-47 (seeding) and :99-134 (block regeneration + tempering).
+#include "icw_mt.h"
+
+#include <cstdio>
+#include <cstring>
+
+#include "icw_kernels.h"
+#include "../../include/icw_b200.h"
+
+namespace icw {
+
+// =============================================================================================
+// host: generator
+// =============================================================================================
+void mt_seed_state(uint32_t seed, uint32_t st[MT_N])
+{
+    uint32_t prev = seed;
+    st[0] = prev;
+    for (uint32_t j = 1; j < MT_N; ++j) {
+        prev = 1812433253u * (prev ^ (prev >> 30)) + j;
+        st[j] = prev;
+    }
+}
+
+void mt_regen_host(uint32_t st[MT_N])
+{
+    for (int k = 0; k < MT_N; ++k) {
+        uint32_t a = st[k], b = st[k + 1 < MT_N ? k + 1 : 0];
+        uint32_t mix = (a & 0x80000000u) | (b & 0x7FFFFFFFu);
+        uint32_t tw = (mix >> 1) ^ ((b & 1u) ? 0x9908B0DFu : 0u);
+        st[k] = st[k + 397 < MT_N ? k + 397 : k + 397 - MT_N] ^ tw;
+    }
+}
+
+// =============================================================================================
+// host: characteristic polynomial by Berlekamp-Massey over GF(2) on the generator's own bits
+// =============================================================================================
+static std::vector<int> compute_charpoly_terms()
+{
+    const int N = 2 * MT_DEG + 128;                 // bits examined
+    const int W = (N + 63) / 64 + 1;
+    std::vector<uint8_t> bits((size_t)N);
+    {
+        uint32_t st[MT_N];
+        mt_seed_state(5489u, st);
+        int n = 0;
+        while (n < N) {
+            mt_regen_host(st);
+            for (int i = 0; i < MT_N && n < N; ++i) bits[n++] = (uint8_t)(st[i] & 1u);
+        }
+    }
+    std::vector<uint64_t> C((size_t)W, 0), B((size_t)W, 0), T((size_t)W, 0), R((size_t)W, 0);
+    C[0] = 1; B[0] = 1;
+    int L = 0, m = 1;
+    for (int n = 0; n < N; ++n) {
+        // R bit j = s[n - j]: shift in the new bit
+        uint64_t carry = bits[n];
+        const int rw = n / 64 + 1 < W ? n / 64 + 1 : W;
+        for (int i = 0; i < rw; ++i) {
+            uint64_t nc = R[i] >> 63;
+            R[i] = (R[i] << 1) | carry;
+            carry = nc;
+        }
+        uint64_t acc = 0;
+        const int lw = L / 64 + 1;
+        for (int i = 0; i < lw; ++i) acc ^= C[i] & R[i];
+        int d = __builtin_parityll(acc);
+        if (!d) { ++m; continue; }
+        const bool grow = 2 * L <= n;
+        if (grow) T = C;
+        // C ^= B << m
+        const int ws = m / 64, bs = m % 64;
+        for (int i = W - 1; i >= ws; --i) {
+            uint64_t v = B[i - ws] << bs;
+            if (bs && i - ws - 1 >= 0) v |= B[i - ws - 1] >> (64 - bs);
+            C[i] ^= v;
+        }
+        if (grow) { L = n + 1 - L; B.swap(T); m = 1; }
+        else ++m;
+    }
+    std::vector<int> terms;
+    if (L != MT_DEG) return terms;                   // caller reports the failure
+    // connection polynomial C(x) = sum c_i x^i  <->  phi(x) = x^L * C(1/x): phi_{L-i} = c_i
+    for (int i = L; i >= 0; --i)
+        if ((C[i / 64] >> (i % 64)) & 1u) terms.push_back(L - i);
+    return terms;                                    // ascending exponents, last = 19937
+}
+
+const std::vector<int> &mt_charpoly_terms()
+{
+    static const std::vector<int> terms = compute_charpoly_terms();
+    return terms;
+}
+
+// =============================================================================================
+// host: polynomials modulo phi
+// =============================================================================================
+void mt_poly_one(MtPoly &p) { memset(&p, 0, sizeof p); p.w[0] = 1; }
+
+static inline void flip(uint64_t *w, int bit) { w[bit >> 6] ^= 1ull << (bit & 63); }
+static inline int get(const uint64_t *w, int bit) { return (int)((w[bit >> 6] >> (bit & 63)) & 1u); }
+
+// wide[0 .. 2*MT_PW) -> reduced into its low MT_DEG bits
+static void reduce_wide(uint64_t *wide)
+{
+    const std::vector<int> &t = mt_charpoly_terms();
+    for (int pos = 2 * MT_PW * 64 - 1; pos >= MT_DEG; --pos) {
+        if (!get(wide, pos)) continue;
+        const int sh = pos - MT_DEG;
+        for (int e : t) flip(wide, sh + e);          // the top term clears bit `pos`
+    }
+}
+
+void mt_poly_square(const MtPoly &a, MtPoly &out)
+{
+    static uint16_t spread[256];
+    static bool init = false;
+    if (!init) {
+        for (int v = 0; v < 256; ++v) {
+            uint16_t s = 0;
+            for (int b = 0; b < 8; ++b) if (v & (1 << b)) s |= (uint16_t)(1u << (2 * b));
+            spread[v] = s;
+        }
+        init = true;
+    }
+    uint64_t wide[2 * MT_PW];
+    for (int i = 0; i < MT_PW; ++i) {
+        uint64_t v = a.w[i], lo = 0, hi = 0;
+        for (int b = 0; b < 4; ++b) lo |= (uint64_t)spread[(v >> (8 * b)) & 0xFF] << (16 * b);
+        for (int b = 0; b < 4; ++b) hi |= (uint64_t)spread[(v >> (32 + 8 * b)) & 0xFF] << (16 * b);
+        wide[2 * i] = lo; wide[2 * i + 1] = hi;
+    }
+    reduce_wide(wide);
+    memcpy(out.w, wide, sizeof out.w);
+}
+
+void mt_poly_mul(const MtPoly &a, const MtPoly &b, MtPoly &out)
+{
+    uint64_t wide[2 * MT_PW];
+    memset(wide, 0, sizeof wide);
+    for (int i = 0; i < MT_PW * 64; ++i) {
+        if (!get(a.w, i)) continue;
+        const int ws = i >> 6, bs = i & 63;
+        for (int j = 0; j < MT_PW; ++j) {
+            wide[ws + j] ^= b.w[j] << bs;
+            if (bs) wide[ws + j + 1] ^= b.w[j] >> (64 - bs);
+        }
+    }
+    reduce_wide(wide);
+    memcpy(out.w, wide, sizeof out.w);
+}
+
+static void poly_mulx(MtPoly &p)
+{
+    uint64_t carry = 0;
+    for (int i = 0; i < MT_PW; ++i) {
+        uint64_t nc = p.w[i] >> 63;
+        p.w[i] = (p.w[i] << 1) | carry;
+        carry = nc;
+    }
+    if (get(p.w, MT_DEG))
+        for (int e : mt_charpoly_terms()) flip(p.w, e);
+}
+
+void mt_poly_mulx_pow(MtPoly &p, uint64_t e) { while (e--) poly_mulx(p); }
+
+void mt_poly_xpow(uint64_t e, MtPoly &out)
+{
+    mt_poly_one(out);
+    if (!e) return;
+    int top = 63;
+    while (!((e >> top) & 1u)) --top;
+    for (int b = top; b >= 0; --b) {
+        MtPoly sq;
+        mt_poly_square(out, sq);
+        out = sq;
+        if ((e >> b) & 1u) poly_mulx(out);
+    }
+}
+
+void mt_apply_host(const MtPoly &g, const uint32_t base[MT_N], uint32_t out[MT_N])
+{
+    const int blocks = 33;
+    std::vector<uint32_t> seq((size_t)blocks * MT_N);
+    memcpy(seq.data(), base, MT_N * sizeof(uint32_t));
+    for (int k = 0; k + MT_N < blocks * MT_N; ++k) {
+        uint32_t a = seq[k], b = seq[k + 1];
+        uint32_t mix = (a & 0x80000000u) | (b & 0x7FFFFFFFu);
+        seq[k + MT_N] = seq[k + 397] ^ (mix >> 1) ^ ((b & 1u) ? 0x9908B0DFu : 0u);
+    }
+    for (int m = 0; m < MT_N; ++m) {
+        uint32_t acc = 0;
+        for (int i = 0; i < MT_DEG; ++i)
+            if (get(g.w, i)) acc ^= seq[i + m];
+        out[m] = acc;
+    }
+}
+
+// =============================================================================================
+// device: apply a jump polynomial to many states at once
+// =============================================================================================
+constexpr int JUMP_THREADS = 640;
+constexpr int JUMP_SEQ = 33 * MT_N;                 // 20592 words >= 19936 + 624
+constexpr size_t JUMP_SMEM = (JUMP_SEQ + MT_N) * sizeof(uint32_t);
+
+// states[dst_first + blockIdx.x] = jump(states[dst_first + blockIdx.x - span]) by the polynomial
+__global__ void __launch_bounds__(JUMP_THREADS)
+mt_jump_kernel(uint32_t *__restrict__ states, const uint32_t *__restrict__ src_states, int dst_first, int span,
+               const uint32_t *__restrict__ poly)
+{
+    extern __shared__ uint32_t sm[];
+    uint32_t *seq = sm;
+    uint32_t *pw = sm + JUMP_SEQ;
+    const int tid = threadIdx.x;
+    const int dst = dst_first + blockIdx.x;
+    const uint32_t *src = src_states ? src_states + (size_t)blockIdx.x * MT_N
+                                     : states + (size_t)(dst - span) * MT_N;
+    for (int i = tid; i < MT_N; i += JUMP_THREADS) { seq[i] = src[i]; pw[i] = poly[i]; }
+    __syncthreads();
+    // continue the sequence: u[k+624] = u[k+397] ^ twist(u[k], u[k+1]); 227 independent words a step
+    for (int k0 = 0; k0 + MT_N < JUMP_SEQ; k0 += 227) {
+        int k = k0 + tid;
+        if (tid < 227 && k + MT_N < JUMP_SEQ) {
+            uint32_t a = seq[k], b = seq[k + 1];
+            uint32_t mix = (a & 0x80000000u) | (b & 0x7FFFFFFFu);
+            seq[k + MT_N] = seq[k + 397] ^ (mix >> 1) ^ ((b & 1u) ? 0x9908B0DFu : 0u);
+        }
+        __syncthreads();
+    }
+    if (tid < MT_N) {
+        uint32_t acc = 0;
+        for (int wi = 0; wi < MT_N; ++wi) {
+            const uint32_t bits = pw[wi];
+            if (!bits) continue;                     // uniform across the CTA
+            const uint32_t *p = seq + wi * 32 + tid;
+#pragma unroll
+            for (int b = 0; b < 32; ++b) acc ^= p[b] & (0u - ((bits >> b) & 1u));
+        }
+        states[(size_t)dst * MT_N + tid] = acc;
+    }
+}
+
+void MtJump::release()
+{
+    for (uint32_t *p : dev_poly_) if (p) cudaFree(p);
+    dev_poly_.clear();
+    host_poly_.clear();
+    if (d_ckpt_) cudaFree(d_ckpt_);
+    if (d_tmp_) cudaFree(d_tmp_);
+    d_ckpt_ = d_tmp_ = nullptr;
+    ckpt_cap_ = 0;
+}
+
+int MtJump::ensure_poly(int k)
+{
+    if (mt_charpoly_terms().empty()) { err_ = "MT19937 characteristic polynomial: Berlekamp-Massey did not reach degree 19937"; return ICW_E_ARG; }
+    while ((int)host_poly_.size() <= k) {
+        MtPoly p;
+        if (host_poly_.empty()) mt_poly_xpow(MT_N, p);              // x^624
+        else mt_poly_square(host_poly_.back(), p);                   // (x^(624*2^(k-1)))^2
+        host_poly_.push_back(p);
+        dev_poly_.push_back(nullptr);
+    }
+    if (!dev_poly_[k]) {
+        if (cudaMalloc(&dev_poly_[k], MT_N * sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); err_ = "cudaMalloc(jump polynomial) failed"; return ICW_E_NOMEM; }
+        if (cudaMemcpy(dev_poly_[k], host_poly_[k].w, MT_N * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) { err_ = "copy of jump polynomial failed"; return ICW_E_CUDA; }
+    }
+    if (!attr_set_) {
+        if (cudaFuncSetAttribute(mt_jump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JUMP_SMEM) != cudaSuccess) { err_ = "cudaFuncSetAttribute(mt_jump_kernel) failed"; return ICW_E_CUDA; }
+        attr_set_ = true;
+    }
+    return ICW_OK;
+}
+
+// S_block (the state array u[624*block .. 624*block+623]) into d_state
+int MtJump::state_at_block(uint32_t seed, uint64_t block, uint32_t *d_state, cudaStream_t stream, uint64_t *launches)
+{
+    uint32_t st[MT_N];
+    mt_seed_state(seed, st);
+    uint64_t rest = 0;
+    if (block >= 1) { mt_regen_host(st); rest = block - 1; }        // never jump from S_0: u[0] carries 31 junk bits
+    // short distances are cheaper sequentially on the host than one jump launch
+    if (rest <= 64) { for (; rest; --rest) mt_regen_host(st); }
+    if (cudaMemcpyAsync(d_state, st, sizeof st, cudaMemcpyHostToDevice, stream) != cudaSuccess) { err_ = "state upload failed"; return ICW_E_CUDA; }
+    if (cudaStreamSynchronize(stream) != cudaSuccess) { err_ = "sync failed"; return ICW_E_CUDA; }   // st is on our stack
+    if (!rest) return ICW_OK;
+    if (!d_tmp_ && cudaMalloc(&d_tmp_, 2 * MT_N * sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); err_ = "cudaMalloc failed"; return ICW_E_NOMEM; }
+    // binary decomposition of the distance, one single-CTA jump per set bit, ping-pong in d_tmp_
+    uint32_t *cur = d_state;
+    int flip = 0;
+    for (int k = 0; k < 64; ++k) {
+        if (!((rest >> k) & 1u)) continue;
+        int rc = ensure_poly(k);
+        if (rc) return rc;
+        uint32_t *dst = d_tmp_ + (size_t)flip * MT_N;
+        mt_jump_kernel<<<1, JUMP_THREADS, JUMP_SMEM, stream>>>(dst, cur, 0, 0, dev_poly_[k]);
+        if (launches) ++*launches;
+        cur = dst;
+        flip ^= 1;
+    }
+    if (cur != d_state && cudaMemcpyAsync(d_state, cur, MT_N * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream) != cudaSuccess) { err_ = "state copy failed"; return ICW_E_CUDA; }
+    if (cudaGetLastError() != cudaSuccess) { err_ = "mt_jump_kernel launch failed"; return ICW_E_CUDA; }
+    return ICW_OK;
+}
+
+int MtJump::generate(uint32_t seed, uint64_t skip, int64_t n, uint32_t *d_out, int sm_count,
+                     cudaStream_t stream, uint64_t *launches)
+{
+    if (n <= 0) return ICW_OK;
+    const uint64_t b0 = skip / MT_N, b1 = (skip + (uint64_t)n - 1) / MT_N;
+    const uint64_t nb = b1 - b0 + 1;
+    // blocks per CTA = 2^kb so that every checkpoint distance has a polynomial in the x^(624*2^k) family
+    const uint64_t max_cta = (uint64_t)sm_count * 4;
+    int kb = 0;
+    while (((nb + (1ull << kb) - 1) >> kb) > max_cta) ++kb;
+    const int n_cta = (int)((nb + (1ull << kb) - 1) >> kb);
+    if ((size_t)n_cta > ckpt_cap_) {
+        if (d_ckpt_) cudaFree(d_ckpt_);
+        d_ckpt_ = nullptr; ckpt_cap_ = 0;
+        size_t want = (size_t)std::max(n_cta, 64);
+        if (cudaMalloc(&d_ckpt_, want * MT_N * sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); err_ = "cudaMalloc(checkpoints) failed"; return ICW_E_NOMEM; }
+        ckpt_cap_ = want;
+    }
+    int rc = state_at_block(seed, b0, d_ckpt_, stream, launches);
+    if (rc) return rc;
+    // doubling: checkpoints [2^j, 2^(j+1)) come from [0, 2^j) by a jump of 2^(kb+j) blocks
+    for (int j = 0; (1 << j) < n_cta; ++j) {
+        rc = ensure_poly(kb + j);
+        if (rc) return rc;
+        const int first = 1 << j;
+        const int count = std::min(n_cta, 2 << j) - first;
+        mt_jump_kernel<<<count, JUMP_THREADS, JUMP_SMEM, stream>>>(d_ckpt_, nullptr, first, first, dev_poly_[kb + j]);
+        if (launches) ++*launches;
+    }
+    cudaError_t e = launch_mt_words(d_ckpt_, n_cta, 1 << kb, (int64_t)(b0 * MT_N), (int64_t)skip, (int64_t)(skip + (uint64_t)n), d_out, stream);
+    if (launches) ++*launches;
+    if (e != cudaSuccess) { err_ = std::string("mt kernels: ") + cudaGetErrorString(e); return ICW_E_CUDA; }
+    return ICW_OK;
+}
+
+}  // namespace icw
+
+// =============================================================================================
+// host-only hooks for CPU tests of the polynomial machinery (no GPU touched)
+// =============================================================================================
+extern "C" int icw_mt_host_charpoly(int *n_terms, int *degree)
+{
+    const std::vector<int> &t = icw::mt_charpoly_terms();
+    if (n_terms) *n_terms = (int)t.size();
+    if (degree) *degree = t.empty() ? -1 : t.back();
+    return t.empty() ? ICW_E_ARG : ICW_OK;
+}
+
+// S_blocks by sequential regeneration
+extern "C" void icw_mt_host_seq_state(uint32_t seed, uint64_t blocks, uint32_t *out624)
+{
+    icw::mt_seed_state(seed, out624);
+    for (uint64_t b = 0; b < blocks; ++b) icw::mt_regen_host(out624);
+}
+
+// S_blocks through x^(624*(blocks-1)) mod phi applied to S_1 (the jump path, all on the host)
+extern "C" int icw_mt_host_jump_state(uint32_t seed, uint64_t blocks, uint32_t *out624)
+{
+    if (icw::mt_charpoly_terms().empty()) return ICW_E_ARG;
+    uint32_t st[icw::MT_N];
+    icw::mt_seed_state(seed, st);
+    if (blocks == 0) { memcpy(out624, st, sizeof st); return ICW_OK; }
+    icw::mt_regen_host(st);
+    icw::MtPoly g;
+    icw::mt_poly_xpow((blocks - 1) * (uint64_t)icw::MT_N, g);
+    icw::mt_apply_host(g, st, out624);
+    return ICW_OK;
+}
+
+// same, but composed from the x^(624*2^k) family exactly as the GPU path composes it
+extern "C" int icw_mt_host_jump_state_family(uint32_t seed, uint64_t blocks, uint32_t *out624)
+{
+    if (icw::mt_charpoly_terms().empty()) return ICW_E_ARG;
+    uint32_t st[icw::MT_N], nx[icw::MT_N];
+    icw::mt_seed_state(seed, st);
+    if (blocks == 0) { memcpy(out624, st, sizeof st); return ICW_OK; }
+    icw::mt_regen_host(st);
+    uint64_t rest = blocks - 1;
+    icw::MtPoly f, sq;
+    icw::mt_poly_xpow(icw::MT_N, f);
+    for (int k = 0; k < 64 && (rest >> k); ++k) {
+        if ((rest >> k) & 1u) { icw::mt_apply_host(f, st, nx); memcpy(st, nx, sizeof st); }
+        icw::mt_poly_square(f, sq);
+        f = sq;
+    }
+    memcpy(out624, st, sizeof st);
+    return ICW_OK;
+}

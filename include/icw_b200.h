@@ -1,0 +1,216 @@
+/* icw_b200.h -- C ABI of the B200 (sm_100a) implementation of the in_cwave signal chain
+ *
+ *      file bytes --unpack--> real/complex double --Hilbert (real input only)--> analytic
+ *                 --modulator graph (DSP list)--> (L, R) double --render--> 16/24-bit LE PCM
+ *
+ * Plain C: opaque handles, POD structs, raw pointers and sizes.  No CUDA or torch types cross
+ * this boundary (a CUDA stream is passed as void*).  Every entry point names the reference
+ * interface it stands in for (paths relative to the reference tree, file:line).
+ *
+ * Vocabulary (the reference's): a FRAME is one L+R sample pair; sample values are doubles in
+ * +-32768 units; a PLUG is one of the 27 cells of the in/out bus (0 = In, 1..26 = A..Z); the
+ * DSP LIST is the modulator graph; a STREAM is one file played through one fresh MOD_CONTEXT.
+ *
+ * Threading: one icw_engine per process and GPU; calls on one session must not overlap.
+ * Errors: every int-returning call gives ICW_OK (0) or a negative ICW_E_* code and leaves a
+ * message in icw_last_error().  There is NO CPU fallback anywhere behind this header.
+ */
+#ifndef ICW_B200_H
+#define ICW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ICW_ABI_VERSION   1
+#define ICW_N_PLUGS       27    /* reference src/in_cwave.h:198  N_INPUTS */
+#define ICW_MAX_NODES     32
+#define ICW_MAX_ORD       20    /* highest half-band filter order, reference src/hblpf.c:740-820 */
+
+enum {
+    ICW_OK = 0,
+    ICW_E_ARG = -1,             /* malformed argument / spec */
+    ICW_E_CUDA = -2,            /* CUDA runtime failure (message has the detail) */
+    ICW_E_UNSUPPORTED = -3,     /* valid in the reference but not modelled on the GPU (says which) */
+    ICW_E_NOMEM = -4
+};
+
+/* input sample encodings.  0..4 = reference HRW_FMT_* (src/in_cwave.h:326-330, unpackers
+ * src/xwave_reader.c:203-239); 16+n = reference HCW_FMT_* n (src/cwave.h:76-84, unpackers
+ * src/xwave_reader.c:171-199). */
+enum {
+    ICW_FMT_WAV_U8 = 0, ICW_FMT_WAV_I16 = 1, ICW_FMT_WAV_I24 = 2, ICW_FMT_WAV_I32 = 3,
+    ICW_FMT_WAV_F32 = 4,
+    ICW_FMT_CW_F64 = 16, ICW_FMT_CW_I16 = 17, ICW_FMT_CW_I16F32 = 18, ICW_FMT_CW_F32 = 19
+};
+/* node kinds, reference src/in_cwave.h:289-292 */
+enum { ICW_MODE_MASTER = 0, ICW_MODE_SHIFT = 1, ICW_MODE_PM = 2, ICW_MODE_MIX = 3 };
+/* channel exchange, reference src/in_cwave.h:186-190 */
+enum { ICW_XCH_NORMAL = 0, ICW_XCH_SWAP = 1, ICW_XCH_LEFTONLY = 2, ICW_XCH_RIGHTONLY = 3, ICW_XCH_MIXLR = 4 };
+/* master output, reference src/in_cwave.h:154-157 */
+enum { ICW_OUT_ADD_REIM = 0, ICW_OUT_SUB_REIM = 1, ICW_OUT_RE = 2, ICW_OUT_IM = 3 };
+/* dither, reference src/sound_render.h:62-66 */
+enum { ICW_RENDER_ROUND = 0, ICW_RENDER_RPDF = 1, ICW_RENDER_TPDF = 2, ICW_RENDER_STPDF = 3, ICW_RENDER_GAUSS = 4 };
+/* how the half-band recurrences are evaluated */
+enum {
+    ICW_HILBERT_EXACT = 0,      /* the reference's own operation order; bit-exact; serial per stream */
+    ICW_HILBERT_SCAN = 1        /* modal block scan; time-parallel; differs from the reference by
+                                   the reference's own rounding noise (DESIGN.md "numerics") */
+};
+
+/* One DSP-list node in EXECUTION order (the reference walks its list tail -> head, so the
+ * master comes last).  Field meaning = NODE_DSP, reference src/in_cwave.h:207-287; the
+ * per-frame arithmetic is reference src/adv_modulator.c:485-583 and :637-751. */
+typedef struct icw_node {
+    int32_t  mode;              /* ICW_MODE_* */
+    uint32_t inputs_mask;       /* bit k set: plug k is summed into this node's input */
+    int32_t  xch_mode;          /* ICW_XCH_* */
+    int32_t  l_iq_invert, r_iq_invert;
+    double   l_gain, r_gain;
+    int32_t  n_out;             /* output plug 1..26 (ignored for the master) */
+    int32_t  l_tout, r_tout;    /* master: ICW_OUT_* */
+    int32_t  l_on, r_on;        /* shift: is_shift; pm: is_pm (0 = copy through) */
+    double   l_p[4], r_p[4];    /* shift: {fr_shift Hz, signed}; pm: {freq, phase, level, angle} */
+} icw_node;
+
+/* Everything the reference keeps in its config (src/config.c:118-207), reader
+ * (src/in_cwave.h:375-405) and DSP list that changes what one frame computes. */
+typedef struct icw_chain_spec {
+    int32_t  fmt;               /* ICW_FMT_* */
+    int32_t  n_channels;        /* 1 or 2 (mono is duplicated to R, src/xwave_reader.c:949,988) */
+    uint32_t sample_rate;       /* Hz, <= 2 000 000 (src/in_cwave.h:160) */
+    int64_t  n_samples;         /* frames in the file: fade-out anchor (src/xwave_reader.c:930) */
+    int64_t  n_fade_in, n_fade_out;     /* frames; 0 = off (src/xwave_reader.c:921-936) */
+    int32_t  filter_no;         /* half-band design 0..5 (src/lpf_hilbert_quad.h:68-84) */
+    int32_t  is_kahan;          /* src/hblpf.c:1008 vs :894 */
+    int32_t  is_subnorm_reject; /* compared as a number, bug-for-bug (src/hblpf.c:915,1046) */
+    int32_t  hilbert_mode;      /* ICW_HILBERT_* */
+    int32_t  is_frmod_scaled;   /* mHz frequency grid + wrapping frame counter (src/adv_modulator.c:612-624) */
+    int32_t  need24bits;
+    double   dth_bits;
+    uint32_t quantz_type;       /* 0 mid tread, 1 mid riser (src/sound_render.h:57-58) */
+    uint32_t render_type;       /* ICW_RENDER_* */
+    uint32_t nshape_type;       /* 0 = flat; others are ICW_E_UNSUPPORTED (serial error feedback) */
+    uint32_t sign_bits16, sign_bits24;
+    int32_t  bypass;            /* src/adv_modulator.c:637,644 */
+    int32_t  n_nodes;
+    icw_node nodes[ICW_MAX_NODES];
+} icw_chain_spec;
+
+/* What persists from frame to frame for one stream: the reference's MOD_CONTEXT
+ * (src/in_cwave.h:410-424) reduced to its arithmetic content. */
+typedef struct icw_stream_state {
+    uint64_t n_frame;                       /* oscillator frame counter */
+    int64_t  pos;                           /* frames already taken from the current file */
+    double   hb[2][2][ICW_MAX_ORD];         /* [channel][0 = I, 1 = Q][j] = filter state j+1 frames ago */
+    uint64_t hb_rejects[2][2];              /* "subnorm reject" hits (src/hblpf.c:918) */
+    uint32_t quad[2];                       /* frame index mod 4 of the fs/4 mixer, per channel */
+    uint32_t mt_seed[2];                    /* MT19937 identity: mtrnd_init_seed(seed) ... */
+    uint64_t mt_drawn[2];                   /* ... advanced by this many 32-bit words */
+    double   prev_rnd[2];                   /* sloped-TPDF memory (src/sound_render.c:729) */
+    uint32_t clips[2];                      /* src/sound_render.c:782-797 */
+    double   peak[2];                       /* max |q|/hi_bound, LINEAR; dB via icw_peak_db() */
+    double   bus[ICW_N_PLUGS][4];           /* (L.re, L.im, R.re, R.im) per plug */
+} icw_stream_state;
+
+typedef struct icw_engine  icw_engine;      /* one GPU: streams, scratch, MT jump tables */
+typedef struct icw_session icw_session;     /* a chain spec + K device-resident stream states */
+
+const char *icw_last_error(void);
+int  icw_abi_version(void);
+
+/* spec with the reference's defaults: src/config.c:118-207, master node src/adv_modulator.c:112-118 */
+void icw_default_spec(icw_chain_spec *spec);
+/* fresh stream == state right after winampGetInModule2(): src/in_cwave.c:46-80 (seeds :69-70) */
+void icw_default_state(icw_stream_state *st);
+int  icw_frame_bytes(const icw_chain_spec *spec);       /* input bytes per frame */
+int  icw_out_frame_bytes(const icw_chain_spec *spec);   /* 4 or 6; src/sound_render.c:682-685 */
+/* 20*log10(peak) or -555 dB for silence; src/sound_render.c:773-775 */
+double icw_peak_db(double peak_linear);
+
+int  icw_engine_create(int device, icw_engine **out);
+void icw_engine_destroy(icw_engine *e);
+
+/* K independent streams sharing one spec; stands in for K fresh MOD_CONTEXTs
+ * (src/in_cwave.c:46-80) plus amod_init (src/adv_modulator.c:216-331). */
+int  icw_session_create(icw_engine *e, const icw_chain_spec *spec, int n_streams, icw_session **out);
+void icw_session_destroy(icw_session *s);
+/* parameter snapshot: what the GUI thread does through adbl_write / srenders_set_vcfg /
+ * mod_context_change_all_hilberts_* (src/amod_gui_control.c:259-312,1555-1602); takes effect at
+ * the next process call.  A new filter_no clears the Hilbert state like the reference does
+ * (src/in_cwave.c:135-150); a render change clears prev_rnd (src/sound_render.c:499-581). */
+int  icw_session_set_spec(icw_session *s, const icw_chain_spec *spec);
+int  icw_session_get_state(icw_session *s, int stream, icw_stream_state *out);
+int  icw_session_set_state(icw_session *s, int stream, const icw_stream_state *in);
+/* mod_context_reset_hilbert / _reset_framecnt (src/in_cwave.c:161,287), counters
+ * (amod_get_clips_peaks isReset, src/adv_modulator.c:445), new file position */
+enum { ICW_RESET_HILBERT = 1, ICW_RESET_FRAMECNT = 2, ICW_RESET_COUNTERS = 4, ICW_RESET_FILEPOS = 8,
+       ICW_RESET_ALL = 255 };
+int  icw_session_reset(icw_session *s, unsigned what);
+
+/* The hot call: n frames of every stream.  Stands in for the frame loop of
+ * amod_process_samples (src/adv_modulator.c:587-763) run n_streams times.
+ * Input stream k starts at in + k*in_stride bytes, output at out + k*out_stride bytes.
+ * _host: pageable or pinned host memory, copies included.  _device: device pointers,
+ * asynchronous on cuda_stream (a cudaStream_t, NULL = engine's own stream). */
+int  icw_session_process_host(icw_session *s, int64_t n_frames, const void *in, size_t in_stride,
+                              void *out, size_t out_stride);
+int  icw_session_process_device(icw_session *s, int64_t n_frames, const void *d_in, size_t in_stride,
+                                void *d_out, size_t out_stride, void *cuda_stream);
+int  icw_session_sync(icw_session *s);
+
+/* sums / maxima over the session's streams: amod_get_clips_peaks (src/adv_modulator.c:445-465),
+ * mod_context_get_desubnorm_counter (src/in_cwave.c:296) */
+typedef struct icw_stats {
+    uint64_t clips[2];
+    double   peak_db[2];
+    uint64_t hb_rejects;
+    uint64_t mt_redraws;        /* dsopen re-draws seen (src/mt_jrnd.c:249-253); !=0 => resync needed */
+    uint64_t kernel_launches;   /* our kernels launched by this session so far */
+} icw_stats;
+int  icw_session_stats(icw_session *s, icw_stats *out);
+
+/* leaf entry points (device buffers in, device buffers out) for stage-wise parity:
+ * hq_rp_process (src/lpf_hilbert_quad.c:129-156) over n samples of n_chan independent channels,
+ * x[c*n + i] -> out_iq[(c*n + i)*2 + {0,1}]; state per channel in/out on the host. */
+int  icw_hilbert_device(icw_engine *e, int filter_no, int is_kahan, int is_reject, int mode,
+                        int n_chan, int64_t n, const double *d_x, double *d_out_iq,
+                        icw_stream_state *chan_state /* uses hb[0], quad[0], hb_rejects[0] */);
+/* mtrnd_gen_ui32 stream (src/mt_jrnd.c:99-134): words [skip, skip+n) after mtrnd_init_seed(seed),
+ * produced on the GPU through the jump-ahead path */
+int  icw_mt_words_device(icw_engine *e, uint32_t seed, uint64_t skip, int64_t n, uint32_t *d_out);
+
+/* ---- measurement: per-kernel device time from CUDA events on the launching stream ---------- */
+enum { ICW_K_HILBERT = 0, ICW_K_CHAIN = 1, ICW_K_MT = 2, ICW_K_MISC = 3, ICW_K_COUNT = 4 };
+typedef struct icw_profile {
+    double   ms[ICW_K_COUNT];       /* summed device time per kernel class since the last reset */
+    uint64_t launches[ICW_K_COUNT];
+} icw_profile;
+/* on != 0: bracket every kernel class of this session with events (a few us each); reading syncs */
+int  icw_session_profile(icw_session *s, int on);
+int  icw_session_profile_read(icw_session *s, icw_profile *out, int reset);
+const char *icw_kernel_class_name(int k);
+
+/* ---- diagnostics used by the parity tests (not part of the reference's surface) -------------- */
+/* device buffers that receive, per stream and frame, the whole bus [ICW_N_PLUGS][4] and the
+ * master output [2] of the next process calls (NULL = off) */
+int  icw_session_set_taps(icw_session *s, double *d_tap_bus, double *d_tap_lr);
+/* oscillator leaf: out[i] = { norm_omega, fmod(norm_omega * f, 2*pi) } for frame counter n0+i,
+ * f = |freq_hz| on the spec's frequency grid (reference src/adv_modulator.c:36-38,537,611-625) */
+int  icw_debug_phase_device(icw_engine *e, const icw_chain_spec *spec, uint64_t n0, int64_t n,
+                            double freq_hz, double *d_out);
+/* host-only checks of the MT19937 jump-ahead mathematics (no GPU is touched):
+ * characteristic polynomial found by Berlekamp-Massey; the state array after `blocks` block
+ * regenerations computed sequentially, through x^J mod phi, and through the x^(624*2^k) family */
+int  icw_mt_host_charpoly(int *n_terms, int *degree);
+void icw_mt_host_seq_state(uint32_t seed, uint64_t blocks, uint32_t *out624);
+int  icw_mt_host_jump_state(uint32_t seed, uint64_t blocks, uint32_t *out624);
+int  icw_mt_host_jump_state_family(uint32_t seed, uint64_t blocks, uint32_t *out624);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICW_B200_H */

@@ -231,6 +231,12 @@ int64_t icwref_process_file(const char *path, unsigned read_quant,
     return frames;
 }
 
+/* transcode.c exports these without a header declaration (Winamp resolves them by name) */
+intptr_t winampGetExtendedRead_open(const TCHAR *filename, int *size, int *bps, int *nch, int *srate);
+intptr_t winampGetExtendedRead_getData(intptr_t handle, char *dest, int len, int *killswitch);
+int winampGetExtendedRead_setTime(intptr_t handle, int decode_pos_ms);
+void winampGetExtendedRead_close(intptr_t handle);
+
 /* The exported transcode wrapper itself (src/transcode.c:40-118), chunk = bytes per getData */
 int64_t icwref_transcode_file(const char *path, int chunk, char *pcm, int64_t pcm_cap, int info[4])
 {

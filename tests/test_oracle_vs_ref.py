@@ -1,0 +1,158 @@
+"""The port oracle against the compiled reference itself, on fresh random inputs and at the leaf
+level.  Skipped where oracle/_ref was not built (it needs /root/reference, i.e. the build
+container); the committed golden vectors in test_oracle_golden.py cover the GPU box."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from in_cwave_b200 import spec as S
+from in_cwave_b200 import synth
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.skipif(not po.have_ref(), reason="oracle/_ref/libicw_ref.so not built")
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+@pytest.mark.parametrize("ft", range(6))
+@pytest.mark.parametrize("kahan", [0, 1])
+@pytest.mark.parametrize("reject", [0, 1])
+def test_hilbert_leaf(ft, kahan, reject):
+    rng = np.random.default_rng(100 + ft)
+    n = 6000
+    x = (rng.random(n) - 0.5) * 30000.0
+    x[100:140] = 0.0
+    ri, rq = np.zeros(n), np.zeros(n)
+    cnt = po.ref().icwref_hilbert(ft, kahan, reject, _dp(x), n, _dp(ri), _dp(rq))
+    pi, pq = np.zeros(n), np.zeros(n)
+    lpf = (po.Iir * 2)()
+    quad = C.c_uint(0)
+    po.port().icwo_hilbert(ft, kahan, reject, lpf, C.byref(quad), _dp(x), n, _dp(pi), _dp(pq))
+    assert np.array_equal(ri, pi) and np.array_equal(rq, pq)
+    assert cnt == lpf[0].rejects + lpf[1].rejects
+    assert quad.value == n % 4
+
+
+def test_hilbert_silence_rejects():
+    """Digital silence / decaying tail: the |w| < 1 zeroing makes the filter non-linear."""
+    n = 30000
+    x = np.zeros(n)
+    x[:50] = 1000.0
+    for kahan in (0, 1):
+        ri, rq = np.zeros(n), np.zeros(n)
+        cnt = po.ref().icwref_hilbert(1, kahan, 1, _dp(x), n, _dp(ri), _dp(rq))
+        pi, pq = np.zeros(n), np.zeros(n)
+        lpf = (po.Iir * 2)()
+        quad = C.c_uint(0)
+        po.port().icwo_hilbert(1, kahan, 1, lpf, C.byref(quad), _dp(x), n, _dp(pi), _dp(pq))
+        assert np.array_equal(ri, pi) and np.array_equal(rq, pq)
+        assert cnt == lpf[0].rejects + lpf[1].rejects
+
+
+@pytest.mark.parametrize("rt", range(5))
+@pytest.mark.parametrize("need24,bits", [(1, 24), (1, 17), (0, 16), (0, 9)])
+@pytest.mark.parametrize("qt", [0, 1])
+def test_render_leaf(rt, need24, bits, qt):
+    rng = np.random.default_rng(rt * 10 + bits)
+    n = 5000
+    x = (rng.random(n) - 0.5) * 70000.0          # beyond full scale: clips on both sides
+    d = S.default_spec(render_type=rt, need24bits=need24, quantz_type=qt, dth_bits=2.5,
+                       sign_bits24=bits if need24 else 24, sign_bits16=bits if not need24 else 16)
+    cfg = po.make_refcfg(d)
+    buf = C.create_string_buffer(n * 3)
+    clips, peak = C.c_uint(0), C.c_double(0)
+    nb = po.ref().icwref_render(C.byref(cfg), 0x13579BDF, _dp(x), n, buf, C.byref(clips), C.byref(peak))
+    sp = po.make_spec(d)
+    mt = po.Mt()
+    po.port().icwo_mt_seed(C.byref(mt), 0x13579BDF)
+    out = np.zeros(n * 3, dtype=np.uint8)
+    pclips, ppeak, prev = C.c_uint(0), C.c_double(-555.0), C.c_double(0)
+    pb = po.port().icwo_render(C.byref(sp), C.byref(mt), C.byref(prev), _dp(x), n,
+                               out.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(pclips), C.byref(ppeak))
+    assert nb == pb
+    assert bytes(out[:pb]) == buf.raw[:nb]
+    assert clips.value == pclips.value and clips.value > 0
+    assert peak.value == ppeak.value
+
+
+@pytest.mark.parametrize("fmt", ["wav_u8", "wav_i16", "wav_i24", "wav_i32", "wav_f32",
+                                 "cw_f64", "cw_i16", "cw_i16f32", "cw_f32"])
+@pytest.mark.parametrize("nch", [1, 2])
+def test_every_format_end_to_end(fmt, nch):
+    d = S.default_spec(fmt=fmt, n_channels=nch, sample_rate=32000)
+    n = 2500
+    if fmt in ("wav_u8", "wav_i16", "wav_i24", "wav_i32", "cw_i16"):
+        raw = np.random.default_rng(5).integers(0, 256, size=n * S.frame_bytes(d), dtype=np.uint8)
+    else:
+        raw = synth.stream_bytes(d, n, stream_id=3)
+    a = po.port_process(d, raw, taps=[0])
+    b = po.ref_process(d, raw, taps=[0])
+    assert np.array_equal(a["pcm"], b["pcm"])
+    assert np.array_equal(a["bus"], b["bus"])
+
+
+def test_extensible_wav_header_same_result():
+    d = S.config_c1()
+    raw = synth.stream_bytes(d, 1200, stream_id=9)
+    a = po.ref_process(d, raw)
+    b = po.ref_process(dict(d, wav_extensible=1), raw)
+    assert np.array_equal(a["pcm"], b["pcm"])
+
+
+def test_state_survives_files():
+    """Frame counter, Hilbert delay lines and the dither stream continue into the next file
+    (reference defaults CLR_NFRAME_PT = CLR_HILB_PT = 0, src/config.c:171,174)."""
+    d = S.config_c2()
+    fb = S.frame_bytes(d)
+    raw = synth.stream_bytes(d, 3000, stream_id=11)
+    r1 = po.ref_process(d, raw[: 1000 * fb])
+    r2 = po.ref_process(d, raw[1000 * fb:], reset=False)
+    st = po.new_state()
+    p1 = po.port_process(d, raw[: 1000 * fb], state=st)
+    st.pos = 0                                  # new file: fade position restarts, the rest persists
+    p2 = po.port_process(d, raw[1000 * fb:], state=st)
+    assert np.array_equal(r1["pcm"], p1["pcm"]) and np.array_equal(r2["pcm"], p2["pcm"])
+
+
+def test_frame_counter_wrap():
+    """Scaled counter wraps at sample_rate*1000 frames (src/adv_modulator.c:614-617)."""
+    d = S.default_spec(fmt="cw_i16", sample_rate=8, need24bits=0,
+                       nodes=[dict(mode="shift", inputs=[0], out=1, l_p=[1.3], r_p=[-0.7]),
+                              dict(mode="master", inputs=[1], l_gain=0.9, r_gain=0.9)])
+    n = 8 * 1000 + 700
+    raw = np.random.default_rng(2).integers(0, 256, size=n * S.frame_bytes(d), dtype=np.uint8)
+    a = po.port_process(d, raw, taps=[1])
+    b = po.ref_process(d, raw, taps=[1])
+    assert a["state"].n_frame == b["stats"].n_frame == 700
+    assert np.array_equal(a["bus"], b["bus"]) and np.array_equal(a["pcm"], b["pcm"])
+
+
+def test_transcode_entry_points_agree():
+    """winampGetExtendedRead_* (src/transcode.c:40-118) == the direct frame loop."""
+    d = S.config_c1()
+    n = 5000
+    raw = synth.stream_bytes(d, n, stream_id=21)
+    direct = po.ref_process(d, raw)
+    import os, tempfile
+    cfg = po.make_refcfg(d)
+    po.ref().icwref_reset(C.byref(cfg))
+    nodes = d["nodes"]
+    arr = (po.Node * len(nodes))()
+    for i, nd in enumerate(nodes):
+        po.fill_node(arr[i], nd)
+    assert po.ref().icwref_set_graph(arr, len(nodes), 0) == 0
+    fd, path = tempfile.mkstemp(suffix=".wav")
+    os.write(fd, po.wav_bytes(d, raw))
+    os.close(fd)
+    try:
+        pcm = np.zeros(n * 6, dtype=np.uint8)
+        info = (C.c_int * 4)()
+        got = po.ref().icwref_transcode_file(path.encode(), 4096, pcm.ctypes.data_as(C.c_char_p), pcm.size, info)
+    finally:
+        os.unlink(path)
+    assert got == n * 6
+    assert list(info) == [n * 6, 24, 2, 48000]
+    assert np.array_equal(pcm, direct["pcm"])
