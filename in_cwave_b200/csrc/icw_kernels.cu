@@ -27,45 +27,175 @@ __device__ __forceinline__ void comp_add(Comp &a, double x)
     a.s = t;
 }
 
-// one sample through one filter; z[j] = state j+1 samples ago (newest first, the order the
-// reference's circular walk visits them)
-template <int ORD, bool KAHAN>
-__device__ __forceinline__ double hb_step(double (&z)[ORD], const HbCoef &k, double x, int reject,
-                                          unsigned long long &rejects)
+// three independent compensated sums advanced in lock step, written stage by stage so that the
+// instruction stream alternates between the chains (ptxas otherwise emits one chain after another
+// and every DADD waits its full 8-cycle latency)
+__device__ __forceinline__ void comp_add3(Comp &a, double xa, Comp &b, double xb, Comp &c, double xc)
 {
-    double w, y;
-    if (KAHAN) {
-        Comp in, out;
-        in.s = x; in.c = 0.0;
-        double t = __dmul_rn(z[0], k.fb[0]);
-        comp_add(in, t);
-        out.s = __dmul_rn(z[0], k.ff[0]); out.c = 0.0;
-        comp_add(out, __dmul_rn(t, k.d0));
+    double ya = __dsub_rn(xa, a.c), yb = __dsub_rn(xb, b.c), yc = __dsub_rn(xc, c.c);
+    double ta = __dadd_rn(a.s, ya), tb = __dadd_rn(b.s, yb), tc = __dadd_rn(c.s, yc);
+    double da = __dsub_rn(ta, a.s), db = __dsub_rn(tb, b.s), dc = __dsub_rn(tc, c.s);
+    a.c = __dsub_rn(da, ya); b.c = __dsub_rn(db, yb); c.c = __dsub_rn(dc, yc);
+    a.s = ta; b.s = tb; c.s = tc;
+}
+__device__ __forceinline__ void comp_add2(Comp &a, double xa, Comp &b, double xb)
+{
+    double ya = __dsub_rn(xa, a.c), yb = __dsub_rn(xb, b.c);
+    double ta = __dadd_rn(a.s, ya), tb = __dadd_rn(b.s, yb);
+    double da = __dsub_rn(ta, a.s), db = __dsub_rn(tb, b.s);
+    a.c = __dsub_rn(da, ya); b.c = __dsub_rn(db, yb);
+    a.s = ta; b.s = tb;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One half-band recurrence over n samples.  z[j] = state j+1 samples ago (newest first: the order
+// the reference's circular walk visits them).  `in(i)` gives the mixed-down input of sample i,
+// `out(i, y)` receives the filter output of sample i.
+//
+// Kahan variant: per sample the reference forms two compensated sums -- the state sum
+// (x, z0*fb0, z1*fb1, ...: 4 dependent DADDs per term, 76 in a row) and the output sum
+// (z0*ff0, (z0*fb0)*d0, z1*ff1, ...: 148 in a row).  Only the first feeds the next sample, so
+// the output sum of sample n-1 (first half) and of sample n-2 (second half) are evaluated while
+// the state sum of sample n runs: three independent dependency chains of ~75 DADDs each per
+// iteration instead of one of ~225.  Every operation and its order within each sum is the
+// reference's; only the interleaving in time differs, which rounding cannot see.
+// ---------------------------------------------------------------------------------------------
+template <int ORD, int I0, int I1, int OFF>
+__device__ __forceinline__ void out_sum_part(Comp &o, const double (&z)[ORD + 2], const HbCoef &k)
+{
 #pragma unroll
-        for (int i = 1; i < ORD; ++i) {
-            t = __dmul_rn(z[i], k.fb[i]);
-            comp_add(in, t);
-            comp_add(out, __dmul_rn(z[i], k.ff[i]));
-            comp_add(out, __dmul_rn(t, k.d0));
-        }
-        w = in.s;
-        y = out.s;                                  // no d0*x term: bug-for-bug (hblpf.c:1056)
-        if (reject && fabs(w) < (double)reject) { w = 0.0; ++rejects; }
-    } else {
-        double acc_in = x, acc_out = 0.0;
-#pragma unroll
-        for (int i = 0; i < ORD; ++i) {
-            acc_in = __dadd_rn(acc_in, __dmul_rn(z[i], k.fb[i]));
-            acc_out = __dadd_rn(acc_out, __dmul_rn(z[i], k.ff[i]));
-        }
-        w = acc_in;
-        if (reject && fabs(w) < (double)reject) { w = 0.0; ++rejects; }
-        y = __dadd_rn(__dmul_rn(w, k.d0), acc_out);
+    for (int i = I0; i < I1; ++i) {
+        const double zi = z[i + OFF];
+        const double t = __dmul_rn(zi, k.fb[i]);
+        if (i == 0) { o.s = __dmul_rn(zi, k.ff[0]); o.c = 0.0; }
+        else comp_add(o, __dmul_rn(zi, k.ff[i]));
+        comp_add(o, __dmul_rn(t, k.d0));
     }
+}
+
+template <int ORD, bool KAHAN, class In, class Out>
+__device__ __forceinline__ void hb_run(double *zstate, unsigned long long &rejects, const HbCoef &k,
+                                       int reject, int64_t n, In in, Out out)
+{
+    const double thr = (double)reject;              // compared as a number, bug-for-bug (hblpf.c:915,1046)
+    if (n <= 0) return;
+    if (KAHAN) {
+        constexpr int H = (ORD + 1) / 2;
+        double z[ORD + 2];
 #pragma unroll
-    for (int i = ORD - 1; i > 0; --i) z[i] = z[i - 1];
-    z[0] = w;
-    return y;
+        for (int i = 0; i < ORD; ++i) z[i] = zstate[i];
+        z[ORD] = z[ORD + 1] = 0.0;                  // only reach outputs of samples before this call
+        Comp o_half; o_half.s = 0.0; o_half.c = 0.0;
+        double xc = in(0);
+        for (int64_t i = 0; i < n; ++i) {
+            const double xn = in(i + 1 < n ? i + 1 : i);        // next input is fetched a sample ahead
+            // ---- one basic block: three independent dependency chains, interleaved by hand ------
+            // term lists in the reference's order:
+            //   state sum  a : x, z0*fb0, z1*fb1, ...                      (ORD additions)
+            //   output sum of sample i-1, first half  (o_new):  z1*ff0 | t0*d0, z2*ff1, t1*d0, ...
+            //   output sum of sample i-2, second half (o_half): z[H+2]*ffH, tH*d0, ...
+            Comp a; a.s = xc; a.c = 0.0;
+            Comp o_new;
+            {
+                constexpr int NA = ORD;                 // additions into a
+                constexpr int NB = 2 * H - 1;           // additions into o_new (its first term initialises)
+                constexpr int NC = 2 * (ORD - H);       // additions into o_half
+                const double tb0 = __dmul_rn(z[1], k.fb[0]);
+                o_new.s = __dmul_rn(z[1], k.ff[0]); o_new.c = 0.0;
+                constexpr int NSTEP = NA > NB ? (NA > NC ? NA : NC) : (NB > NC ? NB : NC);
+#pragma unroll
+                for (int st = 0; st < NSTEP; ++st) {
+                    // the st-th addend of each chain (compile-time indices)
+                    const double xa = st < NA ? __dmul_rn(z[st < NA ? st : 0], k.fb[st < NA ? st : 0]) : 0.0;
+                    // o_new addends: st = 0 -> t0*d0; then pairs (z*ff[i], t_i*d0) for i = 1..H-1
+                    const int ib = (st + 1) / 2;                                   // filter tap index
+                    const int ibc = ib < H ? ib : 0;
+                    const double xb = st < NB
+                        ? ((st & 1) == 0 ? __dmul_rn(st == 0 ? tb0 : __dmul_rn(z[ibc + 1], k.fb[ibc]), k.d0)
+                                         : __dmul_rn(z[ibc + 1], k.ff[ibc]))
+                        : 0.0;
+                    // o_half addends: pairs (z*ff[i], t_i*d0) for i = H..ORD-1
+                    const int ic = H + st / 2;
+                    const int icc = ic < ORD ? ic : H;
+                    const double xc2 = st < NC
+                        ? ((st & 1) == 0 ? __dmul_rn(z[icc + 2], k.ff[icc])
+                                         : __dmul_rn(__dmul_rn(z[icc + 2], k.fb[icc]), k.d0))
+                        : 0.0;
+                    if (st < NA && st < NB && st < NC) comp_add3(a, xa, o_new, xb, o_half, xc2);
+                    else if (st < NA && st < NB) comp_add2(a, xa, o_new, xb);
+                    else if (st < NA && st < NC) comp_add2(a, xa, o_half, xc2);
+                    else if (st < NB && st < NC) comp_add2(o_new, xb, o_half, xc2);
+                    else if (st < NA) comp_add(a, xa);
+                    else if (st < NB) comp_add(o_new, xb);
+                    else if (st < NC) comp_add(o_half, xc2);
+                }
+            }
+            double w = a.s;
+            const bool rj = (reject != 0) & (fabs(w) < thr);
+            w = rj ? 0.0 : w;
+            rejects += rj ? 1ull : 0ull;
+            const double y2 = o_half.s;                         // no d0*x term: bug-for-bug (hblpf.c:1056)
+            // ------------------------------------------------------------------------------------
+            if (i >= 2) out(i - 2, y2);
+            o_half = o_new;
+#pragma unroll
+            for (int j = ORD + 1; j > 0; --j) z[j] = z[j - 1];
+            z[0] = w;
+            xc = xn;
+        }
+        // drain the two output sums still in flight (no shift in between: both read z[1..])
+        {
+            Comp o_new; o_new.s = 0.0; o_new.c = 0.0;
+            out_sum_part<ORD, 0, H, 1>(o_new, z, k);
+            out_sum_part<ORD, H, ORD, 2>(o_half, z, k);
+            if (n >= 2) out(n - 2, o_half.s);
+            out_sum_part<ORD, H, ORD, 1>(o_new, z, k);
+            out(n - 1, o_new.s);
+        }
+#pragma unroll
+        for (int i = 0; i < ORD; ++i) zstate[i] = z[i];
+    } else {
+        double z[ORD];
+#pragma unroll
+        for (int i = 0; i < ORD; ++i) z[i] = zstate[i];
+        double xc = in(0);
+        for (int64_t i = 0; i < n; ++i) {
+            const double xn = in(i + 1 < n ? i + 1 : i);
+            double acc_in = xc, acc_out = 0.0;
+#pragma unroll
+            for (int j = 0; j < ORD; ++j) {
+                acc_in = __dadd_rn(acc_in, __dmul_rn(z[j], k.fb[j]));
+                acc_out = __dadd_rn(acc_out, __dmul_rn(z[j], k.ff[j]));
+            }
+            double w = acc_in;
+            const bool rj = (reject != 0) & (fabs(w) < thr);
+            w = rj ? 0.0 : w;
+            rejects += rj ? 1ull : 0ull;
+            out(i, __dadd_rn(__dmul_rn(w, k.d0), acc_out));
+#pragma unroll
+            for (int j = ORD - 1; j > 0; --j) z[j] = z[j - 1];
+            z[0] = w;
+            xc = xn;
+        }
+#pragma unroll
+        for (int i = 0; i < ORD; ++i) zstate[i] = z[i];
+    }
+}
+
+// fs/4 mixer around one filter (reference src/lpf_hilbert_quad.c:132-153).  Down-mix: the I filter
+// gets (+x, 0, -x, 0), the Q filter (0, -x, 0, +x).  Up-mix and *2: the I filter feeds
+// (+re, +im, -re, -im), the Q filter (+im, -re, -im, +re); slot 0 = re, 1 = im.
+__device__ __forceinline__ double mix_down(int iq, unsigned q, double x)
+{
+    if (iq == 0) return (q == 0) ? x : (q == 2) ? -x : 0.0;
+    return (q == 1) ? -x : (q == 3) ? x : 0.0;
+}
+__device__ __forceinline__ double mix_up(int iq, unsigned q, double y, int &slot)
+{
+    double v = __dmul_rn(y, 2.0);
+    if (iq == 0) { slot = q & 1; if (q >= 2) v = -v; }
+    else         { slot = (q & 1) ^ 1; if (q == 1 || q == 2) v = -v; }
+    return v;
 }
 
 // chain id = ((stream * 2 + channel) * 2 + iq).  Output: analytic frames as 4 doubles
@@ -87,36 +217,31 @@ hb_exact_kernel(const __grid_constant__ HbCoef coef, const __grid_constant__ Dev
 #pragma unroll
     for (int i = 0; i < ORD; ++i) z[i] = st.hb[chan][iq][i];
     unsigned long long rejects = st.hb_rejects[chan][iq];
-    unsigned q = st.quad[chan];
+    const unsigned q0 = st.quad[chan];
     const int64_t pos0 = st.pos;
-    const uint8_t *src = in + (size_t)stream * in_stride;
     // mono: the right channel filters the (already faded) left value (xwave_reader.c:988-998)
-    const int src_chan = ch.n_channels > 1 ? chan : 0;
+    const uint8_t *src = in + (size_t)stream * in_stride + (ch.n_channels > 1 ? chan : 0) * ch.chan_bytes;
     double *dst = analytic + (size_t)stream * (size_t)n_frames * 4 + chan * 2;
     const bool fading = (ch.n_fade_in | ch.n_fade_out) != 0;
 
-    for (int64_t i = 0; i < n_frames; ++i, q = (q + 1) & 3u) {
-        double x = unpack_real(ch.fmt, src + i * ch.frame_bytes + src_chan * ch.chan_bytes);
-        if (fading) {
-            double g = fade_gain(ch, pos0 + i);
-            if (g >= 0.0) x *= g;
-        }
-        // fs/4 down-mix: I gets (+x, 0, -x, 0), Q gets (0, -x, 0, +x)   (lpf_hilbert_quad.c:132-153)
-        double u;
-        if (iq == 0) u = (q == 0) ? x : (q == 2) ? -x : 0.0;
-        else         u = (q == 1) ? -x : (q == 3) ? x : 0.0;
-        double y = hb_step<ORD, KAHAN>(z, coef, u, ch.reject_flag, rejects);
-        // up-mix and *2: I filter feeds re at q = 0,2 and im at q = 1,3; Q filter the reverse
-        double v = __dmul_rn(y, 2.0);
-        int slot;
-        if (iq == 0) { slot = q & 1; if (q >= 2) v = -v; }                  // +re, +im, -re, -im
-        else         { slot = (q & 1) ^ 1; if (q == 1 || q == 2) v = -v; }  // +im, -re, -im, +re
-        dst[i * 4 + slot] = v;
-    }
+    hb_run<ORD, KAHAN>(z, rejects, coef, ch.reject_flag, n_frames,
+        [&](int64_t i) {
+            double x = unpack_real(ch.fmt, src + i * ch.frame_bytes);
+            if (fading) {
+                double g = fade_gain(ch, pos0 + i);
+                if (g >= 0.0) x *= g;
+            }
+            return mix_down(iq, (q0 + (unsigned)i) & 3u, x);
+        },
+        [&](int64_t i, double y) {
+            int slot;
+            double v = mix_up(iq, (q0 + (unsigned)i) & 3u, y, slot);
+            dst[i * 4 + slot] = v;
+        });
 #pragma unroll
     for (int i = 0; i < ORD; ++i) st.hb[chan][iq][i] = z[i];
     st.hb_rejects[chan][iq] = rejects;
-    // quad is advanced by the state-update kernel once per launch (both iq threads share it)
+    // quad is advanced by advance_streams_kernel once per call (both iq threads share it)
 }
 
 template <int ORD>
@@ -160,21 +285,16 @@ hb_leaf_kernel(const __grid_constant__ HbCoef coef, int reject, int n_chan, int6
 #pragma unroll
     for (int i = 0; i < ORD; ++i) z[i] = st.z[iq][i];
     unsigned long long rejects = st.rejects[iq];
-    unsigned q = st.quad;
+    const unsigned q0 = st.quad;
     const double *src = x + (size_t)chan * n;
     double *dst = out_iq + (size_t)chan * n * 2;
-    for (int64_t i = 0; i < n; ++i, q = (q + 1) & 3u) {
-        double xv = src[i];
-        double u;
-        if (iq == 0) u = (q == 0) ? xv : (q == 2) ? -xv : 0.0;
-        else         u = (q == 1) ? -xv : (q == 3) ? xv : 0.0;
-        double y = hb_step<ORD, KAHAN>(z, coef, u, reject, rejects);
-        double v = __dmul_rn(y, 2.0);
-        int slot;
-        if (iq == 0) { slot = q & 1; if (q >= 2) v = -v; }
-        else         { slot = (q & 1) ^ 1; if (q == 1 || q == 2) v = -v; }
-        dst[i * 2 + slot] = v;
-    }
+    hb_run<ORD, KAHAN>(z, rejects, coef, reject, n,
+        [&](int64_t i) { return mix_down(iq, (q0 + (unsigned)i) & 3u, src[i]); },
+        [&](int64_t i, double y) {
+            int slot;
+            double v = mix_up(iq, (q0 + (unsigned)i) & 3u, y, slot);
+            dst[i * 2 + slot] = v;
+        });
 #pragma unroll
     for (int i = 0; i < ORD; ++i) st.z[iq][i] = z[i];
     st.rejects[iq] = rejects;

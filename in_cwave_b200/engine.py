@@ -151,7 +151,9 @@ class Session:
             in_stride = d_in.stride(0) * d_in.element_size() if hasattr(d_in, "stride") and d_in.dim() > 1 else n * self.frame_bytes
         if out_stride is None:
             out_stride = d_out.stride(0) * d_out.element_size() if hasattr(d_out, "stride") and d_out.dim() > 1 else n * self.out_frame_bytes
-        cs = 0 if stream is None else int(stream)
+        # torch's default stream has handle 0, which this ABI reads as "engine stream": name the
+        # legacy default stream explicitly (cudaStreamLegacy == 0x1)
+        cs = 0 if stream is None else (int(stream) or 1)
         _abi.check(_abi.lib().icw_session_process_device(self._h, n, pin, in_stride, pout, out_stride, cs))
 
     def enable_taps(self, n_frames: int):
