@@ -55,6 +55,7 @@ class StreamState(C.Structure):
         ("quad", C.c_uint32 * 2), ("mt_seed", C.c_uint32 * 2), ("mt_drawn", C.c_uint64 * 2),
         ("prev_rnd", C.c_double * 2), ("clips", C.c_uint32 * 2), ("peak", C.c_double * 2),
         ("bus", (C.c_double * 4) * N_PLUGS),
+        ("hb_basis", C.c_uint32), ("reserved", C.c_uint32),
     ]
 
 

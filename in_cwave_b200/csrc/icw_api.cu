@@ -15,6 +15,7 @@
 #include "icw_internal.h"
 #include "icw_kernels.h"
 #include "icw_mt.h"
+#include "icw_scan.h"
 #include "icw_hb_tables.inc"
 
 using namespace icw;
@@ -68,6 +69,10 @@ struct icw_engine {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     Scratch analytic, mtw[2], ckpt, io_in, io_out, leaf;
+    bool unfused = false;               // ICW_UNFUSED=1: keep the two-kernel exact path (A/B measurements)
+    Scratch scan_scratch;
+    struct ScanPlan { bool ready = false; ModalCoef mc; double *d_pw = nullptr; };
+    ScanPlan scan[ICW_HB_NTYPES][2];    // [filter_no][baseline]
     MtJump mt;                          // MT19937 checkpoint service (icw_mt.cu)
 };
 
@@ -82,6 +87,8 @@ struct icw_session {
     std::vector<uint32_t> mt_seed[2];
     std::vector<uint64_t> mt_drawn[2];
     uint64_t launches = 0;
+    int hb_basis = 0;                   // basis of the Hilbert state on the device
+    bool hb_live = false;               // that state is not all-zero / has been used
     double *d_tap_bus = nullptr;        // test taps, set through icw_session_set_taps
     double *d_tap_lr = nullptr;
     // measurement: event pairs around each kernel class (icw_session_profile)
@@ -338,6 +345,7 @@ extern "C" int icw_engine_create(int device, icw_engine **out)
     e->device = device;
     e->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    { const char *u = getenv("ICW_UNFUSED"); e->unfused = u && *u == '1'; }
     *out = e;
     return ICW_OK;
 }
@@ -348,7 +356,8 @@ extern "C" void icw_engine_destroy(icw_engine *e)
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     e->analytic.release(); e->mtw[0].release(); e->mtw[1].release(); e->ckpt.release();
-    e->io_in.release(); e->io_out.release(); e->leaf.release();
+    e->io_in.release(); e->io_out.release(); e->leaf.release(); e->scan_scratch.release();
+    for (auto &row : e->scan) for (auto &pl : row) if (pl.d_pw) cudaFree(pl.d_pw);
     e->mt.release();
     cudaStreamDestroy(e->stream);
     delete e;
@@ -373,6 +382,7 @@ static void to_dev(const icw_stream_state &s, DevStream &d)
         d.peak[c] = s.peak[c];
     }
     memcpy(d.bus, s.bus, sizeof d.bus);
+    d.hb_basis = s.hb_basis;
 }
 
 static void from_dev(const DevStream &d, icw_stream_state &s)
@@ -391,6 +401,7 @@ static void from_dev(const DevStream &d, icw_stream_state &s)
         s.peak[c] = d.peak[c];
     }
     memcpy(s.bus, d.bus, sizeof s.bus);
+    s.hb_basis = d.hb_basis;
 }
 
 extern "C" int icw_session_create(icw_engine *e, const icw_chain_spec *spec, int n_streams, icw_session **out)
@@ -450,6 +461,7 @@ extern "C" int icw_session_get_state(icw_session *s, int k, icw_stream_state *ou
     CK(cudaStreamSynchronize(s->e->stream));
     CK(cudaMemcpy(&d, s->d_streams + k, sizeof d, cudaMemcpyDeviceToHost));
     from_dev(d, *out);
+    out->hb_basis = (uint32_t)s->hb_basis;
     return ICW_OK;
 }
 
@@ -461,6 +473,14 @@ extern "C" int icw_session_set_state(icw_session *s, int k, const icw_stream_sta
     CK(cudaStreamSynchronize(s->e->stream));
     CK(cudaMemcpy(s->d_streams + k, &d, sizeof d, cudaMemcpyHostToDevice));
     for (int c = 0; c < 2; ++c) { s->mt_seed[c][k] = in->mt_seed[c]; s->mt_drawn[c][k] = in->mt_drawn[c]; }
+    bool any = false;
+    for (int c = 0; c < 2 && !any; ++c) for (int f = 0; f < 2 && !any; ++f) for (int i = 0; i < ICW_MAX_ORD; ++i) if (in->hb[c][f][i] != 0.0) { any = true; break; }
+    if (any) {
+        if (s->hb_live && s->hb_basis != (int)in->hb_basis)
+            return fail(ICW_E_ARG, "stream %d: hb_basis %u differs from the session's live Hilbert state basis %d", k, in->hb_basis, s->hb_basis);
+        s->hb_basis = (int)in->hb_basis;
+        s->hb_live = true;
+    }
     return ICW_OK;
 }
 
@@ -477,6 +497,7 @@ static int rewrite_states(icw_session *s, void (*fn)(DevStream &, void *), void 
 extern "C" int icw_session_reset(icw_session *s, unsigned what)
 {
     if (!s) return fail(ICW_E_ARG, "NULL session");
+    if (what & ICW_RESET_HILBERT) s->hb_live = false;
     return rewrite_states(s, [](DevStream &d, void *a) {
         unsigned w = *(unsigned *)a;
         if (w & ICW_RESET_HILBERT) {            // hq_rp_reset, reference src/lpf_hilbert_quad.c:160-165
@@ -499,7 +520,7 @@ extern "C" int icw_session_set_spec(icw_session *s, const icw_chain_spec *spec)
     if (rc) return rc;
     unsigned flags = 0;
     // a different half-band design replaces the converters (reference src/in_cwave.c:135-150,177-191)
-    if (spec->filter_no != s->spec.filter_no) flags |= 1;
+    if (spec->filter_no != s->spec.filter_no) { flags |= 1; s->hb_live = false; }
     // any sound_render_setup / set_outbits clears prev_rnd (reference src/sound_render.c:509)
     if (memcmp(&ch.render, &s->ch.render, sizeof ch.render) != 0) flags |= 2;
     // iir_rp_setcfg clears the reject counters (reference src/hblpf.c:1114-1125)
@@ -565,6 +586,87 @@ static int make_dither_words(icw_session *s, int64_t n_frames, cudaStream_t st, 
     return ICW_OK;
 }
 
+static int get_scan_plan(icw_engine *e, int filter_no, bool baseline, double d0, icw_engine::ScanPlan **out)
+{
+    icw_engine::ScanPlan &pl = e->scan[filter_no][baseline ? 1 : 0];
+    if (!pl.ready) {
+        std::vector<double> pw;
+        scan_make_coef(filter_no, baseline, d0, pl.mc, pw);
+        if (cudaMalloc(&pl.d_pw, pw.size() * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return fail(ICW_E_NOMEM, "cudaMalloc(scan power table) failed"); }
+        CK(cudaMemcpy(pl.d_pw, pw.data(), pw.size() * sizeof(double), cudaMemcpyHostToDevice));
+        pl.ready = true;
+    }
+    *out = &pl;
+    return ICW_OK;
+}
+
+// one launch group: n_frames of every stream, state read from and left in the DevStream array
+static int process_group(icw_session *s, int64_t n_frames, const uint8_t *d_in, size_t in_stride,
+                         uint8_t *d_out, size_t out_stride, cudaStream_t st)
+{
+    icw_engine *e = s->e;
+    const DevChain &ch = s->ch;
+    const int K = s->n_streams;
+    int mt_shared, rc;
+    const uint32_t *wl, *wr;
+    {
+        ProfSpan ps(s, st, ICW_K_MT);
+        rc = make_dither_words(s, n_frames, st, mt_shared, wl, wr);
+    }
+    if (rc) return rc;
+    const bool scan = !ch.is_complex && s->spec.hilbert_mode == ICW_HILBERT_SCAN;
+    if (!ch.is_complex && !scan && !e->unfused) {
+        // real input, reference-exact Hilbert: the whole chain in one kernel
+        ProfSpan ps(s, st, ICW_K_HILBERT);
+        CK(launch_hb_fused(s->coef, ch, s->d_streams, K, n_frames, d_in, in_stride, wl, wr, mt_shared,
+                           d_out, out_stride, s->d_tap_bus, s->d_tap_lr, st));
+        s->launches++;
+    } else {
+        const uint8_t *src = d_in;
+        size_t src_stride = in_stride;
+        int from_analytic = 0;
+        if (!ch.is_complex) {
+            const size_t per = (size_t)n_frames * 4 * sizeof(double);
+            rc = e->analytic.reserve(per * (size_t)K);
+            if (rc) return rc;
+            ProfSpan ps(s, st, ICW_K_HILBERT);
+            if (scan) {
+                // time-parallel modal scan (icw_scan.cu): chunk end states -> carries -> apply
+                icw_engine::ScanPlan *plp;
+                rc = get_scan_plan(e, s->spec.filter_no, !s->spec.is_kahan, s->coef.d0, &plp);
+                if (rc) return rc;
+                icw_engine::ScanPlan &pl = *plp;
+                rc = e->scan_scratch.reserve(scan_scratch_doubles(K, n_frames) * sizeof(double));
+                if (rc) return rc;
+                int nl = 0;
+                CK(launch_hb_scan(pl.mc, ch, s->d_streams, K, n_frames, src, in_stride, pl.d_pw,
+                                  (double *)e->scan_scratch.p, (double *)e->analytic.p, st, &nl));
+                s->launches += nl;
+            } else {
+                // unfused exact pair (ICW_UNFUSED=1): recurrences -> analytic scratch -> pointwise kernel
+                CK(launch_hb_exact(s->coef, ch, s->d_streams, K, n_frames, src, in_stride, (double *)e->analytic.p, st));
+                s->launches++;
+            }
+            src = (const uint8_t *)e->analytic.p;
+            src_stride = per;
+            from_analytic = 1;
+        }
+        ProfSpan ps(s, st, ICW_K_CHAIN);
+        CK(launch_chain(ch, s->d_streams, K, n_frames, src, src_stride, from_analytic, wl, wr, mt_shared,
+                        d_out, out_stride, s->d_tap_bus, s->d_tap_lr, e->sm_count, st));
+        s->launches++;
+    }
+    {
+        ProfSpan ps(s, st, ICW_K_MISC);
+        CK(launch_advance(ch, s->d_streams, K, n_frames, !ch.is_complex, st));
+    }
+    s->launches++;
+    const uint64_t words = (uint64_t)n_frames * (uint64_t)ch.render.words_per_sample;
+    for (int c = 0; c < 2; ++c)
+        for (int k = 0; k < K; ++k) s->mt_drawn[c][k] += words;
+    return ICW_OK;
+}
+
 extern "C" int icw_session_process_device(icw_session *s, int64_t n_frames, const void *d_in, size_t in_stride,
                                           void *d_out, size_t out_stride, void *cuda_stream)
 {
@@ -572,6 +674,12 @@ extern "C" int icw_session_process_device(icw_session *s, int64_t n_frames, cons
     if (n_frames < 0) return fail(ICW_E_ARG, "negative frame count");
     if (n_frames == 0) return ICW_OK;
     icw_engine *e = s->e;
+    {
+        // typed loads are only legal when every sample sits on its natural alignment
+        const int cb = s->ch.chan_bytes;
+        const size_t a = (cb == 2 || cb == 4) ? (size_t)cb : 0;
+        s->ch.aligned = a && ((size_t)(uintptr_t)d_in % a == 0) && (s->n_streams == 1 || in_stride % a == 0);
+    }
     const DevChain &ch = s->ch;
     const int K = s->n_streams;
     if (K > 1 && (in_stride < (size_t)n_frames * ch.frame_bytes || out_stride < (size_t)n_frames * ch.out_frame_bytes))
@@ -579,45 +687,28 @@ extern "C" int icw_session_process_device(icw_session *s, int64_t n_frames, cons
     CK(cudaSetDevice(e->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
 
-    const uint8_t *src = (const uint8_t *)d_in;
-    size_t src_stride = in_stride;
-    int from_analytic = 0;
-    if (!ch.is_complex) {
-        if (s->spec.hilbert_mode != ICW_HILBERT_EXACT)
-            return fail(ICW_E_UNSUPPORTED, "hilbert_mode %d is not available in this build", s->spec.hilbert_mode);
-        size_t per = (size_t)n_frames * 4 * sizeof(double);
-        int rc = e->analytic.reserve(per * (size_t)K);
+    const bool real_in = !ch.is_complex;
+    const int mode = s->spec.hilbert_mode;
+    if (real_in) {
+        if (mode != ICW_HILBERT_EXACT && mode != ICW_HILBERT_SCAN) return fail(ICW_E_ARG, "hilbert_mode out of range");
+        if (s->hb_live && s->hb_basis != mode)
+            return fail(ICW_E_UNSUPPORTED, "the streams' Hilbert state is in the %s basis; switching a live stream to %s mode "
+                                           "needs icw_session_reset(ICW_RESET_HILBERT) first (state conversion is not built)",
+                        s->hb_basis ? "modal (scan)" : "delay-line (exact)", mode ? "scan" : "exact");
+    }
+    // scan mode and the unfused path go through per-frame scratch: bound it by walking the call in segments
+    const bool scratchy = (real_in && (mode == ICW_HILBERT_SCAN || e->unfused)) || ch.render.words_per_sample != 0;
+    const int64_t seg = scratchy ? SCAN_SEGMENT / (K > 64 ? 64 : K) / SCAN_L / SCAN_CH * (SCAN_L * SCAN_CH) : n_frames;
+    const int64_t step = seg < SCAN_L * SCAN_CH ? SCAN_L * SCAN_CH : seg;
+    if ((s->d_tap_bus || s->d_tap_lr) && n_frames > step)
+        return fail(ICW_E_ARG, "taps are a test aid for calls of at most %lld frames", (long long)step);
+    for (int64_t f0 = 0; f0 < n_frames; f0 += step) {
+        const int64_t n = n_frames - f0 < step ? n_frames - f0 : step;
+        int rc = process_group(s, n, (const uint8_t *)d_in + (size_t)f0 * ch.frame_bytes, in_stride,
+                               (uint8_t *)d_out + (size_t)f0 * ch.out_frame_bytes, out_stride, st);
         if (rc) return rc;
-        {
-            ProfSpan ps(s, st, ICW_K_HILBERT);
-            CK(launch_hb_exact(s->coef, ch, s->d_streams, K, n_frames, src, in_stride, (double *)e->analytic.p, st));
-        }
-        s->launches++;
-        src = (const uint8_t *)e->analytic.p;
-        src_stride = per;
-        from_analytic = 1;
     }
-    int mt_shared;
-    const uint32_t *wl, *wr;
-    int rc;
-    {
-        ProfSpan ps(s, st, ICW_K_MT);
-        rc = make_dither_words(s, n_frames, st, mt_shared, wl, wr);
-    }
-    if (rc) return rc;
-    {
-        ProfSpan ps(s, st, ICW_K_CHAIN);
-        CK(launch_chain(ch, s->d_streams, K, n_frames, src, src_stride, from_analytic, wl, wr, mt_shared,
-                        (uint8_t *)d_out, out_stride, s->d_tap_bus, s->d_tap_lr, e->sm_count, st));
-    }
-    {
-        ProfSpan ps(s, st, ICW_K_MISC);
-        CK(launch_advance(ch, s->d_streams, K, n_frames, !ch.is_complex, st));
-    }
-    s->launches += 2;
-    const uint64_t words = (uint64_t)n_frames * (uint64_t)ch.render.words_per_sample;
-    for (int c = 0; c < 2; ++c)
-        for (int k = 0; k < K; ++k) s->mt_drawn[c][k] += words;
+    if (real_in) { s->hb_basis = mode; s->hb_live = true; }
     return ICW_OK;
 }
 
@@ -706,8 +797,47 @@ extern "C" int icw_hilbert_device(icw_engine *e, int filter_no, int is_kahan, in
 {
     if (!e || !d_x || !d_out_iq || !chan_state || n_chan < 1 || n < 0) return fail(ICW_E_ARG, "bad argument");
     if (filter_no < 0 || filter_no >= ICW_HB_NTYPES) return fail(ICW_E_ARG, "filter_no must be 0..5");
-    if (mode != ICW_HILBERT_EXACT) return fail(ICW_E_UNSUPPORTED, "hilbert_mode %d is not available in this build", mode);
+    if (mode != ICW_HILBERT_EXACT && mode != ICW_HILBERT_SCAN) return fail(ICW_E_ARG, "hilbert_mode out of range");
     CK(cudaSetDevice(e->device));
+    if (mode == ICW_HILBERT_SCAN) {
+        // every channel becomes a mono stream of doubles; the L half of the analytic frame is the answer
+        if (n == 0) return ICW_OK;
+        const double a0 = word_as_double(ICW_HB_A[filter_no][0]);
+        const double d0 = word_as_double(ICW_HB_B[filter_no][0]) / a0;
+        icw_engine::ScanPlan *pl;
+        int rc = get_scan_plan(e, filter_no, !is_kahan, d0, &pl);
+        if (rc) return rc;
+        DevChain ch;
+        memset(&ch, 0, sizeof ch);
+        ch.fmt = ICW_FMT_INTERNAL_F64; ch.n_channels = 1; ch.chan_bytes = 8; ch.frame_bytes = 8;
+        std::vector<DevStream> ds((size_t)n_chan);
+        for (int c = 0; c < n_chan; ++c) {
+            memset(&ds[c], 0, sizeof(DevStream));
+            for (int ch2 = 0; ch2 < 2; ++ch2) {
+                memcpy(ds[c].hb[ch2], chan_state[c].hb[0], sizeof ds[c].hb[ch2]);
+                ds[c].quad[ch2] = chan_state[c].quad[0] & 3u;
+            }
+        }
+        rc = e->leaf.reserve(sizeof(DevStream) * ds.size());
+        if (rc) return rc;
+        rc = e->analytic.reserve((size_t)n_chan * (size_t)n * 4 * sizeof(double));
+        if (rc) return rc;
+        rc = e->scan_scratch.reserve(scan_scratch_doubles(n_chan, n) * sizeof(double));
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(e->leaf.p, ds.data(), sizeof(DevStream) * ds.size(), cudaMemcpyHostToDevice, e->stream));
+        int nl = 0;
+        CK(launch_hb_scan(pl->mc, ch, (DevStream *)e->leaf.p, n_chan, n, (const uint8_t *)d_x, (size_t)n * 8, pl->d_pw,
+                          (double *)e->scan_scratch.p, (double *)e->analytic.p, e->stream, &nl));
+        CK(cudaMemcpy2DAsync(d_out_iq, 16, e->analytic.p, 32, 16, (size_t)n_chan * (size_t)n, cudaMemcpyDeviceToDevice, e->stream));
+        CK(cudaMemcpyAsync(ds.data(), e->leaf.p, sizeof(DevStream) * ds.size(), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        for (int c = 0; c < n_chan; ++c) {
+            memcpy(chan_state[c].hb[0], ds[c].hb[0], sizeof ds[c].hb[0]);
+            chan_state[c].quad[0] = (uint32_t)((chan_state[c].quad[0] + (uint64_t)n) & 3u);
+            chan_state[c].hb_basis = 1;
+        }
+        return ICW_OK;
+    }
     HbCoef coef;
     memset(&coef, 0, sizeof coef);
     const int ord = ICW_HB_ORDER[filter_no];

@@ -1,0 +1,218 @@
+// icw_fused.cu -- the whole chain for real (WAV) input in ONE kernel, reference-exact Hilbert:
+//
+//     unpack + fade -> fs/4 mix -> 4 half-band recurrences per stream -> un-mix
+//                  -> oscillator -> DSP list -> dither + quantise -> PCM
+//
+// One CTA owns 32 streams for the whole call (the recurrences are serial in time) and walks them
+// in tiles of T frames.  Warps 0-3 are CHAIN warps: thread = one recurrence (stream x channel x I/Q),
+// state in registers, one warp per SM sub-partition, nothing but FP64 adds and multiplies in their
+// loop.  Warps 4-11 are HELPER warps (two per sub-partition, so their latencies overlap): while the chain warps run tile s they unpack tile s+1 from
+// HBM into shared memory and turn the filter outputs of tile s-1 into PCM (modulator + renderer).
+// Both directions go through double-buffered shared-memory tiles; one __syncthreads per tile.
+// HBM traffic is the algorithmic minimum: input bytes in, PCM bytes out (+ shared dither words).
+//
+// The FP64 pipe is the bound: 4 chain warps need ~2*281 issue cycles per sample each, the
+// latency of the serial state sum is ~76*8 cycles per sample, and the helpers' ~120 op/frame
+// fit in the slack.
+#include "icw_dev.cuh"
+#include "icw_kernels.h"
+#include "icw_hb.cuh"
+#include "icw_frame.cuh"
+
+namespace icw {
+
+constexpr int FUSED_T = 32;                 // frames per tile
+constexpr int FUSED_STREAMS = 32;           // streams per CTA
+constexpr int FUSED_ROWS = FUSED_T + 2;     // output window: T frames + the Kahan lag
+constexpr int FUSED_HPS = 8;                // helper threads per stream (8 helper warps per CTA)
+constexpr int FUSED_THREADS = 128 + FUSED_STREAMS * FUSED_HPS;
+
+template <int ORD, bool KAHAN>
+__global__ void __launch_bounds__(FUSED_THREADS, 1)
+hb_fused_kernel(const __grid_constant__ HbCoef coef, const __grid_constant__ DevChain ch,
+                DevStream *__restrict__ streams, int n_streams, int64_t n_frames,
+                const uint8_t *__restrict__ in, size_t in_stride,
+                const uint32_t *__restrict__ mtw_l, const uint32_t *__restrict__ mtw_r, int mt_shared,
+                uint8_t *__restrict__ out, size_t out_stride,
+                double *__restrict__ tap_bus, double *__restrict__ tap_lr)
+{
+    using Chain = typename ChainSel<ORD, KAHAN>::type;
+    constexpr int LAG = Chain::LAG;
+    // xs[b][t][stream_local*2 + chan]: unpacked, faded sample;  ys[b][row][chain_local]: filter output
+    extern __shared__ __align__(16) unsigned char fused_smem[];
+    double (*xs)[FUSED_T][FUSED_STREAMS * 2] = reinterpret_cast<double (*)[FUSED_T][FUSED_STREAMS * 2]>(fused_smem);
+    double (*ys)[FUSED_ROWS][FUSED_STREAMS * 4] =
+        reinterpret_cast<double (*)[FUSED_ROWS][FUSED_STREAMS * 4]>(fused_smem + sizeof(double) * 2 * FUSED_T * FUSED_STREAMS * 2);
+
+    const int tid = threadIdx.x;
+    const bool is_chain = tid < 128;
+    const int stream0 = blockIdx.x * FUSED_STREAMS;
+    const int64_t n_tiles = (n_frames + FUSED_T - 1) / FUSED_T;
+
+    // ---- chain-warp state -----------------------------------------------------------------------
+    const int c_local = tid & 127;                      // chain index inside the CTA
+    const int c_iq = c_local & 1, c_chan = (c_local >> 1) & 1, c_sl = c_local >> 2;
+    const bool c_live = is_chain && stream0 + c_sl < n_streams;
+    Chain chain;
+    unsigned long long rejects = 0;
+    unsigned q0c = 0;
+    const double thr = (double)ch.reject_flag;
+    if (c_live) {
+        DevStream &st = streams[stream0 + c_sl];
+        chain.load(st.hb[c_chan][c_iq]);
+        rejects = st.hb_rejects[c_chan][c_iq];
+        q0c = st.quad[c_chan];
+    } else if (is_chain) {
+        double zero[ORD];
+#pragma unroll
+        for (int i = 0; i < ORD; ++i) zero[i] = 0.0;
+        chain.load(zero);
+    }
+
+    // ---- helper-warp state ------------------------------------------------------------------------
+    const int h = tid - 128;                            // helper index
+    const int h_sl = h / FUSED_HPS, h_part = h % FUSED_HPS;
+    const bool h_live = !is_chain && stream0 + h_sl < n_streams;
+    FrameAcc acc;
+    FrameIO io;
+    io.mtw_l = io.mtw_r = nullptr; io.dst = nullptr; io.tap_bus = io.tap_lr = nullptr;
+    const uint8_t *h_src = nullptr;
+    int64_t h_pos0 = 0;
+    unsigned h_q0[2] = { 0, 0 };
+    double bus[ICW_N_PLUGS][4];
+    if (h_live) {
+        const int stream = stream0 + h_sl;
+        DevStream &st = streams[stream];
+        const size_t mt_off = mt_shared ? 0 : (size_t)stream * (size_t)n_frames * ch.render.words_per_sample;
+        io.mtw_l = mtw_l ? mtw_l + mt_off : nullptr;
+        io.mtw_r = mtw_r ? mtw_r + mt_off : nullptr;
+        io.dst = out + (size_t)stream * out_stride;
+        io.tap_bus = tap_bus ? tap_bus + (size_t)stream * n_frames * (ICW_N_PLUGS * 4) : nullptr;
+        io.tap_lr = tap_lr ? tap_lr + (size_t)stream * n_frames * 2 : nullptr;
+        h_src = in + (size_t)stream * in_stride;
+        h_pos0 = st.pos;
+        h_q0[0] = st.quad[0]; h_q0[1] = st.quad[1];
+        load_bus(st, bus);
+    }
+
+    // step s: chains run tile s; helpers unpack tile s+1 and finish the output window of tile s-1
+    for (int64_t s = -1; s <= n_tiles; ++s) {
+        if (is_chain) {
+            if (s >= 0 && s < n_tiles) {
+                const int b = (int)(s & 1);
+                const int64_t i0 = s * FUSED_T;
+                const int len = (int)((n_frames - i0 < FUSED_T) ? n_frames - i0 : FUSED_T);
+                const int64_t wbase = i0 - LAG > 0 ? i0 - LAG : 0;      // first frame of the output window
+                const int col = c_sl * 2 + c_chan;
+                double xc = mix_down(c_iq, (q0c + (unsigned)i0) & 3u, xs[b][0][col]);
+                for (int t = 0; t < len; ++t) {
+                    const int tn = t + 1 < len ? t + 1 : t;
+                    const double xn = mix_down(c_iq, (q0c + (unsigned)(i0 + tn)) & 3u, xs[b][tn][col]);
+                    const double y = chain.step(xc, coef, ch.reject_flag, thr, rejects);
+                    const int64_t fo = i0 + t - LAG;                    // frame this output belongs to
+                    if (fo >= 0) ys[b][(int)(fo - wbase)][c_local] = y;
+                    xc = xn;
+                }
+                if (LAG && s == n_tiles - 1) {
+                    double y2, y1;
+                    chain.drain(coef, y2, y1);
+                    if (n_frames >= 2) ys[b][(int)(n_frames - 2 - wbase)][c_local] = y2;
+                    ys[b][(int)(n_frames - 1 - wbase)][c_local] = y1;
+                }
+            }
+        } else {
+            // ---- A(s+1): unpack tile s+1 -----------------------------------------------------------
+            if (s + 1 < n_tiles && h_live) {
+                const int b = (int)((s + 1) & 1);
+                const int64_t i0 = (s + 1) * FUSED_T;
+                const int len = (int)((n_frames - i0 < FUSED_T) ? n_frames - i0 : FUSED_T);
+                for (int t = h_part; t < len; t += FUSED_HPS) {
+                    double v[4];
+                    unpack_frame(ch, h_src + (i0 + t) * ch.frame_bytes, h_pos0 + i0 + t, v);
+                    xs[b][t][h_sl * 2] = v[0];
+                    xs[b][t][h_sl * 2 + 1] = v[2];
+                }
+            }
+            // ---- C(s-1): output window of tile s-1 -> PCM --------------------------------------------
+            if (s >= 1 && h_live) {
+                const int64_t sp = s - 1;
+                const int b = (int)(sp & 1);
+                const int64_t i0 = sp * FUSED_T;
+                const int64_t wbase = i0 - LAG > 0 ? i0 - LAG : 0;
+                const int64_t tile_end = (i0 + FUSED_T < n_frames) ? i0 + FUSED_T : n_frames;
+                const int64_t wend = (sp == n_tiles - 1) ? n_frames : tile_end - LAG;
+                for (int64_t f = wbase + h_part; f < wend; f += FUSED_HPS) {
+                    const double *y = &ys[b][(int)(f - wbase)][h_sl * 4];
+                    double v[4];
+                    int slot;
+                    // up-mix: (yI, yQ) of each channel -> (re, im), reference lpf_hilbert_quad.c:132-153
+                    {
+                        const unsigned q = (h_q0[0] + (unsigned)f) & 3u;
+                        double a = mix_up(0, q, y[0], slot); v[slot] = a;
+                        double c = mix_up(1, q, y[1], slot); v[slot] = c;
+                    }
+                    {
+                        const unsigned q = (h_q0[1] + (unsigned)f) & 3u;
+                        double a = mix_up(0, q, y[2], slot); v[2 + slot] = a;
+                        double c = mix_up(1, q, y[3], slot); v[2 + slot] = c;
+                    }
+                    finish_frame(ch, streams[stream0 + h_sl], f, n_frames, v, bus, io, acc);
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    if (c_live) {
+        DevStream &st = streams[stream0 + c_sl];
+        chain.store(st.hb[c_chan][c_iq]);
+        st.hb_rejects[c_chan][c_iq] = rejects;
+    }
+    if (!is_chain) commit_acc(h_live ? &streams[stream0 + h_sl] : nullptr, acc, FUSED_HPS);   // all lanes shuffle
+}
+
+constexpr size_t FUSED_SMEM = sizeof(double) * (2 * FUSED_T * FUSED_STREAMS * 2 + 2 * FUSED_ROWS * FUSED_STREAMS * 4);
+
+template <int ORD>
+static cudaError_t launch_fused_ord(bool kahan, const HbCoef &coef, const DevChain &ch, DevStream *streams,
+                                    int n_streams, int64_t n_frames, const uint8_t *in, size_t in_stride,
+                                    const uint32_t *mtw_l, const uint32_t *mtw_r, int mt_shared,
+                                    uint8_t *out, size_t out_stride, double *tap_bus, double *tap_lr, cudaStream_t s)
+{
+    const int blocks = (n_streams + FUSED_STREAMS - 1) / FUSED_STREAMS;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e1 = cudaFuncSetAttribute(hb_fused_kernel<ORD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUSED_SMEM);
+        cudaError_t e2 = cudaFuncSetAttribute(hb_fused_kernel<ORD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUSED_SMEM);
+        if (e1 != cudaSuccess) return e1;
+        if (e2 != cudaSuccess) return e2;
+        attr_done = true;
+    }
+    if (kahan)
+        hb_fused_kernel<ORD, true><<<blocks, FUSED_THREADS, FUSED_SMEM, s>>>(coef, ch, streams, n_streams, n_frames, in, in_stride,
+                                                          mtw_l, mtw_r, mt_shared, out, out_stride, tap_bus, tap_lr);
+    else
+        hb_fused_kernel<ORD, false><<<blocks, FUSED_THREADS, FUSED_SMEM, s>>>(coef, ch, streams, n_streams, n_frames, in, in_stride,
+                                                           mtw_l, mtw_r, mt_shared, out, out_stride, tap_bus, tap_lr);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_hb_fused(const HbCoef &coef, const DevChain &ch, DevStream *streams, int n_streams,
+                            int64_t n_frames, const uint8_t *in, size_t in_stride,
+                            const uint32_t *mtw_l, const uint32_t *mtw_r, int mt_shared,
+                            uint8_t *out, size_t out_stride, double *tap_bus, double *tap_lr, cudaStream_t s)
+{
+#define ICW_FUSED_CASE(O) \
+    case O: return launch_fused_ord<O>(ch.is_kahan, coef, ch, streams, n_streams, n_frames, in, in_stride, \
+                                       mtw_l, mtw_r, mt_shared, out, out_stride, tap_bus, tap_lr, s)
+    switch (ch.hb_ord) {
+        ICW_FUSED_CASE(15);
+        ICW_FUSED_CASE(18);
+        ICW_FUSED_CASE(19);
+        ICW_FUSED_CASE(20);
+    default: return cudaErrorInvalidValue;
+    }
+#undef ICW_FUSED_CASE
+}
+
+}  // namespace icw

@@ -11,6 +11,7 @@
 #define ICW_SQRT6       2.4494897427831780981972840747059       // reference src/sound_render.c:50
 #define ICW_HZ_SCALE    1000u                                   // reference src/in_cwave.h:162
 #define ICW_SILENCE_DB  (-555.0)                                // reference src/sound_render.h:103
+#define ICW_FMT_INTERNAL_F64 8     // not part of the ABI: real doubles, used by the Hilbert leaf
 #define ICW_MT_N        624
 #define ICW_MT_M        397
 
@@ -45,6 +46,7 @@ struct DevRender {
 struct DevChain {
     int32_t  fmt, n_channels, chan_bytes, frame_bytes, out_frame_bytes;
     int32_t  is_complex;
+    int32_t  aligned;                   // per call: base pointer and row stride keep samples naturally aligned
     int32_t  is_frmod_scaled;
     int32_t  bypass, n_nodes;
     int32_t  filter_no, hb_ord, is_kahan, reject_flag;
@@ -72,6 +74,8 @@ struct DevStream {
     double   peak[2];
     double   bus[ICW_N_PLUGS][4];
     unsigned long long mt_redraws;
+    double   prev_rnd_next[2];          // written by the last frame of a call, committed by advance
+    uint32_t hb_basis, pad0;            // 0 = hb[] is the DF-II delay line, 1 = modal states
 };
 
 }  // namespace icw

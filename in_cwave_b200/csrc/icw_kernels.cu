@@ -9,6 +9,8 @@
 #include <cstdio>
 #include "icw_dev.cuh"
 #include "icw_kernels.h"
+#include "icw_hb.cuh"
+#include "icw_frame.cuh"
 
 namespace icw {
 
@@ -16,187 +18,6 @@ namespace icw {
 // exact half-band recurrences (reference src/hblpf.c:894-926 baseline, :1008-1057 Kahan;
 // mixer src/lpf_hilbert_quad.c:129-156)
 // =============================================================================================
-
-struct Comp { double s, c; };
-__device__ __forceinline__ void comp_add(Comp &a, double x)
-{
-    // hblpf.c:991-997 -- y = x - c; t = s + y; c = (t - s) - y; s = t
-    double y = __dsub_rn(x, a.c);
-    double t = __dadd_rn(a.s, y);
-    a.c = __dsub_rn(__dsub_rn(t, a.s), y);
-    a.s = t;
-}
-
-// three independent compensated sums advanced in lock step, written stage by stage so that the
-// instruction stream alternates between the chains (ptxas otherwise emits one chain after another
-// and every DADD waits its full 8-cycle latency)
-__device__ __forceinline__ void comp_add3(Comp &a, double xa, Comp &b, double xb, Comp &c, double xc)
-{
-    double ya = __dsub_rn(xa, a.c), yb = __dsub_rn(xb, b.c), yc = __dsub_rn(xc, c.c);
-    double ta = __dadd_rn(a.s, ya), tb = __dadd_rn(b.s, yb), tc = __dadd_rn(c.s, yc);
-    double da = __dsub_rn(ta, a.s), db = __dsub_rn(tb, b.s), dc = __dsub_rn(tc, c.s);
-    a.c = __dsub_rn(da, ya); b.c = __dsub_rn(db, yb); c.c = __dsub_rn(dc, yc);
-    a.s = ta; b.s = tb; c.s = tc;
-}
-__device__ __forceinline__ void comp_add2(Comp &a, double xa, Comp &b, double xb)
-{
-    double ya = __dsub_rn(xa, a.c), yb = __dsub_rn(xb, b.c);
-    double ta = __dadd_rn(a.s, ya), tb = __dadd_rn(b.s, yb);
-    double da = __dsub_rn(ta, a.s), db = __dsub_rn(tb, b.s);
-    a.c = __dsub_rn(da, ya); b.c = __dsub_rn(db, yb);
-    a.s = ta; b.s = tb;
-}
-
-// ---------------------------------------------------------------------------------------------
-// One half-band recurrence over n samples.  z[j] = state j+1 samples ago (newest first: the order
-// the reference's circular walk visits them).  `in(i)` gives the mixed-down input of sample i,
-// `out(i, y)` receives the filter output of sample i.
-//
-// Kahan variant: per sample the reference forms two compensated sums -- the state sum
-// (x, z0*fb0, z1*fb1, ...: 4 dependent DADDs per term, 76 in a row) and the output sum
-// (z0*ff0, (z0*fb0)*d0, z1*ff1, ...: 148 in a row).  Only the first feeds the next sample, so
-// the output sum of sample n-1 (first half) and of sample n-2 (second half) are evaluated while
-// the state sum of sample n runs: three independent dependency chains of ~75 DADDs each per
-// iteration instead of one of ~225.  Every operation and its order within each sum is the
-// reference's; only the interleaving in time differs, which rounding cannot see.
-// ---------------------------------------------------------------------------------------------
-template <int ORD, int I0, int I1, int OFF>
-__device__ __forceinline__ void out_sum_part(Comp &o, const double (&z)[ORD + 2], const HbCoef &k)
-{
-#pragma unroll
-    for (int i = I0; i < I1; ++i) {
-        const double zi = z[i + OFF];
-        const double t = __dmul_rn(zi, k.fb[i]);
-        if (i == 0) { o.s = __dmul_rn(zi, k.ff[0]); o.c = 0.0; }
-        else comp_add(o, __dmul_rn(zi, k.ff[i]));
-        comp_add(o, __dmul_rn(t, k.d0));
-    }
-}
-
-template <int ORD, bool KAHAN, class In, class Out>
-__device__ __forceinline__ void hb_run(double *zstate, unsigned long long &rejects, const HbCoef &k,
-                                       int reject, int64_t n, In in, Out out)
-{
-    const double thr = (double)reject;              // compared as a number, bug-for-bug (hblpf.c:915,1046)
-    if (n <= 0) return;
-    if (KAHAN) {
-        constexpr int H = (ORD + 1) / 2;
-        double z[ORD + 2];
-#pragma unroll
-        for (int i = 0; i < ORD; ++i) z[i] = zstate[i];
-        z[ORD] = z[ORD + 1] = 0.0;                  // only reach outputs of samples before this call
-        Comp o_half; o_half.s = 0.0; o_half.c = 0.0;
-        double xc = in(0);
-        for (int64_t i = 0; i < n; ++i) {
-            const double xn = in(i + 1 < n ? i + 1 : i);        // next input is fetched a sample ahead
-            // ---- one basic block: three independent dependency chains, interleaved by hand ------
-            // term lists in the reference's order:
-            //   state sum  a : x, z0*fb0, z1*fb1, ...                      (ORD additions)
-            //   output sum of sample i-1, first half  (o_new):  z1*ff0 | t0*d0, z2*ff1, t1*d0, ...
-            //   output sum of sample i-2, second half (o_half): z[H+2]*ffH, tH*d0, ...
-            Comp a; a.s = xc; a.c = 0.0;
-            Comp o_new;
-            {
-                constexpr int NA = ORD;                 // additions into a
-                constexpr int NB = 2 * H - 1;           // additions into o_new (its first term initialises)
-                constexpr int NC = 2 * (ORD - H);       // additions into o_half
-                const double tb0 = __dmul_rn(z[1], k.fb[0]);
-                o_new.s = __dmul_rn(z[1], k.ff[0]); o_new.c = 0.0;
-                constexpr int NSTEP = NA > NB ? (NA > NC ? NA : NC) : (NB > NC ? NB : NC);
-#pragma unroll
-                for (int st = 0; st < NSTEP; ++st) {
-                    // the st-th addend of each chain (compile-time indices)
-                    const double xa = st < NA ? __dmul_rn(z[st < NA ? st : 0], k.fb[st < NA ? st : 0]) : 0.0;
-                    // o_new addends: st = 0 -> t0*d0; then pairs (z*ff[i], t_i*d0) for i = 1..H-1
-                    const int ib = (st + 1) / 2;                                   // filter tap index
-                    const int ibc = ib < H ? ib : 0;
-                    const double xb = st < NB
-                        ? ((st & 1) == 0 ? __dmul_rn(st == 0 ? tb0 : __dmul_rn(z[ibc + 1], k.fb[ibc]), k.d0)
-                                         : __dmul_rn(z[ibc + 1], k.ff[ibc]))
-                        : 0.0;
-                    // o_half addends: pairs (z*ff[i], t_i*d0) for i = H..ORD-1
-                    const int ic = H + st / 2;
-                    const int icc = ic < ORD ? ic : H;
-                    const double xc2 = st < NC
-                        ? ((st & 1) == 0 ? __dmul_rn(z[icc + 2], k.ff[icc])
-                                         : __dmul_rn(__dmul_rn(z[icc + 2], k.fb[icc]), k.d0))
-                        : 0.0;
-                    if (st < NA && st < NB && st < NC) comp_add3(a, xa, o_new, xb, o_half, xc2);
-                    else if (st < NA && st < NB) comp_add2(a, xa, o_new, xb);
-                    else if (st < NA && st < NC) comp_add2(a, xa, o_half, xc2);
-                    else if (st < NB && st < NC) comp_add2(o_new, xb, o_half, xc2);
-                    else if (st < NA) comp_add(a, xa);
-                    else if (st < NB) comp_add(o_new, xb);
-                    else if (st < NC) comp_add(o_half, xc2);
-                }
-            }
-            double w = a.s;
-            const bool rj = (reject != 0) & (fabs(w) < thr);
-            w = rj ? 0.0 : w;
-            rejects += rj ? 1ull : 0ull;
-            const double y2 = o_half.s;                         // no d0*x term: bug-for-bug (hblpf.c:1056)
-            // ------------------------------------------------------------------------------------
-            if (i >= 2) out(i - 2, y2);
-            o_half = o_new;
-#pragma unroll
-            for (int j = ORD + 1; j > 0; --j) z[j] = z[j - 1];
-            z[0] = w;
-            xc = xn;
-        }
-        // drain the two output sums still in flight (no shift in between: both read z[1..])
-        {
-            Comp o_new; o_new.s = 0.0; o_new.c = 0.0;
-            out_sum_part<ORD, 0, H, 1>(o_new, z, k);
-            out_sum_part<ORD, H, ORD, 2>(o_half, z, k);
-            if (n >= 2) out(n - 2, o_half.s);
-            out_sum_part<ORD, H, ORD, 1>(o_new, z, k);
-            out(n - 1, o_new.s);
-        }
-#pragma unroll
-        for (int i = 0; i < ORD; ++i) zstate[i] = z[i];
-    } else {
-        double z[ORD];
-#pragma unroll
-        for (int i = 0; i < ORD; ++i) z[i] = zstate[i];
-        double xc = in(0);
-        for (int64_t i = 0; i < n; ++i) {
-            const double xn = in(i + 1 < n ? i + 1 : i);
-            double acc_in = xc, acc_out = 0.0;
-#pragma unroll
-            for (int j = 0; j < ORD; ++j) {
-                acc_in = __dadd_rn(acc_in, __dmul_rn(z[j], k.fb[j]));
-                acc_out = __dadd_rn(acc_out, __dmul_rn(z[j], k.ff[j]));
-            }
-            double w = acc_in;
-            const bool rj = (reject != 0) & (fabs(w) < thr);
-            w = rj ? 0.0 : w;
-            rejects += rj ? 1ull : 0ull;
-            out(i, __dadd_rn(__dmul_rn(w, k.d0), acc_out));
-#pragma unroll
-            for (int j = ORD - 1; j > 0; --j) z[j] = z[j - 1];
-            z[0] = w;
-            xc = xn;
-        }
-#pragma unroll
-        for (int i = 0; i < ORD; ++i) zstate[i] = z[i];
-    }
-}
-
-// fs/4 mixer around one filter (reference src/lpf_hilbert_quad.c:132-153).  Down-mix: the I filter
-// gets (+x, 0, -x, 0), the Q filter (0, -x, 0, +x).  Up-mix and *2: the I filter feeds
-// (+re, +im, -re, -im), the Q filter (+im, -re, -im, +re); slot 0 = re, 1 = im.
-__device__ __forceinline__ double mix_down(int iq, unsigned q, double x)
-{
-    if (iq == 0) return (q == 0) ? x : (q == 2) ? -x : 0.0;
-    return (q == 1) ? -x : (q == 3) ? x : 0.0;
-}
-__device__ __forceinline__ double mix_up(int iq, unsigned q, double y, int &slot)
-{
-    double v = __dmul_rn(y, 2.0);
-    if (iq == 0) { slot = q & 1; if (q >= 2) v = -v; }
-    else         { slot = (q & 1) ^ 1; if (q == 1 || q == 2) v = -v; }
-    return v;
-}
 
 // chain id = ((stream * 2 + channel) * 2 + iq).  Output: analytic frames as 4 doubles
 // (L.re, L.im, R.re, R.im) == the layout of ICW_FMT_CW_F64 stereo, so chain_kernel reads it back
@@ -385,46 +206,9 @@ cudaError_t launch_mt_words(const uint32_t *ckpt, int n_cta, int blocks_per_cta,
 // the pointwise chain: unpack -> oscillator -> DSP list -> render
 // =============================================================================================
 
-__device__ __forceinline__ double dither_value(const DevRender &r, const uint32_t *w, double prev_tr,
-                                               double &tr_out, unsigned &redraws)
-{
-    // reference src/sound_render.c:711-751; w = this sample's tempered words
-    bool rd;
-    double v;
-    switch (r.render_type) {
-    case ICW_RENDER_RPDF:
-        v = div_const(mt_dsopen(w[0], w[1], rd), ICW_SQRT2, ICW_RSQRT2);
-        redraws += rd;
-        return v;
-    case ICW_RENDER_TPDF:
-        v = mt_dsopen(w[0], w[1], rd); redraws += rd;
-        v += mt_dsopen(w[2], w[3], rd); redraws += rd;
-        return v * 0.5;                                         // /2.0, exact
-    case ICW_RENDER_STPDF:
-        tr_out = mt_dsopen(w[0], w[1], rd); redraws += rd;
-        return (tr_out - prev_tr) * 0.5;
-    case ICW_RENDER_GAUSS: {
-        v = mt_dsopen(w[0], w[1], rd); redraws += rd;
-#pragma unroll
-        for (int j = 1; j < 12; ++j) { v += mt_dsopen(w[2 * j], w[2 * j + 1], rd); redraws += rd; }
-        const double d = 2.0 * ICW_SQRT6;
-        return div_const(v, d, 1.0 / d);
-    }
-    default:
-        return 0.0;
-    }
-}
-
-__device__ __forceinline__ void store_pcm(uint8_t *p, int val, int bytes)
-{
-    p[0] = (uint8_t)val;
-    p[1] = (uint8_t)(val >> 8);
-    if (bytes == 3) p[2] = (uint8_t)(val >> 16);
-}
-
 // one thread per frame, grid-stride inside a stream (blockIdx.y = stream).
 // src: raw file bytes (complex formats) or the analytic scratch written by hb_exact_kernel
-// (fmt_override = ICW_FMT_CW_F64, no fade: it was applied before the Hilbert converter).
+// (from_analytic: 4 doubles per frame, no fade -- it was applied before the Hilbert converter).
 __global__ void __launch_bounds__(256)
 chain_kernel(const __grid_constant__ DevChain ch, DevStream *__restrict__ streams, int64_t n_frames,
              const uint8_t *__restrict__ in, size_t in_stride, int from_analytic,
@@ -436,19 +220,17 @@ chain_kernel(const __grid_constant__ DevChain ch, DevStream *__restrict__ stream
     const int stream = blockIdx.y;
     DevStream &st = streams[stream];
     const uint8_t *src = in + (size_t)stream * in_stride;
-    uint8_t *dst = out + (size_t)stream * out_stride;
-    const DevRender &rq = ch.render;
-    const int wps = rq.words_per_sample;
-    const size_t mt_off = mt_shared ? 0 : (size_t)stream * (size_t)n_frames * wps;
+    const size_t mt_off = mt_shared ? 0 : (size_t)stream * (size_t)n_frames * ch.render.words_per_sample;
+    FrameIO io;
+    io.mtw_l = mtw_l ? mtw_l + mt_off : nullptr;
+    io.mtw_r = mtw_r ? mtw_r + mt_off : nullptr;
+    io.dst = out + (size_t)stream * out_stride;
+    io.tap_bus = tap_bus ? tap_bus + (size_t)stream * n_frames * (ICW_N_PLUGS * 4) : nullptr;
+    io.tap_lr = tap_lr ? tap_lr + (size_t)stream * n_frames * 2 : nullptr;
 
-    unsigned clips_l = 0, clips_r = 0, redraws = 0;
-    double peak_l = 0.0, peak_r = 0.0;
+    FrameAcc acc;
     double bus[ICW_N_PLUGS][4];
-    // plugs nobody writes keep whatever the context held (normally 0.0)
-    for (int k = 1; k < ICW_N_PLUGS; ++k) {
-        bus[k][0] = st.bus[k][0]; bus[k][1] = st.bus[k][1]; bus[k][2] = st.bus[k][2]; bus[k][3] = st.bus[k][3];
-    }
-
+    load_bus(st, bus);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_frames;
          i += (int64_t)gridDim.x * blockDim.x) {
         double v[4];
@@ -458,72 +240,9 @@ chain_kernel(const __grid_constant__ DevChain ch, DevStream *__restrict__ stream
         } else {
             unpack_frame(ch, src + i * ch.frame_bytes, st.pos + i, v);
         }
-        bus[0][0] = v[0]; bus[0][1] = v[1]; bus[0][2] = v[2]; bus[0][3] = v[3];
-        double omega = norm_omega(ch, frame_counter(ch, st.n_frame, (uint64_t)i));
-        double lo, ro;
-        run_graph(ch, bus, omega, lo, ro);
-
-        double dl = 0.0, dr = 0.0;
-        if (wps) {
-            uint32_t wl[24], wr[24];
-            for (int j = 0; j < wps; ++j) {
-                wl[j] = mtw_l[mt_off + (size_t)i * wps + j];
-                wr[j] = mtw_r[mt_off + (size_t)i * wps + j];
-            }
-            double prev_l = 0.0, prev_r = 0.0, tr;
-            if (rq.render_type == ICW_RENDER_STPDF) {
-                // previous frame's draw: recompute it from that frame's words (frame 0: carried state)
-                bool rd;
-                if (i == 0) { prev_l = st.prev_rnd[0]; prev_r = st.prev_rnd[1]; }
-                else {
-                    prev_l = mt_dsopen(mtw_l[mt_off + (size_t)(i - 1) * wps], mtw_l[mt_off + (size_t)(i - 1) * wps + 1], rd);
-                    prev_r = mt_dsopen(mtw_r[mt_off + (size_t)(i - 1) * wps], mtw_r[mt_off + (size_t)(i - 1) * wps + 1], rd);
-                }
-            }
-            dl = dither_value(rq, wl, prev_l, tr, redraws);
-            dr = dither_value(rq, wr, prev_r, tr, redraws);
-        }
-        RenderOut a = render_one(rq, lo, dl);
-        RenderOut b = render_one(rq, ro, dr);
-        clips_l += a.clipped; clips_r += b.clipped;
-        peak_l = fmax(peak_l, a.level); peak_r = fmax(peak_r, b.level);
-        uint8_t *p = dst + i * ch.out_frame_bytes;
-        store_pcm(p, a.val, rq.bytes);
-        store_pcm(p + rq.bytes, b.val, rq.bytes);
-        if (tap_bus) {
-            double *t = tap_bus + ((size_t)stream * n_frames + i) * (ICW_N_PLUGS * 4);
-            for (int k = 0; k < ICW_N_PLUGS; ++k) { t[k * 4] = bus[k][0]; t[k * 4 + 1] = bus[k][1]; t[k * 4 + 2] = bus[k][2]; t[k * 4 + 3] = bus[k][3]; }
-        }
-        if (tap_lr) {
-            double *t = tap_lr + ((size_t)stream * n_frames + i) * 2;
-            t[0] = lo; t[1] = ro;
-        }
-        if (i == n_frames - 1) {
-            // the context's bus after the call == the last frame's values (adv_modulator.c:634-751)
-            for (int k = 0; k < ICW_N_PLUGS; ++k) { st.bus[k][0] = bus[k][0]; st.bus[k][1] = bus[k][1]; st.bus[k][2] = bus[k][2]; st.bus[k][3] = bus[k][3]; }
-            if (rq.render_type == ICW_RENDER_STPDF) {
-                bool rd;
-                st.prev_rnd[0] = mt_dsopen(mtw_l[mt_off + (size_t)i * wps], mtw_l[mt_off + (size_t)i * wps + 1], rd);
-                st.prev_rnd[1] = mt_dsopen(mtw_r[mt_off + (size_t)i * wps], mtw_r[mt_off + (size_t)i * wps + 1], rd);
-            }
-        }
+        finish_frame(ch, st, i, n_frames, v, bus, io, acc);
     }
-
-    // counters: warp-reduce, then one atomic per warp (peak >= 0, so its bit pattern orders like an integer)
-    for (int o = 16; o; o >>= 1) {
-        clips_l += __shfl_xor_sync(0xffffffffu, clips_l, o);
-        clips_r += __shfl_xor_sync(0xffffffffu, clips_r, o);
-        redraws += __shfl_xor_sync(0xffffffffu, redraws, o);
-        peak_l = fmax(peak_l, __shfl_xor_sync(0xffffffffu, peak_l, o));
-        peak_r = fmax(peak_r, __shfl_xor_sync(0xffffffffu, peak_r, o));
-    }
-    if ((threadIdx.x & 31) == 0) {
-        if (clips_l) atomicAdd(&st.clips[0], clips_l);
-        if (clips_r) atomicAdd(&st.clips[1], clips_r);
-        if (redraws) atomicAdd(&st.mt_redraws, (unsigned long long)redraws);
-        atomicMax(reinterpret_cast<unsigned long long *>(&st.peak[0]), (unsigned long long)__double_as_longlong(peak_l));
-        atomicMax(reinterpret_cast<unsigned long long *>(&st.peak[1]), (unsigned long long)__double_as_longlong(peak_r));
-    }
+    commit_acc(&st, acc, 32);
 }
 
 cudaError_t launch_chain(const DevChain &ch, DevStream *streams, int n_streams, int64_t n_frames,
@@ -559,6 +278,7 @@ __global__ void advance_streams_kernel(const __grid_constant__ DevChain ch, DevS
         st.quad[0] = (unsigned)((st.quad[0] + (uint64_t)n_frames) & 3u);
         st.quad[1] = (unsigned)((st.quad[1] + (uint64_t)n_frames) & 3u);
     }
+    if (ch.render.render_type == ICW_RENDER_STPDF) { st.prev_rnd[0] = st.prev_rnd_next[0]; st.prev_rnd[1] = st.prev_rnd_next[1]; }
     uint64_t words = (uint64_t)n_frames * (uint64_t)ch.render.words_per_sample;
     st.mt_drawn[0] += words;
     st.mt_drawn[1] += words;

@@ -1,0 +1,35 @@
+// icw_scan.h -- scan-mode (time-parallel) Hilbert converter: constants and launch wrapper.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <vector>
+#include <cuda_runtime.h>
+#include "icw_internal.h"
+
+namespace icw {
+
+constexpr int SCAN_L = 256;                 // frames per chunk (one thread each, per channel); multiple of 4
+constexpr int SCAN_CH = 128;                // chunks per tile
+constexpr int SCAN_NMAX = 10;               // modes per filter (conjugate pairs + the real pole)
+constexpr int64_t SCAN_SEGMENT = 1 << 25;   // frames per launch group (bounds the analytic scratch)
+
+// partial-fraction form of one half-band design, folded for the two-sample step (icw_scan.cu)
+struct ModalCoef {
+    int    nm, baseline;
+    double d0;
+    double p_re[SCAN_NMAX], p_im[SCAN_NMAX];        // pole
+    double p2_re[SCAN_NMAX], p2_im[SCAN_NMAX];      // pole^2
+    double pinv_re[SCAN_NMAX], pinv_im[SCAN_NMAX];  // 1 / pole
+    double c_re[SCAN_NMAX], c_im[SCAN_NMAX];        // y += c_re*s_re + c_im*s_im  == 2 Re(r s)
+    double cp_re[SCAN_NMAX], cp_im[SCAN_NMAX];      // the same for r*p
+    double pl_re[SCAN_NMAX], pl_im[SCAN_NMAX];      // pole^L
+    double pt_re[SCAN_NMAX], pt_im[SCAN_NMAX];      // pole^(L*CH)
+};
+
+void scan_make_coef(int filter_no, bool baseline, double d0, ModalCoef &mc, std::vector<double> &pw_table);
+size_t scan_scratch_doubles(int n_streams, int64_t n_frames);
+cudaError_t launch_hb_scan(const ModalCoef &mc, const DevChain &ch, DevStream *streams, int n_streams,
+                           int64_t n_frames, const uint8_t *in, size_t in_stride, const double *pw,
+                           double *scratch, double *analytic, cudaStream_t s, int *launches);
+
+}  // namespace icw

@@ -114,6 +114,9 @@ typedef struct icw_stream_state {
     uint32_t clips[2];                      /* src/sound_render.c:782-797 */
     double   peak[2];                       /* max |q|/hi_bound, LINEAR; dB via icw_peak_db() */
     double   bus[ICW_N_PLUGS][4];           /* (L.re, L.im, R.re, R.im) per plug */
+    uint32_t hb_basis;                      /* what hb[] holds: 0 = delay line (exact mode), 1 = modal states
+                                               (scan mode: hb[c][f][2m], [2m+1] = Re, Im of mode m) */
+    uint32_t reserved;
 } icw_stream_state;
 
 typedef struct icw_engine  icw_engine;      /* one GPU: streams, scratch, MT jump tables */

@@ -313,6 +313,50 @@ void icwo_hilbert(int filter_no, int is_kahan, int is_reject, icwo_iir lpf[2], u
 }
 
 /* ------------------------------------------------------------------------------------------
+ * "truth": the same converter with every recurrence evaluated in IEEE binary128 (libquadmath),
+ * i.e. the exact-arithmetic value of the reference's filter with its rounded coefficients, to
+ * ~1e-30.  It is what the reference's FP64 evaluation approximates (to 1e-9 .. 1e-3 of RMS,
+ * depending on the design) and what the GPU scan mode is held to (1e-12).  The |w|<1 zeroing
+ * is not modelled (it only acts on all-zero / fully decayed state).  drop_direct selects the
+ * Kahan path's output, which omits the d0*x term (hblpf.c:1056).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct hbq_filter { __float128 z[ICWO_MAX_ORD]; } hbq_filter;
+
+static double hbq_step(const hb_design *h, hbq_filter *f, double x, int drop_direct)
+{
+    __float128 w = x, o = 0;
+    for (int i = 0; i < h->ord; ++i) {
+        w += f->z[i] * (__float128)h->fb[i];
+        o += f->z[i] * (__float128)h->ff[i];
+    }
+    for (int i = h->ord - 1; i > 0; --i) f->z[i] = f->z[i - 1];
+    f->z[0] = w;
+    __float128 y = w * (__float128)h->d0 + o;
+    if (drop_direct) y -= (__float128)h->d0 * (__float128)x;
+    return (double)y;
+}
+
+void icwo_hilbert_truth(int filter_no, int drop_direct, unsigned quad0, const double *x, int64_t n,
+                        double *out_i, double *out_q)
+{
+    hb_design h;
+    hbq_filter fi, fq;
+    hb_load(filter_no, &h);
+    memset(&fi, 0, sizeof fi);
+    memset(&fq, 0, sizeof fq);
+    unsigned q = quad0 & 3u;
+    for (int64_t k = 0; k < n; ++k, q = (q + 1) & 3u) {
+        double a, b;
+        switch (q) {
+        case 0:  a = hbq_step(&h, &fi,  x[k], drop_direct); b = hbq_step(&h, &fq, 0.0, drop_direct); out_i[k] =  a * 2.0; out_q[k] =  b * 2.0; break;
+        case 1:  a = hbq_step(&h, &fq, -x[k], drop_direct); b = hbq_step(&h, &fi, 0.0, drop_direct); out_i[k] = -a * 2.0; out_q[k] =  b * 2.0; break;
+        case 2:  a = hbq_step(&h, &fi, -x[k], drop_direct); b = hbq_step(&h, &fq, 0.0, drop_direct); out_i[k] = -a * 2.0; out_q[k] = -b * 2.0; break;
+        default: a = hbq_step(&h, &fq,  x[k], drop_direct); b = hbq_step(&h, &fi, 0.0, drop_direct); out_i[k] =  a * 2.0; out_q[k] = -b * 2.0; break;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
  * renderer (reference src/sound_render.c:499-581 setup, :691-810 per value)
  * ---------------------------------------------------------------------------------------- */
 typedef struct quant_plan {

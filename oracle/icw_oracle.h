@@ -121,6 +121,9 @@ void    icwo_hilbert(int filter_no, int is_kahan, int is_reject, icwo_iir lpf[2]
                      const double *x, int64_t n, double *out_i, double *out_q);
 void    icwo_iir_run(int filter_no, int is_kahan, int is_reject, icwo_iir *f,
                      const double *x, int64_t n, double *y);
+/* exact-arithmetic (binary128) value of the same converter from zero state; see icw_oracle.c */
+void    icwo_hilbert_truth(int filter_no, int drop_direct, unsigned quad0, const double *x, int64_t n,
+                           double *out_i, double *out_q);
 int64_t icwo_render(const icwo_spec *sp, icwo_mt *mt, double *prev_rnd, const double *in, int64_t n,
                     uint8_t *out, unsigned *clips, double *peak_db);
 

@@ -138,11 +138,21 @@ def port():
         L.icwo_hilbert.argtypes = [C.c_int, C.c_int, C.c_int, _p(Iir), _p(C.c_uint), _dbl_p,
                                    C.c_int64, _dbl_p, _dbl_p]
         L.icwo_iir_run.argtypes = [C.c_int, C.c_int, C.c_int, _p(Iir), _dbl_p, C.c_int64, _dbl_p]
+        L.icwo_hilbert_truth.argtypes = [C.c_int, C.c_int, C.c_uint, _dbl_p, C.c_int64, _dbl_p, _dbl_p]
         L.icwo_render.argtypes = [_p(Spec), _p(Mt), _dbl_p, _dbl_p, C.c_int64, _u8_p,
                                   _p(C.c_uint), _dbl_p]
         L.icwo_render.restype = C.c_int64
         _port = L
     return _port
+
+
+def hilbert_truth(x: np.ndarray, filter_no: int = 1, drop_direct: int = 1, quad0: int = 0):
+    """binary128 evaluation of the converter from zero state -> (I, Q) as float64 arrays."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    oi, oq = np.zeros(x.size), np.zeros(x.size)
+    port().icwo_hilbert_truth(filter_no, drop_direct, quad0, _arr(x, C.c_double), x.size,
+                              _arr(oi, C.c_double), _arr(oq, C.c_double))
+    return oi, oq
 
 
 def have_ref() -> bool:
