@@ -50,16 +50,16 @@ def workload(name: str) -> dict:
                     bytes_per_frame=14, hilbert="exact")
     if name == "c1":
         return dict(name="c1", desc="48 kHz stereo f32 WAV, 60 s: Hilbert + 100 Hz shift + 24-bit render (one stream)",
-                    spec=S.config_c1(hilbert_mode="exact"), streams=1, frames=2_880_000, chunk=2_880_000,
-                    bytes_per_frame=14, hilbert="exact")
+                    spec=S.config_c1(hilbert_mode="scan"), streams=1, frames=2_880_000, chunk=2_880_000,
+                    bytes_per_frame=14, hilbert="scan")
     if name == "c3":
         return dict(name="c3", desc="CWAVE f32 I/Q 96 kHz stereo, 600 s: 2 shifts + PM + mix, 16-bit render",
                     spec=S.config_c3(), streams=1, frames=57_600_000, chunk=57_600_000,
                     bytes_per_frame=20, hilbert="none")
     if name == "c2":
         return dict(name="c2", desc="192 kHz 24-bit PCM stereo, 1 h: Hilbert + 100 Hz shift + TPDF dither + 24-bit render (one stream)",
-                    spec=S.config_c2(hilbert_mode="exact"), streams=1, frames=691_200_000, chunk=691_200_000,
-                    bytes_per_frame=12, hilbert="exact")
+                    spec=S.config_c2(hilbert_mode="scan"), streams=1, frames=691_200_000, chunk=691_200_000,
+                    bytes_per_frame=12, hilbert="scan")
     raise SystemExit(f"unknown workload {name}")
 
 

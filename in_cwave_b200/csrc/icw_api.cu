@@ -552,9 +552,12 @@ extern "C" int icw_session_set_taps(icw_session *s, double *d_tap_bus, double *d
 // ---------------------------------------------------------------------------------------------
 // the hot call
 // ---------------------------------------------------------------------------------------------
-static int make_dither_words(icw_session *s, int64_t n_frames, cudaStream_t st, int &mt_shared,
-                             const uint32_t *&wl, const uint32_t *&wr)
+struct DitherWords { const uint32_t *l = nullptr, *r = nullptr; size_t stream_stride = 0; };
+
+static int make_dither_words(icw_session *s, int64_t n_frames, cudaStream_t st, DitherWords &dw)
 {
+    int mt_shared;
+    const uint32_t *wl, *wr;
     icw_engine *e = s->e;
     const int wps = s->ch.render.words_per_sample;
     wl = wr = nullptr;
@@ -583,6 +586,8 @@ static int make_dither_words(icw_session *s, int64_t n_frames, cudaStream_t st, 
     }
     wl = (const uint32_t *)e->mtw[0].p;
     wr = (const uint32_t *)e->mtw[1].p;
+    dw.l = wl; dw.r = wr;
+    dw.stream_stride = mt_shared ? 0 : (size_t)words;
     return ICW_OK;
 }
 
@@ -601,19 +606,23 @@ static int get_scan_plan(icw_engine *e, int filter_no, bool baseline, double d0,
 }
 
 // one launch group: n_frames of every stream, state read from and left in the DevStream array
+// `pre`: dither words generated once for the whole call (pointing at this group's first frame), or NULL
 static int process_group(icw_session *s, int64_t n_frames, const uint8_t *d_in, size_t in_stride,
-                         uint8_t *d_out, size_t out_stride, cudaStream_t st)
+                         uint8_t *d_out, size_t out_stride, cudaStream_t st, const DitherWords *pre)
 {
     icw_engine *e = s->e;
     const DevChain &ch = s->ch;
     const int K = s->n_streams;
-    int mt_shared, rc;
-    const uint32_t *wl, *wr;
-    {
+    int rc;
+    DitherWords dw;
+    if (pre) dw = *pre;
+    else {
         ProfSpan ps(s, st, ICW_K_MT);
-        rc = make_dither_words(s, n_frames, st, mt_shared, wl, wr);
+        rc = make_dither_words(s, n_frames, st, dw);
+        if (rc) return rc;
     }
-    if (rc) return rc;
+    const uint32_t *wl = dw.l, *wr = dw.r;
+    const size_t mt_shared = dw.stream_stride;      // words between consecutive streams' dither (0 = shared)
     const bool scan = !ch.is_complex && s->spec.hilbert_mode == ICW_HILBERT_SCAN;
     if (!ch.is_complex && !scan && !e->unfused) {
         // real input, reference-exact Hilbert: the whole chain in one kernel
@@ -702,10 +711,22 @@ extern "C" int icw_session_process_device(icw_session *s, int64_t n_frames, cons
     const int64_t step = seg < SCAN_L * SCAN_CH ? SCAN_L * SCAN_CH : seg;
     if ((s->d_tap_bus || s->d_tap_lr) && n_frames > step)
         return fail(ICW_E_ARG, "taps are a test aid for calls of at most %lld frames", (long long)step);
+    // dither words for the whole call in one go when they fit (one jump tree instead of one per segment)
+    DitherWords all;
+    bool pre = false;
+    const int wps = ch.render.words_per_sample;
+    if (wps && n_frames > step && (double)n_frames * wps * 4.0 * 2.0 * (K > 1 ? K : 1) <= 48e9) {
+        ProfSpan ps(s, st, ICW_K_MT);
+        int rc = make_dither_words(s, n_frames, st, all);
+        if (rc) return rc;
+        pre = true;
+    }
     for (int64_t f0 = 0; f0 < n_frames; f0 += step) {
         const int64_t n = n_frames - f0 < step ? n_frames - f0 : step;
+        DitherWords here = all;
+        if (pre) { here.l += (size_t)f0 * wps; here.r += (size_t)f0 * wps; }
         int rc = process_group(s, n, (const uint8_t *)d_in + (size_t)f0 * ch.frame_bytes, in_stride,
-                               (uint8_t *)d_out + (size_t)f0 * ch.out_frame_bytes, out_stride, st);
+                               (uint8_t *)d_out + (size_t)f0 * ch.out_frame_bytes, out_stride, st, pre ? &here : nullptr);
         if (rc) return rc;
     }
     if (real_in) { s->hb_basis = mode; s->hb_live = true; }

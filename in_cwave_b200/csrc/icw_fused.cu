@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
 hb_fused_kernel(const __grid_constant__ HbCoef coef, const __grid_constant__ DevChain ch,
                 DevStream *__restrict__ streams, int n_streams, int64_t n_frames,
                 const uint8_t *__restrict__ in, size_t in_stride,
-                const uint32_t *__restrict__ mtw_l, const uint32_t *__restrict__ mtw_r, int mt_shared,
+                const uint32_t *__restrict__ mtw_l, const uint32_t *__restrict__ mtw_r, size_t mt_stream_stride,
                 uint8_t *__restrict__ out, size_t out_stride,
                 double *__restrict__ tap_bus, double *__restrict__ tap_lr)
 {
@@ -83,7 +83,7 @@ hb_fused_kernel(const __grid_constant__ HbCoef coef, const __grid_constant__ Dev
     if (h_live) {
         const int stream = stream0 + h_sl;
         DevStream &st = streams[stream];
-        const size_t mt_off = mt_shared ? 0 : (size_t)stream * (size_t)n_frames * ch.render.words_per_sample;
+        const size_t mt_off = (size_t)stream * mt_stream_stride;
         io.mtw_l = mtw_l ? mtw_l + mt_off : nullptr;
         io.mtw_r = mtw_r ? mtw_r + mt_off : nullptr;
         io.dst = out + (size_t)stream * out_stride;
@@ -176,7 +176,7 @@ constexpr size_t FUSED_SMEM = sizeof(double) * (2 * FUSED_T * FUSED_STREAMS * 2 
 template <int ORD>
 static cudaError_t launch_fused_ord(bool kahan, const HbCoef &coef, const DevChain &ch, DevStream *streams,
                                     int n_streams, int64_t n_frames, const uint8_t *in, size_t in_stride,
-                                    const uint32_t *mtw_l, const uint32_t *mtw_r, int mt_shared,
+                                    const uint32_t *mtw_l, const uint32_t *mtw_r, size_t mt_stream_stride,
                                     uint8_t *out, size_t out_stride, double *tap_bus, double *tap_lr, cudaStream_t s)
 {
     const int blocks = (n_streams + FUSED_STREAMS - 1) / FUSED_STREAMS;
@@ -190,21 +190,21 @@ static cudaError_t launch_fused_ord(bool kahan, const HbCoef &coef, const DevCha
     }
     if (kahan)
         hb_fused_kernel<ORD, true><<<blocks, FUSED_THREADS, FUSED_SMEM, s>>>(coef, ch, streams, n_streams, n_frames, in, in_stride,
-                                                          mtw_l, mtw_r, mt_shared, out, out_stride, tap_bus, tap_lr);
+                                                          mtw_l, mtw_r, mt_stream_stride, out, out_stride, tap_bus, tap_lr);
     else
         hb_fused_kernel<ORD, false><<<blocks, FUSED_THREADS, FUSED_SMEM, s>>>(coef, ch, streams, n_streams, n_frames, in, in_stride,
-                                                           mtw_l, mtw_r, mt_shared, out, out_stride, tap_bus, tap_lr);
+                                                           mtw_l, mtw_r, mt_stream_stride, out, out_stride, tap_bus, tap_lr);
     return cudaGetLastError();
 }
 
 cudaError_t launch_hb_fused(const HbCoef &coef, const DevChain &ch, DevStream *streams, int n_streams,
                             int64_t n_frames, const uint8_t *in, size_t in_stride,
-                            const uint32_t *mtw_l, const uint32_t *mtw_r, int mt_shared,
+                            const uint32_t *mtw_l, const uint32_t *mtw_r, size_t mt_stream_stride,
                             uint8_t *out, size_t out_stride, double *tap_bus, double *tap_lr, cudaStream_t s)
 {
 #define ICW_FUSED_CASE(O) \
     case O: return launch_fused_ord<O>(ch.is_kahan, coef, ch, streams, n_streams, n_frames, in, in_stride, \
-                                       mtw_l, mtw_r, mt_shared, out, out_stride, tap_bus, tap_lr, s)
+                                       mtw_l, mtw_r, mt_stream_stride, out, out_stride, tap_bus, tap_lr, s)
     switch (ch.hb_ord) {
         ICW_FUSED_CASE(15);
         ICW_FUSED_CASE(18);

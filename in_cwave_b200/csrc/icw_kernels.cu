@@ -162,7 +162,9 @@ cudaError_t launch_hb_leaf(const HbCoef &coef, int ord, bool kahan, int reject, 
 __global__ void __launch_bounds__(256)
 mt_words_kernel(const uint32_t *__restrict__ ckpt /* [cta][624] */, int blocks_per_cta,
                 int64_t first_word /* stream word index of block 0's first word */,
-                int64_t want_lo, int64_t want_hi, uint32_t *__restrict__ out /* out[w - want_lo] */)
+                int64_t want_lo, int64_t want_hi, uint32_t *__restrict__ out /* out[w - want_lo] */,
+                int64_t tail_block /* relative index of the block holding the last wanted word */,
+                uint32_t *__restrict__ tail /* [2][624]: state before and after that block, for the next call */)
 {
     __shared__ uint32_t a[ICW_MT_N], b[ICW_MT_N];
     uint32_t *cur = a, *nxt = b;
@@ -170,6 +172,9 @@ mt_words_kernel(const uint32_t *__restrict__ ckpt /* [cta][624] */, int blocks_p
     for (int i = tid; i < ICW_MT_N; i += blockDim.x) cur[i] = ckpt[(size_t)blockIdx.x * ICW_MT_N + i];
     __syncthreads();
     for (int blk = 0; blk < blocks_per_cta; ++blk) {
+        const int64_t rel = (int64_t)blockIdx.x * blocks_per_cta + blk;
+        if (rel == tail_block && tail)
+            for (int i = tid; i < ICW_MT_N; i += blockDim.x) tail[i] = cur[i];
         // phase A: i in [0,227): new[i] = old[i+397] ^ tw(old[i], old[i+1])
         // phase B: i in [227,454): new[i] = new[i-227] ^ tw(old[i], old[i+1])
         // phase C: i in [454,624): same, and i = 623 pairs old[623] with new[0]
@@ -185,20 +190,24 @@ mt_words_kernel(const uint32_t *__restrict__ ckpt /* [cta][624] */, int blocks_p
             }
             __syncthreads();
         }
-        int64_t w0 = first_word + ((int64_t)blockIdx.x * blocks_per_cta + blk) * ICW_MT_N;
+        int64_t w0 = first_word + rel * ICW_MT_N;
+        if (w0 >= want_hi) break;                               // uniform: nothing further is wanted
         for (int i = tid; i < ICW_MT_N; i += blockDim.x) {
             int64_t w = w0 + i;
             if (w >= want_lo && w < want_hi) out[w - want_lo] = mt_temper(nxt[i]);
         }
+        if (rel == tail_block && tail)
+            for (int i = tid; i < ICW_MT_N; i += blockDim.x) tail[ICW_MT_N + i] = nxt[i];
         uint32_t *t = cur; cur = nxt; nxt = t;
         __syncthreads();
     }
 }
 
 cudaError_t launch_mt_words(const uint32_t *ckpt, int n_cta, int blocks_per_cta, int64_t first_word,
-                            int64_t want_lo, int64_t want_hi, uint32_t *out, cudaStream_t s)
+                            int64_t want_lo, int64_t want_hi, uint32_t *out, int64_t tail_block, uint32_t *tail,
+                            cudaStream_t s)
 {
-    mt_words_kernel<<<n_cta, 256, 0, s>>>(ckpt, blocks_per_cta, first_word, want_lo, want_hi, out);
+    mt_words_kernel<<<n_cta, 256, 0, s>>>(ckpt, blocks_per_cta, first_word, want_lo, want_hi, out, tail_block, tail);
     return cudaGetLastError();
 }
 
@@ -212,7 +221,7 @@ cudaError_t launch_mt_words(const uint32_t *ckpt, int n_cta, int blocks_per_cta,
 __global__ void __launch_bounds__(256)
 chain_kernel(const __grid_constant__ DevChain ch, DevStream *__restrict__ streams, int64_t n_frames,
              const uint8_t *__restrict__ in, size_t in_stride, int from_analytic,
-             const uint32_t *__restrict__ mtw_l, const uint32_t *__restrict__ mtw_r, int mt_shared,
+             const uint32_t *__restrict__ mtw_l, const uint32_t *__restrict__ mtw_r, size_t mt_stream_stride,
              uint8_t *__restrict__ out, size_t out_stride,
              double *__restrict__ tap_bus /* optional [stream][frame][ICW_N_PLUGS][4] */,
              double *__restrict__ tap_lr /* optional [stream][frame][2] */)
@@ -220,7 +229,7 @@ chain_kernel(const __grid_constant__ DevChain ch, DevStream *__restrict__ stream
     const int stream = blockIdx.y;
     DevStream &st = streams[stream];
     const uint8_t *src = in + (size_t)stream * in_stride;
-    const size_t mt_off = mt_shared ? 0 : (size_t)stream * (size_t)n_frames * ch.render.words_per_sample;
+    const size_t mt_off = (size_t)stream * mt_stream_stride;    // 0 when every stream shares one generator state
     FrameIO io;
     io.mtw_l = mtw_l ? mtw_l + mt_off : nullptr;
     io.mtw_r = mtw_r ? mtw_r + mt_off : nullptr;
@@ -247,7 +256,7 @@ chain_kernel(const __grid_constant__ DevChain ch, DevStream *__restrict__ stream
 
 cudaError_t launch_chain(const DevChain &ch, DevStream *streams, int n_streams, int64_t n_frames,
                          const uint8_t *in, size_t in_stride, int from_analytic,
-                         const uint32_t *mtw_l, const uint32_t *mtw_r, int mt_shared,
+                         const uint32_t *mtw_l, const uint32_t *mtw_r, size_t mt_stream_stride,
                          uint8_t *out, size_t out_stride, double *tap_bus, double *tap_lr,
                          int sm_count, cudaStream_t s)
 {
@@ -260,7 +269,7 @@ cudaError_t launch_chain(const DevChain &ch, DevStream *streams, int n_streams, 
     if (per_stream > cap) per_stream = cap;
     dim3 grid(per_stream, n_streams);
     chain_kernel<<<grid, threads, 0, s>>>(ch, streams, n_frames, in, in_stride, from_analytic, mtw_l, mtw_r,
-                                          mt_shared, out, out_stride, tap_bus, tap_lr);
+                                          mt_stream_stride, out, out_stride, tap_bus, tap_lr);
     return cudaGetLastError();
 }
 

@@ -27,15 +27,16 @@ cudaError_t launch_hb_exact(const HbCoef &coef, const DevChain &ch, DevStream *s
                             cudaStream_t s);
 cudaError_t launch_hb_fused(const HbCoef &coef, const DevChain &ch, DevStream *streams, int n_streams,
                             int64_t n_frames, const uint8_t *in, size_t in_stride,
-                            const uint32_t *mtw_l, const uint32_t *mtw_r, int mt_shared,
+                            const uint32_t *mtw_l, const uint32_t *mtw_r, size_t mt_stream_stride,
                             uint8_t *out, size_t out_stride, double *tap_bus, double *tap_lr, cudaStream_t s);
 cudaError_t launch_hb_leaf(const HbCoef &coef, int ord, bool kahan, int reject, int n_chan, int64_t n,
                            const double *x, double *out, HbLeafState *st, cudaStream_t s);
 cudaError_t launch_mt_words(const uint32_t *ckpt, int n_cta, int blocks_per_cta, int64_t first_word,
-                            int64_t want_lo, int64_t want_hi, uint32_t *out, cudaStream_t s);
+                            int64_t want_lo, int64_t want_hi, uint32_t *out, int64_t tail_block, uint32_t *tail,
+                            cudaStream_t s);
 cudaError_t launch_chain(const DevChain &ch, DevStream *streams, int n_streams, int64_t n_frames,
                          const uint8_t *in, size_t in_stride, int from_analytic,
-                         const uint32_t *mtw_l, const uint32_t *mtw_r, int mt_shared,
+                         const uint32_t *mtw_l, const uint32_t *mtw_r, size_t mt_stream_stride,
                          uint8_t *out, size_t out_stride, double *tap_bus, double *tap_lr,
                          int sm_count, cudaStream_t s);
 cudaError_t launch_advance(const DevChain &ch, DevStream *streams, int n_streams, int64_t n_frames,

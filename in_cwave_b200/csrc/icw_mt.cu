@@ -230,13 +230,17 @@ mt_jump_kernel(uint32_t *__restrict__ states, const uint32_t *__restrict__ src_s
         __syncthreads();
     }
     if (tid < MT_N) {
+        // shared-memory bandwidth is the limit here (one 4-byte load per lane per set bit), so walk
+        // only the set bits of the polynomial: the branch is uniform across the CTA
         uint32_t acc = 0;
         for (int wi = 0; wi < MT_N; ++wi) {
-            const uint32_t bits = pw[wi];
-            if (!bits) continue;                     // uniform across the CTA
+            uint32_t bits = pw[wi];
             const uint32_t *p = seq + wi * 32 + tid;
-#pragma unroll
-            for (int b = 0; b < 32; ++b) acc ^= p[b] & (0u - ((bits >> b) & 1u));
+            while (bits) {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                acc ^= p[b];
+            }
         }
         states[(size_t)dst * MT_N + tid] = acc;
     }
@@ -249,7 +253,9 @@ void MtJump::release()
     host_poly_.clear();
     if (d_ckpt_) cudaFree(d_ckpt_);
     if (d_tmp_) cudaFree(d_tmp_);
-    d_ckpt_ = d_tmp_ = nullptr;
+    if (d_tail_) cudaFree(d_tail_);
+    d_ckpt_ = d_tmp_ = d_tail_ = nullptr;
+    for (auto &t : tails_) t.valid = false;
     ckpt_cap_ = 0;
 }
 
@@ -277,6 +283,11 @@ int MtJump::ensure_poly(int k)
 // S_block (the state array u[624*block .. 624*block+623]) into d_state
 int MtJump::state_at_block(uint32_t seed, uint64_t block, uint32_t *d_state, cudaStream_t stream, uint64_t *launches)
 {
+    for (int i = 0; i < NTAIL * 2; ++i)
+        if (tails_[i].valid && tails_[i].stream == stream && tails_[i].seed == seed && tails_[i].block == block) {
+            if (cudaMemcpyAsync(d_state, d_tail_ + (size_t)i * MT_N, MT_N * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream) != cudaSuccess) { err_ = "tail state copy failed"; return ICW_E_CUDA; }
+            return ICW_OK;
+        }
     uint32_t st[MT_N];
     mt_seed_state(seed, st);
     uint64_t rest = 0;
@@ -312,7 +323,9 @@ int MtJump::generate(uint32_t seed, uint64_t skip, int64_t n, uint32_t *d_out, i
     const uint64_t b0 = skip / MT_N, b1 = (skip + (uint64_t)n - 1) / MT_N;
     const uint64_t nb = b1 - b0 + 1;
     // blocks per CTA = 2^kb so that every checkpoint distance has a polynomial in the x^(624*2^k) family
-    const uint64_t max_cta = (uint64_t)sm_count * 4;
+    // enough CTAs that one CTA regenerates at most ~2048 blocks, between 4 and 16 per SM
+    uint64_t max_cta = (uint64_t)sm_count * 4;
+    while (max_cta < (uint64_t)sm_count * 16 && nb / max_cta > 2048) max_cta *= 2;
     int kb = 0;
     while (((nb + (1ull << kb) - 1) >> kb) > max_cta) ++kb;
     const int n_cta = (int)((nb + (1ull << kb) - 1) >> kb);
@@ -334,7 +347,14 @@ int MtJump::generate(uint32_t seed, uint64_t skip, int64_t n, uint32_t *d_out, i
         mt_jump_kernel<<<count, JUMP_THREADS, JUMP_SMEM, stream>>>(d_ckpt_, nullptr, first, first, dev_poly_[kb + j]);
         if (launches) ++*launches;
     }
-    cudaError_t e = launch_mt_words(d_ckpt_, n_cta, 1 << kb, (int64_t)(b0 * MT_N), (int64_t)skip, (int64_t)(skip + (uint64_t)n), d_out, stream);
+    if (!d_tail_ && cudaMalloc(&d_tail_, (size_t)NTAIL * 2 * MT_N * sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); err_ = "cudaMalloc(tail states) failed"; return ICW_E_NOMEM; }
+    const int slot = tail_next_;
+    tail_next_ = (tail_next_ + 1) % NTAIL;
+    tails_[2 * slot].valid = tails_[2 * slot + 1].valid = false;
+    cudaError_t e = launch_mt_words(d_ckpt_, n_cta, 1 << kb, (int64_t)(b0 * MT_N), (int64_t)skip, (int64_t)(skip + (uint64_t)n), d_out,
+                                    (int64_t)(b1 - b0), d_tail_ + (size_t)slot * 2 * MT_N, stream);
+    tails_[2 * slot] = { seed, b1, true, stream };          // state that regenerates into block b1
+    tails_[2 * slot + 1] = { seed, b1 + 1, true, stream };  // state after block b1
     if (launches) ++*launches;
     if (e != cudaSuccess) { err_ = std::string("mt kernels: ") + cudaGetErrorString(e); return ICW_E_CUDA; }
     return ICW_OK;

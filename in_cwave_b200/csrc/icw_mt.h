@@ -50,6 +50,13 @@ private:
     uint32_t *d_ckpt_ = nullptr;        // checkpoint states [count][624]
     size_t ckpt_cap_ = 0;
     uint32_t *d_tmp_ = nullptr;         // ping-pong for sequential jumps
+    // generator states left behind by earlier calls: a stream that continues where the last call
+    // stopped finds its start state here instead of jumping there from the seed
+    struct Tail { uint32_t seed; uint64_t block; bool valid; cudaStream_t stream; };   // stream-ordered: only valid on the stream that wrote it
+    static constexpr int NTAIL = 8;     // buffers of 2 states each
+    uint32_t *d_tail_ = nullptr;        // [NTAIL][2][624]
+    Tail tails_[NTAIL * 2] = {};
+    int tail_next_ = 0;
     bool attr_set_ = false;
     std::string err_;
 };

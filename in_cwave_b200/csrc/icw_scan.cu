@@ -67,6 +67,11 @@ void scan_make_coef(int filter_no, bool baseline, double d0, ModalCoef &mc, std:
         mc.cp_re[m] = (double)(w * rp.re); mc.cp_im[m] = (double)(-w * rp.im);
         mc.pl_re[m] = (double)pl.re;     mc.pl_im[m] = (double)pl.im;
         mc.pt_re[m] = (double)pt.re;     mc.pt_im[m] = (double)pt.im;
+        cld pj = pl;
+        for (int j = 0; j < 16; ++j) {                  // p^(L*(j+1))
+            mc.plp_re[j][m] = (double)pj.re; mc.plp_im[j][m] = (double)pj.im;
+            pj = cmul(pj, pl);
+        }
         cld acc = { 1.0L, 0.0L };
         for (int j = 0; j < SCAN_CH; ++j) {             // p^(L*j)
             pw_table[((size_t)j * SCAN_NMAX + m) * 2] = (double)acc.re;
@@ -112,84 +117,121 @@ __device__ __forceinline__ size_t e_index(int stream, int comp, int chan, int64_
     return (((size_t)stream * (4 * SCAN_NMAX) + comp) * 2 + chan) * (size_t)n_chunks + (size_t)chunk;
 }
 
-// pass 1: end state of every full chunk, started from zero
+// pass 1 + 2a: end state of every full chunk started from zero, then -- inside the CTA, which is
+// exactly one tile of 128 chunks -- the carry scan over chunks: warp shuffles (16 chunks per warp),
+// one shared-memory hop across the 8 warps.  Writes, per chunk, its carry-in from the tile start
+// (exclusive prefix) and, per tile, the tile's end state.
 template <int NM>
 __global__ void __launch_bounds__(256)
 scan_local_kernel(const __grid_constant__ ModalCoef mc, const __grid_constant__ DevChain ch,
-                  const DevStream *__restrict__ streams, int64_t n_frames, int64_t n_chunks,
-                  const uint8_t *__restrict__ in, size_t in_stride, double *__restrict__ E)
+                  const DevStream *__restrict__ streams, int64_t n_frames, int64_t n_chunks, int64_t n_tiles,
+                  const uint8_t *__restrict__ in, size_t in_stride, double *__restrict__ E,
+                  double *__restrict__ Tend /* [stream][tile][chan][filter][mode][2] */)
 {
+    __shared__ double wtot[8][2][2][SCAN_NMAX][2];      // inclusive total of each warp's 16 chunks
+    __shared__ double wcar[8][2][2][SCAN_NMAX][2];      // carry into each warp from the tile start
     const int stream = blockIdx.y;
-    const int64_t chunk = (int64_t)blockIdx.x * (blockDim.x / 2) + (threadIdx.x >> 1);
+    const int64_t tile = blockIdx.x;
+    const int cl = threadIdx.x >> 1;                    // chunk inside the tile, 0..127
+    const int64_t chunk = tile * SCAN_CH + cl;
     const int chan = threadIdx.x & 1;
-    if (chunk >= n_chunks - 1) return;                          // the last chunk's end state is not needed here
+    const int warp = threadIdx.x >> 5, cw = cl & 15;    // chunk inside the warp
+    const bool have = chunk < n_chunks - 1;             // the call's last chunk has no end state to hand on
     const DevStream &st = streams[stream];
     const unsigned q0 = st.quad[chan];
-    const int xiq = q0 & 1;                                     // filter fed on the first sample of a pair
-    const uint8_t *row = in + (size_t)stream * in_stride;
-    const int chan_off = (ch.n_channels > 1 ? chan : 0) * ch.chan_bytes;
-    const bool fading = (ch.n_fade_in | ch.n_fade_out) != 0;
-    const int64_t f0 = chunk * SCAN_L;
+    const int xiq = q0 & 1;                             // filter fed on the first sample of a pair
 
-    Cx A[NM], B[NM];
+    Cx s[2][NM];                                        // [filter I/Q][mode]
 #pragma unroll
-    for (int m = 0; m < NM; ++m) { A[m].re = A[m].im = 0.0; B[m].re = B[m].im = 0.0; }
-    for (int k = 0; k < SCAN_L; k += 2) {
-        const double x0 = scan_sample(ch, row, f0 + k, chan_off, st.pos, fading);
-        const double x1 = scan_sample(ch, row, f0 + k + 1, chan_off, st.pos, fading);
-        const unsigned qa = (q0 + (unsigned)k) & 3u;            // f0 is a multiple of 4
-        const double ux = mix_down(xiq, qa, x0);
-        const double uy = mix_down(xiq ^ 1, (qa + 1) & 3u, x1);
+    for (int m = 0; m < NM; ++m) { s[0][m].re = s[0][m].im = 0.0; s[1][m].re = s[1][m].im = 0.0; }
+    if (have) {
+        const uint8_t *row = in + (size_t)stream * in_stride;
+        const int chan_off = (ch.n_channels > 1 ? chan : 0) * ch.chan_bytes;
+        const bool fading = (ch.n_fade_in | ch.n_fade_out) != 0;
+        const int64_t f0 = chunk * SCAN_L;
+        Cx A[NM], B[NM];
+#pragma unroll
+        for (int m = 0; m < NM; ++m) { A[m].re = A[m].im = 0.0; B[m].re = B[m].im = 0.0; }
+        for (int k = 0; k < SCAN_L; k += 2) {
+            const double x0 = scan_sample(ch, row, f0 + k, chan_off, st.pos, fading);
+            const double x1 = scan_sample(ch, row, f0 + k + 1, chan_off, st.pos, fading);
+            const unsigned qa = (q0 + (unsigned)k) & 3u;        // f0 is a multiple of 4
+            const double ux = mix_down(xiq, qa, x0);
+            const double uy = mix_down(xiq ^ 1, (qa + 1) & 3u, x1);
+#pragma unroll
+            for (int m = 0; m < NM; ++m) {
+                cx_step(A[m], mc.p2_re[m], mc.p2_im[m], ux);
+                cx_step(B[m], mc.p2_re[m], mc.p2_im[m], uy);
+            }
+        }
+        // state after the last (second-of-pair) sample: X filter p*A, Y filter B
 #pragma unroll
         for (int m = 0; m < NM; ++m) {
-            cx_step(A[m], mc.p2_re[m], mc.p2_im[m], ux);
-            cx_step(B[m], mc.p2_re[m], mc.p2_im[m], uy);
+            Cx sx = cx_mul(mc.p_re[m], mc.p_im[m], A[m]);
+            if (xiq == 0) { s[0][m] = sx; s[1][m] = B[m]; }
+            else          { s[1][m] = sx; s[0][m] = B[m]; }
         }
     }
-    // state after the last (second-of-pair) sample: X filter p*A, Y filter B
-#pragma unroll
-    for (int m = 0; m < NM; ++m) {
-        Cx sx = cx_mul(mc.p_re[m], mc.p_im[m], A[m]);
-        Cx sy = B[m];
-        const int fx = xiq, fy = xiq ^ 1;
-        E[e_index(stream, (fx * SCAN_NMAX + m) * 2, chan, chunk, n_chunks)] = sx.re;
-        E[e_index(stream, (fx * SCAN_NMAX + m) * 2 + 1, chan, chunk, n_chunks)] = sx.im;
-        E[e_index(stream, (fy * SCAN_NMAX + m) * 2, chan, chunk, n_chunks)] = sy.re;
-        E[e_index(stream, (fy * SCAN_NMAX + m) * 2 + 1, chan, chunk, n_chunks)] = sy.im;
-    }
-}
 
-// pass 2a: inside every tile, replace each chunk's end state by its carry-in from the tile start
-// (exclusive prefix with multiplier p^L) and record the tile's end state
-__global__ void __launch_bounds__(128)
-scan_tile_prefix_kernel(const __grid_constant__ ModalCoef mc, int64_t n_chunks, int64_t n_tiles,
-                        double *__restrict__ E, double *__restrict__ Tend /* [stream][tile][chan][filter][mode][2] */)
-{
-    const int stream = blockIdx.y;
-    const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int per_tile = 2 * 2 * mc.nm;
-    if (id >= n_tiles * per_tile) return;
-    const int64_t tile = id / per_tile;
-    int r = (int)(id % per_tile);
-    const int m = r % mc.nm; r /= mc.nm;
-    const int f = r & 1, chan = r >> 1;
-    const int comp = (f * SCAN_NMAX + m) * 2;
-    Cx acc; acc.re = acc.im = 0.0;
-    const double lr = mc.pl_re[m], li = mc.pl_im[m];
-    for (int j = 0; j < SCAN_CH; ++j) {
-        const int64_t chunk = tile * SCAN_CH + j;
-        if (chunk >= n_chunks) break;
-        const size_t ir = e_index(stream, comp, chan, chunk, n_chunks), ii = e_index(stream, comp + 1, chan, chunk, n_chunks);
-        Cx e; e.re = e.im = 0.0;
-        if (chunk < n_chunks - 1) { e.re = E[ir]; e.im = E[ii]; }
-        E[ir] = acc.re; E[ii] = acc.im;
-        // acc <- p^L * acc + e
-        const double nr = fma(lr, acc.re, fma(-li, acc.im, e.re));
-        const double ni = fma(lr, acc.im, fma(li, acc.re, e.im));
-        acc.re = nr; acc.im = ni;
+    // inclusive scan over the warp's 16 chunks (lanes of one channel are 2 apart)
+#pragma unroll
+    for (int d = 1; d < 16; d <<= 1) {
+#pragma unroll
+        for (int f = 0; f < 2; ++f)
+#pragma unroll
+            for (int m = 0; m < NM; ++m) {
+                const double ore = __shfl_up_sync(0xffffffffu, s[f][m].re, 2 * d);
+                const double oim = __shfl_up_sync(0xffffffffu, s[f][m].im, 2 * d);
+                if (cw >= d) {
+                    Cx o; o.re = ore; o.im = oim;
+                    Cx w = cx_mul(mc.plp_re[d - 1][m], mc.plp_im[d - 1][m], o);     // p^(L*d) * earlier
+                    s[f][m].re += w.re; s[f][m].im += w.im;
+                }
+            }
     }
-    double *t = Tend + ((((size_t)stream * n_tiles + tile) * 2 + chan) * 2 + f) * (SCAN_NMAX * 2) + m * 2;
-    t[0] = acc.re; t[1] = acc.im;
+    if (cw == 15) {
+#pragma unroll
+        for (int f = 0; f < 2; ++f)
+#pragma unroll
+            for (int m = 0; m < NM; ++m) { wtot[warp][chan][f][m][0] = s[f][m].re; wtot[warp][chan][f][m][1] = s[f][m].im; }
+    }
+    __syncthreads();
+    // carry into each warp: sequential over the 8 warps, one thread per (chan, filter, mode)
+    if (threadIdx.x < 2 * 2 * NM) {
+        int r = threadIdx.x;
+        const int m = r % NM; r /= NM;
+        const int f = r & 1, c = r >> 1;
+        Cx acc; acc.re = acc.im = 0.0;
+        for (int w = 0; w < 8; ++w) {
+            wcar[w][c][f][m][0] = acc.re; wcar[w][c][f][m][1] = acc.im;
+            // acc <- p^(16 L) * acc + total(w)
+            const double nr = fma(mc.plp_re[15][m], acc.re, fma(-mc.plp_im[15][m], acc.im, wtot[w][c][f][m][0]));
+            const double ni = fma(mc.plp_re[15][m], acc.im, fma(mc.plp_im[15][m], acc.re, wtot[w][c][f][m][1]));
+            acc.re = nr; acc.im = ni;
+        }
+    }
+    __syncthreads();
+    // inclusive prefix from the tile start, then shift by one chunk for the carry-IN of this chunk
+#pragma unroll
+    for (int f = 0; f < 2; ++f)
+#pragma unroll
+        for (int m = 0; m < NM; ++m) {
+            Cx c; c.re = wcar[warp][chan][f][m][0]; c.im = wcar[warp][chan][f][m][1];
+            Cx w = cx_mul(mc.plp_re[cw][m], mc.plp_im[cw][m], c);                   // p^(L*(cw+1)) * warp carry
+            const double inc_re = s[f][m].re + w.re, inc_im = s[f][m].im + w.im;
+            double ex_re = __shfl_up_sync(0xffffffffu, inc_re, 2);
+            double ex_im = __shfl_up_sync(0xffffffffu, inc_im, 2);
+            if (cw == 0) { ex_re = c.re; ex_im = c.im; }
+            if (chunk < n_chunks) {
+                const int comp = (f * SCAN_NMAX + m) * 2;
+                E[e_index(stream, comp, chan, chunk, n_chunks)] = ex_re;
+                E[e_index(stream, comp + 1, chan, chunk, n_chunks)] = ex_im;
+            }
+            if (cl == SCAN_CH - 1) {
+                double *t = Tend + ((((size_t)stream * n_tiles + tile) * 2 + chan) * 2 + f) * (SCAN_NMAX * 2) + m * 2;
+                t[0] = inc_re; t[1] = inc_im;
+            }
+        }
 }
 
 // pass 2b: carry into every tile.  The filters forget: |p|^(tile) <= 1e-3, so eight tiles back is
@@ -355,14 +397,10 @@ static cudaError_t scan_launch_nm(const ModalCoef &mc, const DevChain &ch, DevSt
     double *E = scratch;
     double *Tend = E + (size_t)n_streams * (4 * SCAN_NMAX) * 2 * (size_t)n_chunks;
     double *Tin = Tend + (size_t)n_streams * (size_t)n_tiles * 2 * 2 * (SCAN_NMAX * 2);
-    const unsigned cgrid = (unsigned)((n_chunks + 127) / 128);
-    if (n_chunks > 1) {
-        scan_local_kernel<NM><<<dim3(cgrid, n_streams), 256, 0, s>>>(mc, ch, streams, n_frames, n_chunks, in, in_stride, E);
-        ++*launches;
-    }
+    const unsigned cgrid = (unsigned)n_tiles;                   // one CTA = one tile of 128 chunks x 2 channels
+    scan_local_kernel<NM><<<dim3(cgrid, n_streams), 256, 0, s>>>(mc, ch, streams, n_frames, n_chunks, n_tiles, in, in_stride, E, Tend);
     const int64_t items = n_tiles * 2 * 2 * mc.nm;
     const unsigned tgrid = (unsigned)((items + 127) / 128);
-    scan_tile_prefix_kernel<<<dim3(tgrid, n_streams), 128, 0, s>>>(mc, n_chunks, n_tiles, E, Tend);
     scan_tile_carry_kernel<<<dim3(tgrid, n_streams), 128, 0, s>>>(mc, streams, n_tiles, Tend, Tin);
     scan_apply_kernel<NM><<<dim3(cgrid, n_streams), 256, 0, s>>>(mc, ch, streams, n_frames, n_chunks, n_tiles, in, in_stride,
                                                                E, Tin, pw, analytic);

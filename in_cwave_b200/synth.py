@@ -68,36 +68,38 @@ def stream_bytes(spec: dict, n: int, stream_id: int = 0, level: float = 0.25) ->
 
 
 def device_fill(spec: dict, n_streams: int, n: int, device, row_align: int = 16):
-    """Resident synthetic input: torch uint8 [n_streams, stride] generated on the GPU (noise + sine),
-    same family of signal as ``signal`` but produced with torch's generator (seeded per call)."""
+    """Resident synthetic input: torch uint8 [n_streams, stride] generated on the GPU (noise + two
+    sines, same family as ``signal``), in blocks of at most 2^24 sample values at a time."""
     import torch
+    from .spec import frame_bytes
     fmt = spec.get("fmt", "wav_f32")
     nch = int(spec.get("n_channels", 2))
     cols = nch * (2 if fmt.startswith("cw_") else 1)
     sr = int(spec.get("sample_rate", 48000))
-    from .spec import frame_bytes
     fb = frame_bytes(spec)
     stride = (n * fb + row_align - 1) // row_align * row_align
     out = torch.zeros((n_streams, stride), dtype=torch.uint8, device=device)
     g = torch.Generator(device=device)
     g.manual_seed(0x1C0A7E5EED)
-    chunk = max(1, min(n_streams, (1 << 26) // max(1, n * cols)))
-    t = torch.arange(n, dtype=torch.float64, device=device)[:, None]
-    tone = 0.0625 * torch.sin(2 * torch.pi * 997.0 / sr * t) + 0.0625 * torch.sin(2 * torch.pi * 0.155 * t)
-    for s0 in range(0, n_streams, chunk):
-        k = min(chunk, n_streams - s0)
-        x = (torch.rand((k, n, cols), generator=g, device=device, dtype=torch.float32) - 0.5) * 0.25
-        x = x + tone.to(torch.float32)[None]
-        if fmt == "wav_f32":
-            b = x.contiguous().view(torch.uint8).reshape(k, -1)
-        elif fmt == "cw_f32":
-            b = (x * 32768.0).contiguous().view(torch.uint8).reshape(k, -1)
-        elif fmt == "wav_i16":
-            b = torch.clamp(torch.round(x * 32768.0), -32768, 32767).to(torch.int16).contiguous().view(torch.uint8).reshape(k, -1)
-        elif fmt == "wav_i24":
-            v = torch.clamp(torch.round(x.double() * 8388608.0), -2**23, 2**23 - 1).to(torch.int32)
-            b = v.contiguous().view(torch.uint8).reshape(k, n, cols, 4)[..., :3].contiguous().reshape(k, -1)
-        else:
-            raise ValueError(f"device_fill: format {fmt} not wired")
-        out[s0:s0 + k, : n * fb] = b
+    tblk = max(1, min(n, (1 << 24) // cols))
+    sblk = max(1, min(n_streams, (1 << 24) // (tblk * cols)))
+    for t0 in range(0, n, tblk):
+        tn = min(tblk, n - t0)
+        t = torch.arange(t0, t0 + tn, dtype=torch.float64, device=device)[:, None]
+        tone = (0.0625 * torch.sin(2 * torch.pi * 997.0 / sr * t) + 0.0625 * torch.sin(2 * torch.pi * 0.155 * t)).to(torch.float32)
+        for s0 in range(0, n_streams, sblk):
+            k = min(sblk, n_streams - s0)
+            x = (torch.rand((k, tn, cols), generator=g, device=device, dtype=torch.float32) - 0.5) * 0.25 + tone[None]
+            if fmt == "wav_f32":
+                b = x.contiguous().view(torch.uint8).reshape(k, -1)
+            elif fmt == "cw_f32":
+                b = (x * 32768.0).contiguous().view(torch.uint8).reshape(k, -1)
+            elif fmt == "wav_i16":
+                b = torch.clamp(torch.round(x * 32768.0), -32768, 32767).to(torch.int16).contiguous().view(torch.uint8).reshape(k, -1)
+            elif fmt == "wav_i24":
+                v = torch.clamp(torch.round(x.double() * 8388608.0), -2**23, 2**23 - 1).to(torch.int32)
+                b = v.contiguous().view(torch.uint8).reshape(k, tn, cols, 4)[..., :3].contiguous().reshape(k, -1)
+            else:
+                raise ValueError(f"device_fill: format {fmt} not wired")
+            out[s0:s0 + k, t0 * fb:(t0 + tn) * fb] = b
     return out
