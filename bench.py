@@ -60,6 +60,13 @@ def workload(name: str) -> dict:
         return dict(name="c2", desc="192 kHz 24-bit PCM stereo, 1 h: Hilbert + 100 Hz shift + TPDF dither + 24-bit render (one stream)",
                     spec=S.config_c2(hilbert_mode="scan"), streams=1, frames=691_200_000, chunk=691_200_000,
                     bytes_per_frame=12, hilbert="scan")
+    if name == "c5":
+        # one 384 kHz stereo f32 stream cut in time across the ranks: 3 h (1/8 of 24 h) per GPU,
+        # NCCL hand-off of the Hilbert state at every cut (in_cwave_b200.dist.run_time_sharded)
+        return dict(name="c5", desc="384 kHz stereo f32, 24 h stream time-sharded: 3 h per GPU, Hilbert + 100 Hz shift + 24-bit render, "
+                                    "NCCL filter-state hand-off between neighbours",
+                    spec=S.config_c1(hilbert_mode="scan", sample_rate=384000), streams=1, frames=4_147_200_000,
+                    chunk=4_147_200_000, bytes_per_frame=14, hilbert="scan", time_sharded=True)
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -210,6 +217,20 @@ def reference_arm(args, wl):
     print(json.dumps(line), flush=True)
 
 
+class _NoDist:
+    """world == 1: the time-sharded path has nobody to talk to."""
+    class ReduceOp:
+        SUM = MAX = None
+
+    @staticmethod
+    def batch_isend_irecv(ops):
+        return []
+
+    @staticmethod
+    def all_reduce(t, op=None, group=None):
+        return None
+
+
 # ---------------------------------------------------------------------------------------------
 # the GPU arm
 # ---------------------------------------------------------------------------------------------
@@ -218,7 +239,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default=os.environ.get("ICW_WORKLOAD", "c4"))
+    ap.add_argument("--workload", default=os.environ.get("ICW_WORKLOAD", "c2"))
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--streams", type=int, default=0, help="override the workload's stream count")
     ap.add_argument("--frames", type=int, default=0, help="override frames per stream")
@@ -263,8 +284,20 @@ def main():
     d_out = torch.empty((K, out_stride), dtype=torch.uint8, device=dev)
     cs = torch.cuda.current_stream().cuda_stream
 
+    shard_be = None
+    if wl.get("time_sharded"):
+        from in_cwave_b200 import dist as D
+        shard_be = D.CudaBackend(eng, spec)
+        shard_be.ses.close()
+        shard_be.ses = ses                            # profile / count launches on the session bench reads
+
     def one_step():
         ses.reset()                                   # every step = the same fresh streams
+        if shard_be is not None:
+            # rank r plays frames [r*N, (r+1)*N) of one stream of world*N frames
+            D.run_time_sharded(shard_be, dist if world > 1 else _NoDist(), spec, d_in[0, : N * fb], rank * N, rank, world,
+                               device=dev, d_out=d_out[0])
+            return
         for f0 in range(0, N, chunk):
             n = min(chunk, N - f0)
             ses.process_device(d_in.data_ptr() + f0 * fb, n, d_out.data_ptr() + f0 * ob,
@@ -319,7 +352,7 @@ def main():
 
     # ---- end to end through the host entry point ----------------------------------------------------
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not wl.get("time_sharded"):
         try:
             h_in = torch.empty((K, N * fb), dtype=torch.uint8, pin_memory=True)
             h_out = torch.empty((K, N * ob), dtype=torch.uint8, pin_memory=True)
@@ -352,6 +385,8 @@ def main():
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) ------------------------------------
     cpu = None
+    if wl.get("time_sharded"):
+        args.no_cpu = True
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = host_cores()
         fr = min(N, 480_000)
@@ -364,6 +399,11 @@ def main():
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
                     data="synthetic",
+                    parity=dict(hilbert=wl["hilbert"],
+                                note=("exact: bit-exact with the reference (tests/test_gpu_parity.py)" if wl["hilbert"] != "scan" else
+                                      "scan: analytic signal within 1e-12 of the binary128 evaluation of the reference's filter; "
+                                      "everything downstream byte-exact; the reference's own FP64 rounding noise (5e-5 of RMS for the "
+                                      "default design) separates its PCM from ours (tests/test_gpu_scan.py)")),
                     config=dict(workload=wl["desc"], streams_per_gpu=K, frames_per_stream=N, frames_per_launch=units_per_launch,
                                 hilbert=wl["hilbert"], l2="inputs larger than L2 (per-step input %.1f GB)" % (K * N * fb / 1e9)),
                     roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks,

@@ -44,6 +44,8 @@ def needs_build() -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not needs_build():
+        if not PLUGIN.exists() or PLUGIN.stat().st_mtime < (PKG / "host" / "icw_plugin.c").stat().st_mtime:
+            build_plugin()
         return LIB
     cmd = [nvcc_path(), *NVCC_FLAGS, "-o", str(LIB)] + [str(CSRC / s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -54,7 +56,23 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         raise RuntimeError("nvcc failed; see in_cwave_b200/build.log")
     if verbose:
         print(log)
+    build_plugin()
     return LIB
+
+
+PLUGIN = PKG / "libicw_plugin.so"
+
+
+def build_plugin() -> Path:
+    """The host C layer (reference entry points over the C ABI): plain gcc, links libicw_b200.so."""
+    cmd = ["gcc", "-std=c99", "-O2", "-Wall", "-fPIC", "-shared", "-I", str(PKG.parent / "include"),
+           "-o", str(PLUGIN), str(PKG / "host" / "icw_plugin.c"), "-L", str(PKG), "-licw_b200",
+           "-Wl,-rpath,$ORIGIN"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("gcc failed on host/icw_plugin.c")
+    return PLUGIN
 
 
 if __name__ == "__main__":

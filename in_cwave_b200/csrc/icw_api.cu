@@ -68,6 +68,12 @@ struct icw_engine {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t aux = nullptr;         // dither words are generated here, concurrently with the Hilbert kernels
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t h2d = nullptr, d2h = nullptr;      // copy streams of the host entry point's pipeline
+    cudaEvent_t ev_in[2] = { nullptr, nullptr }, ev_comp[2] = { nullptr, nullptr }, ev_out[2] = { nullptr, nullptr };
+    int n_sessions = 0;
+    bool dying = false;                 // icw_engine_destroy was called while sessions were alive
     Scratch analytic, mtw[2], ckpt, io_in, io_out, leaf;
     bool unfused = false;               // ICW_UNFUSED=1: keep the two-kernel exact path (A/B measurements)
     Scratch scan_scratch;
@@ -345,20 +351,39 @@ extern "C" int icw_engine_create(int device, icw_engine **out)
     e->device = device;
     e->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&e->aux, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
     { const char *u = getenv("ICW_UNFUSED"); e->unfused = u && *u == '1'; }
     *out = e;
     return ICW_OK;
 }
 
+static void engine_free(icw_engine *e);
+
 extern "C" void icw_engine_destroy(icw_engine *e)
 {
     if (!e) return;
+    if (e->n_sessions > 0) { e->dying = true; return; }     // the last session to go frees the engine
+    engine_free(e);
+}
+
+static void engine_free(icw_engine *e)
+{
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     e->analytic.release(); e->mtw[0].release(); e->mtw[1].release(); e->ckpt.release();
     e->io_in.release(); e->io_out.release(); e->leaf.release(); e->scan_scratch.release();
     for (auto &row : e->scan) for (auto &pl : row) if (pl.d_pw) cudaFree(pl.d_pw);
     e->mt.release();
+    cudaStreamSynchronize(e->aux);
+    if (e->h2d) {
+        cudaStreamSynchronize(e->h2d); cudaStreamSynchronize(e->d2h);
+        for (int i = 0; i < 2; ++i) { cudaEventDestroy(e->ev_in[i]); cudaEventDestroy(e->ev_comp[i]); cudaEventDestroy(e->ev_out[i]); }
+        cudaStreamDestroy(e->h2d); cudaStreamDestroy(e->d2h);
+    }
+    cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_join);
+    cudaStreamDestroy(e->aux);
     cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -432,6 +457,7 @@ extern "C" int icw_session_create(icw_engine *e, const icw_chain_spec *spec, int
         s->mt_seed[c].assign((size_t)n_streams, fresh.mt_seed[c]);
         s->mt_drawn[c].assign((size_t)n_streams, 0);
     }
+    e->n_sessions++;
     *out = s;
     return ICW_OK;
 }
@@ -444,7 +470,9 @@ extern "C" void icw_session_destroy(icw_session *s)
     if (s->d_streams) cudaFree(s->d_streams);
     for (auto &sp : s->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto ev : s->ev_pool) cudaEventDestroy(ev);
+    icw_engine *e = s->e;
     delete s;
+    if (--e->n_sessions == 0 && e->dying) engine_free(e);
 }
 
 extern "C" int icw_session_sync(icw_session *s)
@@ -552,7 +580,7 @@ extern "C" int icw_session_set_taps(icw_session *s, double *d_tap_bus, double *d
 // ---------------------------------------------------------------------------------------------
 // the hot call
 // ---------------------------------------------------------------------------------------------
-struct DitherWords { const uint32_t *l = nullptr, *r = nullptr; size_t stream_stride = 0; };
+struct DitherWords { const uint32_t *l = nullptr, *r = nullptr; size_t stream_stride = 0; cudaEvent_t join = nullptr; };
 
 static int make_dither_words(icw_session *s, int64_t n_frames, cudaStream_t st, DitherWords &dw)
 {
@@ -626,6 +654,7 @@ static int process_group(icw_session *s, int64_t n_frames, const uint8_t *d_in, 
     const bool scan = !ch.is_complex && s->spec.hilbert_mode == ICW_HILBERT_SCAN;
     if (!ch.is_complex && !scan && !e->unfused) {
         // real input, reference-exact Hilbert: the whole chain in one kernel
+        if (dw.join) CK(cudaStreamWaitEvent(st, dw.join, 0));
         ProfSpan ps(s, st, ICW_K_HILBERT);
         CK(launch_hb_fused(s->coef, ch, s->d_streams, K, n_frames, d_in, in_stride, wl, wr, mt_shared,
                            d_out, out_stride, s->d_tap_bus, s->d_tap_lr, st));
@@ -660,6 +689,7 @@ static int process_group(icw_session *s, int64_t n_frames, const uint8_t *d_in, 
             src_stride = per;
             from_analytic = 1;
         }
+        if (dw.join) CK(cudaStreamWaitEvent(st, dw.join, 0));
         ProfSpan ps(s, st, ICW_K_CHAIN);
         CK(launch_chain(ch, s->d_streams, K, n_frames, src, src_stride, from_analytic, wl, wr, mt_shared,
                         d_out, out_stride, s->d_tap_bus, s->d_tap_lr, e->sm_count, st));
@@ -676,6 +706,90 @@ static int process_group(icw_session *s, int64_t n_frames, const uint8_t *d_in, 
     return ICW_OK;
 }
 
+// ---- one API call = begin (checks, dither words for the whole call) + ranges + end ------------------
+struct CallCtx {
+    DitherWords all;
+    bool pre = false;
+    int64_t step = 0;       // frames per launch group
+    int mode = 0;
+    bool real_in = false;
+};
+
+static int call_begin(icw_session *s, int64_t n_total, cudaStream_t st, CallCtx &cx)
+{
+    icw_engine *e = s->e;
+    const DevChain &ch = s->ch;
+    const int K = s->n_streams;
+    cx.real_in = !ch.is_complex;
+    cx.mode = s->spec.hilbert_mode;
+    if (cx.real_in) {
+        if (cx.mode != ICW_HILBERT_EXACT && cx.mode != ICW_HILBERT_SCAN) return fail(ICW_E_ARG, "hilbert_mode out of range");
+        if (s->hb_live && s->hb_basis != cx.mode)
+            return fail(ICW_E_UNSUPPORTED, "the streams' Hilbert state is in the %s basis; switching a live stream to %s mode "
+                                           "needs icw_session_reset(ICW_RESET_HILBERT) first (state conversion is not built)",
+                        s->hb_basis ? "modal (scan)" : "delay-line (exact)", cx.mode ? "scan" : "exact");
+    }
+    // scan mode and the unfused path go through per-frame scratch: bound it by walking the call in groups
+    const bool scratchy = cx.real_in && (cx.mode == ICW_HILBERT_SCAN || e->unfused);
+    const int64_t seg = scratchy ? SCAN_SEGMENT / (K > 64 ? 64 : K) / SCAN_L / SCAN_CH * (SCAN_L * SCAN_CH) : n_total;
+    cx.step = seg < SCAN_L * SCAN_CH ? SCAN_L * SCAN_CH : seg;
+    // dither words for the whole call in one go when they fit (one jump tree instead of one per group)
+    const int wps = ch.render.words_per_sample;
+    if (wps && (double)n_total * wps * 4.0 * 2.0 * (K > 1 ? K : 1) <= 48e9) {
+        // integer work on the aux stream next to the FP64-bound Hilbert kernels on `st`; the word
+        // buffers may still be read by the previous call, so the aux stream first joins `st`
+        CK(cudaEventRecord(e->ev_fork, st));
+        CK(cudaStreamWaitEvent(e->aux, e->ev_fork, 0));
+        {
+            ProfSpan ps(s, e->aux, ICW_K_MT);
+            int rc = make_dither_words(s, n_total, e->aux, cx.all);
+            if (rc) return rc;
+        }
+        CK(cudaEventRecord(e->ev_join, e->aux));
+        cx.all.join = e->ev_join;
+        cx.pre = true;
+    } else if (wps) {
+        cx.step = std::min<int64_t>(cx.step, SCAN_SEGMENT);     // per-group word buffers
+    }
+    return ICW_OK;
+}
+
+// frames [f0, f0 + n) of the call; d_in / d_out point at frame f0
+static int call_range(icw_session *s, CallCtx &cx, int64_t f0, int64_t n, const uint8_t *d_in, size_t in_stride,
+                      uint8_t *d_out, size_t out_stride, cudaStream_t st)
+{
+    const DevChain &ch = s->ch;
+    const int wps = ch.render.words_per_sample;
+    if ((s->d_tap_bus || s->d_tap_lr) && n > cx.step)
+        return fail(ICW_E_ARG, "taps are a test aid for calls of at most %lld frames", (long long)cx.step);
+    for (int64_t g0 = 0; g0 < n; g0 += cx.step) {
+        const int64_t gn = n - g0 < cx.step ? n - g0 : cx.step;
+        DitherWords here = cx.all;
+        if (cx.pre) {
+            here.l += (size_t)(f0 + g0) * wps; here.r += (size_t)(f0 + g0) * wps;
+            here.join = cx.all.join;                            // waited for once, by the first group that runs
+            cx.all.join = nullptr;
+        }
+        int rc = process_group(s, gn, d_in + (size_t)g0 * ch.frame_bytes, in_stride,
+                               d_out + (size_t)g0 * ch.out_frame_bytes, out_stride, st, cx.pre ? &here : nullptr);
+        if (rc) return rc;
+    }
+    return ICW_OK;
+}
+
+static void call_end(icw_session *s, const CallCtx &cx)
+{
+    if (cx.real_in) { s->hb_basis = cx.mode; s->hb_live = true; }
+}
+
+static void note_alignment(icw_session *s, const void *d_in, size_t in_stride)
+{
+    // typed loads are only legal when every sample sits on its natural alignment
+    const int cb = s->ch.chan_bytes;
+    const size_t a = (cb == 2 || cb == 4) ? (size_t)cb : 0;
+    s->ch.aligned = a && ((size_t)(uintptr_t)d_in % a == 0) && (s->n_streams == 1 || in_stride % a == 0);
+}
+
 extern "C" int icw_session_process_device(icw_session *s, int64_t n_frames, const void *d_in, size_t in_stride,
                                           void *d_out, size_t out_stride, void *cuda_stream)
 {
@@ -683,77 +797,90 @@ extern "C" int icw_session_process_device(icw_session *s, int64_t n_frames, cons
     if (n_frames < 0) return fail(ICW_E_ARG, "negative frame count");
     if (n_frames == 0) return ICW_OK;
     icw_engine *e = s->e;
-    {
-        // typed loads are only legal when every sample sits on its natural alignment
-        const int cb = s->ch.chan_bytes;
-        const size_t a = (cb == 2 || cb == 4) ? (size_t)cb : 0;
-        s->ch.aligned = a && ((size_t)(uintptr_t)d_in % a == 0) && (s->n_streams == 1 || in_stride % a == 0);
-    }
+    note_alignment(s, d_in, in_stride);
     const DevChain &ch = s->ch;
-    const int K = s->n_streams;
-    if (K > 1 && (in_stride < (size_t)n_frames * ch.frame_bytes || out_stride < (size_t)n_frames * ch.out_frame_bytes))
+    if (s->n_streams > 1 && (in_stride < (size_t)n_frames * ch.frame_bytes || out_stride < (size_t)n_frames * ch.out_frame_bytes))
         return fail(ICW_E_ARG, "stream strides are shorter than one stream's data");
     CK(cudaSetDevice(e->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
-
-    const bool real_in = !ch.is_complex;
-    const int mode = s->spec.hilbert_mode;
-    if (real_in) {
-        if (mode != ICW_HILBERT_EXACT && mode != ICW_HILBERT_SCAN) return fail(ICW_E_ARG, "hilbert_mode out of range");
-        if (s->hb_live && s->hb_basis != mode)
-            return fail(ICW_E_UNSUPPORTED, "the streams' Hilbert state is in the %s basis; switching a live stream to %s mode "
-                                           "needs icw_session_reset(ICW_RESET_HILBERT) first (state conversion is not built)",
-                        s->hb_basis ? "modal (scan)" : "delay-line (exact)", mode ? "scan" : "exact");
-    }
-    // scan mode and the unfused path go through per-frame scratch: bound it by walking the call in segments
-    const bool scratchy = (real_in && (mode == ICW_HILBERT_SCAN || e->unfused)) || ch.render.words_per_sample != 0;
-    const int64_t seg = scratchy ? SCAN_SEGMENT / (K > 64 ? 64 : K) / SCAN_L / SCAN_CH * (SCAN_L * SCAN_CH) : n_frames;
-    const int64_t step = seg < SCAN_L * SCAN_CH ? SCAN_L * SCAN_CH : seg;
-    if ((s->d_tap_bus || s->d_tap_lr) && n_frames > step)
-        return fail(ICW_E_ARG, "taps are a test aid for calls of at most %lld frames", (long long)step);
-    // dither words for the whole call in one go when they fit (one jump tree instead of one per segment)
-    DitherWords all;
-    bool pre = false;
-    const int wps = ch.render.words_per_sample;
-    if (wps && n_frames > step && (double)n_frames * wps * 4.0 * 2.0 * (K > 1 ? K : 1) <= 48e9) {
-        ProfSpan ps(s, st, ICW_K_MT);
-        int rc = make_dither_words(s, n_frames, st, all);
-        if (rc) return rc;
-        pre = true;
-    }
-    for (int64_t f0 = 0; f0 < n_frames; f0 += step) {
-        const int64_t n = n_frames - f0 < step ? n_frames - f0 : step;
-        DitherWords here = all;
-        if (pre) { here.l += (size_t)f0 * wps; here.r += (size_t)f0 * wps; }
-        int rc = process_group(s, n, (const uint8_t *)d_in + (size_t)f0 * ch.frame_bytes, in_stride,
-                               (uint8_t *)d_out + (size_t)f0 * ch.out_frame_bytes, out_stride, st, pre ? &here : nullptr);
-        if (rc) return rc;
-    }
-    if (real_in) { s->hb_basis = mode; s->hb_live = true; }
+    CallCtx cx;
+    int rc = call_begin(s, n_frames, st, cx);
+    if (rc) return rc;
+    rc = call_range(s, cx, 0, n_frames, (const uint8_t *)d_in, in_stride, (uint8_t *)d_out, out_stride, st);
+    if (rc) return rc;
+    call_end(s, cx);
     return ICW_OK;
 }
 
+// Host buffers: the call is cut into time segments that flow through a three-stage pipeline --
+// H2D copy (copy stream), kernels (engine stream), D2H copy (second copy stream) -- over
+// double-buffered device staging, so that on a long call the PCIe transfers of neighbouring
+// segments hide behind the kernels.  Works from pageable memory too (the copies then stage
+// through the driver and overlap less).
 extern "C" int icw_session_process_host(icw_session *s, int64_t n_frames, const void *in, size_t in_stride,
                                         void *out, size_t out_stride)
 {
     if (!s || !in || !out) return fail(ICW_E_ARG, "NULL argument");
     if (n_frames <= 0) return n_frames ? fail(ICW_E_ARG, "negative frame count") : ICW_OK;
     icw_engine *e = s->e;
+    const DevChain &ch = s->ch;
     const int K = s->n_streams;
-    const size_t in_row = (size_t)n_frames * s->ch.frame_bytes, out_row = (size_t)n_frames * s->ch.out_frame_bytes;
+    const size_t in_row = (size_t)n_frames * ch.frame_bytes, out_row = (size_t)n_frames * ch.out_frame_bytes;
     if (K > 1 && (in_stride < in_row || out_stride < out_row)) return fail(ICW_E_ARG, "stream strides too short");
-    // device rows are padded to 16 bytes so every stream starts on a vector boundary
-    const size_t din_stride = (in_row + 15) & ~(size_t)15, dout_stride = (out_row + 15) & ~(size_t)15;
+    const size_t h_in_stride = K > 1 ? in_stride : in_row, h_out_stride = K > 1 ? out_stride : out_row;
     CK(cudaSetDevice(e->device));
-    int rc = e->io_in.reserve(din_stride * K);
+
+    // segment length: a multiple of the scan tile, about 2^24 frames over all streams
+    int64_t seg = ((int64_t)1 << 24) / K;
+    seg = seg / (SCAN_L * SCAN_CH) * (SCAN_L * SCAN_CH);
+    if (seg < 4096) seg = 4096;
+    if (seg > n_frames) seg = n_frames;
+    const int nbuf = seg < n_frames ? 2 : 1;
+    // device rows are padded to 16 bytes so every stream starts on a vector boundary
+    const size_t din_stride = ((size_t)seg * ch.frame_bytes + 15) & ~(size_t)15;
+    const size_t dout_stride = ((size_t)seg * ch.out_frame_bytes + 15) & ~(size_t)15;
+    int rc = e->io_in.reserve(din_stride * K * nbuf);
     if (rc) return rc;
-    rc = e->io_out.reserve(dout_stride * K);
+    rc = e->io_out.reserve(dout_stride * K * nbuf);
     if (rc) return rc;
-    CK(cudaMemcpy2DAsync(e->io_in.p, din_stride, in, K > 1 ? in_stride : in_row, in_row, K, cudaMemcpyHostToDevice, e->stream));
-    rc = icw_session_process_device(s, n_frames, e->io_in.p, din_stride, e->io_out.p, dout_stride, e->stream);
+    if (!e->h2d) {
+        CK(cudaStreamCreateWithFlags(&e->h2d, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&e->d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&e->ev_comp[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&e->ev_out[i], cudaEventDisableTiming));
+        }
+    }
+    note_alignment(s, e->io_in.p, din_stride);
+    cudaStream_t st = e->stream;
+    CallCtx cx;
+    rc = call_begin(s, n_frames, st, cx);
     if (rc) return rc;
-    CK(cudaMemcpy2DAsync(out, K > 1 ? out_stride : out_row, e->io_out.p, dout_stride, out_row, K, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
+    int64_t k = 0;
+    for (int64_t f0 = 0; f0 < n_frames; f0 += seg, ++k) {
+        const int64_t n = n_frames - f0 < seg ? n_frames - f0 : seg;
+        const int b = (int)(k & 1) % nbuf;
+        uint8_t *din = (uint8_t *)e->io_in.p + (size_t)b * din_stride * K;
+        uint8_t *dout = (uint8_t *)e->io_out.p + (size_t)b * dout_stride * K;
+        // the staging input of this slot is free once the kernels of segment k-2 are done
+        if (k >= 2) CK(cudaStreamWaitEvent(e->h2d, e->ev_comp[b], 0));
+        CK(cudaMemcpy2DAsync(din, din_stride, (const uint8_t *)in + (size_t)f0 * ch.frame_bytes, h_in_stride,
+                             (size_t)n * ch.frame_bytes, K, cudaMemcpyHostToDevice, e->h2d));
+        CK(cudaEventRecord(e->ev_in[b], e->h2d));
+        CK(cudaStreamWaitEvent(st, e->ev_in[b], 0));
+        if (k >= 2) CK(cudaStreamWaitEvent(st, e->ev_out[b], 0));   // and its staging output once segment k-2 left
+        rc = call_range(s, cx, f0, n, din, din_stride, dout, dout_stride, st);
+        if (rc) return rc;
+        CK(cudaEventRecord(e->ev_comp[b], st));
+        CK(cudaStreamWaitEvent(e->d2h, e->ev_comp[b], 0));
+        CK(cudaMemcpy2DAsync((uint8_t *)out + (size_t)f0 * ch.out_frame_bytes, h_out_stride, dout, dout_stride,
+                             (size_t)n * ch.out_frame_bytes, K, cudaMemcpyDeviceToHost, e->d2h));
+        CK(cudaEventRecord(e->ev_out[b], e->d2h));
+    }
+    CK(cudaStreamSynchronize(e->d2h));
+    CK(cudaStreamSynchronize(st));
+    call_end(s, cx);
     return ICW_OK;
 }
 

@@ -6,28 +6,44 @@
 
 namespace icw {
 
-__device__ __forceinline__ double dither_value(const DevRender &r, const uint32_t *w, double prev_tr,
-                                               double &tr_out, unsigned &redraws)
+// tempered words of sample i of one channel are w[i*wps .. i*wps + wps): 8- or 16-byte aligned
+__device__ __forceinline__ double dsopen2(uint2 w, unsigned &redraws)
 {
-    // reference src/sound_render.c:711-751; w = this sample's tempered words
     bool rd;
-    double v;
+    double v = mt_dsopen(w.x, w.y, rd);
+    redraws += rd;
+    return v;
+}
+
+// the dither value of sample i (reference src/sound_render.c:711-751)
+__device__ __forceinline__ double dither_sample(const DevRender &r, const uint32_t *w, int64_t i, double prev_tr,
+                                                unsigned &redraws)
+{
     switch (r.render_type) {
-    case ICW_RENDER_RPDF:
-        v = div_const(mt_dsopen(w[0], w[1], rd), ICW_SQRT2, ICW_RSQRT2);
-        redraws += rd;
-        return v;
-    case ICW_RENDER_TPDF:
-        v = mt_dsopen(w[0], w[1], rd); redraws += rd;
-        v += mt_dsopen(w[2], w[3], rd); redraws += rd;
+    case ICW_RENDER_RPDF: {
+        const uint2 a = *reinterpret_cast<const uint2 *>(w + (size_t)i * 2);
+        return div_const(dsopen2(a, redraws), ICW_SQRT2, ICW_RSQRT2);
+    }
+    case ICW_RENDER_TPDF: {
+        const uint4 a = *reinterpret_cast<const uint4 *>(w + (size_t)i * 4);
+        double v = dsopen2(make_uint2(a.x, a.y), redraws);
+        v += dsopen2(make_uint2(a.z, a.w), redraws);
         return v * 0.5;                                         // /2.0, exact
-    case ICW_RENDER_STPDF:
-        tr_out = mt_dsopen(w[0], w[1], rd); redraws += rd;
-        return (tr_out - prev_tr) * 0.5;
+    }
+    case ICW_RENDER_STPDF: {
+        const uint2 a = *reinterpret_cast<const uint2 *>(w + (size_t)i * 2);
+        return (dsopen2(a, redraws) - prev_tr) * 0.5;
+    }
     case ICW_RENDER_GAUSS: {
-        v = mt_dsopen(w[0], w[1], rd); redraws += rd;
+        const uint4 *q = reinterpret_cast<const uint4 *>(w + (size_t)i * 24);
+        double v = 0.0;
 #pragma unroll
-        for (int j = 1; j < 12; ++j) { v += mt_dsopen(w[2 * j], w[2 * j + 1], rd); redraws += rd; }
+        for (int j = 0; j < 6; ++j) {
+            const uint4 a = q[j];
+            const double d0 = dsopen2(make_uint2(a.x, a.y), redraws);
+            v = j == 0 ? d0 : v + d0;
+            v += dsopen2(make_uint2(a.z, a.w), redraws);
+        }
         const double d = 2.0 * ICW_SQRT6;
         return div_const(v, d, 1.0 / d);
     }
@@ -36,6 +52,27 @@ __device__ __forceinline__ double dither_value(const DevRender &r, const uint32_
     }
 }
 
+// first draw of sample i (sloped TPDF needs the previous sample's)
+__device__ __forceinline__ double first_draw(const uint32_t *w, int64_t i)
+{
+    bool rd;
+    const uint2 a = *reinterpret_cast<const uint2 *>(w + (size_t)i * 2);
+    return mt_dsopen(a.x, a.y, rd);
+}
+
+// interleaved L,R little-endian: 2 x 2 bytes as one 32-bit store, 2 x 3 bytes as three 16-bit stores
+// (frame i starts at byte 4*i or 6*i of a 16-byte aligned row)
+__device__ __forceinline__ void store_frame_pcm(uint8_t *p, int l, int r, int bytes)
+{
+    if (bytes == 2) {
+        *reinterpret_cast<uint32_t *>(p) = ((uint32_t)l & 0xFFFFu) | ((uint32_t)r << 16);
+    } else {
+        uint16_t *q = reinterpret_cast<uint16_t *>(p);
+        q[0] = (uint16_t)l;
+        q[1] = (uint16_t)(((uint32_t)l >> 16) & 0xFFu) | (uint16_t)(((uint32_t)r & 0xFFu) << 8);
+        q[2] = (uint16_t)((uint32_t)r >> 8);
+    }
+}
 __device__ __forceinline__ void store_pcm(uint8_t *p, int val, int bytes)
 {
     p[0] = (uint8_t)val;
@@ -51,47 +88,40 @@ struct FrameAcc {
 struct FrameIO {
     const uint32_t *mtw_l, *mtw_r;  // tempered MT words of this stream's call range (or NULL)
     uint8_t *dst;                   // this stream's output row
+    int dst_aligned;                // row start is 4-byte aligned: frames can be stored as 16/32-bit words
     double *tap_bus, *tap_lr;       // optional test taps for this stream ([frame][27][4], [frame][2])
 };
 
 // frame i of the call; v = (L.re, L.im, R.re, R.im) on plug 0; bus = thread-private plug values
 __device__ __forceinline__ void finish_frame(const DevChain &ch, DevStream &st, int64_t i, int64_t n_frames,
-                                             const double v[4], double (*bus)[4], const FrameIO &io, FrameAcc &acc)
+                                             const double v[4], double (*bus)[4], const FrameIO &io, FrameAcc &acc,
+                                             OscCounter &osc)
 {
     const DevRender &rq = ch.render;
     const int wps = rq.words_per_sample;
     bus[0][0] = v[0]; bus[0][1] = v[1]; bus[0][2] = v[2]; bus[0][3] = v[3];
-    double omega = norm_omega(ch, frame_counter(ch, st.n_frame, (uint64_t)i));
+    double omega = norm_omega(ch, osc.at(ch, i));
     double lo, ro;
     run_graph(ch, bus, omega, lo, ro);
 
     double dl = 0.0, dr = 0.0;
     if (wps) {
-        uint32_t wl[24], wr[24];
-        for (int j = 0; j < wps; ++j) {
-            wl[j] = io.mtw_l[(size_t)i * wps + j];
-            wr[j] = io.mtw_r[(size_t)i * wps + j];
-        }
-        double prev_l = 0.0, prev_r = 0.0, tr;
+        double prev_l = 0.0, prev_r = 0.0;
         if (rq.render_type == ICW_RENDER_STPDF) {
             // the previous frame's draw, recomputed from that frame's words (frame 0: carried state)
-            bool rd;
             if (i == 0) { prev_l = st.prev_rnd[0]; prev_r = st.prev_rnd[1]; }
-            else {
-                prev_l = mt_dsopen(io.mtw_l[(size_t)(i - 1) * wps], io.mtw_l[(size_t)(i - 1) * wps + 1], rd);
-                prev_r = mt_dsopen(io.mtw_r[(size_t)(i - 1) * wps], io.mtw_r[(size_t)(i - 1) * wps + 1], rd);
-            }
+            else { prev_l = first_draw(io.mtw_l, i - 1); prev_r = first_draw(io.mtw_r, i - 1); }
         }
-        dl = dither_value(rq, wl, prev_l, tr, acc.redraws);
-        dr = dither_value(rq, wr, prev_r, tr, acc.redraws);
+        dl = dither_sample(rq, io.mtw_l, i, prev_l, acc.redraws);
+        dr = dither_sample(rq, io.mtw_r, i, prev_r, acc.redraws);
     }
     RenderOut a = render_one(rq, lo, dl);
     RenderOut b = render_one(rq, ro, dr);
     acc.clips_l += a.clipped; acc.clips_r += b.clipped;
     acc.peak_l = fmax(acc.peak_l, a.level); acc.peak_r = fmax(acc.peak_r, b.level);
     uint8_t *p = io.dst + i * ch.out_frame_bytes;
-    store_pcm(p, a.val, rq.bytes);
-    store_pcm(p + rq.bytes, b.val, rq.bytes);
+    if (io.dst_aligned) store_frame_pcm(p, a.val, b.val, rq.bytes);
+    else { store_pcm(p, a.val, rq.bytes); store_pcm(p + rq.bytes, b.val, rq.bytes); }
     if (io.tap_bus) {
         double *t = io.tap_bus + (size_t)i * (ICW_N_PLUGS * 4);
         for (int k = 0; k < ICW_N_PLUGS; ++k) { t[k * 4] = bus[k][0]; t[k * 4 + 1] = bus[k][1]; t[k * 4 + 2] = bus[k][2]; t[k * 4 + 3] = bus[k][3]; }
@@ -101,10 +131,9 @@ __device__ __forceinline__ void finish_frame(const DevChain &ch, DevStream &st, 
         // the context's bus after the call == the last frame's values (adv_modulator.c:634-751)
         for (int k = 0; k < ICW_N_PLUGS; ++k) { st.bus[k][0] = bus[k][0]; st.bus[k][1] = bus[k][1]; st.bus[k][2] = bus[k][2]; st.bus[k][3] = bus[k][3]; }
         if (rq.render_type == ICW_RENDER_STPDF) {
-            bool rd;
             // frame 0 of this call may still be reading prev_rnd in another CTA: write the shadow copy
-            st.prev_rnd_next[0] = mt_dsopen(io.mtw_l[(size_t)i * wps], io.mtw_l[(size_t)i * wps + 1], rd);
-            st.prev_rnd_next[1] = mt_dsopen(io.mtw_r[(size_t)i * wps], io.mtw_r[(size_t)i * wps + 1], rd);
+            st.prev_rnd_next[0] = first_draw(io.mtw_l, i);
+            st.prev_rnd_next[1] = first_draw(io.mtw_r, i);
         }
     }
 }

@@ -75,7 +75,9 @@ hb_fused_kernel(const __grid_constant__ HbCoef coef, const __grid_constant__ Dev
     const bool h_live = !is_chain && stream0 + h_sl < n_streams;
     FrameAcc acc;
     FrameIO io;
-    io.mtw_l = io.mtw_r = nullptr; io.dst = nullptr; io.tap_bus = io.tap_lr = nullptr;
+    io.mtw_l = io.mtw_r = nullptr; io.dst = nullptr; io.dst_aligned = 0; io.tap_bus = io.tap_lr = nullptr;
+    OscCounter osc;
+    osc.frame = 0; osc.value = 0;
     const uint8_t *h_src = nullptr;
     int64_t h_pos0 = 0;
     unsigned h_q0[2] = { 0, 0 };
@@ -87,12 +89,14 @@ hb_fused_kernel(const __grid_constant__ HbCoef coef, const __grid_constant__ Dev
         io.mtw_l = mtw_l ? mtw_l + mt_off : nullptr;
         io.mtw_r = mtw_r ? mtw_r + mt_off : nullptr;
         io.dst = out + (size_t)stream * out_stride;
+        io.dst_aligned = ((size_t)(uintptr_t)io.dst & 3u) == 0;
         io.tap_bus = tap_bus ? tap_bus + (size_t)stream * n_frames * (ICW_N_PLUGS * 4) : nullptr;
         io.tap_lr = tap_lr ? tap_lr + (size_t)stream * n_frames * 2 : nullptr;
         h_src = in + (size_t)stream * in_stride;
         h_pos0 = st.pos;
         h_q0[0] = st.quad[0]; h_q0[1] = st.quad[1];
         load_bus(st, bus);
+        osc.init(ch, st.n_frame, 0);
     }
 
     // step s: chains run tile s; helpers unpack tile s+1 and finish the output window of tile s-1
@@ -156,7 +160,7 @@ hb_fused_kernel(const __grid_constant__ HbCoef coef, const __grid_constant__ Dev
                         double a = mix_up(0, q, y[2], slot); v[2 + slot] = a;
                         double c = mix_up(1, q, y[3], slot); v[2 + slot] = c;
                     }
-                    finish_frame(ch, streams[stream0 + h_sl], f, n_frames, v, bus, io, acc);
+                    finish_frame(ch, streams[stream0 + h_sl], f, n_frames, v, bus, io, acc, osc);
                 }
             }
         }

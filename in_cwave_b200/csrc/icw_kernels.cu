@@ -155,59 +155,92 @@ cudaError_t launch_hb_leaf(const HbCoef &coef, int ord, bool kahan, int reject, 
 // MT19937 words (reference src/mersene_twister/mt_jrnd.c:99-134)
 // =============================================================================================
 
-// One CTA regenerates `blocks_per_cta` consecutive 624-word blocks starting from its checkpoint
+// One WARP regenerates `blocks_per_unit` consecutive 624-word blocks starting from its checkpoint
 // (the untempered state array that PRECEDES its first block) and writes the tempered words.
-// Regeneration is three dependent phases of <= 227 independent words each (new[i] needs
-// new[i-227] from the phase before), double-buffered in shared memory.
-__global__ void __launch_bounds__(256)
-mt_words_kernel(const uint32_t *__restrict__ ckpt /* [cta][624] */, int blocks_per_cta,
+// The state lives in registers, word i in lane i%32 of register i/32 (20 registers, the last one
+// half used).  new[i] = far ^ twist(old[i], old[i+1]) with far = old[i+397] for i < 227 and
+// new[i-227] after that: walking the registers in order makes every operand either not yet
+// overwritten (old) or already final (new), so the update is in place and needs no barrier --
+// neighbours come from warp shuffles.  32 warps per SM hide each other's latencies.
+template <int R>
+__device__ __forceinline__ void mt_step(uint32_t (&w)[20], int lane)
+{
+    const uint32_t u = w[R];
+    // old[i+1]: the next lane's word; lane 31 wraps into the next register's lane 0; the very last
+    // word of the block (i = 623) pairs with the ALREADY NEW word 0 (mt_jrnd.c:121)
+    uint32_t v = __shfl_down_sync(0xffffffffu, w[R], 1);
+    const uint32_t nxt0 = __shfl_sync(0xffffffffu, w[R < 19 ? R + 1 : 0], 0);
+    if (lane == (R < 19 ? 31 : 15)) v = nxt0;
+    uint32_t far;
+    if (R <= 6) {               // i + 397 < 624: old words, registers R+12 / R+13
+        const uint32_t a = __shfl_sync(0xffffffffu, w[R + 12], (lane + 13) & 31);
+        const uint32_t b = __shfl_sync(0xffffffffu, w[R + 13 <= 19 ? R + 13 : 19], (lane - 19) & 31);
+        far = lane < 19 ? a : b;
+    } else if (R == 7) {        // the switch from old[i+397] to new[i-227] falls inside this register
+        const uint32_t a = __shfl_sync(0xffffffffu, w[19], (lane + 13) & 31);
+        const uint32_t b = __shfl_sync(0xffffffffu, w[0], (lane - 3) & 31);
+        far = lane < 3 ? a : b;
+    } else {                    // new words, registers R-7 / R-8
+        const uint32_t a = __shfl_sync(0xffffffffu, w[R - 7], (lane - 3) & 31);
+        const uint32_t b = __shfl_sync(0xffffffffu, w[R - 8], (lane + 29) & 31);
+        far = lane >= 3 ? a : b;
+    }
+    const uint32_t mix = (u & 0x80000000u) | (v & 0x7FFFFFFFu);
+    const uint32_t nw = far ^ (mix >> 1) ^ ((v & 1u) ? 0x9908B0DFu : 0u);
+    if (R < 19 || lane < 16) w[R] = nw;
+}
+
+template <int R>
+__device__ __forceinline__ void mt_regen_regs(uint32_t (&w)[20], int lane)
+{
+    if constexpr (R < 20) {
+        mt_step<R>(w, lane);
+        mt_regen_regs<R + 1>(w, lane);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+mt_words_kernel(const uint32_t *__restrict__ ckpt /* [unit][624] */, int n_units, int blocks_per_unit,
                 int64_t first_word /* stream word index of block 0's first word */,
                 int64_t want_lo, int64_t want_hi, uint32_t *__restrict__ out /* out[w - want_lo] */,
                 int64_t tail_block /* relative index of the block holding the last wanted word */,
                 uint32_t *__restrict__ tail /* [2][624]: state before and after that block, for the next call */)
 {
-    __shared__ uint32_t a[ICW_MT_N], b[ICW_MT_N];
-    uint32_t *cur = a, *nxt = b;
-    const int tid = threadIdx.x;
-    for (int i = tid; i < ICW_MT_N; i += blockDim.x) cur[i] = ckpt[(size_t)blockIdx.x * ICW_MT_N + i];
-    __syncthreads();
-    for (int blk = 0; blk < blocks_per_cta; ++blk) {
-        const int64_t rel = (int64_t)blockIdx.x * blocks_per_cta + blk;
-        if (rel == tail_block && tail)
-            for (int i = tid; i < ICW_MT_N; i += blockDim.x) tail[i] = cur[i];
-        // phase A: i in [0,227): new[i] = old[i+397] ^ tw(old[i], old[i+1])
-        // phase B: i in [227,454): new[i] = new[i-227] ^ tw(old[i], old[i+1])
-        // phase C: i in [454,624): same, and i = 623 pairs old[623] with new[0]
-        for (int ph = 0; ph < 3; ++ph) {
-            int i = ph * 227 + tid;
-            if (tid < 227 && i < ICW_MT_N) {
-                uint32_t u = cur[i];
-                uint32_t v = (i + 1 < ICW_MT_N) ? cur[i + 1] : nxt[0];
-                uint32_t mix = (u & 0x80000000u) | (v & 0x7FFFFFFFu);
-                uint32_t tw = (mix >> 1) ^ ((v & 1u) ? 0x9908B0DFu : 0u);
-                uint32_t far = (ph == 0) ? cur[i + ICW_MT_M] : nxt[i - 227];
-                nxt[i] = far ^ tw;
-            }
-            __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int unit = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (unit >= n_units) return;                                // whole warps leave together
+    uint32_t w[20];
+#pragma unroll
+    for (int r = 0; r < 20; ++r) w[r] = (r < 19 || lane < 16) ? ckpt[(size_t)unit * ICW_MT_N + r * 32 + lane] : 0u;
+    for (int blk = 0; blk < blocks_per_unit; ++blk) {
+        const int64_t rel = (int64_t)unit * blocks_per_unit + blk;
+        const int64_t w0 = first_word + rel * ICW_MT_N;
+        if (w0 >= want_hi) break;                               // nothing further is wanted
+        const bool is_tail = rel == tail_block && tail != nullptr;
+        if (is_tail) {
+#pragma unroll
+            for (int r = 0; r < 20; ++r) if (r < 19 || lane < 16) tail[r * 32 + lane] = w[r];
         }
-        int64_t w0 = first_word + rel * ICW_MT_N;
-        if (w0 >= want_hi) break;                               // uniform: nothing further is wanted
-        for (int i = tid; i < ICW_MT_N; i += blockDim.x) {
-            int64_t w = w0 + i;
-            if (w >= want_lo && w < want_hi) out[w - want_lo] = mt_temper(nxt[i]);
+        mt_regen_regs<0>(w, lane);
+#pragma unroll
+        for (int r = 0; r < 20; ++r) {
+            const int64_t wi = w0 + r * 32 + lane;
+            if ((r < 19 || lane < 16) && wi >= want_lo && wi < want_hi) out[wi - want_lo] = mt_temper(w[r]);
         }
-        if (rel == tail_block && tail)
-            for (int i = tid; i < ICW_MT_N; i += blockDim.x) tail[ICW_MT_N + i] = nxt[i];
-        uint32_t *t = cur; cur = nxt; nxt = t;
-        __syncthreads();
+        if (is_tail) {
+#pragma unroll
+            for (int r = 0; r < 20; ++r) if (r < 19 || lane < 16) tail[ICW_MT_N + r * 32 + lane] = w[r];
+        }
     }
 }
 
-cudaError_t launch_mt_words(const uint32_t *ckpt, int n_cta, int blocks_per_cta, int64_t first_word,
+cudaError_t launch_mt_words(const uint32_t *ckpt, int n_units, int blocks_per_unit, int64_t first_word,
                             int64_t want_lo, int64_t want_hi, uint32_t *out, int64_t tail_block, uint32_t *tail,
                             cudaStream_t s)
 {
-    mt_words_kernel<<<n_cta, 256, 0, s>>>(ckpt, blocks_per_cta, first_word, want_lo, want_hi, out, tail_block, tail);
+    const int warps = 4;
+    mt_words_kernel<<<(n_units + warps - 1) / warps, warps * 32, 0, s>>>(ckpt, n_units, blocks_per_unit, first_word,
+                                                                          want_lo, want_hi, out, tail_block, tail);
     return cudaGetLastError();
 }
 
@@ -234,12 +267,15 @@ chain_kernel(const __grid_constant__ DevChain ch, DevStream *__restrict__ stream
     io.mtw_l = mtw_l ? mtw_l + mt_off : nullptr;
     io.mtw_r = mtw_r ? mtw_r + mt_off : nullptr;
     io.dst = out + (size_t)stream * out_stride;
+    io.dst_aligned = ((size_t)(uintptr_t)io.dst & 3u) == 0;
     io.tap_bus = tap_bus ? tap_bus + (size_t)stream * n_frames * (ICW_N_PLUGS * 4) : nullptr;
     io.tap_lr = tap_lr ? tap_lr + (size_t)stream * n_frames * 2 : nullptr;
 
     FrameAcc acc;
     double bus[ICW_N_PLUGS][4];
     load_bus(st, bus);
+    OscCounter osc;
+    osc.init(ch, st.n_frame, (int64_t)blockIdx.x * blockDim.x + threadIdx.x);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_frames;
          i += (int64_t)gridDim.x * blockDim.x) {
         double v[4];
@@ -249,7 +285,7 @@ chain_kernel(const __grid_constant__ DevChain ch, DevStream *__restrict__ stream
         } else {
             unpack_frame(ch, src + i * ch.frame_bytes, st.pos + i, v);
         }
-        finish_frame(ch, st, i, n_frames, v, bus, io, acc);
+        finish_frame(ch, st, i, n_frames, v, bus, io, acc, osc);
     }
     commit_acc(&st, acc, 32);
 }

@@ -203,9 +203,12 @@ void mt_apply_host(const MtPoly &g, const uint32_t base[MT_N], uint32_t out[MT_N
 // =============================================================================================
 constexpr int JUMP_THREADS = 640;
 constexpr int JUMP_SEQ = 33 * MT_N;                 // 20592 words >= 19936 + 624
-constexpr size_t JUMP_SMEM = (JUMP_SEQ + MT_N) * sizeof(uint32_t);
+constexpr size_t JUMP_SMEM = (JUMP_SEQ + MT_N) * sizeof(uint32_t);     // 85 KB: two CTAs per SM
 
-// states[dst_first + blockIdx.x] = jump(states[dst_first + blockIdx.x - span]) by the polynomial
+// states[dst_first + blockIdx.x] = jump(states[dst_first + blockIdx.x - span]) by the polynomial.
+// One thread per output word walks the set bits of the polynomial (the branch is uniform across the
+// CTA); 40 warps per SM keep the shared-memory pipe busy.  gridDim.y CTAs may share one target:
+// each takes a slice of the polynomial and XORs its part into the (pre-zeroed) target.
 __global__ void __launch_bounds__(JUMP_THREADS)
 mt_jump_kernel(uint32_t *__restrict__ states, const uint32_t *__restrict__ src_states, int dst_first, int span,
                const uint32_t *__restrict__ poly)
@@ -230,10 +233,10 @@ mt_jump_kernel(uint32_t *__restrict__ states, const uint32_t *__restrict__ src_s
         __syncthreads();
     }
     if (tid < MT_N) {
-        // shared-memory bandwidth is the limit here (one 4-byte load per lane per set bit), so walk
-        // only the set bits of the polynomial: the branch is uniform across the CTA
         uint32_t acc = 0;
-        for (int wi = 0; wi < MT_N; ++wi) {
+        const int per = (MT_N + gridDim.y - 1) / gridDim.y;
+        const int w_lo = blockIdx.y * per, w_hi = min(MT_N, w_lo + per);
+        for (int wi = w_lo; wi < w_hi; ++wi) {
             uint32_t bits = pw[wi];
             const uint32_t *p = seq + wi * 32 + tid;
             while (bits) {
@@ -242,8 +245,17 @@ mt_jump_kernel(uint32_t *__restrict__ states, const uint32_t *__restrict__ src_s
                 acc ^= p[b];
             }
         }
-        states[(size_t)dst * MT_N + tid] = acc;
+        if (gridDim.y == 1) states[(size_t)dst * MT_N + tid] = acc;
+        else atomicXor(&states[(size_t)dst * MT_N + tid], acc);     // the target was zeroed before the launch
     }
+}
+
+// few targets: the launch is latency-bound by one CTA's walk over the polynomial -> slice it
+static int jump_slices(int count, int sm_count)
+{
+    int s = 1;
+    while (s < 8 && count * s <= sm_count) s *= 2;
+    return s;
 }
 
 void MtJump::release()
@@ -306,7 +318,8 @@ int MtJump::state_at_block(uint32_t seed, uint64_t block, uint32_t *d_state, cud
         int rc = ensure_poly(k);
         if (rc) return rc;
         uint32_t *dst = d_tmp_ + (size_t)flip * MT_N;
-        mt_jump_kernel<<<1, JUMP_THREADS, JUMP_SMEM, stream>>>(dst, cur, 0, 0, dev_poly_[k]);
+        cudaMemsetAsync(dst, 0, MT_N * sizeof(uint32_t), stream);
+        mt_jump_kernel<<<dim3(1, 8), JUMP_THREADS, JUMP_SMEM, stream>>>(dst, cur, 0, 0, dev_poly_[k]);
         if (launches) ++*launches;
         cur = dst;
         flip ^= 1;
@@ -323,9 +336,9 @@ int MtJump::generate(uint32_t seed, uint64_t skip, int64_t n, uint32_t *d_out, i
     const uint64_t b0 = skip / MT_N, b1 = (skip + (uint64_t)n - 1) / MT_N;
     const uint64_t nb = b1 - b0 + 1;
     // blocks per CTA = 2^kb so that every checkpoint distance has a polynomial in the x^(624*2^k) family
-    // enough CTAs that one CTA regenerates at most ~2048 blocks, between 4 and 16 per SM
-    uint64_t max_cta = (uint64_t)sm_count * 4;
-    while (max_cta < (uint64_t)sm_count * 16 && nb / max_cta > 2048) max_cta *= 2;
+    // one warp per checkpoint (mt_words_kernel): 8 warps per SM for short ranges, up to 32 for long ones
+    uint64_t max_cta = (uint64_t)sm_count * 8;
+    while (max_cta < (uint64_t)sm_count * 16 && nb / max_cta > 256) max_cta *= 2;
     int kb = 0;
     while (((nb + (1ull << kb) - 1) >> kb) > max_cta) ++kb;
     const int n_cta = (int)((nb + (1ull << kb) - 1) >> kb);
@@ -344,7 +357,9 @@ int MtJump::generate(uint32_t seed, uint64_t skip, int64_t n, uint32_t *d_out, i
         if (rc) return rc;
         const int first = 1 << j;
         const int count = std::min(n_cta, 2 << j) - first;
-        mt_jump_kernel<<<count, JUMP_THREADS, JUMP_SMEM, stream>>>(d_ckpt_, nullptr, first, first, dev_poly_[kb + j]);
+        const int sl = jump_slices(count, sm_count);
+        if (sl > 1) cudaMemsetAsync(d_ckpt_ + (size_t)first * MT_N, 0, (size_t)count * MT_N * sizeof(uint32_t), stream);
+        mt_jump_kernel<<<dim3(count, sl), JUMP_THREADS, JUMP_SMEM, stream>>>(d_ckpt_, nullptr, first, first, dev_poly_[kb + j]);
         if (launches) ++*launches;
     }
     if (!d_tail_ && cudaMalloc(&d_tail_, (size_t)NTAIL * 2 * MT_N * sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); err_ = "cudaMalloc(tail states) failed"; return ICW_E_NOMEM; }

@@ -100,10 +100,12 @@ __device__ __forceinline__ void cx_step(Cx &s, double mr, double mi, double u)
     s.re = nr; s.im = ni;
 }
 
+// FMT is a compile-time constant: the format switch folds away inside the sample loops
+template <int FMT>
 __device__ __forceinline__ double scan_sample(const DevChain &ch, const uint8_t *row, int64_t frame, int chan_off,
                                               int64_t pos0, bool fading)
 {
-    double x = unpack_real(ch.fmt, row + frame * ch.frame_bytes + chan_off, ch.aligned);
+    double x = unpack_real(FMT, row + frame * ch.frame_bytes + chan_off, ch.aligned);
     if (fading) {
         double g = fade_gain(ch, pos0 + frame);
         if (g >= 0.0) x *= g;
@@ -117,121 +119,113 @@ __device__ __forceinline__ size_t e_index(int stream, int comp, int chan, int64_
     return (((size_t)stream * (4 * SCAN_NMAX) + comp) * 2 + chan) * (size_t)n_chunks + (size_t)chunk;
 }
 
+// Thread = one recurrence set: (chunk, channel, filter I/Q) with the filter's NM modal states in
+// registers -- the same decomposition as the exact kernel's "one thread per half-band filter".
+// The filter fed on the first sample of every pair (phase parity of the chunk start) is "X", the
+// other "Y"; a thread only ever touches the samples that feed its own filter.
+//
 // pass 1 + 2a: end state of every full chunk started from zero, then -- inside the CTA, which is
-// exactly one tile of 128 chunks -- the carry scan over chunks: warp shuffles (16 chunks per warp),
-// one shared-memory hop across the 8 warps.  Writes, per chunk, its carry-in from the tile start
+// exactly one tile of 128 chunks -- the carry scan over chunks: warp shuffles (8 chunks per warp),
+// one shared-memory hop across the 16 warps.  Writes, per chunk, its carry-in from the tile start
 // (exclusive prefix) and, per tile, the tile's end state.
-template <int NM>
-__global__ void __launch_bounds__(256)
+template <int NM, int FMT>
+__global__ void __launch_bounds__(512, 1)
 scan_local_kernel(const __grid_constant__ ModalCoef mc, const __grid_constant__ DevChain ch,
                   const DevStream *__restrict__ streams, int64_t n_frames, int64_t n_chunks, int64_t n_tiles,
                   const uint8_t *__restrict__ in, size_t in_stride, double *__restrict__ E,
                   double *__restrict__ Tend /* [stream][tile][chan][filter][mode][2] */)
 {
-    __shared__ double wtot[8][2][2][SCAN_NMAX][2];      // inclusive total of each warp's 16 chunks
-    __shared__ double wcar[8][2][2][SCAN_NMAX][2];      // carry into each warp from the tile start
+    __shared__ double wtot[16][2][2][SCAN_NMAX][2];     // inclusive total of each warp's 8 chunks
+    __shared__ double wcar[16][2][2][SCAN_NMAX][2];     // carry into each warp from the tile start
     const int stream = blockIdx.y;
     const int64_t tile = blockIdx.x;
-    const int cl = threadIdx.x >> 1;                    // chunk inside the tile, 0..127
+    const int filt = threadIdx.x & 1, chan = (threadIdx.x >> 1) & 1;
+    const int cl = threadIdx.x >> 2;                    // chunk inside the tile, 0..127
     const int64_t chunk = tile * SCAN_CH + cl;
-    const int chan = threadIdx.x & 1;
-    const int warp = threadIdx.x >> 5, cw = cl & 15;    // chunk inside the warp
+    const int warp = threadIdx.x >> 5, cw = cl & 7;     // chunk inside the warp
     const bool have = chunk < n_chunks - 1;             // the call's last chunk has no end state to hand on
     const DevStream &st = streams[stream];
     const unsigned q0 = st.quad[chan];
-    const int xiq = q0 & 1;                             // filter fed on the first sample of a pair
+    const bool is_x = filt == (int)(q0 & 1);            // fed on the first sample of a pair
 
-    Cx s[2][NM];                                        // [filter I/Q][mode]
+    Cx s[NM];
 #pragma unroll
-    for (int m = 0; m < NM; ++m) { s[0][m].re = s[0][m].im = 0.0; s[1][m].re = s[1][m].im = 0.0; }
+    for (int m = 0; m < NM; ++m) s[m].re = s[m].im = 0.0;
     if (have) {
         const uint8_t *row = in + (size_t)stream * in_stride;
         const int chan_off = (ch.n_channels > 1 ? chan : 0) * ch.chan_bytes;
         const bool fading = (ch.n_fade_in | ch.n_fade_out) != 0;
-        const int64_t f0 = chunk * SCAN_L;
-        Cx A[NM], B[NM];
-#pragma unroll
-        for (int m = 0; m < NM; ++m) { A[m].re = A[m].im = 0.0; B[m].re = B[m].im = 0.0; }
+        const int64_t f0 = chunk * SCAN_L + (is_x ? 0 : 1);     // this filter's first input sample
+        const unsigned qf = (q0 + (is_x ? 0u : 1u)) & 3u;       // its mixer phase (f0 is a multiple of 4)
+        double x = scan_sample<FMT>(ch, row, f0, chan_off, st.pos, fading);
         for (int k = 0; k < SCAN_L; k += 2) {
-            const double x0 = scan_sample(ch, row, f0 + k, chan_off, st.pos, fading);
-            const double x1 = scan_sample(ch, row, f0 + k + 1, chan_off, st.pos, fading);
-            const unsigned qa = (q0 + (unsigned)k) & 3u;        // f0 is a multiple of 4
-            const double ux = mix_down(xiq, qa, x0);
-            const double uy = mix_down(xiq ^ 1, (qa + 1) & 3u, x1);
+            const int kn = k + 2 < SCAN_L ? k + 2 : k;          // fetched one pair ahead
+            const double xn = scan_sample<FMT>(ch, row, f0 + kn, chan_off, st.pos, fading);
+            const double u = mix_down(filt, (qf + (unsigned)k) & 3u, x);
 #pragma unroll
-            for (int m = 0; m < NM; ++m) {
-                cx_step(A[m], mc.p2_re[m], mc.p2_im[m], ux);
-                cx_step(B[m], mc.p2_re[m], mc.p2_im[m], uy);
-            }
+            for (int m = 0; m < NM; ++m) cx_step(s[m], mc.p2_re[m], mc.p2_im[m], u);
+            x = xn;
         }
-        // state after the last (second-of-pair) sample: X filter p*A, Y filter B
+        // state after the chunk's last sample (a Y-input sample): X has idled one sample since its input
+        if (is_x) {
 #pragma unroll
-        for (int m = 0; m < NM; ++m) {
-            Cx sx = cx_mul(mc.p_re[m], mc.p_im[m], A[m]);
-            if (xiq == 0) { s[0][m] = sx; s[1][m] = B[m]; }
-            else          { s[1][m] = sx; s[0][m] = B[m]; }
+            for (int m = 0; m < NM; ++m) s[m] = cx_mul(mc.p_re[m], mc.p_im[m], s[m]);
         }
     }
 
-    // inclusive scan over the warp's 16 chunks (lanes of one channel are 2 apart)
+    // inclusive scan over the warp's 8 chunks (lanes of one recurrence are 4 apart)
 #pragma unroll
-    for (int d = 1; d < 16; d <<= 1) {
+    for (int d = 1; d < 8; d <<= 1) {
 #pragma unroll
-        for (int f = 0; f < 2; ++f)
-#pragma unroll
-            for (int m = 0; m < NM; ++m) {
-                const double ore = __shfl_up_sync(0xffffffffu, s[f][m].re, 2 * d);
-                const double oim = __shfl_up_sync(0xffffffffu, s[f][m].im, 2 * d);
-                if (cw >= d) {
-                    Cx o; o.re = ore; o.im = oim;
-                    Cx w = cx_mul(mc.plp_re[d - 1][m], mc.plp_im[d - 1][m], o);     // p^(L*d) * earlier
-                    s[f][m].re += w.re; s[f][m].im += w.im;
-                }
+        for (int m = 0; m < NM; ++m) {
+            const double ore = __shfl_up_sync(0xffffffffu, s[m].re, 4 * d);
+            const double oim = __shfl_up_sync(0xffffffffu, s[m].im, 4 * d);
+            if (cw >= d) {
+                Cx o; o.re = ore; o.im = oim;
+                Cx w = cx_mul(mc.plp_re[d - 1][m], mc.plp_im[d - 1][m], o);         // p^(L*d) * earlier
+                s[m].re += w.re; s[m].im += w.im;
             }
+        }
     }
-    if (cw == 15) {
+    if (cw == 7) {
 #pragma unroll
-        for (int f = 0; f < 2; ++f)
-#pragma unroll
-            for (int m = 0; m < NM; ++m) { wtot[warp][chan][f][m][0] = s[f][m].re; wtot[warp][chan][f][m][1] = s[f][m].im; }
+        for (int m = 0; m < NM; ++m) { wtot[warp][chan][filt][m][0] = s[m].re; wtot[warp][chan][filt][m][1] = s[m].im; }
     }
     __syncthreads();
-    // carry into each warp: sequential over the 8 warps, one thread per (chan, filter, mode)
+    // carry into each warp: sequential over the 16 warps, one thread per (chan, filter, mode)
     if (threadIdx.x < 2 * 2 * NM) {
         int r = threadIdx.x;
         const int m = r % NM; r /= NM;
         const int f = r & 1, c = r >> 1;
         Cx acc; acc.re = acc.im = 0.0;
-        for (int w = 0; w < 8; ++w) {
+        for (int w = 0; w < 16; ++w) {
             wcar[w][c][f][m][0] = acc.re; wcar[w][c][f][m][1] = acc.im;
-            // acc <- p^(16 L) * acc + total(w)
-            const double nr = fma(mc.plp_re[15][m], acc.re, fma(-mc.plp_im[15][m], acc.im, wtot[w][c][f][m][0]));
-            const double ni = fma(mc.plp_re[15][m], acc.im, fma(mc.plp_im[15][m], acc.re, wtot[w][c][f][m][1]));
+            // acc <- p^(8 L) * acc + total(w)
+            const double nr = fma(mc.plp_re[7][m], acc.re, fma(-mc.plp_im[7][m], acc.im, wtot[w][c][f][m][0]));
+            const double ni = fma(mc.plp_re[7][m], acc.im, fma(mc.plp_im[7][m], acc.re, wtot[w][c][f][m][1]));
             acc.re = nr; acc.im = ni;
         }
     }
     __syncthreads();
     // inclusive prefix from the tile start, then shift by one chunk for the carry-IN of this chunk
 #pragma unroll
-    for (int f = 0; f < 2; ++f)
-#pragma unroll
-        for (int m = 0; m < NM; ++m) {
-            Cx c; c.re = wcar[warp][chan][f][m][0]; c.im = wcar[warp][chan][f][m][1];
-            Cx w = cx_mul(mc.plp_re[cw][m], mc.plp_im[cw][m], c);                   // p^(L*(cw+1)) * warp carry
-            const double inc_re = s[f][m].re + w.re, inc_im = s[f][m].im + w.im;
-            double ex_re = __shfl_up_sync(0xffffffffu, inc_re, 2);
-            double ex_im = __shfl_up_sync(0xffffffffu, inc_im, 2);
-            if (cw == 0) { ex_re = c.re; ex_im = c.im; }
-            if (chunk < n_chunks) {
-                const int comp = (f * SCAN_NMAX + m) * 2;
-                E[e_index(stream, comp, chan, chunk, n_chunks)] = ex_re;
-                E[e_index(stream, comp + 1, chan, chunk, n_chunks)] = ex_im;
-            }
-            if (cl == SCAN_CH - 1) {
-                double *t = Tend + ((((size_t)stream * n_tiles + tile) * 2 + chan) * 2 + f) * (SCAN_NMAX * 2) + m * 2;
-                t[0] = inc_re; t[1] = inc_im;
-            }
+    for (int m = 0; m < NM; ++m) {
+        Cx c; c.re = wcar[warp][chan][filt][m][0]; c.im = wcar[warp][chan][filt][m][1];
+        Cx w = cx_mul(mc.plp_re[cw][m], mc.plp_im[cw][m], c);                       // p^(L*(cw+1)) * warp carry
+        const double inc_re = s[m].re + w.re, inc_im = s[m].im + w.im;
+        double ex_re = __shfl_up_sync(0xffffffffu, inc_re, 4);
+        double ex_im = __shfl_up_sync(0xffffffffu, inc_im, 4);
+        if (cw == 0) { ex_re = c.re; ex_im = c.im; }
+        if (chunk < n_chunks) {
+            const int comp = (filt * SCAN_NMAX + m) * 2;
+            E[e_index(stream, comp, chan, chunk, n_chunks)] = ex_re;
+            E[e_index(stream, comp + 1, chan, chunk, n_chunks)] = ex_im;
         }
+        if (cl == SCAN_CH - 1) {
+            double *t = Tend + ((((size_t)stream * n_tiles + tile) * 2 + chan) * 2 + filt) * (SCAN_NMAX * 2) + m * 2;
+            t[0] = inc_re; t[1] = inc_im;
+        }
+    }
 }
 
 // pass 2b: carry into every tile.  The filters forget: |p|^(tile) <= 1e-3, so eight tiles back is
@@ -270,9 +264,10 @@ scan_tile_carry_kernel(const __grid_constant__ ModalCoef mc, const DevStream *__
     o[0] = acc.re; o[1] = acc.im;
 }
 
-// pass 3: every chunk again, from its true initial state, producing the analytic signal
-template <int NM>
-__global__ void __launch_bounds__(256)
+// pass 3: every chunk again, from its true initial state, producing the analytic signal.
+// Each thread writes its own filter's half of every frame: re or im, alternating with the phase.
+template <int NM, int FMT>
+__global__ void __launch_bounds__(256, 2)
 scan_apply_kernel(const __grid_constant__ ModalCoef mc, const __grid_constant__ DevChain ch,
                   DevStream *__restrict__ streams, int64_t n_frames, int64_t n_chunks, int64_t n_tiles,
                   const uint8_t *__restrict__ in, size_t in_stride,
@@ -280,12 +275,12 @@ scan_apply_kernel(const __grid_constant__ ModalCoef mc, const __grid_constant__ 
                   double *__restrict__ analytic /* [stream][frame][4] */)
 {
     const int stream = blockIdx.y;
-    const int64_t chunk = (int64_t)blockIdx.x * (blockDim.x / 2) + (threadIdx.x >> 1);
-    const int chan = threadIdx.x & 1;
+    const int filt = threadIdx.x & 1, chan = (threadIdx.x >> 1) & 1;
+    const int64_t chunk = (int64_t)blockIdx.x * (blockDim.x / 4) + (threadIdx.x >> 2);
     if (chunk >= n_chunks) return;
     DevStream &st = streams[stream];
     const unsigned q0 = st.quad[chan];
-    const int xiq = q0 & 1, yiq = xiq ^ 1;
+    const bool is_x = filt == (int)(q0 & 1);
     const uint8_t *row = in + (size_t)stream * in_stride;
     const int chan_off = (ch.n_channels > 1 ? chan : 0) * ch.chan_bytes;
     const bool fading = (ch.n_fade_in | ch.n_fade_out) != 0;
@@ -296,81 +291,85 @@ scan_apply_kernel(const __grid_constant__ ModalCoef mc, const __grid_constant__ 
     double *dst = analytic + ((size_t)stream * (size_t)n_frames + (size_t)f0) * 4 + chan * 2;
 
     // carried state after the sample before this chunk: prefix inside the tile + p^(L*j) * tile carry
-    Cx A[NM], B[NM];
+    Cx S[NM];
 #pragma unroll
     for (int m = 0; m < NM; ++m) {
-        Cx s[2];
-#pragma unroll
-        for (int f = 0; f < 2; ++f) {
-            const int comp = (f * SCAN_NMAX + m) * 2;
-            const double *t = Tin + ((((size_t)stream * n_tiles + tile) * 2 + chan) * 2 + f) * (SCAN_NMAX * 2) + m * 2;
-            Cx c; c.re = t[0]; c.im = t[1];
-            const double wr = pw[((size_t)jl * SCAN_NMAX + m) * 2], wi = pw[((size_t)jl * SCAN_NMAX + m) * 2 + 1];
-            Cx cw = cx_mul(wr, wi, c);
-            s[f].re = E[e_index(stream, comp, chan, chunk, n_chunks)] + cw.re;
-            s[f].im = E[e_index(stream, comp + 1, chan, chunk, n_chunks)] + cw.im;
-        }
-        // the X filter last saw input two samples ago: step it back one sample (exact algebra: A = s / p)
-        A[m] = cx_mul(mc.pinv_re[m], mc.pinv_im[m], s[xiq]);
-        B[m] = s[yiq];
+        const int comp = (filt * SCAN_NMAX + m) * 2;
+        const double *t = Tin + ((((size_t)stream * n_tiles + tile) * 2 + chan) * 2 + filt) * (SCAN_NMAX * 2) + m * 2;
+        Cx c; c.re = t[0]; c.im = t[1];
+        const double wr = pw[((size_t)jl * SCAN_NMAX + m) * 2], wi = pw[((size_t)jl * SCAN_NMAX + m) * 2 + 1];
+        Cx cw = cx_mul(wr, wi, c);
+        Cx s0;
+        s0.re = E[e_index(stream, comp, chan, chunk, n_chunks)] + cw.re;
+        s0.im = E[e_index(stream, comp + 1, chan, chunk, n_chunks)] + cw.im;
+        // X last saw input two samples ago: step it back one sample (exact algebra: S = s / p)
+        S[m] = is_x ? cx_mul(mc.pinv_re[m], mc.pinv_im[m], s0) : s0;
     }
 
+    const int off = is_x ? 0 : 1;                               // this filter's input sample inside a pair
     const int npair = len >> 1;
+    const bool odd = len & 1;
+    const int n_in = is_x ? npair + (odd ? 1 : 0) : npair;      // samples that feed this filter
+    double x = n_in ? scan_sample<FMT>(ch, row, f0 + off, chan_off, st.pos, fading) : 0.0;
     for (int k2 = 0; k2 < npair; ++k2) {
         const int k = 2 * k2;
-        const double x0 = scan_sample(ch, row, f0 + k, chan_off, st.pos, fading);
-        const double x1 = scan_sample(ch, row, f0 + k + 1, chan_off, st.pos, fading);
+        const int kn = (k2 + 1 < n_in) ? k + 2 : k;             // next input of this filter, fetched ahead
+        const double xn = scan_sample<FMT>(ch, row, f0 + kn + off, chan_off, st.pos, fading);
         const unsigned qa = (q0 + (unsigned)k) & 3u, qb = (qa + 1) & 3u;
-        const double ux = mix_down(xiq, qa, x0);
-        const double uy = mix_down(yiq, qb, x1);
-        double yx1 = mc.baseline ? mc.d0 * ux : 0.0, yy1 = 0.0, yx2 = 0.0, yy2 = mc.baseline ? mc.d0 * uy : 0.0;
+        const double u = mix_down(filt, is_x ? qa : qb, x);
+        double y1 = 0.0, y2 = 0.0;
+        if (is_x) {
+            if (mc.baseline) y1 = mc.d0 * u;
 #pragma unroll
-        for (int m = 0; m < NM; ++m) {
-            yx1 = fma(mc.cp_re[m], A[m].re, fma(mc.cp_im[m], A[m].im, yx1));    // X one sample after its input: r*p
-            yy1 = fma(mc.c_re[m], B[m].re, fma(mc.c_im[m], B[m].im, yy1));
-            yy2 = fma(mc.cp_re[m], B[m].re, fma(mc.cp_im[m], B[m].im, yy2));
-            cx_step(A[m], mc.p2_re[m], mc.p2_im[m], ux);
-            yx2 = fma(mc.c_re[m], A[m].re, fma(mc.c_im[m], A[m].im, yx2));
-            cx_step(B[m], mc.p2_re[m], mc.p2_im[m], uy);
+            for (int m = 0; m < NM; ++m) {
+                y1 = fma(mc.cp_re[m], S[m].re, fma(mc.cp_im[m], S[m].im, y1));      // one sample after its input: r*p
+                cx_step(S[m], mc.p2_re[m], mc.p2_im[m], u);
+                y2 = fma(mc.c_re[m], S[m].re, fma(mc.c_im[m], S[m].im, y2));
+            }
+        } else {
+            if (mc.baseline) y2 = mc.d0 * u;
+#pragma unroll
+            for (int m = 0; m < NM; ++m) {
+                y1 = fma(mc.c_re[m], S[m].re, fma(mc.c_im[m], S[m].im, y1));
+                y2 = fma(mc.cp_re[m], S[m].re, fma(mc.cp_im[m], S[m].im, y2));
+                cx_step(S[m], mc.p2_re[m], mc.p2_im[m], u);
+            }
         }
-        // up-mix (reference lpf_hilbert_quad.c:132-153): X filter is I when xiq == 0
+        // up-mix (reference lpf_hilbert_quad.c:132-153): which of re / im this filter feeds depends on the phase
         int slot;
-        double v2[2];
-        double a = mix_up(xiq, qa, yx1, slot); v2[slot] = a;
-        double b = mix_up(yiq, qa, yy1, slot); v2[slot] = b;
-        *reinterpret_cast<double2 *>(dst + (size_t)k * 4) = make_double2(v2[0], v2[1]);
-        a = mix_up(xiq, qb, yx2, slot); v2[slot] = a;
-        b = mix_up(yiq, qb, yy2, slot); v2[slot] = b;
-        *reinterpret_cast<double2 *>(dst + (size_t)(k + 1) * 4) = make_double2(v2[0], v2[1]);
+        double v = mix_up(filt, qa, y1, slot);
+        dst[(size_t)k * 4 + slot] = v;
+        v = mix_up(filt, qb, y2, slot);
+        dst[(size_t)(k + 1) * 4 + slot] = v;
+        x = xn;
     }
-    const bool odd = len & 1;
     if (odd) {
-        const int k = len - 1;
-        const double x0 = scan_sample(ch, row, f0 + k, chan_off, st.pos, fading);
+        const int k = len - 1;                                  // a first-of-pair sample: feeds X only
         const unsigned qa = (q0 + (unsigned)k) & 3u;
-        const double ux = mix_down(xiq, qa, x0);
-        double yx1 = mc.baseline ? mc.d0 * ux : 0.0, yy1 = 0.0;
+        double y1 = 0.0;
+        if (is_x) {
+            const double u = mix_down(filt, qa, x);
+            if (mc.baseline) y1 = mc.d0 * u;
 #pragma unroll
-        for (int m = 0; m < NM; ++m) {
-            yx1 = fma(mc.cp_re[m], A[m].re, fma(mc.cp_im[m], A[m].im, yx1));
-            yy1 = fma(mc.c_re[m], B[m].re, fma(mc.c_im[m], B[m].im, yy1));
-            cx_step(A[m], mc.p2_re[m], mc.p2_im[m], ux);
+            for (int m = 0; m < NM; ++m) {
+                y1 = fma(mc.cp_re[m], S[m].re, fma(mc.cp_im[m], S[m].im, y1));
+                cx_step(S[m], mc.p2_re[m], mc.p2_im[m], u);
+            }
+        } else {
+#pragma unroll
+            for (int m = 0; m < NM; ++m) y1 = fma(mc.c_re[m], S[m].re, fma(mc.c_im[m], S[m].im, y1));
         }
         int slot;
-        double v2[2];
-        double a = mix_up(xiq, qa, yx1, slot); v2[slot] = a;
-        double b = mix_up(yiq, qa, yy1, slot); v2[slot] = b;
-        *reinterpret_cast<double2 *>(dst + (size_t)k * 4) = make_double2(v2[0], v2[1]);
+        double v = mix_up(filt, qa, y1, slot);
+        dst[(size_t)k * 4 + slot] = v;
     }
     if (chunk == n_chunks - 1) {
-        // state after the call's last sample, filed under I / Q
+        // state after the call's last sample: a filter that did not take the last input has idled one sample
+        const bool idle = odd ? !is_x : is_x;
 #pragma unroll
         for (int m = 0; m < NM; ++m) {
-            Cx sx, sy;
-            if (odd) { sx = A[m]; sy = cx_mul(mc.p_re[m], mc.p_im[m], B[m]); }     // last sample fed X
-            else     { sx = cx_mul(mc.p_re[m], mc.p_im[m], A[m]); sy = B[m]; }     // last sample fed Y
-            st.hb[chan][xiq][2 * m] = sx.re; st.hb[chan][xiq][2 * m + 1] = sx.im;
-            st.hb[chan][yiq][2 * m] = sy.re; st.hb[chan][yiq][2 * m + 1] = sy.im;
+            Cx e = idle ? cx_mul(mc.p_re[m], mc.p_im[m], S[m]) : S[m];
+            st.hb[chan][filt][2 * m] = e.re; st.hb[chan][filt][2 * m + 1] = e.im;
         }
     }
 }
@@ -387,8 +386,8 @@ size_t scan_scratch_doubles(int n_streams, int64_t n_frames)
     return e + 2 * t;
 }
 
-template <int NM>
-static cudaError_t scan_launch_nm(const ModalCoef &mc, const DevChain &ch, DevStream *streams, int n_streams,
+template <int NM, int FMT>
+static cudaError_t scan_launch_nf(const ModalCoef &mc, const DevChain &ch, DevStream *streams, int n_streams,
                                   int64_t n_frames, const uint8_t *in, size_t in_stride, const double *pw,
                                   double *scratch, double *analytic, cudaStream_t s, int *launches)
 {
@@ -397,15 +396,34 @@ static cudaError_t scan_launch_nm(const ModalCoef &mc, const DevChain &ch, DevSt
     double *E = scratch;
     double *Tend = E + (size_t)n_streams * (4 * SCAN_NMAX) * 2 * (size_t)n_chunks;
     double *Tin = Tend + (size_t)n_streams * (size_t)n_tiles * 2 * 2 * (SCAN_NMAX * 2);
-    const unsigned cgrid = (unsigned)n_tiles;                   // one CTA = one tile of 128 chunks x 2 channels
-    scan_local_kernel<NM><<<dim3(cgrid, n_streams), 256, 0, s>>>(mc, ch, streams, n_frames, n_chunks, n_tiles, in, in_stride, E, Tend);
+    const unsigned cgrid = (unsigned)n_tiles;                   // one CTA = one tile: 128 chunks x 2 channels x 2 filters
+    scan_local_kernel<NM, FMT><<<dim3(cgrid, n_streams), 512, 0, s>>>(mc, ch, streams, n_frames, n_chunks, n_tiles, in, in_stride, E, Tend);
     const int64_t items = n_tiles * 2 * 2 * mc.nm;
     const unsigned tgrid = (unsigned)((items + 127) / 128);
     scan_tile_carry_kernel<<<dim3(tgrid, n_streams), 128, 0, s>>>(mc, streams, n_tiles, Tend, Tin);
-    scan_apply_kernel<NM><<<dim3(cgrid, n_streams), 256, 0, s>>>(mc, ch, streams, n_frames, n_chunks, n_tiles, in, in_stride,
-                                                               E, Tin, pw, analytic);
+    const unsigned agrid = (unsigned)((n_chunks + 63) / 64);
+    scan_apply_kernel<NM, FMT><<<dim3(agrid, n_streams), 256, 0, s>>>(mc, ch, streams, n_frames, n_chunks, n_tiles, in, in_stride,
+                                                                    E, Tin, pw, analytic);
     *launches += 3;
     return cudaGetLastError();
+}
+
+template <int NM>
+static cudaError_t scan_launch_nm(const ModalCoef &mc, const DevChain &ch, DevStream *streams, int n_streams,
+                                  int64_t n_frames, const uint8_t *in, size_t in_stride, const double *pw,
+                                  double *scratch, double *analytic, cudaStream_t s, int *launches)
+{
+#define ICW_SCAN_FMT(F) case F: return scan_launch_nf<NM, F>(mc, ch, streams, n_streams, n_frames, in, in_stride, pw, scratch, analytic, s, launches)
+    switch (ch.fmt) {
+        ICW_SCAN_FMT(ICW_FMT_WAV_U8);
+        ICW_SCAN_FMT(ICW_FMT_WAV_I16);
+        ICW_SCAN_FMT(ICW_FMT_WAV_I24);
+        ICW_SCAN_FMT(ICW_FMT_WAV_I32);
+        ICW_SCAN_FMT(ICW_FMT_WAV_F32);
+        ICW_SCAN_FMT(ICW_FMT_INTERNAL_F64);
+    default: return cudaErrorInvalidValue;
+    }
+#undef ICW_SCAN_FMT
 }
 
 cudaError_t launch_hb_scan(const ModalCoef &mc, const DevChain &ch, DevStream *streams, int n_streams,

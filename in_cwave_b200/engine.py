@@ -6,6 +6,7 @@ boundary; every sample is computed by the kernels in libicw_b200.so.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -19,8 +20,11 @@ class Engine:
         self._h = C.c_void_p()
         _abi.check(_abi.lib().icw_engine_create(int(device), C.byref(self._h)))
         self.device = int(device)
+        self._sessions = weakref.WeakSet()
 
     def close(self) -> None:
+        for ses in list(self._sessions):
+            ses.close()
         if self._h:
             _abi.lib().icw_engine_destroy(self._h)
             self._h = C.c_void_p()
@@ -77,6 +81,7 @@ class Session:
         self.frame_bytes = _abi.lib().icw_frame_bytes(self._c)
         self.out_frame_bytes = _abi.lib().icw_out_frame_bytes(self._c)
         self._taps = None
+        engine._sessions.add(self)
 
     def close(self) -> None:
         if self._h:

@@ -1,0 +1,373 @@
+/* icw_plugin.c -- host C layer: the reference's transcode entry points over libicw_b200.so.
+ * See include/icw_plugin.h.  Plain C99; no CUDA here -- everything numeric happens behind the C ABI. */
+#define _FILE_OFFSET_BITS 64
+#define _POSIX_C_SOURCE 200809L
+#define _DEFAULT_SOURCE
+#include "icw_plugin.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <strings.h>
+#include <sys/types.h>
+
+#define MIN_FILE_SAMPLES 2              /* reference src/in_cwave.h:315 */
+#define MAX_FS_SRC 2000000u             /* reference src/in_cwave.h:160 */
+#define DEFAULT_READAHEAD (1 << 20)
+
+typedef struct reader {
+    FILE    *fp;
+    icwp_fileinfo fi;
+    int      frame_bytes;
+    int64_t  pos_samples, pos_tail;     /* like XWAVE_READER, reference src/in_cwave.h:394-395 */
+} reader;
+
+static struct {
+    int             configured;
+    icw_chain_spec  chain;
+    icwp_options    opt;
+    icw_engine     *engine;
+    icw_session    *session;
+    reader          rd;
+    int             open;
+    int             out_frame_bytes;
+    /* read-ahead: rendered PCM not yet handed to the host */
+    unsigned char  *in_buf, *pcm_buf;
+    size_t          in_cap, pcm_cap;
+    int64_t         pcm_have, pcm_taken;    /* bytes */
+} P;
+
+/* ---- little-endian field readers ---------------------------------------------------------------- */
+static unsigned rd16(const unsigned char *p) { return (unsigned)p[0] | ((unsigned)p[1] << 8); }
+static uint32_t rd32(const unsigned char *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+
+static int64_t file_size(FILE *fp)
+{
+    off_t cur = ftello(fp), end;
+    if (cur < 0 || fseeko(fp, 0, SEEK_END)) return 0;
+    end = ftello(fp);
+    fseeko(fp, cur, SEEK_SET);
+    return end < 0 ? 0 : (int64_t)end;
+}
+
+/* ---- CWAVE header (reference src/cwave.h:47-84, checks src/xwave_reader.c:246-339) ------------------ */
+static int parse_cwave(FILE *fp, icwp_fileinfo *fi)
+{
+    static const int slen[4] = { 16, 4, 6, 8 };     /* bytes per channel sample, formats 0..3 */
+    unsigned char h[48];
+    int64_t fsize = file_size(fp);
+    uint32_t hsize, version, format, nch, nsmp, srate;
+
+    if (fsize < 48 || fread(h, 1, 48, fp) != 48) return 0;
+    if (memcmp(h, "cPLXwAVE", 8)) return 0;
+    hsize = rd32(h + 8); version = rd32(h + 12); format = rd32(h + 16);
+    nch = rd32(h + 20); nsmp = rd32(h + 24); srate = rd32(h + 28);
+    if (hsize < 48 || (int64_t)hsize >= fsize) return 0;
+    if (version != 1 && version != 2) return 0;
+    if (format > 3) return 0;
+    if (nch == 0 || nch > 2) return 0;
+    if (nsmp < MIN_FILE_SAMPLES) return 0;
+    if ((int64_t)nsmp * nch * slen[format] + hsize > fsize) return 0;
+    if (srate == 0) return 0;
+    fi->fmt = ICW_FMT_CW_F64 + (int)format;
+    fi->n_channels = (int)nch;
+    fi->sample_rate = srate;
+    fi->n_samples = nsmp;
+    fi->offset_data = hsize;
+    return 1;
+}
+
+/* ---- RIFF/WAVE (reference src/xwave_reader.c:362-585) ------------------------------------------------ */
+static int pcm_bits_to_fmt(unsigned bits)
+{
+    switch (bits) {
+    case 8: return ICW_FMT_WAV_U8;
+    case 16: return ICW_FMT_WAV_I16;
+    case 24: return ICW_FMT_WAV_I24;
+    case 32: return ICW_FMT_WAV_I32;
+    default: return -1;
+    }
+}
+
+static int parse_wav(FILE *fp, icwp_fileinfo *fi)
+{
+    static const unsigned char guid_tail[14] = { 0x00, 0x00, 0x00, 0x00, 0x10, 0x00, 0x80, 0x00, 0x00, 0xaa, 0x00, 0x38, 0x9b, 0x71 };
+    unsigned char hb[12], ck[8], fmtb[40];
+    int64_t fsize = file_size(fp), fpos = 0;
+    uint32_t clen, dlen;
+    unsigned tag, nch, block, bits, srate;
+    size_t toread;
+    int fmt;
+
+    if (fread(hb, 1, 12, fp) != 12 || memcmp(hb, "RIFF", 4) || memcmp(hb + 8, "WAVE", 4)) return 0;
+    fpos = 12;
+    for (;;) {                                      /* find "fmt "; a "data" chunk before it is an error */
+        if (fread(ck, 1, 8, fp) != 8) return 0;
+        clen = rd32(ck + 4);
+        fpos += 8;
+        if (fpos + (int64_t)clen > fsize) return 0;
+        if (!memcmp(ck, "fmt ", 4)) break;
+        if (!memcmp(ck, "data", 4)) return 0;
+        if (fseeko(fp, (off_t)clen, SEEK_CUR)) return 0;
+        fpos += clen;
+    }
+    if (clen < 14) return 0;
+    toread = clen < 40 ? clen : 40;
+    if (fread(fmtb, 1, toread, fp) != toread) return 0;
+    if (toread < clen && fseeko(fp, (off_t)(clen - toread), SEEK_CUR)) return 0;
+    fpos += clen;
+    tag = rd16(fmtb); nch = rd16(fmtb + 2); srate = rd32(fmtb + 4); block = rd16(fmtb + 12);
+    bits = toread >= 16 ? rd16(fmtb + 14) : 0;
+    bits = (bits + 7) & ~7u;
+    if (!nch || nch > 2 || !srate) return 0;
+    switch (tag) {
+    case 0x0001:                                    /* WAVE_FORMAT_PCM */
+        if (clen < 16) {                            /* bare WAVEFORMAT: derive the width from the block size */
+            if (block % nch) return 0;
+            bits = (block / nch) << 3;
+        }
+        if ((fmt = pcm_bits_to_fmt(bits)) < 0) return 0;
+        break;
+    case 0x0003:                                    /* WAVE_FORMAT_IEEE_FLOAT */
+        if (clen < 16 || bits != 32) return 0;
+        fmt = ICW_FMT_WAV_F32;
+        break;
+    case 0xFFFE:                                    /* WAVE_FORMAT_EXTENSIBLE */
+        if (clen < 40 || rd16(fmtb + 16) < 22) return 0;
+        if (memcmp(fmtb + 26, guid_tail, 14)) return 0;
+        if (rd16(fmtb + 24) == 0x0001) { if ((fmt = pcm_bits_to_fmt(bits)) < 0) return 0; }
+        else if (rd16(fmtb + 24) == 0x0003) { if (bits != 32) return 0; fmt = ICW_FMT_WAV_F32; }
+        else return 0;
+        break;
+    default:
+        return 0;
+    }
+    for (;;) {                                      /* find "data" */
+        if (fread(ck, 1, 8, fp) != 8) return 0;
+        fpos += 8;
+        dlen = rd32(ck + 4);
+        if (fpos + (int64_t)dlen > fsize) return 0;
+        if (!memcmp(ck, "data", 4)) break;
+        if (fseeko(fp, (off_t)dlen, SEEK_CUR)) return 0;
+        fpos += dlen;
+    }
+    {
+        unsigned sample_size = (bits >> 3) * nch;
+        fi->n_samples = dlen / sample_size;
+        if (fi->n_samples < MIN_FILE_SAMPLES || block != sample_size) return 0;
+    }
+    fi->fmt = fmt;
+    fi->n_channels = (int)nch;
+    fi->sample_rate = srate;
+    fi->offset_data = fpos;
+    return 1;
+}
+
+/* everything xwave_reader_create decides (reference src/xwave_reader.c:593-728) */
+static FILE *open_and_parse(const char *name, const icwp_options *opt, icwp_fileinfo *fi)
+{
+    const char *dot;
+    FILE *fp;
+    int is_cw, ok;
+
+    if (!name || !*name) return NULL;
+    dot = strrchr(name, '.');
+    if (!dot || dot == name) return NULL;           /* the extension decides the parser (:125-134) */
+    if (!strcasecmp(dot + 1, "CWAVE")) is_cw = 1;
+    else if (!strcasecmp(dot + 1, "WAV") || !strcasecmp(dot + 1, "RWAVE")) is_cw = 0;
+    else return NULL;
+    if (!(fp = fopen(name, "rb"))) return NULL;
+    memset(fi, 0, sizeof *fi);
+    ok = is_cw ? parse_cwave(fp, fi) : parse_wav(fp, fi);
+    if (!ok || fi->sample_rate > MAX_FS_SRC) { fclose(fp); return NULL; }
+    if (opt && opt->sec_align) {                    /* virtual zero tail up to a multiple of sec_align seconds */
+        int64_t max_tail = (int64_t)fi->sample_rate * (int64_t)opt->sec_align;
+        int64_t rest = fi->n_samples % max_tail;
+        fi->n_tail = rest ? max_tail - rest : 0;
+    }
+    fi->n_fade_in = opt ? (int64_t)(((uint64_t)opt->fade_in_ms * fi->sample_rate) / 1000u) : 0;
+    fi->n_fade_out = opt ? (int64_t)(((uint64_t)opt->fade_out_ms * fi->sample_rate) / 1000u) : 0;
+    if (fi->n_fade_in + fi->n_fade_out >= fi->n_samples) {      /* too short for the faders (:700-716) */
+        if (fi->n_samples < 300) fi->n_fade_in = fi->n_fade_out = 0;
+        else {
+            if (fi->n_fade_in) fi->n_fade_in = fi->n_samples / 3;
+            if (fi->n_fade_out) fi->n_fade_out = fi->n_samples / 3;
+        }
+    }
+    return fp;
+}
+
+int icwp_probe(const char *filename, const icwp_options *opt, icwp_fileinfo *out)
+{
+    icwp_fileinfo fi;
+    FILE *fp = open_and_parse(filename, opt, &fi);
+    if (!fp) return 0;
+    fclose(fp);
+    if (out) *out = fi;
+    return 1;
+}
+
+/* ---- configuration ---------------------------------------------------------------------------------- */
+static void ensure_defaults(void)
+{
+    if (P.configured) return;
+    icw_default_spec(&P.chain);
+    memset(&P.opt, 0, sizeof P.opt);
+    P.configured = 1;
+}
+
+int icwp_configure(const icw_chain_spec *chain, const icwp_options *opt)
+{
+    ensure_defaults();
+    if (chain) P.chain = *chain; else icw_default_spec(&P.chain);
+    if (opt) P.opt = *opt; else memset(&P.opt, 0, sizeof P.opt);
+    if (P.session && !P.open) {
+        /* parameters are snapshotted at the next open */
+    }
+    return ICW_OK;
+}
+
+void icwp_reset(void)
+{
+    if (P.open) winampGetExtendedRead_close((intptr_t)&P);
+    if (P.session) { icw_session_destroy(P.session); P.session = NULL; }
+}
+
+int icwp_stats(icw_stats *out)
+{
+    if (!P.session) return ICW_E_ARG;
+    return icw_session_stats(P.session, out);
+}
+
+/* ---- the reference's entry points -------------------------------------------------------------------- */
+intptr_t winampGetExtendedRead_open(const char *filename, int *size, int *bps, int *nch, int *srate)
+{
+    icw_chain_spec sp;
+    int64_t total, sz;
+    unsigned reset = ICW_RESET_FILEPOS;
+
+    ensure_defaults();
+    if (P.open) return 0;                           /* one transcode at a time, like &the.mc_transcode */
+    P.rd.fp = open_and_parse(filename, &P.opt, &P.rd.fi);
+    if (!P.rd.fp) return 0;
+    sp = P.chain;
+    sp.fmt = P.rd.fi.fmt;
+    sp.n_channels = P.rd.fi.n_channels;
+    sp.sample_rate = P.rd.fi.sample_rate;
+    sp.n_samples = P.rd.fi.n_samples;
+    sp.n_fade_in = P.rd.fi.n_fade_in;
+    sp.n_fade_out = P.rd.fi.n_fade_out;
+    P.rd.frame_bytes = icw_frame_bytes(&sp);
+    P.out_frame_bytes = icw_out_frame_bytes(&sp);
+    total = P.rd.fi.n_samples + P.rd.fi.n_tail;
+    sz = total * P.out_frame_bytes;
+    /* the reference refuses outputs that do not fit a 2 GiB WAV (src/transcode.c:59-68) */
+    if (sz > 0x7FFFFFFFLL - 40 - 12 - 16 - 64) goto fail;
+    if (!P.engine && icw_engine_create(P.opt.device, &P.engine) != ICW_OK) goto fail;
+    if (!P.session) {
+        if (icw_session_create(P.engine, &sp, 1, &P.session) != ICW_OK) goto fail;
+    } else if (icw_session_set_spec(P.session, &sp) != ICW_OK) goto fail;
+    if (P.opt.clr_nframe_trk) reset |= ICW_RESET_FRAMECNT;      /* src/in_cwave.c:226-229 */
+    if (P.opt.clr_hilb_trk) reset |= ICW_RESET_HILBERT;
+    if (icw_session_reset(P.session, reset) != ICW_OK) goto fail;
+    if (fseeko(P.rd.fp, (off_t)P.rd.fi.offset_data, SEEK_SET)) goto fail;
+    P.rd.pos_samples = P.rd.pos_tail = 0;
+    P.pcm_have = P.pcm_taken = 0;
+    P.open = 1;
+    *nch = 2;
+    *srate = (int)P.rd.fi.sample_rate;
+    *bps = P.out_frame_bytes * 4;
+    *size = (int)sz;
+    return (intptr_t)&P;
+fail:
+    fclose(P.rd.fp);
+    P.rd.fp = NULL;
+    return 0;
+}
+
+/* read up to `want` frames (file, then virtual silence) and render them; returns frames rendered */
+static int64_t refill(int64_t want)
+{
+    reader *r = &P.rd;
+    int64_t to_read = 0, to_fill = 0, n;
+    size_t need_in, need_out;
+
+    if (r->pos_samples < r->fi.n_samples) {
+        to_read = r->fi.n_samples - r->pos_samples;
+        if (to_read > want) to_read = want;
+    }
+    if (to_read < want && r->fi.n_tail) {
+        to_fill = r->fi.n_tail - r->pos_tail;
+        if (to_fill > want - to_read) to_fill = want - to_read;
+    }
+    n = to_read + to_fill;
+    if (n <= 0) return 0;
+    need_in = (size_t)n * r->frame_bytes;
+    need_out = (size_t)n * P.out_frame_bytes;
+    if (need_in > P.in_cap) { free(P.in_buf); P.in_buf = malloc(need_in); P.in_cap = P.in_buf ? need_in : 0; }
+    if (need_out > P.pcm_cap) { free(P.pcm_buf); P.pcm_buf = malloc(need_out); P.pcm_cap = P.pcm_buf ? need_out : 0; }
+    if (!P.in_buf || !P.pcm_buf) return 0;
+    if (to_read && fread(P.in_buf, (size_t)r->frame_bytes, (size_t)to_read, r->fp) != (size_t)to_read)
+        return 0;                                   /* short read == broken file == end, as in the reference */
+    if (to_fill) {
+        /* silence: 0x80 for unsigned 8-bit, zero bits otherwise (src/xwave_reader.c:100-105) */
+        memset(P.in_buf + (size_t)to_read * r->frame_bytes, r->fi.fmt == ICW_FMT_WAV_U8 ? 0x80 : 0,
+               (size_t)to_fill * r->frame_bytes);
+    }
+    if (icw_session_process_host(P.session, n, P.in_buf, 0, P.pcm_buf, 0) != ICW_OK) return 0;
+    r->pos_samples += to_read;
+    r->pos_tail += to_fill;
+    return n;
+}
+
+intptr_t winampGetExtendedRead_getData(intptr_t handle, char *dest, int len, int *killswitch)
+{
+    int64_t want_bytes, done = 0;
+    if ((void *)handle != (void *)&P || !P.open || len <= 0 || (killswitch && *killswitch)) return 0;
+    want_bytes = (int64_t)(len / P.out_frame_bytes) * P.out_frame_bytes;       /* whole frames only */
+    while (done < want_bytes) {
+        int64_t avail = P.pcm_have - P.pcm_taken, take;
+        if (avail == 0) {
+            int64_t ra = P.opt.readahead_frames > 0 ? P.opt.readahead_frames : DEFAULT_READAHEAD;
+            int64_t got = refill(ra);
+            if (got <= 0) break;
+            P.pcm_have = got * P.out_frame_bytes;
+            P.pcm_taken = 0;
+            avail = P.pcm_have;
+        }
+        take = want_bytes - done < avail ? want_bytes - done : avail;
+        memcpy(dest + done, P.pcm_buf + P.pcm_taken, (size_t)take);
+        P.pcm_taken += take;
+        done += take;
+    }
+    return (intptr_t)done;
+}
+
+int winampGetExtendedRead_setTime(intptr_t handle, int decode_pos_ms)
+{
+    reader *r = &P.rd;
+    int64_t total, pos;
+    icw_stream_state st;
+    if ((void *)handle != (void *)&P || !P.open) return 0;
+    total = r->fi.n_samples + r->fi.n_tail;
+    pos = (int64_t)decode_pos_ms * (int64_t)r->fi.sample_rate / 1000;
+    if (pos > total) pos = total;
+    if (pos < 0) pos = 0;
+    if (pos <= r->fi.n_samples) { r->pos_samples = pos; r->pos_tail = 0; }
+    else { r->pos_samples = r->fi.n_samples; r->pos_tail = pos - r->fi.n_samples; }
+    if (fseeko(r->fp, (off_t)(r->fi.offset_data + r->pos_samples * r->frame_bytes), SEEK_SET)) return 0;
+    P.pcm_have = P.pcm_taken = 0;                   /* un-served read-ahead is dropped, like the reader's buffer */
+    /* the fades follow the absolute file position (src/xwave_reader.c:923) */
+    if (icw_session_get_state(P.session, 0, &st) != ICW_OK) return 0;
+    st.pos = pos;
+    return icw_session_set_state(P.session, 0, &st) == ICW_OK;
+}
+
+void winampGetExtendedRead_close(intptr_t handle)
+{
+    if ((void *)handle != (void *)&P || !P.open) return;
+    fclose(P.rd.fp);
+    P.rd.fp = NULL;
+    P.open = 0;
+    P.pcm_have = P.pcm_taken = 0;
+}

@@ -1,0 +1,85 @@
+"""ctypes veneer over libicw_plugin.so: the reference's transcode entry points (include/icw_plugin.h)."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+from . import _abi, spec as _spec
+
+PLUGIN_PATH = Path(__file__).resolve().parent / "libicw_plugin.so"
+EXPORTS = ["winampGetExtendedRead_open", "winampGetExtendedRead_getData", "winampGetExtendedRead_setTime",
+           "winampGetExtendedRead_close", "icwp_configure", "icwp_reset", "icwp_stats", "icwp_probe"]
+
+
+class Options(C.Structure):
+    _fields_ = [("sec_align", C.c_uint), ("fade_in_ms", C.c_uint), ("fade_out_ms", C.c_uint),
+                ("clr_nframe_trk", C.c_int), ("clr_hilb_trk", C.c_int), ("device", C.c_int),
+                ("readahead_frames", C.c_int64)]
+
+
+class FileInfo(C.Structure):
+    _fields_ = [("fmt", C.c_int), ("n_channels", C.c_int), ("sample_rate", C.c_uint),
+                ("n_samples", C.c_int64), ("n_tail", C.c_int64), ("offset_data", C.c_int64),
+                ("n_fade_in", C.c_int64), ("n_fade_out", C.c_int64)]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        _abi.lib()                                   # the CUDA library first: the plugin links against it
+        if not PLUGIN_PATH.exists():
+            raise RuntimeError(f"{PLUGIN_PATH} is missing: run in_cwave_b200/build.py")
+        L = C.CDLL(str(PLUGIN_PATH))
+        ip = C.POINTER(C.c_int)
+        L.winampGetExtendedRead_open.argtypes = [C.c_char_p, ip, ip, ip, ip]
+        L.winampGetExtendedRead_open.restype = C.c_ssize_t
+        L.winampGetExtendedRead_getData.argtypes = [C.c_ssize_t, C.c_void_p, C.c_int, ip]
+        L.winampGetExtendedRead_getData.restype = C.c_ssize_t
+        L.winampGetExtendedRead_setTime.argtypes = [C.c_ssize_t, C.c_int]
+        L.winampGetExtendedRead_close.argtypes = [C.c_ssize_t]
+        L.winampGetExtendedRead_close.restype = None
+        L.icwp_configure.argtypes = [C.POINTER(_abi.ChainSpecC), C.POINTER(Options)]
+        L.icwp_reset.restype = None
+        L.icwp_stats.argtypes = [C.POINTER(_abi.Stats)]
+        L.icwp_probe.argtypes = [C.c_char_p, C.POINTER(Options), C.POINTER(FileInfo)]
+        _lib = L
+    return _lib
+
+
+def configure(spec: dict | None, **opt) -> None:
+    o = Options(**opt)
+    rc = lib().icwp_configure(_spec.to_c(spec) if spec is not None else None, C.byref(o))
+    _abi.check(rc)
+
+
+def probe(path: str, **opt):
+    o, fi = Options(**opt), FileInfo()
+    ok = lib().icwp_probe(str(path).encode(), C.byref(o), C.byref(fi))
+    return fi if ok else None
+
+
+def transcode(path: str, chunk: int = 65536, seek_ms: int | None = None):
+    """winampGetExtendedRead_open -> getData loop -> close.  Returns (pcm bytes, (size, bps, nch, srate)) or None."""
+    L = lib()
+    size, bps, nch, srate = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    h = L.winampGetExtendedRead_open(str(path).encode(), C.byref(size), C.byref(bps), C.byref(nch), C.byref(srate))
+    if not h:
+        return None
+    if seek_ms is not None and not L.winampGetExtendedRead_setTime(h, seek_ms):
+        L.winampGetExtendedRead_close(h)
+        raise RuntimeError("setTime failed")
+    out = bytearray()
+    buf = (C.c_char * chunk)()
+    kill = C.c_int(0)
+    while True:
+        got = L.winampGetExtendedRead_getData(h, buf, chunk, C.byref(kill))
+        if got <= 0:
+            break
+        out += buf.raw[:got]
+    L.winampGetExtendedRead_close(h)
+    return np.frombuffer(bytes(out), dtype=np.uint8), (size.value, bps.value, nch.value, srate.value)

@@ -1,0 +1,74 @@
+/* icw_plugin.h -- the reference's own transcode entry points, served by the B200 library.
+ *
+ * libicw_plugin.so exports the four symbols Winamp/XMPlay resolve by name in the reference DLL
+ * (reference src/transcode.c:40-118), with the same signatures, ownership and error conventions:
+ *
+ *   open     -> handle (0 on any failure: unknown extension, bad header, unsupported format,
+ *               output above ~2 GiB, sample rate above 2 MHz); fills *size (output bytes), *bps
+ *               (16 or 24), *nch (always 2), *srate
+ *   getData  -> bytes written into dest (whole frames only), 0 = end of file OR read error
+ *   setTime  -> 1/0, seek to a millisecond position (clamped to the file, reference
+ *               src/xwave_reader.c:782-817)
+ *   close    -> releases the file; the DSP state (frame counter, Hilbert delay lines, dither stream)
+ *               survives into the next file, as in the reference (src/config.c:171,174 defaults)
+ *
+ * The handle is a process-wide singleton like the reference's &the.mc_transcode (one transcode at
+ * a time).  File parsing (RIFF/WAVE fmt 14/16/18/40 bytes, PCM / IEEE float / extensible GUIDs;
+ * CWAVE V1/V2) follows reference src/xwave_reader.c:243-585 and src/cwave.h:47-84; the virtual
+ * silence tail (sec_align) and the fades follow src/xwave_reader.c:593-728,838-904.
+ * Hosts ask for 4-64 KB at a time (src/transcode.c:94); this layer reads ahead in large blocks and
+ * runs them through libicw_b200.so, so a GPU launch is not paid per host call.
+ *
+ * Configuration replaces the reference's config file and GUI (both out of scope): icwp_configure()
+ * takes the chain description (filter, summation, DSP list, render settings; the per-file fields
+ * fmt / n_channels / sample_rate / n_samples / fades are overwritten at open) plus the three
+ * reader options the reference keeps in its config.
+ */
+#ifndef ICW_PLUGIN_H
+#define ICW_PLUGIN_H
+
+#include <stdint.h>
+#include "icw_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* reference src/transcode.c:40 (narrow-character build), :82, :104, :113 */
+intptr_t winampGetExtendedRead_open(const char *filename, int *size, int *bps, int *nch, int *srate);
+intptr_t winampGetExtendedRead_getData(intptr_t handle, char *dest, int len, int *killswitch);
+int      winampGetExtendedRead_setTime(intptr_t handle, int decode_pos_ms);
+void     winampGetExtendedRead_close(intptr_t handle);
+
+/* reader options of the reference config: SEC_ALIGN (s), FADE_IN / FADE_OUT (ms), src/config.c:147-152 */
+typedef struct icwp_options {
+    unsigned sec_align, fade_in_ms, fade_out_ms;
+    int      clr_nframe_trk, clr_hilb_trk;      /* CLR_NFRAME_PT / CLR_HILB_PT, src/config.c:171,174 */
+    int      device;                            /* CUDA device ordinal */
+    int64_t  readahead_frames;                  /* 0 = default (1 Mi frames) */
+} icwp_options;
+
+/* chain = NULL restores the reference defaults (src/config.c:118-207); returns ICW_OK or ICW_E_* */
+int  icwp_configure(const icw_chain_spec *chain, const icwp_options *opt);
+/* fresh plugin state, like calling winampGetInModule2() again (src/in_cwave.c:551-572) */
+void icwp_reset(void);
+/* clips / peaks / reject counters of the transcode context (src/adv_modulator.c:445-465) */
+int  icwp_stats(icw_stats *out);
+
+/* header parsing alone (no GPU touched): what xwave_reader_create (src/xwave_reader.c:593-728)
+ * would accept and report.  Returns 1 if the file is playable, 0 otherwise. */
+typedef struct icwp_fileinfo {
+    int      fmt;               /* ICW_FMT_* */
+    int      n_channels;
+    unsigned sample_rate;
+    int64_t  n_samples;         /* frames in the file */
+    int64_t  n_tail;            /* virtual silence frames appended for sec_align */
+    int64_t  offset_data;       /* byte offset of the first frame */
+    int64_t  n_fade_in, n_fade_out;
+} icwp_fileinfo;
+int  icwp_probe(const char *filename, const icwp_options *opt, icwp_fileinfo *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

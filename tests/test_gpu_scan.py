@@ -157,3 +157,26 @@ def test_mode_switch_on_live_stream_is_refused(engine):
     assert ei.value.code == _abi.E_UNSUPPORTED
     ses.reset(_abi.RESET_HILBERT)
     ses.process_host(raw)
+
+
+def test_time_sharding_stitches_on_one_gpu(engine, oracle):
+    """The multi-GPU time split, emulated on one GPU: shard 1 starts from closed-form scalars and a
+    filter state obtained by a warm-up over the tail of shard 0 (what rank 0 would send over NCCL)."""
+    from in_cwave_b200 import dist as D
+    spec = S.config_c2(hilbert_mode="scan", filter_no=0)       # type 0 forgets fastest: short warm-up suffices
+    fb = S.frame_bytes(spec)
+    n = 120_000
+    raw = rand_bytes(spec, n, 61)
+    whole = engine.session(spec, 1).process_host(raw)[0]
+    a1, _ = D.shard_time(n, 1, 2)
+    be0, be1 = D.CudaBackend(engine, spec), D.CudaBackend(engine, spec)
+    warm = 40_000                                               # 0.99832^40000 ~ 1e-29
+    tail = raw[(a1 - warm) * fb: a1 * fb]
+    state = be0.hilbert_state_after(tail, D.closed_form_state(spec, a1 - warm).quad)
+    be0.start_at(D.closed_form_state(spec, 0), np.zeros(D.STATE_DOUBLES))
+    p0 = be0.process(raw[: a1 * fb])
+    be1.start_at(D.closed_form_state(spec, a1), state)
+    p1 = be1.process(raw[a1 * fb:])
+    rep = pcm_report(np.concatenate([p0, p1]), whole, 3)
+    print(f"[time shards] {rep}")
+    assert rep["max_lsb"] <= 1 and rep["mismatches"] <= 2

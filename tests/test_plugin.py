@@ -1,0 +1,170 @@
+"""The host C layer (include/icw_plugin.h): the reference's transcode entry points over the B200 library.
+
+CPU part: header parsing agrees with the reference's own reader on good and malformed files.
+GPU part: the same file through winampGetExtendedRead_open/getData/close of libicw_plugin.so and of
+the compiled reference gives the same bytes (exact mode)."""
+import ctypes as C
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from in_cwave_b200 import plugin, spec as S, synth
+from oracle import pyoracle as po
+
+
+def _ref_open(path, cfg_over=None):
+    """The reference's winampGetExtendedRead_open on a file: (size, bps, nch, srate) or None."""
+    d = S.default_spec()
+    d.update(cfg_over or {})
+    cfg = po.make_refcfg(d)
+    po.ref().icwref_reset(C.byref(cfg))
+    info = (C.c_int * 4)()
+    pcm = np.zeros(16, dtype=np.uint8)
+    got = po.ref().icwref_transcode_file(str(path).encode(), 4096, pcm.ctypes.data_as(C.c_char_p), 0, info)
+    return None if got < 0 else tuple(info)
+
+
+def _files(tmp_path):
+    rng = np.random.default_rng(3)
+    out = {}
+
+    def put(name, blob):
+        p = tmp_path / name
+        p.write_bytes(blob)
+        out[name] = p
+
+    for fmt, nch in (("wav_u8", 1), ("wav_i16", 2), ("wav_i24", 2), ("wav_i32", 1), ("wav_f32", 2)):
+        d = dict(fmt=fmt, n_channels=nch, sample_rate=44100)
+        raw = rng.integers(0, 256, size=777 * S.frame_bytes(d), dtype=np.uint8)
+        put(f"{fmt}_{nch}.wav", po.wav_bytes(d, raw))
+        put(f"{fmt}_{nch}_ext.wav", po.wav_bytes(d, raw, extensible=True))
+    for fmt in ("cw_f64", "cw_i16", "cw_i16f32", "cw_f32"):
+        d = dict(fmt=fmt, n_channels=2, sample_rate=96000)
+        raw = rng.integers(0, 256, size=500 * S.frame_bytes(d), dtype=np.uint8)
+        put(f"{fmt}.cwave", po.cwave_bytes(d, raw))
+        put(f"{fmt}_v1.cwave", po.cwave_bytes(d, raw, version=1))
+    good = po.wav_bytes(dict(fmt="wav_i16", n_channels=2, sample_rate=48000), rng.integers(0, 256, size=4000, dtype=np.uint8))
+    put("rwave_ext.RWAVE", good)
+    put("wrong_ext.mp3", good)
+    put("truncated.wav", good[:60])
+    put("bad_riff.wav", b"RIFX" + good[4:])
+    put("data_before_fmt.wav", good[:12] + good[36:44] + good[44:60] + good[12:36] + good[60:])
+    junk = b"LIST" + struct.pack("<I", 10) + b"0123456789"
+    put("extra_chunk.wav", good[:12] + junk + good[12:])
+    put("rate_too_high.wav", good[:24] + struct.pack("<I", 3_000_000) + good[28:])
+    put("three_channels.wav", good[:22] + struct.pack("<H", 3) + good[24:])
+    put("one_frame.wav", po.wav_bytes(dict(fmt="wav_i16", n_channels=2, sample_rate=48000), np.zeros(4, dtype=np.uint8)))
+    cw = po.cwave_bytes(dict(fmt="cw_f32", n_channels=2, sample_rate=96000), rng.integers(0, 256, size=1600, dtype=np.uint8))
+    put("bad_magic.cwave", b"cPLXwAVX" + cw[8:])
+    put("bad_version.cwave", cw[:12] + struct.pack("<I", 7) + cw[16:])
+    put("short_data.cwave", cw[:-100])
+    return out
+
+
+@pytest.mark.skipif(not po.have_ref(), reason="oracle/_ref/libicw_ref.so not built")
+def test_header_parsing_agrees_with_the_reference_reader(tmp_path):
+    files = _files(tmp_path)
+    accepted = 0
+    for name, path in sorted(files.items()):
+        ref = _ref_open(path)
+        fi = plugin.probe(path)
+        assert (ref is None) == (fi is None), f"{name}: reference {'rejects' if ref is None else 'accepts'}, we do not agree"
+        if ref is not None:
+            accepted += 1
+            size, bps, nch, srate = ref
+            assert fi.n_samples * 6 == size and fi.sample_rate == srate and nch == 2, name
+    assert accepted >= 19
+
+
+@pytest.mark.skipif(not po.have_ref(), reason="oracle/_ref/libicw_ref.so not built")
+def test_tail_and_fade_geometry(tmp_path):
+    d = dict(fmt="wav_i16", n_channels=2, sample_rate=8000)
+    p = tmp_path / "t.wav"
+    p.write_bytes(po.wav_bytes(d, np.zeros(12345 * 4, dtype=np.uint8)))
+    fi = plugin.probe(p, sec_align=2, fade_in_ms=100, fade_out_ms=250)
+    assert (fi.n_samples, fi.n_tail, fi.n_fade_in, fi.n_fade_out) == (12345, 16000 - 12345, 800, 2000)
+    ref = _ref_open(p, dict(sec_align=2))
+    assert ref[0] == 16000 * 6
+    short = tmp_path / "s.wav"
+    short.write_bytes(po.wav_bytes(d, np.zeros(900 * 4, dtype=np.uint8)))
+    fi = plugin.probe(short, fade_in_ms=100, fade_out_ms=100)
+    assert (fi.n_fade_in, fi.n_fade_out) == (300, 300)          # capped at a third of a short track
+    tiny = tmp_path / "y.wav"
+    tiny.write_bytes(po.wav_bytes(d, np.zeros(200 * 4, dtype=np.uint8)))
+    fi = plugin.probe(tiny, fade_in_ms=100, fade_out_ms=100)
+    assert (fi.n_fade_in, fi.n_fade_out) == (0, 0)
+
+
+def test_plugin_exports_the_reference_symbols():
+    L = plugin.lib()
+    for name in plugin.EXPORTS:
+        assert hasattr(L, name)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not po.have_ref(), reason="oracle/_ref/libicw_ref.so not built")
+@pytest.mark.parametrize("case", ["c1", "c2_tpdf", "c3", "tail_fade"])
+def test_transcode_entry_points_match_the_reference(tmp_path, case):
+    """Same file, same four calls, same bytes (exact Hilbert mode; trig LSB flips counted)."""
+    from util import pcm_report
+    n = 30000
+    opts, over = {}, {}
+    if case == "c1":
+        spec = S.config_c1()
+    elif case == "c2_tpdf":
+        spec = S.config_c2(sample_rate=96000)
+    elif case == "c3":
+        spec = S.config_c3()
+    else:
+        spec = S.config_c1(sample_rate=8000)
+        opts = dict(sec_align=3, fade_in_ms=500, fade_out_ms=1000)
+        over = dict(sec_align=3, fade_in=500, fade_out=1000)
+    raw = synth.stream_bytes(spec, n, stream_id=5)
+    is_cw = spec["fmt"].startswith("cw_")
+    path = tmp_path / ("x.cwave" if is_cw else "x.wav")
+    path.write_bytes(po.cwave_bytes(spec, raw) if is_cw else po.wav_bytes(spec, raw))
+
+    # the reference: fresh plugin, its own transcode loop
+    d = dict(spec); d.update(over)
+    cfg = po.make_refcfg(d)
+    po.ref().icwref_reset(C.byref(cfg))
+    arr = (po.Node * len(spec["nodes"]))()
+    for i, nd in enumerate(spec["nodes"]):
+        po.fill_node(arr[i], nd)
+    assert po.ref().icwref_set_graph(arr, len(spec["nodes"]), 0) == 0
+    cap = (n + 30000) * 6
+    want = np.zeros(cap, dtype=np.uint8)
+    info = (C.c_int * 4)()
+    got = po.ref().icwref_transcode_file(str(path).encode(), 5000, want.ctypes.data_as(C.c_char_p), cap, info)
+    assert got > 0
+    want = want[:got]
+
+    plugin.lib().icwp_reset()
+    plugin.configure(spec, readahead_frames=7001, **opts)
+    pcm, meta = plugin.transcode(path, chunk=5000)
+    assert meta == tuple(info)
+    assert pcm.size == want.size
+    rep = pcm_report(pcm, want, 3 if spec.get("need24bits", 1) else 2)
+    print(f"[plugin {case}] {rep}")
+    assert rep["max_lsb"] <= 1 and rep["mismatches"] <= 1
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not po.have_ref(), reason="oracle/_ref/libicw_ref.so not built")
+def test_state_survives_into_the_next_file(tmp_path):
+    """Two files back to back: counter, delay lines and dither stream continue (reference defaults)."""
+    spec = S.config_c2(sample_rate=48000)
+    fb = S.frame_bytes(spec)
+    raw = synth.stream_bytes(spec, 9000, stream_id=8)
+    a, b = tmp_path / "a.wav", tmp_path / "b.wav"
+    a.write_bytes(po.wav_bytes(spec, raw[: 4000 * fb]))
+    b.write_bytes(po.wav_bytes(spec, raw[4000 * fb:]))
+    r1 = po.ref_process(spec, raw[: 4000 * fb])
+    r2 = po.ref_process(spec, raw[4000 * fb:], reset=False)
+    plugin.lib().icwp_reset()
+    plugin.configure(spec)
+    p1, _ = plugin.transcode(a)
+    p2, _ = plugin.transcode(b)
+    assert np.array_equal(p1, r1["pcm"]) and np.array_equal(p2, r2["pcm"])
