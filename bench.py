@@ -340,15 +340,26 @@ def main():
     # ---- roofline of the dominant kernel --------------------------------------------------------
     pk = peaks()
     dom = max(prof, key=lambda k: prof[k]["ms"])
-    dom_ms = prof[dom]["ms"] / max(1, prof[dom]["launches"])
-    units_per_launch = K * min(chunk, N)
+    spans = max(1, prof[dom]["launches"])
+    dom_ms = prof[dom]["ms"] / spans                         # one span = the class's kernels over one launch group
+    units_per_launch = K * N * args.steps / spans            # frames one such span processes
     algo_bytes = units_per_launch * wl["bytes_per_frame"]
     achieved = algo_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    traffic = None
+    tfile = ROOT / "profiles" / "r1_traffic.json"            # dram bytes per frame from the ncu --set full captures
+    if tfile.exists():
+        t = json.loads(tfile.read_text()).get(wl["name"], {}).get(dom)
+        if t:
+            traffic = t["dram_bytes_per_frame"] * units_per_launch
+    fp64_ops = {"c2": 225 + 150, "c5": 225 + 110, "c1": 225 + 110, "c4": 1124 + 110, "c3": 300}.get(wl["name"], 0)
     roofline = dict(bound="hbm", kernel=dom, achieved=achieved, peak=pk["hbm_gbs"], unit="GB/s",
-                    frac=achieved / pk["hbm_gbs"], traffic=None, peak_source=pk["source"],
+                    frac=achieved / pk["hbm_gbs"], traffic=traffic, peak_source=pk["source"],
                     algorithmic_bytes_per_frame=wl["bytes_per_frame"], frames_per_launch=units_per_launch,
                     avg_launch_ms=dom_ms,
-                    kernel_share={k: v["ms"] / max(1e-9, sum(x["ms"] for x in prof.values())) for k, v in prof.items()})
+                    kernel_share={k: v["ms"] / max(1e-9, sum(x["ms"] for x in prof.values())) for k, v in prof.items()},
+                    binding_bound=dict(kind="fp64 pipe", peak_tops=18.55, peak_source="tools/fp64_probe.cu on this pool's B200",
+                                       approx_ops_per_frame=fp64_ops,
+                                       whole_step_frac=(frames_step / world) * fp64_ops / (ms_step * 1e-3) / 18.55e12))
 
     # ---- end to end through the host entry point ----------------------------------------------------
     e2e = None

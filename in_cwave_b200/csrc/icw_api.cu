@@ -329,6 +329,18 @@ static int fold_spec(const icw_chain_spec &sp, DevChain &ch, HbCoef &coef)
     }
     if (!ch.is_complex && sp.hilbert_mode != ICW_HILBERT_EXACT && sp.hilbert_mode != ICW_HILBERT_SCAN)
         return fail(ICW_E_ARG, "hilbert_mode out of range");
+    // common list shapes get straight-line device code (same operations, no interpreter overhead)
+    ch.shape = ICW_SHAPE_GENERIC;
+    {
+        auto plain = [](const DevNode &d) { return d.xch_mode == ICW_XCH_NORMAL && !d.l_iq_invert && !d.r_iq_invert; };
+        const DevNode &last = ch.nodes[ch.n_nodes - 1];
+        if (!ch.bypass && plain(last)) {
+            if (ch.n_nodes == 1 && last.inputs_mask == 1u) ch.shape = ICW_SHAPE_MASTER;
+            if (ch.n_nodes == 2 && ch.nodes[0].mode == ICW_MODE_SHIFT && plain(ch.nodes[0]) && ch.nodes[0].inputs_mask == 1u &&
+                last.inputs_mask == (1u << ch.nodes[0].n_out))
+                ch.shape = ICW_SHAPE_SHIFT_MASTER;
+        }
+    }
     return ICW_OK;
 }
 

@@ -99,10 +99,23 @@ __device__ __forceinline__ void finish_frame(const DevChain &ch, DevStream &st, 
 {
     const DevRender &rq = ch.render;
     const int wps = rq.words_per_sample;
-    bus[0][0] = v[0]; bus[0][1] = v[1]; bus[0][2] = v[2]; bus[0][3] = v[3];
     double omega = norm_omega(ch, osc.at(ch, i));
     double lo, ro;
-    run_graph(ch, bus, omega, lo, ro);
+    if (ch.shape != ICW_SHAPE_GENERIC) {
+        // straight-line list: the bus only has to be materialised where somebody looks at it
+        double o[4];
+        run_shape(ch, v, omega, o, lo, ro);
+        if (io.tap_bus || i == n_frames - 1) {
+            bus[0][0] = v[0]; bus[0][1] = v[1]; bus[0][2] = v[2]; bus[0][3] = v[3];
+            if (ch.shape == ICW_SHAPE_SHIFT_MASTER) {
+                const int k = ch.nodes[0].n_out;
+                bus[k][0] = o[0]; bus[k][1] = o[1]; bus[k][2] = o[2]; bus[k][3] = o[3];
+            }
+        }
+    } else {
+        bus[0][0] = v[0]; bus[0][1] = v[1]; bus[0][2] = v[2]; bus[0][3] = v[3];
+        run_graph(ch, bus, omega, lo, ro);
+    }
 
     double dl = 0.0, dr = 0.0;
     if (wps) {

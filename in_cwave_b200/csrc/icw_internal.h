@@ -12,6 +12,9 @@
 #define ICW_HZ_SCALE    1000u                                   // reference src/in_cwave.h:162
 #define ICW_SILENCE_DB  (-555.0)                                // reference src/sound_render.h:103
 #define ICW_FMT_INTERNAL_F64 8     // not part of the ABI: real doubles, used by the Hilbert leaf
+#define ICW_SHAPE_GENERIC      0    // interpreted DSP list
+#define ICW_SHAPE_MASTER       1    // Master(In) alone: the reference's default list
+#define ICW_SHAPE_SHIFT_MASTER 2    // Shift(In -> X), Master(X): no exchange, no I/Q swap
 #define ICW_MT_N        624
 #define ICW_MT_M        397
 
@@ -49,6 +52,7 @@ struct DevChain {
     int32_t  aligned;                   // per call: base pointer and row stride keep samples naturally aligned
     int32_t  is_frmod_scaled;
     int32_t  bypass, n_nodes;
+    int32_t  shape;                     // ICW_SHAPE_*: DSP lists common enough to get straight-line code
     int32_t  filter_no, hb_ord, is_kahan, reject_flag;
     int64_t  n_samples, n_fade_in, n_fade_out;
     uint64_t scale_sr;                  // sample_rate * 1000 (scaled) or 0

@@ -85,6 +85,20 @@ void scan_make_coef(int filter_no, bool baseline, double d0, ModalCoef &mc, std:
 // device
 // ---------------------------------------------------------------------------------------------
 struct Cx { double re, im; };
+
+// The per-mode filter constants reach the sample loops through shared memory on purpose: as plain
+// kernel parameters ptxas treats them as warp-uniform, parks ~60 doubles in the 63 uniform
+// registers, spills those into vector registers and pays an R2UR per use -- more instructions than
+// the DFMAs they feed.  Values read back from shared memory are ordinary per-thread registers.
+__device__ __forceinline__ void stage_constants(double (*k)[SCAN_NMAX], const ModalCoef &mc)
+{
+    for (int i = threadIdx.x; i < 6 * SCAN_NMAX; i += blockDim.x) {
+        const int a = i / SCAN_NMAX, m = i % SCAN_NMAX;
+        const double *src = a == 0 ? mc.p2_re : a == 1 ? mc.p2_im : a == 2 ? mc.c_re : a == 3 ? mc.c_im : a == 4 ? mc.cp_re : mc.cp_im;
+        k[a][m] = src[m];
+    }
+    __syncthreads();
+}
 __device__ __forceinline__ Cx cx_mul(double ar, double ai, Cx b)
 {
     Cx r;
@@ -137,6 +151,8 @@ scan_local_kernel(const __grid_constant__ ModalCoef mc, const __grid_constant__ 
 {
     __shared__ double wtot[16][2][2][SCAN_NMAX][2];     // inclusive total of each warp's 8 chunks
     __shared__ double wcar[16][2][2][SCAN_NMAX][2];     // carry into each warp from the tile start
+    __shared__ double kshared[6][SCAN_NMAX];
+    stage_constants(kshared, mc);
     const int stream = blockIdx.y;
     const int64_t tile = blockIdx.x;
     const int filt = threadIdx.x & 1, chan = (threadIdx.x >> 1) & 1;
@@ -157,13 +173,16 @@ scan_local_kernel(const __grid_constant__ ModalCoef mc, const __grid_constant__ 
         const bool fading = (ch.n_fade_in | ch.n_fade_out) != 0;
         const int64_t f0 = chunk * SCAN_L + (is_x ? 0 : 1);     // this filter's first input sample
         const unsigned qf = (q0 + (is_x ? 0u : 1u)) & 3u;       // its mixer phase (f0 is a multiple of 4)
+        double kp2r[NM], kp2i[NM];
+#pragma unroll
+        for (int m = 0; m < NM; ++m) { kp2r[m] = kshared[0][m]; kp2i[m] = kshared[1][m]; }
         double x = scan_sample<FMT>(ch, row, f0, chan_off, st.pos, fading);
         for (int k = 0; k < SCAN_L; k += 2) {
             const int kn = k + 2 < SCAN_L ? k + 2 : k;          // fetched one pair ahead
             const double xn = scan_sample<FMT>(ch, row, f0 + kn, chan_off, st.pos, fading);
             const double u = mix_down(filt, (qf + (unsigned)k) & 3u, x);
 #pragma unroll
-            for (int m = 0; m < NM; ++m) cx_step(s[m], mc.p2_re[m], mc.p2_im[m], u);
+            for (int m = 0; m < NM; ++m) cx_step(s[m], kp2r[m], kp2i[m], u);
             x = xn;
         }
         // state after the chunk's last sample (a Y-input sample): X has idled one sample since its input
@@ -267,13 +286,15 @@ scan_tile_carry_kernel(const __grid_constant__ ModalCoef mc, const DevStream *__
 // pass 3: every chunk again, from its true initial state, producing the analytic signal.
 // Each thread writes its own filter's half of every frame: re or im, alternating with the phase.
 template <int NM, int FMT>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 1)
 scan_apply_kernel(const __grid_constant__ ModalCoef mc, const __grid_constant__ DevChain ch,
                   DevStream *__restrict__ streams, int64_t n_frames, int64_t n_chunks, int64_t n_tiles,
                   const uint8_t *__restrict__ in, size_t in_stride,
                   const double *__restrict__ E, const double *__restrict__ Tin, const double *__restrict__ pw,
                   double *__restrict__ analytic /* [stream][frame][4] */)
 {
+    __shared__ double kshared[6][SCAN_NMAX];
+    stage_constants(kshared, mc);
     const int stream = blockIdx.y;
     const int filt = threadIdx.x & 1, chan = (threadIdx.x >> 1) & 1;
     const int64_t chunk = (int64_t)blockIdx.x * (blockDim.x / 4) + (threadIdx.x >> 2);
@@ -306,6 +327,14 @@ scan_apply_kernel(const __grid_constant__ ModalCoef mc, const __grid_constant__ 
         S[m] = is_x ? cx_mul(mc.pinv_re[m], mc.pinv_im[m], s0) : s0;
     }
 
+    // per-mode constants as ordinary (per-thread) registers for the sample loop
+    double kp2r[NM], kp2i[NM], kcr[NM], kci[NM], kcpr[NM], kcpi[NM];
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+        kp2r[m] = kshared[0][m]; kp2i[m] = kshared[1][m];
+        kcr[m] = kshared[2][m];  kci[m] = kshared[3][m];
+        kcpr[m] = kshared[4][m]; kcpi[m] = kshared[5][m];
+    }
     const int off = is_x ? 0 : 1;                               // this filter's input sample inside a pair
     const int npair = len >> 1;
     const bool odd = len & 1;
@@ -322,17 +351,17 @@ scan_apply_kernel(const __grid_constant__ ModalCoef mc, const __grid_constant__ 
             if (mc.baseline) y1 = mc.d0 * u;
 #pragma unroll
             for (int m = 0; m < NM; ++m) {
-                y1 = fma(mc.cp_re[m], S[m].re, fma(mc.cp_im[m], S[m].im, y1));      // one sample after its input: r*p
-                cx_step(S[m], mc.p2_re[m], mc.p2_im[m], u);
-                y2 = fma(mc.c_re[m], S[m].re, fma(mc.c_im[m], S[m].im, y2));
+                y1 = fma(kcpr[m], S[m].re, fma(kcpi[m], S[m].im, y1));      // one sample after its input: r*p
+                cx_step(S[m], kp2r[m], kp2i[m], u);
+                y2 = fma(kcr[m], S[m].re, fma(kci[m], S[m].im, y2));
             }
         } else {
             if (mc.baseline) y2 = mc.d0 * u;
 #pragma unroll
             for (int m = 0; m < NM; ++m) {
-                y1 = fma(mc.c_re[m], S[m].re, fma(mc.c_im[m], S[m].im, y1));
-                y2 = fma(mc.cp_re[m], S[m].re, fma(mc.cp_im[m], S[m].im, y2));
-                cx_step(S[m], mc.p2_re[m], mc.p2_im[m], u);
+                y1 = fma(kcr[m], S[m].re, fma(kci[m], S[m].im, y1));
+                y2 = fma(kcpr[m], S[m].re, fma(kcpi[m], S[m].im, y2));
+                cx_step(S[m], kp2r[m], kp2i[m], u);
             }
         }
         // up-mix (reference lpf_hilbert_quad.c:132-153): which of re / im this filter feeds depends on the phase
@@ -352,12 +381,12 @@ scan_apply_kernel(const __grid_constant__ ModalCoef mc, const __grid_constant__ 
             if (mc.baseline) y1 = mc.d0 * u;
 #pragma unroll
             for (int m = 0; m < NM; ++m) {
-                y1 = fma(mc.cp_re[m], S[m].re, fma(mc.cp_im[m], S[m].im, y1));
-                cx_step(S[m], mc.p2_re[m], mc.p2_im[m], u);
+                y1 = fma(kcpr[m], S[m].re, fma(kcpi[m], S[m].im, y1));
+                cx_step(S[m], kp2r[m], kp2i[m], u);
             }
         } else {
 #pragma unroll
-            for (int m = 0; m < NM; ++m) y1 = fma(mc.c_re[m], S[m].re, fma(mc.c_im[m], S[m].im, y1));
+            for (int m = 0; m < NM; ++m) y1 = fma(kcr[m], S[m].re, fma(kci[m], S[m].im, y1));
         }
         int slot;
         double v = mix_up(filt, qa, y1, slot);
