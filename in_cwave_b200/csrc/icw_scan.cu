@@ -86,18 +86,40 @@ void scan_make_coef(int filter_no, bool baseline, double d0, ModalCoef &mc, std:
 // ---------------------------------------------------------------------------------------------
 struct Cx { double re, im; };
 
-// The per-mode filter constants reach the sample loops through shared memory on purpose: as plain
-// kernel parameters ptxas treats them as warp-uniform, parks ~60 doubles in the 63 uniform
-// registers, spills those into vector registers and pays an R2UR per use -- more instructions than
-// the DFMAs they feed.  Values read back from shared memory are ordinary per-thread registers.
+// The fs/4 mixer without sign logic.  A filter's inputs arrive every second frame with alternating
+// sign (reference src/lpf_hilbert_quad.c:129-131: I gets +x,0,-x,0; Q gets 0,-x,0,+x), and the up-mix
+// (:132-153) multiplies the two outputs that follow an input by that same sign and by 2.  Carrying
+// S~ = sign * S instead of S turns   S <- p^2 S + sign*x ; out = sign * 2 * sum(c S)   into
+//     out1 = sum(2cp * S~) ; S~ <- (-p^2) S~ - x ; out2 = sum(-2c * S~)
+// with no sign anywhere.  Negation and doubling are exact in binary floating point and round-to-
+// nearest is symmetric, so every stored value is bit-identical to the signed formulation.
+//
+// The constants reach the sample loops through shared memory on purpose: as plain kernel parameters
+// ptxas treats them as warp-uniform, parks ~60 doubles in the 63 uniform registers, spills those
+// into vector registers and pays an R2UR per use -- more instructions than the DFMAs they feed.
+// Values read back from shared memory are ordinary per-thread registers.
+enum { K_PR = 0, K_PI, K_CR, K_CI, K_CPR, K_CPI };
 __device__ __forceinline__ void stage_constants(double (*k)[SCAN_NMAX], const ModalCoef &mc)
 {
     for (int i = threadIdx.x; i < 6 * SCAN_NMAX; i += blockDim.x) {
         const int a = i / SCAN_NMAX, m = i % SCAN_NMAX;
-        const double *src = a == 0 ? mc.p2_re : a == 1 ? mc.p2_im : a == 2 ? mc.c_re : a == 3 ? mc.c_im : a == 4 ? mc.cp_re : mc.cp_im;
-        k[a][m] = src[m];
+        double v;
+        switch (a) {
+        case K_PR:  v = -mc.p2_re[m]; break;
+        case K_PI:  v = -mc.p2_im[m]; break;
+        case K_CR:  v = -2.0 * mc.c_re[m]; break;
+        case K_CI:  v = -2.0 * mc.c_im[m]; break;
+        case K_CPR: v = 2.0 * mc.cp_re[m]; break;
+        default:    v = 2.0 * mc.cp_im[m]; break;
+        }
+        k[a][m] = v;
     }
     __syncthreads();
+}
+// sign of a filter's input at mixer phase q (q has the filter's parity): -1 for I at 2 and Q at 1
+__device__ __forceinline__ double mixer_sign(int filt, unsigned q)
+{
+    return (((q >> 1) ^ (unsigned)filt) & 1u) ? -1.0 : 1.0;
 }
 __device__ __forceinline__ Cx cx_mul(double ar, double ai, Cx b)
 {
@@ -115,12 +137,12 @@ __device__ __forceinline__ void cx_step(Cx &s, double mr, double mi, double u)
 }
 
 // FMT is a compile-time constant: the format switch folds away inside the sample loops
-template <int FMT>
+template <int FMT, bool FADE>
 __device__ __forceinline__ double scan_sample(const DevChain &ch, const uint8_t *row, int64_t frame, int chan_off,
-                                              int64_t pos0, bool fading)
+                                              int64_t pos0)
 {
     double x = unpack_real(FMT, row + frame * ch.frame_bytes + chan_off, ch.aligned);
-    if (fading) {
+    if (FADE) {
         double g = fade_gain(ch, pos0 + frame);
         if (g >= 0.0) x *= g;
     }
@@ -131,6 +153,78 @@ __device__ __forceinline__ double scan_sample(const DevChain &ch, const uint8_t 
 __device__ __forceinline__ size_t e_index(int stream, int comp, int chan, int64_t chunk, int64_t n_chunks)
 {
     return (((size_t)stream * (4 * SCAN_NMAX) + comp) * 2 + chan) * (size_t)n_chunks + (size_t)chunk;
+}
+
+// does any frame of [pos, pos + n) fall inside the file's fade-in or fade-out ramp?
+__device__ __forceinline__ bool chunk_fades(const DevChain &ch, int64_t pos, int n)
+{
+    if ((ch.n_fade_in | ch.n_fade_out) == 0) return false;
+    return pos < ch.n_fade_in || pos + n > ch.n_samples - ch.n_fade_out;
+}
+
+// pass-1 inner loop: SCAN_L / 2 inputs of one filter from a zero state, sign-free form
+template <int NM, int FMT, bool FADE>
+__device__ __forceinline__ void local_run(Cx (&s)[NM], const double (&kpr)[NM], const double (&kpi)[NM], const DevChain &ch,
+                                          const uint8_t *row, int64_t f0, int chan_off, int64_t pos0)
+{
+    double x = scan_sample<FMT, FADE>(ch, row, f0, chan_off, pos0);
+    for (int k = 0; k < SCAN_L; k += 2) {
+        const int kn = k + 2 < SCAN_L ? k + 2 : k;              // fetched one pair ahead
+        const double xn = scan_sample<FMT, FADE>(ch, row, f0 + kn, chan_off, pos0);
+#pragma unroll
+        for (int m = 0; m < NM; ++m) cx_step(s[m], kpr[m], kpi[m], -x);
+        x = xn;
+    }
+}
+
+// pass-3 inner loop: one filter over one chunk from its true state S~, writing its half of every
+// frame.  The filter's inputs sit at frames off, off + 2, ...; the frame of an input gets
+// sum(2cp S~) (+ 2 d0 x) in its re slot, the frame after it sum(-2c S~') in its im slot.
+template <int NM, int FMT, bool FADE>
+__device__ __forceinline__ int apply_run(Cx (&S)[NM], const double (*kshared)[SCAN_NMAX], bool direct, double d0x2, const DevChain &ch,
+                                         const uint8_t *row, int64_t f0, int off, int len, int chan_off, int64_t pos0,
+                                         double *__restrict__ dst)
+{
+    double kpr[NM], kpi[NM], kcr[NM], kci[NM], kcpr[NM], kcpi[NM];
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+        kpr[m] = kshared[K_PR][m];   kpi[m] = kshared[K_PI][m];
+        kcr[m] = kshared[K_CR][m];   kci[m] = kshared[K_CI][m];
+        kcpr[m] = kshared[K_CPR][m]; kcpi[m] = kshared[K_CPI][m];
+    }
+    if (off) {                                                  // frame 0 follows an input of the previous chunk
+        double y2 = 0.0;
+#pragma unroll
+        for (int m = 0; m < NM; ++m) y2 = fma(kcr[m], S[m].re, fma(kci[m], S[m].im, y2));
+        dst[1] = y2;
+    }
+    int j = off, n_in = 0;
+    double x = j < len ? scan_sample<FMT, FADE>(ch, row, f0 + j, chan_off, pos0) : 0.0;
+    for (; j + 1 < len; j += 2, ++n_in) {
+        const int jn = j + 2 < len ? j + 2 : j;                 // next input of this filter, fetched ahead
+        const double xn = scan_sample<FMT, FADE>(ch, row, f0 + jn, chan_off, pos0);
+        double y1 = direct ? d0x2 * x : 0.0, y2 = 0.0;
+#pragma unroll
+        for (int m = 0; m < NM; ++m) {
+            y1 = fma(kcpr[m], S[m].re, fma(kcpi[m], S[m].im, y1));
+            cx_step(S[m], kpr[m], kpi[m], -x);
+            y2 = fma(kcr[m], S[m].re, fma(kci[m], S[m].im, y2));
+        }
+        dst[(size_t)j * 4] = y1;
+        dst[(size_t)(j + 1) * 4 + 1] = y2;
+        x = xn;
+    }
+    if (j < len) {                                              // an input on the call's very last frame
+        double y1 = direct ? d0x2 * x : 0.0;
+#pragma unroll
+        for (int m = 0; m < NM; ++m) {
+            y1 = fma(kcpr[m], S[m].re, fma(kcpi[m], S[m].im, y1));
+            cx_step(S[m], kpr[m], kpi[m], -x);
+        }
+        dst[(size_t)j * 4] = y1;
+        ++n_in;
+    }
+    return n_in;
 }
 
 // Thread = one recurrence set: (chunk, channel, filter I/Q) with the filter's NM modal states in
@@ -170,21 +264,19 @@ scan_local_kernel(const __grid_constant__ ModalCoef mc, const __grid_constant__ 
     if (have) {
         const uint8_t *row = in + (size_t)stream * in_stride;
         const int chan_off = (ch.n_channels > 1 ? chan : 0) * ch.chan_bytes;
-        const bool fading = (ch.n_fade_in | ch.n_fade_out) != 0;
         const int64_t f0 = chunk * SCAN_L + (is_x ? 0 : 1);     // this filter's first input sample
-        const unsigned qf = (q0 + (is_x ? 0u : 1u)) & 3u;       // its mixer phase (f0 is a multiple of 4)
-        double kp2r[NM], kp2i[NM];
+        const unsigned qf = (q0 + (is_x ? 0u : 1u)) & 3u;       // its mixer phase (chunks start on a multiple of 4)
+        double kpr[NM], kpi[NM];
 #pragma unroll
-        for (int m = 0; m < NM; ++m) { kp2r[m] = kshared[0][m]; kp2i[m] = kshared[1][m]; }
-        double x = scan_sample<FMT>(ch, row, f0, chan_off, st.pos, fading);
-        for (int k = 0; k < SCAN_L; k += 2) {
-            const int kn = k + 2 < SCAN_L ? k + 2 : k;          // fetched one pair ahead
-            const double xn = scan_sample<FMT>(ch, row, f0 + kn, chan_off, st.pos, fading);
-            const double u = mix_down(filt, (qf + (unsigned)k) & 3u, x);
+        for (int m = 0; m < NM; ++m) { kpr[m] = kshared[K_PR][m]; kpi[m] = kshared[K_PI][m]; }
+        if (chunk_fades(ch, st.pos + chunk * SCAN_L, SCAN_L))
+            local_run<NM, FMT, true>(s, kpr, kpi, ch, row, f0, chan_off, st.pos);
+        else
+            local_run<NM, FMT, false>(s, kpr, kpi, ch, row, f0, chan_off, st.pos);
+        // S~ -> S: SCAN_L / 2 inputs is an even count, the sign is the first input's
+        const double sg = mixer_sign(filt, qf);
 #pragma unroll
-            for (int m = 0; m < NM; ++m) cx_step(s[m], kp2r[m], kp2i[m], u);
-            x = xn;
-        }
+        for (int m = 0; m < NM; ++m) { s[m].re *= sg; s[m].im *= sg; }
         // state after the chunk's last sample (a Y-input sample): X has idled one sample since its input
         if (is_x) {
 #pragma unroll
@@ -304,7 +396,6 @@ scan_apply_kernel(const __grid_constant__ ModalCoef mc, const __grid_constant__ 
     const bool is_x = filt == (int)(q0 & 1);
     const uint8_t *row = in + (size_t)stream * in_stride;
     const int chan_off = (ch.n_channels > 1 ? chan : 0) * ch.chan_bytes;
-    const bool fading = (ch.n_fade_in | ch.n_fade_out) != 0;
     const int64_t f0 = chunk * SCAN_L;
     const int len = (int)((n_frames - f0 < SCAN_L) ? n_frames - f0 : SCAN_L);
     const int64_t tile = chunk / SCAN_CH;
@@ -327,77 +418,27 @@ scan_apply_kernel(const __grid_constant__ ModalCoef mc, const __grid_constant__ 
         S[m] = is_x ? cx_mul(mc.pinv_re[m], mc.pinv_im[m], s0) : s0;
     }
 
-    // per-mode constants as ordinary (per-thread) registers for the sample loop
-    double kp2r[NM], kp2i[NM], kcr[NM], kci[NM], kcpr[NM], kcpi[NM];
+    // S -> S~ with the sign of this filter's first input of the chunk (chunks start on a multiple of 4)
+    const int off = is_x ? 0 : 1;
+    const double sg = mixer_sign(filt, (q0 + (unsigned)off) & 3u);
 #pragma unroll
-    for (int m = 0; m < NM; ++m) {
-        kp2r[m] = kshared[0][m]; kp2i[m] = kshared[1][m];
-        kcr[m] = kshared[2][m];  kci[m] = kshared[3][m];
-        kcpr[m] = kshared[4][m]; kcpi[m] = kshared[5][m];
-    }
-    const int off = is_x ? 0 : 1;                               // this filter's input sample inside a pair
-    const int npair = len >> 1;
-    const bool odd = len & 1;
-    const int n_in = is_x ? npair + (odd ? 1 : 0) : npair;      // samples that feed this filter
-    double x = n_in ? scan_sample<FMT>(ch, row, f0 + off, chan_off, st.pos, fading) : 0.0;
-    for (int k2 = 0; k2 < npair; ++k2) {
-        const int k = 2 * k2;
-        const int kn = (k2 + 1 < n_in) ? k + 2 : k;             // next input of this filter, fetched ahead
-        const double xn = scan_sample<FMT>(ch, row, f0 + kn + off, chan_off, st.pos, fading);
-        const unsigned qa = (q0 + (unsigned)k) & 3u, qb = (qa + 1) & 3u;
-        const double u = mix_down(filt, is_x ? qa : qb, x);
-        double y1 = 0.0, y2 = 0.0;
-        if (is_x) {
-            if (mc.baseline) y1 = mc.d0 * u;
-#pragma unroll
-            for (int m = 0; m < NM; ++m) {
-                y1 = fma(kcpr[m], S[m].re, fma(kcpi[m], S[m].im, y1));      // one sample after its input: r*p
-                cx_step(S[m], kp2r[m], kp2i[m], u);
-                y2 = fma(kcr[m], S[m].re, fma(kci[m], S[m].im, y2));
-            }
-        } else {
-            if (mc.baseline) y2 = mc.d0 * u;
-#pragma unroll
-            for (int m = 0; m < NM; ++m) {
-                y1 = fma(kcr[m], S[m].re, fma(kci[m], S[m].im, y1));
-                y2 = fma(kcpr[m], S[m].re, fma(kcpi[m], S[m].im, y2));
-                cx_step(S[m], kp2r[m], kp2i[m], u);
-            }
-        }
-        // up-mix (reference lpf_hilbert_quad.c:132-153): which of re / im this filter feeds depends on the phase
-        int slot;
-        double v = mix_up(filt, qa, y1, slot);
-        dst[(size_t)k * 4 + slot] = v;
-        v = mix_up(filt, qb, y2, slot);
-        dst[(size_t)(k + 1) * 4 + slot] = v;
-        x = xn;
-    }
-    if (odd) {
-        const int k = len - 1;                                  // a first-of-pair sample: feeds X only
-        const unsigned qa = (q0 + (unsigned)k) & 3u;
-        double y1 = 0.0;
-        if (is_x) {
-            const double u = mix_down(filt, qa, x);
-            if (mc.baseline) y1 = mc.d0 * u;
-#pragma unroll
-            for (int m = 0; m < NM; ++m) {
-                y1 = fma(kcpr[m], S[m].re, fma(kcpi[m], S[m].im, y1));
-                cx_step(S[m], kp2r[m], kp2i[m], u);
-            }
-        } else {
-#pragma unroll
-            for (int m = 0; m < NM; ++m) y1 = fma(kcr[m], S[m].re, fma(kci[m], S[m].im, y1));
-        }
-        int slot;
-        double v = mix_up(filt, qa, y1, slot);
-        dst[(size_t)k * 4 + slot] = v;
-    }
+    for (int m = 0; m < NM; ++m) { S[m].re *= sg; S[m].im *= sg; }
+    const bool direct = mc.baseline != 0;
+    const double d0x2 = 2.0 * mc.d0;
+    int n_in;
+    if (chunk_fades(ch, st.pos + f0, len))
+        n_in = apply_run<NM, FMT, true>(S, kshared, direct, d0x2, ch, row, f0, off, len, chan_off, st.pos, dst);
+    else
+        n_in = apply_run<NM, FMT, false>(S, kshared, direct, d0x2, ch, row, f0, off, len, chan_off, st.pos, dst);
     if (chunk == n_chunks - 1) {
-        // state after the call's last sample: a filter that did not take the last input has idled one sample
-        const bool idle = odd ? !is_x : is_x;
+        // state after the call's last sample: undo the sign (it flips with every input), and a filter
+        // whose last input was not the last frame has idled one sample since
+        const double se = (n_in & 1) ? -sg : sg;
+        const bool idle = ((len - 1 - off) & 1) != 0;
 #pragma unroll
         for (int m = 0; m < NM; ++m) {
-            Cx e = idle ? cx_mul(mc.p_re[m], mc.p_im[m], S[m]) : S[m];
+            Cx v; v.re = S[m].re * se; v.im = S[m].im * se;
+            Cx e = idle ? cx_mul(mc.p_re[m], mc.p_im[m], v) : v;
             st.hb[chan][filt][2 * m] = e.re; st.hb[chan][filt][2 * m + 1] = e.im;
         }
     }
