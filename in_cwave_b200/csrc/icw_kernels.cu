@@ -155,82 +155,63 @@ cudaError_t launch_hb_leaf(const HbCoef &coef, int ord, bool kahan, int reject, 
 // MT19937 words (reference src/mersene_twister/mt_jrnd.c:99-134)
 // =============================================================================================
 
-// One WARP regenerates `blocks_per_unit` consecutive 624-word blocks starting from its checkpoint
+// One CTA regenerates `blocks_per_unit` consecutive 624-word blocks starting from its checkpoint
 // (the untempered state array that PRECEDES its first block) and writes the tempered words.
-// The state lives in registers, word i in lane i%32 of register i/32 (20 registers, the last one
-// half used).  new[i] = far ^ twist(old[i], old[i+1]) with far = old[i+397] for i < 227 and
-// new[i-227] after that: walking the registers in order makes every operand either not yet
-// overwritten (old) or already final (new), so the update is in place and needs no barrier --
-// neighbours come from warp shuffles.  32 warps per SM hide each other's latencies.
-template <int R>
-__device__ __forceinline__ void mt_step(uint32_t (&w)[20], int lane)
+// new[k] = far ^ twist(old[k], old[k+1]) with far = old[k+397] for k < 227 and new[k-227] after
+// that: thread t < 227 makes the words t, t+227, t+454 as one dependent chain -- each "far" after
+// the first is the word it made the step before -- so a block needs no barrier inside it, only the
+// one that hands the finished block (double-buffered in shared memory) to the next iteration.
+constexpr int MT_WORDS_THREADS = 256;
+
+__device__ __forceinline__ uint32_t mt_twist(uint32_t a, uint32_t b)
 {
-    const uint32_t u = w[R];
-    // old[i+1]: the next lane's word; lane 31 wraps into the next register's lane 0; the very last
-    // word of the block (i = 623) pairs with the ALREADY NEW word 0 (mt_jrnd.c:121)
-    uint32_t v = __shfl_down_sync(0xffffffffu, w[R], 1);
-    const uint32_t nxt0 = __shfl_sync(0xffffffffu, w[R < 19 ? R + 1 : 0], 0);
-    if (lane == (R < 19 ? 31 : 15)) v = nxt0;
-    uint32_t far;
-    if (R <= 6) {               // i + 397 < 624: old words, registers R+12 / R+13
-        const uint32_t a = __shfl_sync(0xffffffffu, w[R + 12], (lane + 13) & 31);
-        const uint32_t b = __shfl_sync(0xffffffffu, w[R + 13 <= 19 ? R + 13 : 19], (lane - 19) & 31);
-        far = lane < 19 ? a : b;
-    } else if (R == 7) {        // the switch from old[i+397] to new[i-227] falls inside this register
-        const uint32_t a = __shfl_sync(0xffffffffu, w[19], (lane + 13) & 31);
-        const uint32_t b = __shfl_sync(0xffffffffu, w[0], (lane - 3) & 31);
-        far = lane < 3 ? a : b;
-    } else {                    // new words, registers R-7 / R-8
-        const uint32_t a = __shfl_sync(0xffffffffu, w[R - 7], (lane - 3) & 31);
-        const uint32_t b = __shfl_sync(0xffffffffu, w[R - 8], (lane + 29) & 31);
-        far = lane >= 3 ? a : b;
-    }
-    const uint32_t mix = (u & 0x80000000u) | (v & 0x7FFFFFFFu);
-    const uint32_t nw = far ^ (mix >> 1) ^ ((v & 1u) ? 0x9908B0DFu : 0u);
-    if (R < 19 || lane < 16) w[R] = nw;
+    const uint32_t mix = (a & 0x80000000u) | (b & 0x7FFFFFFFu);
+    return (mix >> 1) ^ ((b & 1u) ? 0x9908B0DFu : 0u);
 }
 
-template <int R>
-__device__ __forceinline__ void mt_regen_regs(uint32_t (&w)[20], int lane)
-{
-    if constexpr (R < 20) {
-        mt_step<R>(w, lane);
-        mt_regen_regs<R + 1>(w, lane);
-    }
-}
-
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(MT_WORDS_THREADS, 8)
 mt_words_kernel(const uint32_t *__restrict__ ckpt /* [unit][624] */, int n_units, int blocks_per_unit,
                 int64_t first_word /* stream word index of block 0's first word */,
                 int64_t want_lo, int64_t want_hi, uint32_t *__restrict__ out /* out[w - want_lo] */,
                 int64_t tail_block /* relative index of the block holding the last wanted word */,
                 uint32_t *__restrict__ tail /* [2][624]: state before and after that block, for the next call */)
 {
-    const int lane = threadIdx.x & 31;
-    const int unit = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (unit >= n_units) return;                                // whole warps leave together
-    uint32_t w[20];
-#pragma unroll
-    for (int r = 0; r < 20; ++r) w[r] = (r < 19 || lane < 16) ? ckpt[(size_t)unit * ICW_MT_N + r * 32 + lane] : 0u;
+    __shared__ uint32_t buf[2][ICW_MT_N];
+    const int t = threadIdx.x;
+    const int unit = blockIdx.x;
+    for (int i = t; i < ICW_MT_N; i += MT_WORDS_THREADS) buf[0][i] = ckpt[(size_t)unit * ICW_MT_N + i];
+    __syncthreads();
+    int cur = 0;
     for (int blk = 0; blk < blocks_per_unit; ++blk) {
         const int64_t rel = (int64_t)unit * blocks_per_unit + blk;
         const int64_t w0 = first_word + rel * ICW_MT_N;
-        if (w0 >= want_hi) break;                               // nothing further is wanted
+        if (w0 >= want_hi) break;                               // nothing further is wanted (uniform)
+        const uint32_t *old = buf[cur];
+        uint32_t *nw = buf[cur ^ 1];
         const bool is_tail = rel == tail_block && tail != nullptr;
-        if (is_tail) {
-#pragma unroll
-            for (int r = 0; r < 20; ++r) if (r < 19 || lane < 16) tail[r * 32 + lane] = w[r];
+        if (is_tail)
+            for (int i = t; i < ICW_MT_N; i += MT_WORDS_THREADS) tail[i] = old[i];
+        if (t < 227) {
+            const bool all = w0 >= want_lo && w0 + ICW_MT_N <= want_hi;     // interior block: no range checks
+            uint32_t *o = out + (w0 - want_lo);
+            const uint32_t n0 = old[t + 397] ^ mt_twist(old[t], old[t + 1]);
+            const uint32_t n1 = n0 ^ mt_twist(old[t + 227], old[t + 228]);
+            nw[t] = n0;
+            nw[t + 227] = n1;
+            if (all || (w0 + t >= want_lo && w0 + t < want_hi)) o[t] = mt_temper(n0);
+            if (all || (w0 + t + 227 >= want_lo && w0 + t + 227 < want_hi)) o[t + 227] = mt_temper(n1);
+            if (t < 170) {
+                // the block's last word pairs with the NEW word 0 (mt_jrnd.c:121)
+                const uint32_t nxt = t == 169 ? (old[397] ^ mt_twist(old[0], old[1])) : old[t + 455];
+                const uint32_t n2 = n1 ^ mt_twist(old[t + 454], nxt);
+                nw[t + 454] = n2;
+                if (all || (w0 + t + 454 >= want_lo && w0 + t + 454 < want_hi)) o[t + 454] = mt_temper(n2);
+            }
         }
-        mt_regen_regs<0>(w, lane);
-#pragma unroll
-        for (int r = 0; r < 20; ++r) {
-            const int64_t wi = w0 + r * 32 + lane;
-            if ((r < 19 || lane < 16) && wi >= want_lo && wi < want_hi) out[wi - want_lo] = mt_temper(w[r]);
-        }
-        if (is_tail) {
-#pragma unroll
-            for (int r = 0; r < 20; ++r) if (r < 19 || lane < 16) tail[ICW_MT_N + r * 32 + lane] = w[r];
-        }
+        __syncthreads();
+        if (is_tail)
+            for (int i = t; i < ICW_MT_N; i += MT_WORDS_THREADS) tail[ICW_MT_N + i] = nw[i];
+        cur ^= 1;
     }
 }
 
@@ -238,9 +219,8 @@ cudaError_t launch_mt_words(const uint32_t *ckpt, int n_units, int blocks_per_un
                             int64_t want_lo, int64_t want_hi, uint32_t *out, int64_t tail_block, uint32_t *tail,
                             cudaStream_t s)
 {
-    const int warps = 4;
-    mt_words_kernel<<<(n_units + warps - 1) / warps, warps * 32, 0, s>>>(ckpt, n_units, blocks_per_unit, first_word,
-                                                                          want_lo, want_hi, out, tail_block, tail);
+    mt_words_kernel<<<n_units, MT_WORDS_THREADS, 0, s>>>(ckpt, n_units, blocks_per_unit, first_word,
+                                                         want_lo, want_hi, out, tail_block, tail);
     return cudaGetLastError();
 }
 

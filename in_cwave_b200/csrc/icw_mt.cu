@@ -201,52 +201,111 @@ void mt_apply_host(const MtPoly &g, const uint32_t base[MT_N], uint32_t out[MT_N
 // =============================================================================================
 // device: apply a jump polynomial to many states at once
 // =============================================================================================
-constexpr int JUMP_THREADS = 640;
-constexpr int JUMP_SEQ = 33 * MT_N;                 // 20592 words >= 19936 + 624
-constexpr size_t JUMP_SMEM = (JUMP_SEQ + MT_N) * sizeof(uint32_t);     // 85 KB: two CTAs per SM
+constexpr int JUMP_WARPS = 10;
+constexpr int JUMP_THREADS = JUMP_WARPS * 32;
+constexpr int JUMP_R = 20;                          // output words per lane: 32 x 20 = 640 >= 624
+constexpr int JUMP_BLOCKS = 33;
+constexpr int JUMP_SEQ = JUMP_BLOCKS * MT_N;        // 20592 words >= 19936 + 624
+constexpr int JUMP_SEQ_PAD = 20608;                 // + the window overhang of the unused outputs 624..639
+constexpr size_t JUMP_SMEM = (JUMP_SEQ_PAD + MT_N) * sizeof(uint32_t);  // 85 KB: two CTAs per SM
 
-// states[dst_first + blockIdx.x] = jump(states[dst_first + blockIdx.x - span]) by the polynomial.
-// One thread per output word walks the set bits of the polynomial (the branch is uniform across the
-// CTA); 40 warps per SM keep the shared-memory pipe busy.  gridDim.y CTAs may share one target:
-// each takes a slice of the polynomial and XORs its part into the (pre-zeroed) target.
-__global__ void __launch_bounds__(JUMP_THREADS)
+__device__ __forceinline__ uint32_t mt_twist(uint32_t a, uint32_t b)
+{
+    const uint32_t mix = (a & 0x80000000u) | (b & 0x7FFFFFFFu);
+    return (mix >> 1) ^ ((b & 1u) ? 0x9908B0DFu : 0u);
+}
+
+// One block of the sequence from the one before it, by 227 threads without a barrier inside the
+// block: u[k+624] = u[k+397] ^ twist(u[k], u[k+1]), and u[k+397] of the second and third 227 words
+// is the word this same thread made one step earlier (k+397 = (k-227)+624).
+__device__ __forceinline__ void mt_next_block(const uint32_t *old, uint32_t *nw, int t)
+{
+    if (t < 227) {
+        const uint32_t n0 = old[t + 397] ^ mt_twist(old[t], old[t + 1]);
+        const uint32_t n1 = n0 ^ mt_twist(old[t + 227], old[t + 228]);
+        nw[t] = n0;
+        nw[t + 227] = n1;
+        if (t < 170) {
+            // the block's last word pairs with the NEW word 0 (reference mt_jrnd.c:121)
+            const uint32_t nxt = t == 169 ? (old[397] ^ mt_twist(old[0], old[1])) : old[t + 455];
+            nw[t + 454] = n1 ^ mt_twist(old[t + 454], nxt);
+        }
+    }
+}
+
+// states[dst_first + blockIdx.x] = jump(states[dst_first + blockIdx.x - span]) by the polynomial g:
+// out[m] = XOR over the set bits i of g of seq[i + m], seq = the source state continued for 32 blocks.
+//
+// Register-blocked GF(2) convolution.  A lane owns 20 consecutive outputs, a warp all 640 (624
+// real); the warps of a CTA (and of the gridDim.y CTAs that share a target) take the 32-bit words of
+// g round-robin.  For one word of g the lane loads the 52 sequence words its 20 outputs can touch
+// (13 LDS.128, conflict-free at a lane stride of 20 words) and then works from registers: the
+// bits are taken in pairs, and a pair costs 20 three-input LOP3 at most.  The shared-memory pipe
+// that bounded the word-per-XOR version is out of the picture; the bound is the ALU pipe.
+__global__ void __launch_bounds__(JUMP_THREADS, 2)
 mt_jump_kernel(uint32_t *__restrict__ states, const uint32_t *__restrict__ src_states, int dst_first, int span,
                const uint32_t *__restrict__ poly)
 {
-    extern __shared__ uint32_t sm[];
+    extern __shared__ __align__(16) uint32_t sm[];
     uint32_t *seq = sm;
-    uint32_t *pw = sm + JUMP_SEQ;
+    uint32_t *pw = sm + JUMP_SEQ_PAD;
     const int tid = threadIdx.x;
     const int dst = dst_first + blockIdx.x;
     const uint32_t *src = src_states ? src_states + (size_t)blockIdx.x * MT_N
                                      : states + (size_t)(dst - span) * MT_N;
     for (int i = tid; i < MT_N; i += JUMP_THREADS) { seq[i] = src[i]; pw[i] = poly[i]; }
+    if (tid < JUMP_SEQ_PAD - JUMP_SEQ) seq[JUMP_SEQ + tid] = 0u;
     __syncthreads();
-    // continue the sequence: u[k+624] = u[k+397] ^ twist(u[k], u[k+1]); 227 independent words a step
-    for (int k0 = 0; k0 + MT_N < JUMP_SEQ; k0 += 227) {
-        int k = k0 + tid;
-        if (tid < 227 && k + MT_N < JUMP_SEQ) {
-            uint32_t a = seq[k], b = seq[k + 1];
-            uint32_t mix = (a & 0x80000000u) | (b & 0x7FFFFFFFu);
-            seq[k + MT_N] = seq[k + 397] ^ (mix >> 1) ^ ((b & 1u) ? 0x9908B0DFu : 0u);
-        }
+    for (int b = 1; b < JUMP_BLOCKS; ++b) {
+        mt_next_block(seq + (b - 1) * MT_N, seq + b * MT_N, tid);
         __syncthreads();
     }
-    if (tid < MT_N) {
-        uint32_t acc = 0;
-        const int per = (MT_N + gridDim.y - 1) / gridDim.y;
-        const int w_lo = blockIdx.y * per, w_hi = min(MT_N, w_lo + per);
-        for (int wi = w_lo; wi < w_hi; ++wi) {
-            uint32_t bits = pw[wi];
-            const uint32_t *p = seq + wi * 32 + tid;
-            while (bits) {
-                const int b = __ffs(bits) - 1;
-                bits &= bits - 1;
-                acc ^= p[b];
+
+    const int lane = tid & 31, warp = tid >> 5;
+    uint32_t acc[JUMP_R];
+#pragma unroll
+    for (int r = 0; r < JUMP_R; ++r) acc[r] = 0u;
+    const int stride = JUMP_WARPS * gridDim.y;
+    for (int wi = blockIdx.y * JUMP_WARPS + warp; wi < MT_N; wi += stride) {
+        const uint32_t bits = pw[wi];
+        if (!bits) continue;
+        uint32_t win[32 + JUMP_R];
+        const uint4 *p = reinterpret_cast<const uint4 *>(seq + wi * 32 + lane * JUMP_R);
+#pragma unroll
+        for (int q = 0; q < (32 + JUMP_R) / 4; ++q) {
+            const uint4 v = p[q];
+            win[4 * q] = v.x; win[4 * q + 1] = v.y; win[4 * q + 2] = v.z; win[4 * q + 3] = v.w;
+        }
+#pragma unroll
+        for (int b = 0; b < 32; b += 2) {
+            const uint32_t two = (bits >> b) & 3u;
+            if (two == 3u) {
+#pragma unroll
+                for (int r = 0; r < JUMP_R; ++r) acc[r] ^= win[b + r] ^ win[b + 1 + r];
+            } else if (two == 1u) {
+#pragma unroll
+                for (int r = 0; r < JUMP_R; ++r) acc[r] ^= win[b + r];
+            } else if (two == 2u) {
+#pragma unroll
+                for (int r = 0; r < JUMP_R; ++r) acc[r] ^= win[b + 1 + r];
             }
         }
-        if (gridDim.y == 1) states[(size_t)dst * MT_N + tid] = acc;
-        else atomicXor(&states[(size_t)dst * MT_N + tid], acc);     // the target was zeroed before the launch
+    }
+    // XOR the warps' partial results together (the sequence is no longer needed: reuse its space)
+    __syncthreads();
+    uint32_t *red = sm;                              // [warp][640]
+    {
+        uint4 *q = reinterpret_cast<uint4 *>(red + warp * (32 * JUMP_R) + lane * JUMP_R);
+#pragma unroll
+        for (int r = 0; r < JUMP_R; r += 4) q[r / 4] = make_uint4(acc[r], acc[r + 1], acc[r + 2], acc[r + 3]);
+    }
+    __syncthreads();
+    for (int m = tid; m < MT_N; m += JUMP_THREADS) {
+        uint32_t v = 0u;
+#pragma unroll
+        for (int w = 0; w < JUMP_WARPS; ++w) v ^= red[w * (32 * JUMP_R) + m];
+        if (gridDim.y == 1) states[(size_t)dst * MT_N + m] = v;
+        else atomicXor(&states[(size_t)dst * MT_N + m], v);         // the target was zeroed before the launch
     }
 }
 
@@ -336,9 +395,8 @@ int MtJump::generate(uint32_t seed, uint64_t skip, int64_t n, uint32_t *d_out, i
     const uint64_t b0 = skip / MT_N, b1 = (skip + (uint64_t)n - 1) / MT_N;
     const uint64_t nb = b1 - b0 + 1;
     // blocks per CTA = 2^kb so that every checkpoint distance has a polynomial in the x^(624*2^k) family
-    // one warp per checkpoint (mt_words_kernel): 8 warps per SM for short ranges, up to 32 for long ones
-    uint64_t max_cta = (uint64_t)sm_count * 8;
-    while (max_cta < (uint64_t)sm_count * 16 && nb / max_cta > 256) max_cta *= 2;
+    // one CTA of 256 threads per checkpoint (mt_words_kernel), eight of them resident per SM
+    const uint64_t max_cta = (uint64_t)sm_count * 8;
     int kb = 0;
     while (((nb + (1ull << kb) - 1) >> kb) > max_cta) ++kb;
     const int n_cta = (int)((nb + (1ull << kb) - 1) >> kb);
