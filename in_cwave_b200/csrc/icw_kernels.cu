@@ -161,12 +161,53 @@ cudaError_t launch_hb_leaf(const HbCoef &coef, int ord, bool kahan, int reject, 
 // that: thread t < 227 makes the words t, t+227, t+454 as one dependent chain -- each "far" after
 // the first is the word it made the step before -- so a block needs no barrier inside it, only the
 // one that hands the finished block (double-buffered in shared memory) to the next iteration.
+//
+// The thread keeps its own three words in registers from block to block (they are the old[k] of
+// its next step) and reads only the neighbours' from shared memory.  Shifts go through the
+// multiplier (IMAD / IMAD.HI) so that the logic pipe is left with ~7 LOP3 a word: the kernel is
+// then bound by the HBM write of the words, not by instruction issue.
 constexpr int MT_WORDS_THREADS = 256;
 
+__device__ __forceinline__ uint32_t shr_mul(uint32_t y, int k) { return __umulhi(y, 1u << (32 - k)); }   // y >> k on the fma pipe
 __device__ __forceinline__ uint32_t mt_twist(uint32_t a, uint32_t b)
 {
-    const uint32_t mix = (a & 0x80000000u) | (b & 0x7FFFFFFFu);
-    return (mix >> 1) ^ ((b & 1u) ? 0x9908B0DFu : 0u);
+    uint32_t mix, mag;
+    // (a & 0x80000000) | (b & 0x7FFFFFFF) as one bit-select, (b & 1) * 0x9908B0DF as a real multiply
+    asm("lop3.b32 %0, %1, %2, 0x7FFFFFFF, 0xD8;" : "=r"(mix) : "r"(a), "r"(b));     // c ? b : a  == (a & ~c) | (b & c)
+    asm("mul.lo.u32 %0, %1, 0x9908B0DF;" : "=r"(mag) : "r"(b & 1u));
+    return shr_mul(mix, 1) ^ mag;
+}
+__device__ __forceinline__ uint32_t mt_temper_mul(uint32_t y)      // mt_temper with the shifts as multiplies
+{
+    y ^= shr_mul(y, 11);
+    y ^= (y * 128u) & 0x9D2C5680u;
+    y ^= (y * 32768u) & 0xEFC60000u;
+    y ^= shr_mul(y, 18);
+    return y;
+}
+
+// one block: s0, s1, s2 = this thread's words t, t+227, t+454 of `old` on entry, of `nw` on exit
+template <bool EDGE>
+__device__ __forceinline__ void mt_words_block(const uint32_t *__restrict__ old, uint32_t *__restrict__ nw, int t,
+                                               uint32_t &s0, uint32_t &s1, uint32_t &s2, uint32_t *__restrict__ o,
+                                               int64_t w0, int64_t want_lo, int64_t want_hi)
+{
+    const uint32_t n0 = old[t + 397] ^ mt_twist(s0, old[t + 1]);
+    const uint32_t n1 = n0 ^ mt_twist(s1, old[t + 228]);
+    nw[t] = n0;
+    nw[t + 227] = n1;
+    if (!EDGE || (w0 + t >= want_lo && w0 + t < want_hi)) o[0] = mt_temper_mul(n0);
+    if (!EDGE || (w0 + t + 227 >= want_lo && w0 + t + 227 < want_hi)) o[227] = mt_temper_mul(n1);
+    s0 = n0; s1 = n1;
+    if (t < 170) {
+        // the block's last word pairs with the NEW word 0 (mt_jrnd.c:121)
+        uint32_t nxt = old[t + 455];
+        if (t == 169) nxt = old[397] ^ mt_twist(old[0], old[1]);
+        const uint32_t n2 = n1 ^ mt_twist(s2, nxt);
+        nw[t + 454] = n2;
+        if (!EDGE || (w0 + t + 454 >= want_lo && w0 + t + 454 < want_hi)) o[454] = mt_temper_mul(n2);
+        s2 = n2;
+    }
 }
 
 __global__ void __launch_bounds__(MT_WORDS_THREADS, 8)
@@ -176,37 +217,38 @@ mt_words_kernel(const uint32_t *__restrict__ ckpt /* [unit][624] */, int n_units
                 int64_t tail_block /* relative index of the block holding the last wanted word */,
                 uint32_t *__restrict__ tail /* [2][624]: state before and after that block, for the next call */)
 {
-    __shared__ uint32_t buf[2][ICW_MT_N];
+    __shared__ uint32_t buf[2][ICW_MT_N + 8];       // + slack: thread 169 reads old[624] before overriding it
     const int t = threadIdx.x;
     const int unit = blockIdx.x;
     for (int i = t; i < ICW_MT_N; i += MT_WORDS_THREADS) buf[0][i] = ckpt[(size_t)unit * ICW_MT_N + i];
+    if (t < 8) buf[0][ICW_MT_N + t] = buf[1][ICW_MT_N + t] = 0u;
     __syncthreads();
+    const bool active = t < 227;
+    uint32_t s0 = 0u, s1 = 0u, s2 = 0u;
+    if (active) { s0 = buf[0][t]; s1 = buf[0][t + 227]; if (t < 170) s2 = buf[0][t + 454]; }
+    // block b of this unit holds words [u0 + 624 b, u0 + 624 (b + 1)): which of them are wanted
+    // in full, in part (the two ends of the range, and the block whose states go to `tail`), not at all
+    const int64_t u0 = first_word + (int64_t)unit * blocks_per_unit * ICW_MT_N;
+    int64_t nb64 = (want_hi - u0 + ICW_MT_N - 1) / ICW_MT_N;                    // blocks that start below want_hi
+    const int n_blk = (int)(nb64 < 0 ? 0 : nb64 > blocks_per_unit ? blocks_per_unit : nb64);
+    int64_t lo64 = (want_lo - u0 + ICW_MT_N - 1) / ICW_MT_N;                    // first block that starts at or above want_lo
+    const int e_lo = (int)(lo64 < 0 ? 0 : lo64 > n_blk ? n_blk : lo64);
+    int64_t hi64 = (want_hi - u0) / ICW_MT_N;                                   // first block that ends above want_hi
+    int e_hi = (int)(hi64 < 0 ? 0 : hi64 > n_blk ? n_blk : hi64);
+    const int64_t tl = tail ? tail_block - (int64_t)unit * blocks_per_unit : -1;
+    const int tail_blk = (tl >= 0 && tl < n_blk) ? (int)tl : -1;
+    if (tail_blk >= 0 && tail_blk < e_hi) e_hi = tail_blk;
+    uint32_t *o = out + (u0 - want_lo) + t;
     int cur = 0;
-    for (int blk = 0; blk < blocks_per_unit; ++blk) {
-        const int64_t rel = (int64_t)unit * blocks_per_unit + blk;
-        const int64_t w0 = first_word + rel * ICW_MT_N;
-        if (w0 >= want_hi) break;                               // nothing further is wanted (uniform)
+    for (int blk = 0; blk < n_blk; ++blk, o += ICW_MT_N) {
         const uint32_t *old = buf[cur];
         uint32_t *nw = buf[cur ^ 1];
-        const bool is_tail = rel == tail_block && tail != nullptr;
+        const bool is_tail = blk == tail_blk;
         if (is_tail)
             for (int i = t; i < ICW_MT_N; i += MT_WORDS_THREADS) tail[i] = old[i];
-        if (t < 227) {
-            const bool all = w0 >= want_lo && w0 + ICW_MT_N <= want_hi;     // interior block: no range checks
-            uint32_t *o = out + (w0 - want_lo);
-            const uint32_t n0 = old[t + 397] ^ mt_twist(old[t], old[t + 1]);
-            const uint32_t n1 = n0 ^ mt_twist(old[t + 227], old[t + 228]);
-            nw[t] = n0;
-            nw[t + 227] = n1;
-            if (all || (w0 + t >= want_lo && w0 + t < want_hi)) o[t] = mt_temper(n0);
-            if (all || (w0 + t + 227 >= want_lo && w0 + t + 227 < want_hi)) o[t + 227] = mt_temper(n1);
-            if (t < 170) {
-                // the block's last word pairs with the NEW word 0 (mt_jrnd.c:121)
-                const uint32_t nxt = t == 169 ? (old[397] ^ mt_twist(old[0], old[1])) : old[t + 455];
-                const uint32_t n2 = n1 ^ mt_twist(old[t + 454], nxt);
-                nw[t + 454] = n2;
-                if (all || (w0 + t + 454 >= want_lo && w0 + t + 454 < want_hi)) o[t + 454] = mt_temper(n2);
-            }
+        if (active) {
+            if (blk < e_lo || blk >= e_hi) mt_words_block<true>(old, nw, t, s0, s1, s2, o, u0 + (int64_t)blk * ICW_MT_N, want_lo, want_hi);
+            else                           mt_words_block<false>(old, nw, t, s0, s1, s2, o, 0, 0, 0);
         }
         __syncthreads();
         if (is_tail)
