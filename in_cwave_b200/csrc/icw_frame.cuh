@@ -15,25 +15,34 @@ __device__ __forceinline__ double dsopen2(uint2 w, unsigned &redraws)
     return v;
 }
 
-// the dither value of sample i (reference src/sound_render.c:711-751)
-__device__ __forceinline__ double dither_sample(const DevRender &r, const uint32_t *w, int64_t i, double prev_tr,
+// The words of sample i for the 2- and 4-word dither types, fetched at the top of the frame so that
+// the oscillator and the DSP list run under the load's latency (Gauss reads its 24 words late).
+__device__ __forceinline__ uint4 dither_fetch(int wps, const uint32_t *w, int64_t i)
+{
+    uint4 a = make_uint4(0u, 0u, 0u, 0u);
+    if (wps == 4) {
+        a = *reinterpret_cast<const uint4 *>(w + (size_t)i * 4);
+    } else if (wps == 2) {
+        const uint2 b = *reinterpret_cast<const uint2 *>(w + (size_t)i * 2);
+        a.x = b.x; a.y = b.y;
+    }
+    return a;
+}
+
+// the dither value of sample i (reference src/sound_render.c:711-751); a = dither_fetch() of the sample
+__device__ __forceinline__ double dither_sample(const DevRender &r, uint4 a, const uint32_t *w, int64_t i, double prev_tr,
                                                 unsigned &redraws)
 {
     switch (r.render_type) {
-    case ICW_RENDER_RPDF: {
-        const uint2 a = *reinterpret_cast<const uint2 *>(w + (size_t)i * 2);
-        return div_const(dsopen2(a, redraws), ICW_SQRT2, ICW_RSQRT2);
-    }
+    case ICW_RENDER_RPDF:
+        return div_const(dsopen2(make_uint2(a.x, a.y), redraws), ICW_SQRT2, ICW_RSQRT2);
     case ICW_RENDER_TPDF: {
-        const uint4 a = *reinterpret_cast<const uint4 *>(w + (size_t)i * 4);
         double v = dsopen2(make_uint2(a.x, a.y), redraws);
         v += dsopen2(make_uint2(a.z, a.w), redraws);
         return v * 0.5;                                         // /2.0, exact
     }
-    case ICW_RENDER_STPDF: {
-        const uint2 a = *reinterpret_cast<const uint2 *>(w + (size_t)i * 2);
-        return (dsopen2(a, redraws) - prev_tr) * 0.5;
-    }
+    case ICW_RENDER_STPDF:
+        return (dsopen2(make_uint2(a.x, a.y), redraws) - prev_tr) * 0.5;
     case ICW_RENDER_GAUSS: {
         const uint4 *q = reinterpret_cast<const uint4 *>(w + (size_t)i * 24);
         double v = 0.0;
@@ -92,13 +101,17 @@ struct FrameIO {
     double *tap_bus, *tap_lr;       // optional test taps for this stream ([frame][27][4], [frame][2])
 };
 
-// frame i of the call; v = (L.re, L.im, R.re, R.im) on plug 0; bus = thread-private plug values
+// frame i of the call; v = (L.re, L.im, R.re, R.im) on plug 0; bus = thread-private plug values.
+// EARLY_DITHER: fetch the dither words before the DSP list (8 more live registers) or at their use.
+template <bool EARLY_DITHER = true>
 __device__ __forceinline__ void finish_frame(const DevChain &ch, DevStream &st, int64_t i, int64_t n_frames,
                                              const double v[4], double (*bus)[4], const FrameIO &io, FrameAcc &acc,
                                              OscCounter &osc)
 {
     const DevRender &rq = ch.render;
     const int wps = rq.words_per_sample;
+    uint4 wl, wr;
+    if (EARLY_DITHER) { wl = dither_fetch(wps, io.mtw_l, i); wr = dither_fetch(wps, io.mtw_r, i); }
     double omega = norm_omega(ch, osc.at(ch, i));
     double lo, ro;
     if (ch.shape != ICW_SHAPE_GENERIC) {
@@ -125,8 +138,9 @@ __device__ __forceinline__ void finish_frame(const DevChain &ch, DevStream &st, 
             if (i == 0) { prev_l = st.prev_rnd[0]; prev_r = st.prev_rnd[1]; }
             else { prev_l = first_draw(io.mtw_l, i - 1); prev_r = first_draw(io.mtw_r, i - 1); }
         }
-        dl = dither_sample(rq, io.mtw_l, i, prev_l, acc.redraws);
-        dr = dither_sample(rq, io.mtw_r, i, prev_r, acc.redraws);
+        if (!EARLY_DITHER) { wl = dither_fetch(wps, io.mtw_l, i); wr = dither_fetch(wps, io.mtw_r, i); }
+        dl = dither_sample(rq, wl, io.mtw_l, i, prev_l, acc.redraws);
+        dr = dither_sample(rq, wr, io.mtw_r, i, prev_r, acc.redraws);
     }
     RenderOut a = render_one(rq, lo, dl);
     RenderOut b = render_one(rq, ro, dr);
