@@ -273,7 +273,7 @@ cudaError_t launch_mt_words(const uint32_t *ckpt, int n_units, int blocks_per_un
 // one thread per frame, grid-stride inside a stream (blockIdx.y = stream).
 // src: raw file bytes (complex formats) or the analytic scratch written by hb_exact_kernel
 // (from_analytic: 4 doubles per frame, no fade -- it was applied before the Hilbert converter).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 chain_kernel(const __grid_constant__ DevChain ch, DevStream *__restrict__ streams, int64_t n_frames,
              const uint8_t *__restrict__ in, size_t in_stride, int from_analytic,
              const uint32_t *__restrict__ mtw_l, const uint32_t *__restrict__ mtw_r, size_t mt_stream_stride,
