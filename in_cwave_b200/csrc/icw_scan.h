@@ -25,6 +25,7 @@ struct ModalCoef {
     double pl_re[SCAN_NMAX], pl_im[SCAN_NMAX];      // pole^L
     double pt_re[SCAN_NMAX], pt_im[SCAN_NMAX];      // pole^(L*CH)
     double plp_re[16][SCAN_NMAX], plp_im[16][SCAN_NMAX];   // pole^(L*(j+1)), j = 0..15: in-CTA carry scan
+    double k[6][SCAN_NMAX];                         // sample-loop constants of the sign-free form: -p^2 (re, im), -2c, 2cp
 };
 
 void scan_make_coef(int filter_no, bool baseline, double d0, ModalCoef &mc, std::vector<double> &pw_table);

@@ -51,6 +51,32 @@ __global__ void thr_kernel(double *out, long long *cyc, int iters, double a, dou
     if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
 }
 
+// DFMA with three distinct VECTOR-register operands (the modal recurrences: state x constant + state):
+// x[k] = fma(y[k], z[k], x[k]) then rotate roles so nothing is loop-invariant for the compiler to fold.
+template <int ILP>
+__global__ void thr3_kernel(double *out, long long *cyc, int iters, const double *seed)
+{
+    double x[ILP], y[ILP], z[ILP];
+#pragma unroll
+    for (int k = 0; k < ILP; ++k) { x[k] = seed[threadIdx.x + k]; y[k] = seed[threadIdx.x + k + 64]; z[k] = seed[threadIdx.x + k + 128]; }
+    __syncthreads();
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+#pragma unroll
+            for (int k = 0; k < ILP; ++k) x[k] = __fma_rn(y[k], z[k], x[k]);
+        }
+    }
+    __syncthreads();
+    long long t1 = clock64();
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < ILP; ++k) s += x[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+}
+
 int main()
 {
     double *out; long long *cyc, h;
@@ -80,6 +106,18 @@ int main()
             double ops = (double)iters * 16 * 4 * warps * 32;
             printf("%s throughput, %2d warps/SM x ILP4: %.2f lanes/clk/SM (%.1f cycles per warp-instruction per SMSP)\n",
                    names[op], warps, ops / h, (double)h / ((double)iters * 16 * 4 * ((warps + 3) / 4)));
+        }
+    }
+    {
+        double *seed; cudaMalloc(&seed, 4096 * 8); cudaMemset(seed, 0, 4096 * 8);
+        for (int warps = 1; warps <= 32; warps *= 2) {
+            for (int rep = 0; rep < 2; ++rep) {
+                thr3_kernel<8><<<p.multiProcessorCount, warps * 32>>>(out, cyc, iters, seed);
+                cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+            }
+            double ops = (double)iters * 16 * 8 * warps * 32;
+            printf("DFMA 3 vector operands, %2d warps/SM x ILP8: %.2f lanes/clk/SM (%.1f cycles per warp-instruction per SMSP)\n",
+                   warps, ops / h, (double)h / ((double)iters * 16 * 8 * ((warps + 3) / 4)));
         }
     }
     // wall-clock rate for the whole chip (DADD, 16 warps/SM, ILP4)
