@@ -219,9 +219,10 @@ __device__ __forceinline__ int apply_run(Cx (&S)[NM], const ModalCoef &mc, const
     }
     int j = off, n_in = 0;
     double x = j < len ? scan_sample<FMT, FADE>(ch, row, f0 + j, chan_off, pos0) : 0.0;
+    double xn = j + 2 < len ? scan_sample<FMT, FADE>(ch, row, f0 + j + 2, chan_off, pos0) : x;
     for (; j + 1 < len; j += 2, ++n_in) {
-        const int jn = j + 2 < len ? j + 2 : j;                 // next input of this filter, fetched ahead
-        const double xn = scan_sample<FMT, FADE>(ch, row, f0 + jn, chan_off, pos0);
+        const int jn = j + 4 < len ? j + 4 : j;                 // this filter's input after next, fetched two steps ahead
+        const double xnn = scan_sample<FMT, FADE>(ch, row, f0 + jn, chan_off, pos0);
         scan_prefetch<FMT>(ch, row, f0 + jn, chan_off, row_last);
         double y1 = direct ? d0x2 * x : 0.0, y2 = 0.0;
 #pragma unroll
@@ -232,7 +233,7 @@ __device__ __forceinline__ int apply_run(Cx (&S)[NM], const ModalCoef &mc, const
         }
         dst[(size_t)j * 4] = y1;
         dst[(size_t)(j + 1) * 4 + 1] = y2;
-        x = xn;
+        x = xn; xn = xnn;
     }
     if (j < len) {                                              // an input on the call's very last frame
         double y1 = direct ? d0x2 * x : 0.0;
