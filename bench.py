@@ -10,7 +10,8 @@ the whole per-GPU workload; value = frames of all ranks / max-over-ranks device 
 
   value      stereo Mframes/s with inputs resident in HBM (CUDA events around the timed steps)
   e2e        the same through the C ABI's host entry point: pinned host buffers, H2D + kernels + D2H
-  roofline   HBM roofline of the dominant kernel: algorithmic bytes / its event-timed duration
+  roofline   HBM roofline of the dominant kernel (per-kernel CUDA events on the launching stream):
+             algorithmic bytes of the path per launch / that kernel's average launch duration
   cpu_baseline  the reference's own C code (oracle/_ref) or our port of it, timed on host cores
 
 `--impl reference` times the reference's CPU implementation alone, on all host threads.
@@ -91,7 +92,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -237,7 +238,7 @@ class _NoDist:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default=os.environ.get("ICW_WORKLOAD", "c2"))
     ap.add_argument("--impl", default="ours")
@@ -351,13 +352,17 @@ def main():
         t = json.loads(tfile.read_text()).get(wl["name"], {}).get(dom)
         if t:
             traffic = t["dram_bytes_per_frame"] * units_per_launch
-    fp64_ops = {"c2": 225 + 150, "c5": 225 + 110, "c1": 225 + 110, "c4": 1124 + 110, "c3": 300}.get(wl["name"], 0)
+    # FP64 thread-operations per frame (counted from the SASS of the sample loops) and the
+    # measured issue rate of the FP64 pipe (tools/fp64_probe.cu): 64 lanes/clk/SM when an instruction reads two
+    # vector registers (the third operand uniform), 42.7 when it reads three -- most of the modal DFMAs do
+    fp64_ops = {"c2": 164 + 82 + 105, "c5": 164 + 82 + 70, "c1": 164 + 82 + 70, "c4": 1124 + 70, "c3": 300}.get(wl["name"], 0)
     roofline = dict(bound="hbm", kernel=dom, achieved=achieved, peak=pk["hbm_gbs"], unit="GB/s",
                     frac=achieved / pk["hbm_gbs"], traffic=traffic, peak_source=pk["source"],
                     algorithmic_bytes_per_frame=wl["bytes_per_frame"], frames_per_launch=units_per_launch,
                     avg_launch_ms=dom_ms,
                     kernel_share={k: v["ms"] / max(1e-9, sum(x["ms"] for x in prof.values())) for k, v in prof.items()},
-                    binding_bound=dict(kind="fp64 pipe", peak_tops=18.55, peak_source="tools/fp64_probe.cu on this pool's B200",
+                    binding_bound=dict(kind="fp64 pipe / instruction issue (not HBM)", peak_tops=18.55, peak_tops_3_vector_operands=12.37,
+                                       peak_source="tools/fp64_probe.cu on this pool's B200 (profiles/r1_fp64_probe_b200.txt)",
                                        approx_ops_per_frame=fp64_ops,
                                        whole_step_frac=(frames_step / world) * fp64_ops / (ms_step * 1e-3) / 18.55e12))
 

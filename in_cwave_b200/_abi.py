@@ -66,11 +66,11 @@ class Stats(C.Structure):
     ]
 
 
-K_NAMES = ["hilbert", "chain", "mt", "misc"]
+K_NAMES = ["hilbert", "chain", "mt", "misc", "scan_local", "scan_apply"]
 
 
 class Profile(C.Structure):
-    _fields_ = [("ms", C.c_double * 4), ("launches", C.c_uint64 * 4)]
+    _fields_ = [("ms", C.c_double * len(K_NAMES)), ("launches", C.c_uint64 * len(K_NAMES))]
 
 
 # every symbol include/icw_b200.h declares; tests/test_abi.py checks the library exports them all

@@ -102,8 +102,8 @@ struct icw_session {
     std::vector<cudaEvent_t> ev_pool;
     struct Span { int k; cudaEvent_t a, b; };
     std::vector<Span> spans;
-    double prof_ms[ICW_K_COUNT] = { 0, 0, 0, 0 };
-    uint64_t prof_n[ICW_K_COUNT] = { 0, 0, 0, 0 };
+    double prof_ms[ICW_K_COUNT] = {};
+    uint64_t prof_n[ICW_K_COUNT] = {};
 };
 
 // RAII: records an event pair around a group of launches of one kernel class
@@ -679,7 +679,6 @@ static int process_group(icw_session *s, int64_t n_frames, const uint8_t *d_in, 
             const size_t per = (size_t)n_frames * 4 * sizeof(double);
             rc = e->analytic.reserve(per * (size_t)K);
             if (rc) return rc;
-            ProfSpan ps(s, st, ICW_K_HILBERT);
             if (scan) {
                 // time-parallel modal scan (icw_scan.cu): chunk end states -> carries -> apply
                 icw_engine::ScanPlan *plp;
@@ -689,11 +688,23 @@ static int process_group(icw_session *s, int64_t n_frames, const uint8_t *d_in, 
                 rc = e->scan_scratch.reserve(scan_scratch_doubles(K, n_frames) * sizeof(double));
                 if (rc) return rc;
                 int nl = 0;
+                // profiling: one span for passes 1 + 2, one for pass 3 (two events recorded between them)
+                cudaEvent_t a = nullptr, m0 = nullptr, m1 = nullptr, b = nullptr;
+                if (s->profiling) {
+                    a = ProfSpan::take(s); m0 = ProfSpan::take(s); m1 = ProfSpan::take(s); b = ProfSpan::take(s);
+                    cudaEventRecord(a, st);
+                }
                 CK(launch_hb_scan(pl.mc, ch, s->d_streams, K, n_frames, src, in_stride, pl.d_pw,
-                                  (double *)e->scan_scratch.p, (double *)e->analytic.p, st, &nl));
+                                  (double *)e->scan_scratch.p, (double *)e->analytic.p, st, &nl, m0, m1));
+                if (a) {
+                    cudaEventRecord(b, st);
+                    s->spans.push_back({ ICW_K_SCAN_LOCAL, a, m0 });
+                    s->spans.push_back({ ICW_K_SCAN_APPLY, m1, b });
+                }
                 s->launches += nl;
             } else {
                 // unfused exact pair (ICW_UNFUSED=1): recurrences -> analytic scratch -> pointwise kernel
+                ProfSpan ps(s, st, ICW_K_HILBERT);
                 CK(launch_hb_exact(s->coef, ch, s->d_streams, K, n_frames, src, in_stride, (double *)e->analytic.p, st));
                 s->launches++;
             }
@@ -922,7 +933,7 @@ extern "C" int icw_session_profile_read(icw_session *s, icw_profile *out, int re
 
 extern "C" const char *icw_kernel_class_name(int k)
 {
-    static const char *names[ICW_K_COUNT] = { "hilbert", "chain", "mt", "misc" };
+    static const char *names[ICW_K_COUNT] = { "hilbert", "chain", "mt", "misc", "scan_local", "scan_apply" };
     return (k >= 0 && k < ICW_K_COUNT) ? names[k] : "?";
 }
 

@@ -482,7 +482,8 @@ size_t scan_scratch_doubles(int n_streams, int64_t n_frames)
 template <int NM, int FMT>
 static cudaError_t scan_launch_nf(const ModalCoef &mc, const DevChain &ch, DevStream *streams, int n_streams,
                                   int64_t n_frames, const uint8_t *in, size_t in_stride, const double *pw,
-                                  double *scratch, double *analytic, cudaStream_t s, int *launches)
+                                  double *scratch, double *analytic, cudaStream_t s, int *launches,
+                                  cudaEvent_t mid_end, cudaEvent_t mid_start)
 {
     const int64_t n_chunks = (n_frames + SCAN_L - 1) / SCAN_L;
     const int64_t n_tiles = (n_chunks + SCAN_CH - 1) / SCAN_CH;
@@ -494,6 +495,7 @@ static cudaError_t scan_launch_nf(const ModalCoef &mc, const DevChain &ch, DevSt
     const int64_t items = n_tiles * 2 * 2 * mc.nm;
     const unsigned tgrid = (unsigned)((items + 127) / 128);
     scan_tile_carry_kernel<<<dim3(tgrid, n_streams), 128, 0, s>>>(mc, streams, n_tiles, Tend, Tin);
+    if (mid_end) { cudaEventRecord(mid_end, s); cudaEventRecord(mid_start, s); }
     const unsigned agrid = (unsigned)((n_chunks + 63) / 64);
     scan_apply_kernel<NM, FMT><<<dim3(agrid, n_streams), 256, 0, s>>>(mc, ch, streams, n_frames, n_chunks, n_tiles, in, in_stride,
                                                                     E, Tin, pw, analytic);
@@ -504,9 +506,10 @@ static cudaError_t scan_launch_nf(const ModalCoef &mc, const DevChain &ch, DevSt
 template <int NM>
 static cudaError_t scan_launch_nm(const ModalCoef &mc, const DevChain &ch, DevStream *streams, int n_streams,
                                   int64_t n_frames, const uint8_t *in, size_t in_stride, const double *pw,
-                                  double *scratch, double *analytic, cudaStream_t s, int *launches)
+                                  double *scratch, double *analytic, cudaStream_t s, int *launches,
+                                  cudaEvent_t mid_end, cudaEvent_t mid_start)
 {
-#define ICW_SCAN_FMT(F) case F: return scan_launch_nf<NM, F>(mc, ch, streams, n_streams, n_frames, in, in_stride, pw, scratch, analytic, s, launches)
+#define ICW_SCAN_FMT(F) case F: return scan_launch_nf<NM, F>(mc, ch, streams, n_streams, n_frames, in, in_stride, pw, scratch, analytic, s, launches, mid_end, mid_start)
     switch (ch.fmt) {
         ICW_SCAN_FMT(ICW_FMT_WAV_U8);
         ICW_SCAN_FMT(ICW_FMT_WAV_I16);
@@ -521,12 +524,12 @@ static cudaError_t scan_launch_nm(const ModalCoef &mc, const DevChain &ch, DevSt
 
 cudaError_t launch_hb_scan(const ModalCoef &mc, const DevChain &ch, DevStream *streams, int n_streams,
                            int64_t n_frames, const uint8_t *in, size_t in_stride, const double *pw,
-                           double *scratch, double *analytic, cudaStream_t s, int *launches)
+                           double *scratch, double *analytic, cudaStream_t s, int *launches, cudaEvent_t mid_end, cudaEvent_t mid_start)
 {
     switch (mc.nm) {
-    case 8:  return scan_launch_nm<8>(mc, ch, streams, n_streams, n_frames, in, in_stride, pw, scratch, analytic, s, launches);
-    case 9:  return scan_launch_nm<9>(mc, ch, streams, n_streams, n_frames, in, in_stride, pw, scratch, analytic, s, launches);
-    case 10: return scan_launch_nm<10>(mc, ch, streams, n_streams, n_frames, in, in_stride, pw, scratch, analytic, s, launches);
+    case 8:  return scan_launch_nm<8>(mc, ch, streams, n_streams, n_frames, in, in_stride, pw, scratch, analytic, s, launches, mid_end, mid_start);
+    case 9:  return scan_launch_nm<9>(mc, ch, streams, n_streams, n_frames, in, in_stride, pw, scratch, analytic, s, launches, mid_end, mid_start);
+    case 10: return scan_launch_nm<10>(mc, ch, streams, n_streams, n_frames, in, in_stride, pw, scratch, analytic, s, launches, mid_end, mid_start);
     default: return cudaErrorInvalidValue;
     }
 }

@@ -32,6 +32,7 @@ void scan_make_coef(int filter_no, bool baseline, double d0, ModalCoef &mc, std:
 size_t scan_scratch_doubles(int n_streams, int64_t n_frames);
 cudaError_t launch_hb_scan(const ModalCoef &mc, const DevChain &ch, DevStream *streams, int n_streams,
                            int64_t n_frames, const uint8_t *in, size_t in_stride, const double *pw,
-                           double *scratch, double *analytic, cudaStream_t s, int *launches);
+                           double *scratch, double *analytic, cudaStream_t s, int *launches,
+                           cudaEvent_t mid_end = nullptr, cudaEvent_t mid_start = nullptr);   // recorded between pass 2 and pass 3
 
 }  // namespace icw

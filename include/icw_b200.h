@@ -187,7 +187,9 @@ int  icw_hilbert_device(icw_engine *e, int filter_no, int is_kahan, int is_rejec
 int  icw_mt_words_device(icw_engine *e, uint32_t seed, uint64_t skip, int64_t n, uint32_t *d_out);
 
 /* ---- measurement: per-kernel device time from CUDA events on the launching stream ---------- */
-enum { ICW_K_HILBERT = 0, ICW_K_CHAIN = 1, ICW_K_MT = 2, ICW_K_MISC = 3, ICW_K_COUNT = 4 };
+/* HILBERT: the exact recurrences (fused with the chain unless ICW_UNFUSED); SCAN_LOCAL / SCAN_APPLY: passes 1+2 and
+ * pass 3 of the time-parallel converter; CHAIN: the pointwise kernel; MT: dither word generation incl. jump-ahead */
+enum { ICW_K_HILBERT = 0, ICW_K_CHAIN = 1, ICW_K_MT = 2, ICW_K_MISC = 3, ICW_K_SCAN_LOCAL = 4, ICW_K_SCAN_APPLY = 5, ICW_K_COUNT = 6 };
 typedef struct icw_profile {
     double   ms[ICW_K_COUNT];       /* summed device time per kernel class since the last reset */
     uint64_t launches[ICW_K_COUNT];
