@@ -175,6 +175,24 @@ def host_cores() -> int:
         return os.cpu_count() or 1
 
 
+def bind_near_gpu(index: int) -> str:
+    """Multi-GPU runs: keep this rank's threads (and so its pinned staging pages, first touch) on the
+    CPUs next to its GPU.  Returns a note for the JSON line; never fatal."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} CPUs local to GPU {index}"
+    except Exception as ex:
+        return f"not bound ({type(ex).__name__})"
+    return "not bound"
+
+
 def cpu_model() -> str:
     try:
         for ln in open("/proc/cpuinfo"):
@@ -272,6 +290,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
+    numa_note = bind_near_gpu(local) if world > 1 else "single rank: not bound"
 
     spec, K, N, chunk = wl["spec"], wl["streams"], wl["frames"], wl["chunk"]
     fb, ob = S.frame_bytes(spec), S.out_frame_bytes(spec)
@@ -394,7 +413,8 @@ def main():
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             e2e = dict(value=frames_step / float(tt.item()) / 1e6, unit=UNIT, h2d_bytes_per_step=K * N * fb,
                        d2h_bytes_per_step=K * N * ob, ms_per_step=float(tt.item()) * 1e3, steps=reps,
-                       how="icw_session_process_host on pinned host buffers; H2D + kernels + D2H inside the timed region")
+                       how="icw_session_process_host on pinned host buffers; H2D + kernels + D2H inside the timed region",
+                       host_affinity=numa_note)
             del h_in, h_out
         except RuntimeError as ex:
             e2e = dict(value=None, unit=UNIT, error=str(ex)[:200])
