@@ -66,12 +66,12 @@ PLUGIN = PKG / "libicw_plugin.so"
 def build_plugin() -> Path:
     """The host C layer (reference entry points over the C ABI): plain gcc, links libicw_b200.so."""
     cmd = ["gcc", "-std=c99", "-O2", "-Wall", "-fPIC", "-shared", "-I", str(PKG.parent / "include"),
-           "-o", str(PLUGIN), str(PKG / "host" / "icw_plugin.c"), "-L", str(PKG), "-licw_b200",
+           "-o", str(PLUGIN), str(PKG / "host" / "icw_plugin.c"), str(PKG / "host" / "icw_config.c"), "-L", str(PKG), "-licw_b200",
            "-Wl,-rpath,$ORIGIN"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("gcc failed on host/icw_plugin.c")
+        raise RuntimeError("gcc failed on host/icw_plugin.c / icw_config.c")
     return PLUGIN
 
 

@@ -10,7 +10,8 @@ from . import _abi, spec as _spec
 
 PLUGIN_PATH = Path(__file__).resolve().parent / "libicw_plugin.so"
 EXPORTS = ["winampGetExtendedRead_open", "winampGetExtendedRead_getData", "winampGetExtendedRead_setTime",
-           "winampGetExtendedRead_close", "icwp_configure", "icwp_reset", "icwp_stats", "icwp_probe"]
+           "winampGetExtendedRead_close", "icwp_configure", "icwp_reset", "icwp_stats", "icwp_probe",
+           "icwp_load_config", "icwp_save_config"]
 
 
 class Options(C.Structure):
@@ -47,6 +48,8 @@ def lib() -> C.CDLL:
         L.icwp_reset.restype = None
         L.icwp_stats.argtypes = [C.POINTER(_abi.Stats)]
         L.icwp_probe.argtypes = [C.c_char_p, C.POINTER(Options), C.POINTER(FileInfo)]
+        L.icwp_load_config.argtypes = [C.c_char_p, C.POINTER(_abi.ChainSpecC), C.POINTER(Options)]
+        L.icwp_save_config.argtypes = [C.c_char_p, C.POINTER(_abi.ChainSpecC), C.POINTER(Options)]
         _lib = L
     return _lib
 
@@ -55,6 +58,23 @@ def configure(spec: dict | None, **opt) -> None:
     o = Options(**opt)
     rc = lib().icwp_configure(_spec.to_c(spec) if spec is not None else None, C.byref(o))
     _abi.check(rc)
+
+
+def _node_tuple(n):
+    return (n.mode, n.inputs_mask, n.xch_mode, n.l_iq_invert, n.r_iq_invert, n.l_gain, n.r_gain,
+            n.n_out if n.mode != 0 else 0, n.l_tout, n.r_tout, n.l_on, n.r_on, tuple(n.l_p), tuple(n.r_p))
+
+
+def load_config(path: str):
+    """The reference's config file -> (accepted, ChainSpecC, Options, nodes in execution order as tuples)."""
+    sp, o = _abi.ChainSpecC(), Options()
+    ok = lib().icwp_load_config(str(path).encode(), C.byref(sp), C.byref(o))
+    return bool(ok), sp, o, [_node_tuple(sp.nodes[i]) for i in range(sp.n_nodes)]
+
+
+def save_config(path: str, spec: dict, **opt) -> bool:
+    o = Options(**opt)
+    return bool(lib().icwp_save_config(str(path).encode(), _spec.to_c(spec), C.byref(o)))
 
 
 def probe(path: str, **opt):

@@ -19,7 +19,7 @@
  * Hosts ask for 4-64 KB at a time (src/transcode.c:94); this layer reads ahead in large blocks and
  * runs them through libicw_b200.so, so a GPU launch is not paid per host call.
  *
- * Configuration replaces the reference's config file and GUI (both out of scope): icwp_configure()
+ * Configuration: icwp_load_config() reads the reference's own config file format; icwp_configure()
  * takes the chain description (filter, summation, DSP list, render settings; the per-file fields
  * fmt / n_channels / sample_rate / n_samples / fades are overwritten at open) plus the three
  * reader options the reference keeps in its config.
@@ -67,6 +67,17 @@ typedef struct icwp_fileinfo {
     int64_t  n_fade_in, n_fade_out;
 } icwp_fileinfo;
 int  icwp_probe(const char *filename, const icwp_options *opt, icwp_fileinfo *out);
+
+/* The reference's configuration file (text, "KEYWORD=values"; src/config.c:815-975, DSP-list lines
+ * :562-774) -> chain + options, with the reference's acceptance rules: bounds clamped; an unknown
+ * keyword, a line without '=' or version != 10 rejects the whole file (defaults left, returns 0) while a
+ * value that does not parse is skipped, as in the reference; the DSP list is
+ * taken only with one master at its head and after the "lock" fix-ups of amod_init
+ * (src/adv_modulator.c:216-331).  Returns 1 when the file was accepted.  opt->device and
+ * opt->readahead_frames are not config items and are preserved. */
+int  icwp_load_config(const char *path, icw_chain_spec *chain, icwp_options *opt);
+/* writes a file the reference's load_config() accepts (doubles as bit patterns, like save_config) */
+int  icwp_save_config(const char *path, const icw_chain_spec *chain, const icwp_options *opt);
 
 #ifdef __cplusplus
 }

@@ -185,6 +185,13 @@ def ref():
         L.icwref_mt_words.argtypes = [C.c_uint32, C.c_int64, C.c_int64, _p(C.c_uint32)]
         L.icwref_mt_words_key.argtypes = [_p(C.c_uint32), C.c_uint32, C.c_int64, _p(C.c_uint32)]
         L.icwref_mt_dsopen.argtypes = [C.c_uint32, C.c_int64, _dbl_p]
+        L.icwref_reset_from_file.argtypes = [C.c_char_p]
+        L.icwref_reset_from_file.restype = C.c_int
+        L.icwref_save_config.argtypes = [C.c_char_p]
+        L.icwref_save_config.restype = C.c_int
+        L.icwref_get_cfg.argtypes = [_p(RefCfg)]
+        L.icwref_get_graph.argtypes = [_p(Node), C.c_int]
+        L.icwref_get_graph.restype = C.c_int
         _ref = L
     return _ref
 
@@ -367,3 +374,39 @@ def ref_process(d: dict, raw: np.ndarray, taps: list[int] | None = None, read_qu
     st = RefStats()
     L.icwref_get_stats(C.byref(st), 0)
     return dict(pcm=pcm[: got * ob], bus=bus, frames=int(got), stats=st)
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's config file, through the reference's own load_config / save_config
+# ---------------------------------------------------------------------------------------------
+def _node_tuple(n: Node):
+    return (n.mode, n.inputs_mask, n.xch_mode, n.l_iq_invert, n.r_iq_invert, n.l_gain, n.r_gain,
+            n.n_out if n.mode != 0 else 0, n.l_tout, n.r_tout, n.l_on, n.r_on, tuple(n.l_p), tuple(n.r_p))
+
+
+def ref_load_config(path: str):
+    """Fresh reference plugin configured from `path`.  Returns (accepted, RefCfg, nodes in execution order)."""
+    L = ref()
+    ok = L.icwref_reset_from_file(str(path).encode())
+    cfg = RefCfg()
+    L.icwref_get_cfg(C.byref(cfg))
+    arr = (Node * 64)()
+    n = L.icwref_get_graph(arr, 64)
+    return bool(ok), cfg, [_node_tuple(arr[i]) for i in range(n)]
+
+
+def ref_save_config(d: dict, path: str) -> bool:
+    """Configure the reference from a spec dict and let ITS save_config() write the file."""
+    L = ref()
+    cfg = make_refcfg(d)
+    L.icwref_reset(C.byref(cfg))
+    nodes = d.get("nodes") or [dict(mode="master", inputs=[0])]
+    arr = (Node * len(nodes))()
+    for i, nd in enumerate(nodes):
+        fill_node(arr[i], nd)
+    rc = L.icwref_set_graph(arr, len(nodes), 0)
+    if rc:
+        raise ValueError(f"icwref_set_graph rc={rc}")
+    ok = L.icwref_save_config(str(path).encode())
+    L.icwref_reset(C.byref(cfg))            # the list was consumed by the writer: re-initialise
+    return bool(ok)

@@ -3,7 +3,9 @@
  * TEST INFRASTRUCTURE ONLY.  This file is compiled together with the reference's own
  * C files (read in place from /root/reference/src, never copied) into
  * oracle/_ref/libicw_ref.so by oracle/Makefile.  It supplies the four symbols that live
- * in reference files we do not compile (config.c, playback.c: Win32 shell / GUI code) and
+ * in reference files we do not compile as they stand (playback.c: GUI code; config.c's default-
+ * path lookup -- config.c itself IS compiled, with its two *_default functions renamed away, so the
+ * reference's own load_config()/save_config() text format is available to the tests) and
  * a ctypes-friendly facade so tests/ and bench.py's cpu_baseline leg can run the reference
  * chain on a file and read back PCM, per-frame bus taps and the counters.
  *
@@ -44,10 +46,16 @@ typedef struct icwref_cfg {
 } icwref_cfg;
 
 static icwref_cfg g_cfg;
+static const char *g_cfg_path;      /* non-NULL: the next plugin init reads this reference-format config file */
+static int g_cfg_loaded;            /* what load_config() returned for it */
 
 /* ---- the four symbols from files we do not build -------------------------------------- */
 BOOL load_config_default(void)
 {
+    if (g_cfg_path) {
+        g_cfg_loaded = load_config(g_cfg_path);     /* src/config.c:815: defaults + NULL list on any error */
+        return g_cfg_loaded;
+    }
     the.cfg.ver_config            = 10;
     the.cfg.is_wav_support        = TRUE;
     the.cfg.is_rwave_support      = FALSE;
@@ -105,6 +113,49 @@ void icwref_reset(const icwref_cfg *c)
 {
     g_cfg = *c;
     (void)winampGetInModule2();
+}
+
+/* fresh plugin state configured by the reference's own parser from a config file; returns load_config()'s verdict */
+int icwref_reset_from_file(const char *path)
+{
+    g_cfg_path = path;
+    g_cfg_loaded = 0;
+    (void)winampGetInModule2();
+    g_cfg_path = NULL;
+    return g_cfg_loaded;
+}
+
+/* the live configuration, flattened */
+void icwref_get_cfg(icwref_cfg *c)
+{
+    memset(c, 0, sizeof(*c));
+    c->filter_no = (int)the.cfg.iir_filter_no;
+    c->is_kahan = the.cfg.iir_comp_config.is_kahan;
+    c->is_subnorm_reject = the.cfg.iir_comp_config.is_subnorm_reject;
+    c->subnorm_thr = the.cfg.iir_comp_config.subnorm_thr;
+    c->is_frmod_scaled = the.cfg.is_frmod_scaled;
+    c->need24bits = the.cfg.need24bits;
+    c->is_fp_check = the.cfg.is_fp_check;
+    c->dth_bits = the.cfg.sr_config.dth_bits;
+    c->quantz_type = the.cfg.sr_config.quantz_type;
+    c->render_type = the.cfg.sr_config.render_type;
+    c->nshape_type = the.cfg.sr_config.nshape_type;
+    c->sign_bits16 = the.cfg.sr_config.sign_bits16;
+    c->sign_bits24 = the.cfg.sr_config.sign_bits24;
+    c->sec_align = the.cfg.sec_align;
+    c->fade_in = the.cfg.fade_in;
+    c->fade_out = the.cfg.fade_out;
+    c->clr_nframe_trk = the.cfg.is_clr_nframe_trk;
+    c->clr_hilb_trk = the.cfg.is_clr_hilb_trk;
+}
+
+/* Write the live configuration and DSP list with the reference's save_config() (src/config.c:924).
+ * As in the reference's module_cleanup (src/in_cwave.c:575-595) the list is handed to the config and
+ * freed while it is written: the plugin must be re-initialised (icwref_reset*) afterwards. */
+int icwref_save_config(const char *path)
+{
+    the.cfg.dsp_list = amod_cleanup(TRUE);
+    return save_config(path);
 }
 
 /* flat description of one DSP-list node, in EXECUTION order (master last) */
@@ -183,6 +234,48 @@ int icwref_set_graph(const icwref_node *nodes, int n, int bypass)
     }
     amod_set_bypass_list_flag(bypass ? TRUE : FALSE);
     return 0;
+}
+
+/* the live DSP list in execution order (tail first, master last); returns the node count or -1 if cap is short */
+int icwref_get_graph(icwref_node *nodes, int cap)
+{
+    NODE_DSP *nd = amod_get_headdsp();
+    int n = 0, k;
+    while (nd->next) nd = nd->next;
+    for (; nd; nd = nd->prev, ++n) {
+        icwref_node *o;
+        if (n >= cap) return -1;
+        o = &nodes[n];
+        memset(o, 0, sizeof(*o));
+        o->mode = nd->mode;
+        for (k = 0; k < N_INPUTS; ++k)
+            if (nd->inputs[k]) o->inputs_mask |= 1u << k;
+        o->xch_mode = nd->xch_mode;
+        o->l_iq_invert = nd->l_iq_invert; o->r_iq_invert = nd->r_iq_invert;
+        o->l_gain = nd->l_gain; o->r_gain = nd->r_gain;
+        switch (nd->mode) {
+        case MODE_MASTER:
+            o->l_tout = nd->dsp.mk_master.le.tout; o->r_tout = nd->dsp.mk_master.ri.tout;
+            break;
+        case MODE_SHIFT:
+            o->n_out = nd->dsp.mk_shift.n_out;
+            o->l_on = nd->dsp.mk_shift.le.is_shift; o->r_on = nd->dsp.mk_shift.ri.is_shift;
+            o->l_p[0] = nd->dsp.mk_shift.le.fr_shift; o->r_p[0] = nd->dsp.mk_shift.ri.fr_shift;
+            break;
+        case MODE_PM:
+            o->n_out = nd->dsp.mk_pm.n_out;
+            o->l_on = nd->dsp.mk_pm.le.is_pm; o->r_on = nd->dsp.mk_pm.ri.is_pm;
+            o->l_p[0] = nd->dsp.mk_pm.le.freq;  o->l_p[1] = nd->dsp.mk_pm.le.phase;
+            o->l_p[2] = nd->dsp.mk_pm.le.level; o->l_p[3] = nd->dsp.mk_pm.le.angle;
+            o->r_p[0] = nd->dsp.mk_pm.ri.freq;  o->r_p[1] = nd->dsp.mk_pm.ri.phase;
+            o->r_p[2] = nd->dsp.mk_pm.ri.level; o->r_p[3] = nd->dsp.mk_pm.ri.angle;
+            break;
+        case MODE_MIX:
+            o->n_out = nd->dsp.mk_mix.n_out;
+            break;
+        }
+    }
+    return n;
 }
 
 /* Run one file through mod_context_fopen / amod_process_samples / mod_context_fclose on the

@@ -105,6 +105,42 @@ def test_plugin_exports_the_reference_symbols():
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not po.have_ref(), reason="oracle/_ref/libicw_ref.so not built")
+def test_a_reference_config_file_drives_both_plugins_to_the_same_bytes(tmp_path):
+    """one config file (written by the reference's save_config), read by the reference's
+    load_config on one side and by icwp_load_config on the other; then the same four transcode calls."""
+    from util import pcm_report
+    spec = S.config_c3(render_type=2, need24bits=1)          # full graph, TPDF, 24 bit
+    n = 20000
+    raw = synth.stream_bytes(spec, n, stream_id=9)
+    path = tmp_path / "x.cwave"
+    path.write_bytes(po.cwave_bytes(spec, raw))
+    cfg_file = tmp_path / "in_cwave.cfg"
+    d = dict(spec, fade_in=200, fade_out=300)
+    assert po.ref_save_config(d, cfg_file)
+
+    ok, _, nodes_r = po.ref_load_config(cfg_file)            # fresh reference plugin configured from the file
+    assert ok and len(nodes_r) == len(spec["nodes"])
+    cap = (n + 1000) * 6
+    want = np.zeros(cap, dtype=np.uint8)
+    info = (C.c_int * 4)()
+    got = po.ref().icwref_transcode_file(str(path).encode(), 4096, want.ctypes.data_as(C.c_char_p), cap, info)
+    assert got > 0
+    want = want[:got]
+
+    ok, sp, o, nodes_o = plugin.load_config(cfg_file)
+    assert ok and nodes_o == nodes_r and (o.fade_in_ms, o.fade_out_ms) == (200, 300)
+    plugin.lib().icwp_reset()
+    o.readahead_frames = 5000
+    assert plugin.lib().icwp_configure(C.byref(sp), C.byref(o)) == 0
+    pcm, meta = plugin.transcode(path, chunk=4096)
+    assert meta == tuple(info) and pcm.size == want.size
+    rep = pcm_report(pcm, want, 3)
+    print(f"[plugin from config file] {rep}")
+    assert rep["max_lsb"] <= 1 and rep["mismatches"] <= 1
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not po.have_ref(), reason="oracle/_ref/libicw_ref.so not built")
 @pytest.mark.parametrize("case", ["c1", "c2_tpdf", "c3", "tail_fade"])
 def test_transcode_entry_points_match_the_reference(tmp_path, case):
     """Same file, same four calls, same bytes (exact Hilbert mode; trig LSB flips counted)."""
