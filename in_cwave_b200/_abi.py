@@ -10,6 +10,7 @@ LIB_PATH = PKG / "libicw_b200.so"
 N_PLUGS = 27
 MAX_NODES = 32
 MAX_ORD = 20
+NS_MAX_TAPS = 20
 
 OK, E_ARG, E_CUDA, E_UNSUPPORTED, E_NOMEM = 0, -1, -2, -3, -4
 
@@ -56,6 +57,8 @@ class StreamState(C.Structure):
         ("prev_rnd", C.c_double * 2), ("clips", C.c_uint32 * 2), ("peak", C.c_double * 2),
         ("bus", (C.c_double * 4) * N_PLUGS),
         ("hb_basis", C.c_uint32), ("reserved", C.c_uint32),
+        ("ns_e", (C.c_double * NS_MAX_TAPS) * 2), ("ns_o", (C.c_double * NS_MAX_TAPS) * 2),
+        ("ns_prev_err", C.c_double * 2),
     ]
 
 

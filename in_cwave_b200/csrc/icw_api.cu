@@ -17,6 +17,7 @@
 #include "icw_mt.h"
 #include "icw_scan.h"
 #include "icw_hb_tables.inc"
+#include "icw_ns_tables.inc"
 
 using namespace icw;
 
@@ -77,6 +78,7 @@ struct icw_engine {
     Scratch analytic, mtw[2], ckpt, io_in, io_out, leaf;
     bool unfused = false;               // ICW_UNFUSED=1: keep the two-kernel exact path (A/B measurements)
     Scratch scan_scratch;
+    Scratch ns_pre;                     // noise shaping: (value, dither) pairs between chain_kernel and ns_render_kernel
     struct ScanPlan { bool ready = false; ModalCoef mc; double *d_pw = nullptr; };
     ScanPlan scan[ICW_HB_NTYPES][2];    // [filter_no][baseline]
     MtJump mt;                          // MT19937 checkpoint service (icw_mt.cu)
@@ -213,9 +215,7 @@ static int fold_spec(const icw_chain_spec &sp, DevChain &ch, HbCoef &coef)
     if (sp.nodes[sp.n_nodes - 1].mode != ICW_MODE_MASTER) return fail(ICW_E_ARG, "the last node must be the master");
     if (sp.render_type > ICW_RENDER_GAUSS) return fail(ICW_E_ARG, "render_type out of range");
     if (sp.quantz_type > 1) return fail(ICW_E_ARG, "quantz_type out of range");
-    if (sp.nshape_type != 0)
-        return fail(ICW_E_UNSUPPORTED, "noise shaping %u: error feedback through the quantiser is serial per channel; "
-                                       "only FLAT runs on the GPU (SURVEY.md 8f N3)", sp.nshape_type);
+    if (sp.nshape_type >= ICW_NS_COUNT) return fail(ICW_E_ARG, "nshape_type out of range");
     if (sp.sign_bits16 < 2 || sp.sign_bits16 > 16 || sp.sign_bits24 < 2 || sp.sign_bits24 > 24)
         return fail(ICW_E_ARG, "significant bits out of range");
     if (sp.n_fade_in < 0 || sp.n_fade_out < 0) return fail(ICW_E_ARG, "negative fade length");
@@ -284,6 +284,12 @@ static int fold_spec(const icw_chain_spec &sp, DevChain &ch, HbCoef &coef)
     q.render_type = (int)sp.render_type;
     static const int wps[5] = { 0, 2, 4, 2, 24 };       // reference src/sound_render.c:711-751
     q.words_per_sample = wps[sp.render_type];
+    q.ns_kind = ICW_NS_KIND[sp.nshape_type];
+    q.ns_order = ICW_NS_ORDER[sp.nshape_type];
+    for (int i = 0; i < 2 * ICW_NS_MAX_TAPS; ++i)
+        q.ns_coef[i] = i < ICW_NS_MAX_TAPS ? word_as_double(ICW_NS_COEF[sp.nshape_type][i]) : 0.0;
+    if (q.ns_kind == 2)     // IIR: [order, 2*order) of the table weigh the filter's own outputs
+        for (int i = 0; i < q.ns_order; ++i) { q.ns_coef[ICW_NS_MAX_TAPS + i] = q.ns_coef[q.ns_order + i]; }
 
     // DSP list
     uint32_t written = 1u;                                // plug 0 is written by the unpacker
@@ -385,7 +391,7 @@ static void engine_free(icw_engine *e)
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     e->analytic.release(); e->mtw[0].release(); e->mtw[1].release(); e->ckpt.release();
-    e->io_in.release(); e->io_out.release(); e->leaf.release(); e->scan_scratch.release();
+    e->io_in.release(); e->io_out.release(); e->leaf.release(); e->scan_scratch.release(); e->ns_pre.release();
     for (auto &row : e->scan) for (auto &pl : row) if (pl.d_pw) cudaFree(pl.d_pw);
     e->mt.release();
     cudaStreamSynchronize(e->aux);
@@ -420,6 +426,9 @@ static void to_dev(const icw_stream_state &s, DevStream &d)
     }
     memcpy(d.bus, s.bus, sizeof d.bus);
     d.hb_basis = s.hb_basis;
+    memcpy(d.ns_e, s.ns_e, sizeof d.ns_e);
+    memcpy(d.ns_o, s.ns_o, sizeof d.ns_o);
+    memcpy(d.ns_prev_err, s.ns_prev_err, sizeof d.ns_prev_err);
 }
 
 static void from_dev(const DevStream &d, icw_stream_state &s)
@@ -439,6 +448,9 @@ static void from_dev(const DevStream &d, icw_stream_state &s)
     }
     memcpy(s.bus, d.bus, sizeof s.bus);
     s.hb_basis = d.hb_basis;
+    memcpy(s.ns_e, d.ns_e, sizeof s.ns_e);
+    memcpy(s.ns_o, d.ns_o, sizeof s.ns_o);
+    memcpy(s.ns_prev_err, d.ns_prev_err, sizeof s.ns_prev_err);
 }
 
 extern "C" int icw_session_create(icw_engine *e, const icw_chain_spec *spec, int n_streams, icw_session **out)
@@ -570,7 +582,11 @@ extern "C" int icw_session_set_spec(icw_session *s, const icw_chain_spec *spec)
             unsigned f = *(unsigned *)a;
             if (f & 1) { memset(d.hb, 0, sizeof d.hb); d.quad[0] = d.quad[1] = 0; }
             if (f & (1 | 4)) memset(d.hb_rejects, 0, sizeof d.hb_rejects);
-            if (f & 2) d.prev_rnd[0] = d.prev_rnd[1] = 0.0;
+            if (f & 2) {            // sound_render_recalc also clears the shaper memory (src/sound_render.c:546-571)
+                d.prev_rnd[0] = d.prev_rnd[1] = 0.0;
+                memset(d.ns_e, 0, sizeof d.ns_e); memset(d.ns_o, 0, sizeof d.ns_o);
+                d.ns_prev_err[0] = d.ns_prev_err[1] = 0.0;
+            }
         }, &flags);
         if (rc) return rc;
     }
@@ -664,7 +680,8 @@ static int process_group(icw_session *s, int64_t n_frames, const uint8_t *d_in, 
     const uint32_t *wl = dw.l, *wr = dw.r;
     const size_t mt_shared = dw.stream_stride;      // words between consecutive streams' dither (0 = shared)
     const bool scan = !ch.is_complex && s->spec.hilbert_mode == ICW_HILBERT_SCAN;
-    if (!ch.is_complex && !scan && !e->unfused) {
+    const bool shaped = ch.render.ns_kind != 0;     // error feedback through the quantiser: serial per channel
+    if (!ch.is_complex && !scan && !e->unfused && !shaped) {
         // real input, reference-exact Hilbert: the whole chain in one kernel
         if (dw.join) CK(cudaStreamWaitEvent(st, dw.join, 0));
         ProfSpan ps(s, st, ICW_K_HILBERT);
@@ -713,10 +730,20 @@ static int process_group(icw_session *s, int64_t n_frames, const uint8_t *d_in, 
             from_analytic = 1;
         }
         if (dw.join) CK(cudaStreamWaitEvent(st, dw.join, 0));
+        double *pre = nullptr;
+        if (shaped) {
+            rc = e->ns_pre.reserve((size_t)n_frames * 4 * sizeof(double) * (size_t)K);
+            if (rc) return rc;
+            pre = (double *)e->ns_pre.p;
+        }
         ProfSpan ps(s, st, ICW_K_CHAIN);
         CK(launch_chain(ch, s->d_streams, K, n_frames, src, src_stride, from_analytic, wl, wr, mt_shared,
-                        d_out, out_stride, s->d_tap_bus, s->d_tap_lr, e->sm_count, st));
+                        d_out, out_stride, s->d_tap_bus, s->d_tap_lr, pre, e->sm_count, st));
         s->launches++;
+        if (shaped) {
+            CK(launch_ns_render(ch, s->d_streams, K, n_frames, pre, d_out, out_stride, st));
+            s->launches++;
+        }
     }
     {
         ProfSpan ps(s, st, ICW_K_MISC);

@@ -99,6 +99,8 @@ struct FrameIO {
     uint8_t *dst;                   // this stream's output row
     int dst_aligned;                // row start is 4-byte aligned: frames can be stored as 16/32-bit words
     double *tap_bus, *tap_lr;       // optional test taps for this stream ([frame][27][4], [frame][2])
+    double *pre;                    // noise shaping on: [frame][4] = (L value, L dither, R value, R dither) for
+                                    // ns_render_kernel instead of PCM (the error feedback is serial per channel)
 };
 
 // frame i of the call; v = (L.re, L.im, R.re, R.im) on plug 0; bus = thread-private plug values.
@@ -142,13 +144,18 @@ __device__ __forceinline__ void finish_frame(const DevChain &ch, DevStream &st, 
         dl = dither_sample(rq, wl, io.mtw_l, i, prev_l, acc.redraws);
         dr = dither_sample(rq, wr, io.mtw_r, i, prev_r, acc.redraws);
     }
-    RenderOut a = render_one(rq, lo, dl);
-    RenderOut b = render_one(rq, ro, dr);
-    acc.clips_l += a.clipped; acc.clips_r += b.clipped;
-    acc.peak_l = fmax(acc.peak_l, a.level); acc.peak_r = fmax(acc.peak_r, b.level);
-    uint8_t *p = io.dst + i * ch.out_frame_bytes;
-    if (io.dst_aligned) store_frame_pcm(p, a.val, b.val, rq.bytes);
-    else { store_pcm(p, a.val, rq.bytes); store_pcm(p + rq.bytes, b.val, rq.bytes); }
+    if (io.pre) {
+        double4 *q = reinterpret_cast<double4 *>(io.pre) + i;
+        *q = make_double4(lo, dl, ro, dr);
+    } else {
+        RenderOut a = render_one(rq, lo, dl);
+        RenderOut b = render_one(rq, ro, dr);
+        acc.clips_l += a.clipped; acc.clips_r += b.clipped;
+        acc.peak_l = fmax(acc.peak_l, a.level); acc.peak_r = fmax(acc.peak_r, b.level);
+        uint8_t *p = io.dst + i * ch.out_frame_bytes;
+        if (io.dst_aligned) store_frame_pcm(p, a.val, b.val, rq.bytes);
+        else { store_pcm(p, a.val, rq.bytes); store_pcm(p + rq.bytes, b.val, rq.bytes); }
+    }
     if (io.tap_bus) {
         double *t = io.tap_bus + (size_t)i * (ICW_N_PLUGS * 4);
         for (int k = 0; k < ICW_N_PLUGS; ++k) { t[k * 4] = bus[k][0]; t[k * 4 + 1] = bus[k][1]; t[k * 4 + 2] = bus[k][2]; t[k * 4 + 3] = bus[k][3]; }

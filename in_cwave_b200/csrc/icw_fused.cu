@@ -75,7 +75,7 @@ hb_fused_kernel(const __grid_constant__ HbCoef coef, const __grid_constant__ Dev
     const bool h_live = !is_chain && stream0 + h_sl < n_streams;
     FrameAcc acc;
     FrameIO io;
-    io.mtw_l = io.mtw_r = nullptr; io.dst = nullptr; io.dst_aligned = 0; io.tap_bus = io.tap_lr = nullptr;
+    io.mtw_l = io.mtw_r = nullptr; io.dst = nullptr; io.dst_aligned = 0; io.tap_bus = io.tap_lr = nullptr; io.pre = nullptr;
     OscCounter osc;
     osc.frame = 0; osc.value = 0;
     const uint8_t *h_src = nullptr;

@@ -44,6 +44,9 @@ struct DevRender {
     int32_t neg_delta, shift, bytes;    // bytes per channel sample: 2 or 3
     int32_t render_type;
     int32_t words_per_sample;           // MT words per channel sample: 0/2/4/2/24
+    // noise shaping (reference src/sound_render.c:403-489): 0 = flat, 1 = FIR, 2 = IIR of ns_order
+    int32_t ns_kind, ns_order;
+    double  ns_coef[2 * ICW_NS_MAX_TAPS];
 };
 
 struct DevChain {
@@ -80,6 +83,7 @@ struct DevStream {
     unsigned long long mt_redraws;
     double   prev_rnd_next[2];          // written by the last frame of a call, committed by advance
     uint32_t hb_basis, pad0;            // 0 = hb[] is the DF-II delay line, 1 = modal states
+    double   ns_e[2][ICW_NS_MAX_TAPS], ns_o[2][ICW_NS_MAX_TAPS], ns_prev_err[2];   // age-ordered shaper memory
 };
 
 }  // namespace icw

@@ -279,7 +279,8 @@ chain_kernel(const __grid_constant__ DevChain ch, DevStream *__restrict__ stream
              const uint32_t *__restrict__ mtw_l, const uint32_t *__restrict__ mtw_r, size_t mt_stream_stride,
              uint8_t *__restrict__ out, size_t out_stride,
              double *__restrict__ tap_bus /* optional [stream][frame][ICW_N_PLUGS][4] */,
-             double *__restrict__ tap_lr /* optional [stream][frame][2] */)
+             double *__restrict__ tap_lr /* optional [stream][frame][2] */,
+             double *__restrict__ pre /* noise shaping: [stream][frame][4] values + dither instead of PCM */)
 {
     const int stream = blockIdx.y;
     DevStream &st = streams[stream];
@@ -292,6 +293,7 @@ chain_kernel(const __grid_constant__ DevChain ch, DevStream *__restrict__ stream
     io.dst_aligned = ((size_t)(uintptr_t)io.dst & 3u) == 0;
     io.tap_bus = tap_bus ? tap_bus + (size_t)stream * n_frames * (ICW_N_PLUGS * 4) : nullptr;
     io.tap_lr = tap_lr ? tap_lr + (size_t)stream * n_frames * 2 : nullptr;
+    io.pre = pre ? pre + (size_t)stream * n_frames * 4 : nullptr;
 
     FrameAcc acc;
     double bus[ICW_N_PLUGS][4];
@@ -315,7 +317,7 @@ chain_kernel(const __grid_constant__ DevChain ch, DevStream *__restrict__ stream
 cudaError_t launch_chain(const DevChain &ch, DevStream *streams, int n_streams, int64_t n_frames,
                          const uint8_t *in, size_t in_stride, int from_analytic,
                          const uint32_t *mtw_l, const uint32_t *mtw_r, size_t mt_stream_stride,
-                         uint8_t *out, size_t out_stride, double *tap_bus, double *tap_lr,
+                         uint8_t *out, size_t out_stride, double *tap_bus, double *tap_lr, double *pre,
                          int sm_count, cudaStream_t s)
 {
     int threads = 256;
@@ -327,7 +329,106 @@ cudaError_t launch_chain(const DevChain &ch, DevStream *streams, int n_streams, 
     if (per_stream > cap) per_stream = cap;
     dim3 grid(per_stream, n_streams);
     chain_kernel<<<grid, threads, 0, s>>>(ch, streams, n_frames, in, in_stride, from_analytic, mtw_l, mtw_r,
-                                          mt_stream_stride, out, out_stride, tap_bus, tap_lr);
+                                          mt_stream_stride, out, out_stride, tap_bus, tap_lr, pre);
+    return cudaGetLastError();
+}
+
+// =============================================================================================
+// noise-shaped quantiser (reference src/sound_render.c:403-489 filters, :753-810 the feedback)
+// =============================================================================================
+// The shaper feeds the quantisation error of sample n into sample n + 1: one thread per
+// (stream, channel) walks its channel in order -- parallel over streams only, which is why
+// chain_kernel stops before the quantiser (FrameIO::pre) when a shaper is on.  The error memory is a
+// register array ordered by age (static indices after unrolling), the reference's circular buffer
+// read newest-first is the same sum.  ORD is the shaper's order; plain mul + add as in the reference.
+template <int ORD, bool IIR>
+__global__ void __launch_bounds__(64)
+ns_render_kernel(const __grid_constant__ DevChain ch, DevStream *__restrict__ streams, int n_streams, int64_t n_frames,
+                 const double *__restrict__ pre, uint8_t *__restrict__ out, size_t out_stride)
+{
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n_streams * 2) return;
+    const int stream = id >> 1, c = id & 1;
+    const DevRender &q = ch.render;
+    DevStream &st = streams[stream];
+    double e[ORD], o[IIR ? ORD : 1], ce[ORD], co[IIR ? ORD : 1];
+#pragma unroll
+    for (int i = 0; i < ORD; ++i) { e[i] = st.ns_e[c][i]; ce[i] = q.ns_coef[i]; }
+    if (IIR) {
+#pragma unroll
+        for (int i = 0; i < ORD; ++i) { o[i] = st.ns_o[c][i]; co[i] = q.ns_coef[ICW_NS_MAX_TAPS + i]; }
+    }
+    double prev_err = st.ns_prev_err[c];
+    unsigned clips = 0;
+    double peak = 0.0;
+    const double2 *src = reinterpret_cast<const double2 *>(pre + (size_t)stream * n_frames * 4) + c;
+    uint8_t *dst = out + (size_t)stream * out_stride + c * q.bytes;
+    double2 cur = n_frames > 0 ? src[0] : make_double2(0.0, 0.0);
+    for (int64_t i = 0; i < n_frames; ++i) {
+        const double2 nxt = src[2 * (i + 1 < n_frames ? i + 1 : i)];       // (value, dither) of the next frame
+        const double v = cur.x * q.norm_mul - prev_err;
+        double qv = v + cur.y * q.dth_mul;
+        int delta;
+        if (qv < 0.0) { qv -= q.round_off; delta = q.neg_delta; }
+        else          { qv += q.round_off; delta = 0; }
+        peak = fmax(peak, fabs(qv) * q.inv_hi);
+        if (qv >= q.hi) { qv = q.hi - 1.0; ++clips; }
+        if (qv <= q.lo) { qv = q.lo + 1.0; ++clips; }
+        int val = __double2int_rz(qv) + delta;
+        // the error of this sample through the shaper
+        const double err = (double)val - v;
+#pragma unroll
+        for (int k = ORD - 1; k > 0; --k) e[k] = e[k - 1];
+        e[0] = err;
+        double res = 0.0;
+        if (IIR) {
+#pragma unroll
+            for (int k = 0; k < ORD; ++k) res = res + (ce[k] * e[k] - co[k] * o[k]);
+#pragma unroll
+            for (int k = ORD - 1; k > 0; --k) o[k] = o[k - 1];
+            o[0] = res;
+        } else {
+#pragma unroll
+            for (int k = 0; k < ORD; ++k) res = res + ce[k] * e[k];
+        }
+        prev_err = res;
+        val = (int)((unsigned)val << q.shift);
+        store_pcm(dst + i * ch.out_frame_bytes, val, q.bytes);
+        cur = nxt;
+    }
+#pragma unroll
+    for (int i = 0; i < ORD; ++i) st.ns_e[c][i] = e[i];
+    if (IIR) {
+#pragma unroll
+        for (int i = 0; i < ORD; ++i) st.ns_o[c][i] = o[i];
+    }
+    st.ns_prev_err[c] = prev_err;
+    st.clips[c] += clips;
+    st.peak[c] = fmax(st.peak[c], peak);
+}
+
+cudaError_t launch_ns_render(const DevChain &ch, DevStream *streams, int n_streams, int64_t n_frames,
+                             const double *pre, uint8_t *out, size_t out_stride, cudaStream_t s)
+{
+    const int threads = 64;
+    const int grid = (n_streams * 2 + threads - 1) / threads;
+#define ICW_NS_CASE(O, I) ns_render_kernel<O, I><<<grid, threads, 0, s>>>(ch, streams, n_streams, n_frames, pre, out, out_stride); break
+    if (ch.render.ns_kind == 2) {
+        switch (ch.render.ns_order) {
+        case 4: ICW_NS_CASE(4, true);
+        default: return cudaErrorInvalidValue;
+        }
+    } else {
+        switch (ch.render.ns_order) {
+        case 5:  ICW_NS_CASE(5, false);
+        case 9:  ICW_NS_CASE(9, false);
+        case 15: ICW_NS_CASE(15, false);
+        case 16: ICW_NS_CASE(16, false);
+        case 20: ICW_NS_CASE(20, false);
+        default: return cudaErrorInvalidValue;
+        }
+    }
+#undef ICW_NS_CASE
     return cudaGetLastError();
 }
 

@@ -37,8 +37,11 @@ cudaError_t launch_mt_words(const uint32_t *ckpt, int n_cta, int blocks_per_cta,
 cudaError_t launch_chain(const DevChain &ch, DevStream *streams, int n_streams, int64_t n_frames,
                          const uint8_t *in, size_t in_stride, int from_analytic,
                          const uint32_t *mtw_l, const uint32_t *mtw_r, size_t mt_stream_stride,
-                         uint8_t *out, size_t out_stride, double *tap_bus, double *tap_lr,
+                         uint8_t *out, size_t out_stride, double *tap_bus, double *tap_lr, double *pre,
                          int sm_count, cudaStream_t s);
+// noise shaping on: chain_kernel leaves (value, dither) pairs in `pre`; one thread per (stream, channel) quantises
+cudaError_t launch_ns_render(const DevChain &ch, DevStream *streams, int n_streams, int64_t n_frames,
+                             const double *pre, uint8_t *out, size_t out_stride, cudaStream_t s);
 cudaError_t launch_advance(const DevChain &ch, DevStream *streams, int n_streams, int64_t n_frames,
                            int advance_quad, cudaStream_t s);
 cudaError_t launch_phase_leaf(const DevChain &ch, uint64_t n0, int64_t n, double f, double *out, cudaStream_t s);

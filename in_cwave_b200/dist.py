@@ -75,6 +75,8 @@ class CudaBackend:
     def __init__(self, engine, spec: dict):
         if spec.get("hilbert_mode", "exact") not in ("scan", 1):
             raise ValueError("time sharding needs hilbert_mode='scan': the exact recurrences are serial in time")
+        if int(spec.get("nshape_type", 0)):
+            raise ValueError("time sharding needs FLAT noise shaping: the error feedback is serial in time (SURVEY.md 8e)")
         self.engine, self.spec = engine, dict(spec)
         self.ses = engine.session(spec, 1)
 

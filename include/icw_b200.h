@@ -28,6 +28,7 @@ extern "C" {
 #define ICW_ABI_VERSION   1
 #define ICW_N_PLUGS       27    /* reference src/in_cwave.h:198  N_INPUTS */
 #define ICW_MAX_NODES     32
+#define ICW_NS_MAX_TAPS   20      /* longest noise-shaping filter (src/sound_render.c:75-235) */
 #define ICW_MAX_ORD       20    /* highest half-band filter order, reference src/hblpf.c:740-820 */
 
 enum {
@@ -93,7 +94,8 @@ typedef struct icw_chain_spec {
     double   dth_bits;
     uint32_t quantz_type;       /* 0 mid tread, 1 mid riser (src/sound_render.h:57-58) */
     uint32_t render_type;       /* ICW_RENDER_* */
-    uint32_t nshape_type;       /* 0 = flat; others are ICW_E_UNSUPPORTED (serial error feedback) */
+    uint32_t nshape_type;       /* 0 = flat, 1..15 FIR, 16..17 IIR shapers (src/sound_render.h:73-92): the error
+                                   feedback is serial per channel -> one thread per (stream, channel) */
     uint32_t sign_bits16, sign_bits24;
     int32_t  bypass;            /* src/adv_modulator.c:637,644 */
     int32_t  n_nodes;
@@ -117,6 +119,11 @@ typedef struct icw_stream_state {
     uint32_t hb_basis;                      /* what hb[] holds: 0 = delay line (exact mode), 1 = modal states
                                                (scan mode: hb[c][f][2m], [2m+1] = Re, Im of mode m) */
     uint32_t reserved;
+    /* noise-shaper memory per channel (reference NS_SHAPER, src/sound_render.h:113-139) ordered by AGE:
+     * ns_e[c][0] = latest quantisation error, ns_o[c][0] = the IIR shapers' latest output; ns_prev_err[c] =
+     * what the next sample subtracts (src/sound_render.c:756,800).  All zero for FLAT shaping. */
+    double   ns_e[2][ICW_NS_MAX_TAPS], ns_o[2][ICW_NS_MAX_TAPS];
+    double   ns_prev_err[2];
 } icw_stream_state;
 
 typedef struct icw_engine  icw_engine;      /* one GPU: streams, scratch, MT jump tables */

@@ -18,6 +18,7 @@
 #include <string.h>
 
 #include "icwo_hb_tables.inc"
+#include "icwo_ns_tables.inc"
 
 #define ICWO_PI     3.1415926535897932384626433832795029   /* reference src/in_cwave.h:148 */
 #define ICWO_SQRT2  1.4142135623730950488016887242097      /* reference src/adv_modulator.c:43 */
@@ -412,15 +413,37 @@ static double dither_draw(unsigned type, icwo_mt *mt, double *prev)
     }
 }
 
-int64_t icwo_render(const icwo_spec *sp, icwo_mt *mt, double *prev_rnd, const double *in, int64_t n,
+/* noise shaping: the error of this sample through the shaper -> what the NEXT sample subtracts
+ * (src/sound_render.c:403-489).  FIR: sum c_i * err[i samples ago], newest first, plain mul + add.
+ * IIR: sum (c_i * err_i - d_i * out_i), then the sum joins the outputs. */
+static double ns_step(unsigned type, icwo_ns *ns, double err)
+{
+    const int kind = ICW_NS_KIND[type], ord = ICW_NS_ORDER[type];
+    const double *c = (const double *)ICW_NS_COEF[type];
+    double res = 0.0;
+    if (!kind) return 0.0;
+    for (int i = ord - 1; i > 0; --i) ns->e[i] = ns->e[i - 1];
+    ns->e[0] = err;
+    if (kind == 1) {
+        for (int i = 0; i < ord; ++i) res += c[i] * ns->e[i];
+    } else {
+        for (int i = 0; i < ord; ++i) res += c[i] * ns->e[i] - c[i + ord] * ns->o[i];
+        for (int i = ord - 1; i > 0; --i) ns->o[i] = ns->o[i - 1];
+        ns->o[0] = res;
+    }
+    return res;
+}
+
+int64_t icwo_render(const icwo_spec *sp, icwo_mt *mt, double *prev_rnd, icwo_ns *ns, const double *in, int64_t n,
                     uint8_t *out, unsigned *clips, double *peak_db)
 {
     quant_plan q;
     uint8_t *p = out;
+    const unsigned nst = sp->nshape_type < ICW_NS_COUNT ? sp->nshape_type : 0;   /* src/sound_render.c:546 */
     quant_setup(sp, &q);
     for (int64_t k = 0; k < n; ++k) {
         double rnd = dither_draw(sp->render_type, mt, prev_rnd);
-        double v = in[k] * q.norm_mul - 0.0;            /* flat shaping: previous error is 0 */
+        double v = in[k] * q.norm_mul - (nst ? ns->prev_err : 0.0);
         double qv = v + rnd * q.dth_mul;
         int delta;
         if (qv < 0.0) { qv -= q.round_off; delta = q.neg_delta; }
@@ -434,6 +457,7 @@ int64_t icwo_render(const icwo_spec *sp, icwo_mt *mt, double *prev_rnd, const do
         if (qv <= q.lo) { qv = q.lo + 1.0; ++*clips; }
 
         int val = (int)qv + delta;
+        if (nst) ns->prev_err = ns_step(nst, ns, (double)val - v);      /* src/sound_render.c:800 */
         val = (int)((unsigned)val << q.shift);          /* same bits as the reference's signed << */
         *p++ = (uint8_t)val;
         *p++ = (uint8_t)(val >> 8);
@@ -608,7 +632,7 @@ int icwo_process(const icwo_spec *sp, icwo_state *st, const uint8_t *in, int64_t
     int ob = icwo_out_frame_bytes(sp);
     int is_complex = sp->fmt >= ICWO_FMT_CW_F64;
 
-    if (fb < 0 || sp->nshape_type != 0 || sp->n_nodes < 1 || sp->n_nodes > ICWO_MAX_NODES ||
+    if (fb < 0 || sp->n_nodes < 1 || sp->n_nodes > ICWO_MAX_NODES ||
         sp->nodes[sp->n_nodes - 1].mode != ICWO_MODE_MASTER || sp->filter_no < 0 ||
         sp->filter_no >= ICW_HB_NTYPES)
         return -1;
@@ -667,8 +691,8 @@ int icwo_process(const icwo_spec *sp, icwo_state *st, const uint8_t *in, int64_t
         if (pcm) {
             uint8_t tmpl[BLK * 3], tmpr[BLK * 3];
             int sb = ob / 2;
-            icwo_render(sp, &st->mt[0], &st->prev_rnd[0], lo, m, tmpl, &st->clips[0], &st->peak_db[0]);
-            icwo_render(sp, &st->mt[1], &st->prev_rnd[1], ro, m, tmpr, &st->clips[1], &st->peak_db[1]);
+            icwo_render(sp, &st->mt[0], &st->prev_rnd[0], &st->ns[0], lo, m, tmpl, &st->clips[0], &st->peak_db[0]);
+            icwo_render(sp, &st->mt[1], &st->prev_rnd[1], &st->ns[1], ro, m, tmpr, &st->clips[1], &st->peak_db[1]);
             for (int k = 0; k < m; ++k) {
                 memcpy(pcm + (base + k) * ob, tmpl + k * sb, sb);
                 memcpy(pcm + (base + k) * ob + sb, tmpr + k * sb, sb);

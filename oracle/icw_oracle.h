@@ -66,7 +66,7 @@ typedef struct icwo_spec {
     double   dth_bits;
     unsigned quantz_type;       /* 0 mid tread, 1 mid riser */
     unsigned render_type;       /* ICWO_DITHER_* */
-    unsigned nshape_type;       /* 0 (flat) only */
+    unsigned nshape_type;       /* 0 flat, 1..15 FIR shapers, 16..17 IIR shapers (src/sound_render.h:73-92) */
     unsigned sign_bits16, sign_bits24;
     int      bypass;
     int      n_nodes;
@@ -86,6 +86,15 @@ typedef struct icwo_mt {
 } icwo_mt;
 
 /* everything that persists from frame to frame (reference MOD_CONTEXT, src/in_cwave.h:410-424) */
+/* noise-shaper memory of one channel (reference NS_SHAPER, src/sound_render.h:113-139), ordered by AGE:
+ * e[0] = the latest quantisation error, o[0] = the filter's latest output (IIR shapers).  The
+ * reference keeps circular buffers + an index; the sums run newest-first either way. */
+#define ICWO_NS_MAX_TAPS 20
+typedef struct icwo_ns {
+    double e[ICWO_NS_MAX_TAPS], o[ICWO_NS_MAX_TAPS];
+    double prev_err;                    /* what the next sample subtracts (src/sound_render.c:756) */
+} icwo_ns;
+
 typedef struct icwo_state {
     uint64_t n_frame;                   /* oscillator frame counter */
     int64_t  pos;                       /* frames already taken from the current file */
@@ -96,6 +105,7 @@ typedef struct icwo_state {
     double   prev_rnd[2];
     unsigned clips[2];
     double   peak_db[2];
+    icwo_ns  ns[2];
 } icwo_state;
 
 void    icwo_default_spec(icwo_spec *sp);
@@ -124,7 +134,8 @@ void    icwo_iir_run(int filter_no, int is_kahan, int is_reject, icwo_iir *f,
 /* exact-arithmetic (binary128) value of the same converter from zero state; see icw_oracle.c */
 void    icwo_hilbert_truth(int filter_no, int drop_direct, unsigned quad0, const double *x, int64_t n,
                            double *out_i, double *out_q);
-int64_t icwo_render(const icwo_spec *sp, icwo_mt *mt, double *prev_rnd, const double *in, int64_t n,
+/* ns may be NULL when sp->nshape_type == 0 */
+int64_t icwo_render(const icwo_spec *sp, icwo_mt *mt, double *prev_rnd, icwo_ns *ns, const double *in, int64_t n,
                     uint8_t *out, unsigned *clips, double *peak_db);
 
 #ifdef __cplusplus

@@ -65,6 +65,13 @@ class Mt(C.Structure):
     _fields_ = [("w", C.c_uint32 * MT_N), ("pos", C.c_int), ("drawn", C.c_uint64)]
 
 
+NS_MAX_TAPS = 20
+
+
+class Ns(C.Structure):
+    _fields_ = [("e", C.c_double * NS_MAX_TAPS), ("o", C.c_double * NS_MAX_TAPS), ("prev_err", C.c_double)]
+
+
 class State(C.Structure):
     _fields_ = [
         ("n_frame", C.c_uint64), ("pos", C.c_int64),
@@ -72,6 +79,7 @@ class State(C.Structure):
         ("lpf", (Iir * 2) * 2), ("quad", C.c_uint * 2),
         ("mt", Mt * 2), ("prev_rnd", C.c_double * 2),
         ("clips", C.c_uint * 2), ("peak_db", C.c_double * 2),
+        ("ns", Ns * 2),
     ]
 
 
@@ -139,7 +147,7 @@ def port():
                                    C.c_int64, _dbl_p, _dbl_p]
         L.icwo_iir_run.argtypes = [C.c_int, C.c_int, C.c_int, _p(Iir), _dbl_p, C.c_int64, _dbl_p]
         L.icwo_hilbert_truth.argtypes = [C.c_int, C.c_int, C.c_uint, _dbl_p, C.c_int64, _dbl_p, _dbl_p]
-        L.icwo_render.argtypes = [_p(Spec), _p(Mt), _dbl_p, _dbl_p, C.c_int64, _u8_p,
+        L.icwo_render.argtypes = [_p(Spec), _p(Mt), _dbl_p, _p(Ns), _dbl_p, C.c_int64, _u8_p,
                                   _p(C.c_uint), _dbl_p]
         L.icwo_render.restype = C.c_int64
         _port = L

@@ -70,11 +70,44 @@ def test_render_leaf(rt, need24, bits, qt):
     po.port().icwo_mt_seed(C.byref(mt), 0x13579BDF)
     out = np.zeros(n * 3, dtype=np.uint8)
     pclips, ppeak, prev = C.c_uint(0), C.c_double(-555.0), C.c_double(0)
-    pb = po.port().icwo_render(C.byref(sp), C.byref(mt), C.byref(prev), _dp(x), n,
+    pb = po.port().icwo_render(C.byref(sp), C.byref(mt), C.byref(prev), None, _dp(x), n,
                                out.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(pclips), C.byref(ppeak))
     assert nb == pb
     assert bytes(out[:pb]) == buf.raw[:nb]
     assert clips.value == pclips.value and clips.value > 0
+    assert peak.value == ppeak.value
+
+
+@pytest.mark.parametrize("ns", range(1, 18))
+@pytest.mark.parametrize("rt,need24,bits,qt", [(0, 1, 24, 1), (2, 0, 16, 1), (4, 1, 20, 0), (3, 0, 12, 0)])
+def test_render_leaf_with_noise_shaping(ns, rt, need24, bits, qt):
+    """All 15 FIR and 2 IIR shapers (src/sound_render.c:75-235, 403-489): the error feedback makes every
+    byte depend on every earlier one, so byte equality over 20 000 samples pins coefficients and order."""
+    rng = np.random.default_rng(ns * 7 + rt)
+    n = 20000
+    x = (rng.random(n) - 0.5) * 50000.0
+    x[n // 2:] *= 1.5                               # second half clips now and then
+    d = S.default_spec(render_type=rt, need24bits=need24, quantz_type=qt, dth_bits=1.0, nshape_type=ns,
+                       sign_bits24=bits if need24 else 24, sign_bits16=bits if not need24 else 16)
+    cfg = po.make_refcfg(d)
+    buf = C.create_string_buffer(n * 3)
+    clips, peak = C.c_uint(0), C.c_double(0)
+    nb = po.ref().icwref_render(C.byref(cfg), 0x479B22AB, _dp(x), n, buf, C.byref(clips), C.byref(peak))
+    sp = po.make_spec(d)
+    mt = po.Mt()
+    po.port().icwo_mt_seed(C.byref(mt), 0x479B22AB)
+    out = np.zeros(n * 3, dtype=np.uint8)
+    pclips, ppeak, prev, nss = C.c_uint(0), C.c_double(-555.0), C.c_double(0), po.Ns()
+    # two calls: the shaper memory must carry over
+    h = n // 3
+    u8 = C.POINTER(C.c_uint8)
+    pb = po.port().icwo_render(C.byref(sp), C.byref(mt), C.byref(prev), C.byref(nss), _dp(x), h,
+                               out.ctypes.data_as(u8), C.byref(pclips), C.byref(ppeak))
+    pb += po.port().icwo_render(C.byref(sp), C.byref(mt), C.byref(prev), C.byref(nss), _dp(x[h:]), n - h,
+                                out[pb:].ctypes.data_as(u8), C.byref(pclips), C.byref(ppeak))
+    assert nb == pb
+    assert bytes(out[:pb]) == buf.raw[:nb]
+    assert clips.value == pclips.value
     assert peak.value == ppeak.value
 
 
