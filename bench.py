@@ -49,6 +49,12 @@ def workload(name: str) -> dict:
         return dict(name="c4", desc="4096 x 48 kHz stereo f32 WAV, 10 s each: Hilbert(T1,Kahan,reject) + 100 Hz shift + 24-bit render, no dither",
                     spec=S.config_c1(hilbert_mode="exact"), streams=4096, frames=480_000, chunk=16_384,
                     bytes_per_frame=14, hilbert="exact")
+    if name == "c4ns":
+        # C4 with a noise shaper: the quantiser's error feedback is serial per channel
+        return dict(name="c4ns", desc="4096 x 44.1 kHz stereo f32 WAV, 10 s each: Hilbert(T1,Kahan,reject) + 100 Hz shift + TPDF + "
+                                      "20-tap Shibata noise shaper, 24-bit render",
+                    spec=S.config_c1(hilbert_mode="exact", sample_rate=44100, render_type=2, nshape_type=6), streams=4096,
+                    frames=441_000, chunk=16_384, bytes_per_frame=14, hilbert="exact")
     if name == "c1":
         return dict(name="c1", desc="48 kHz stereo f32 WAV, 60 s: Hilbert + 100 Hz shift + 24-bit render (one stream)",
                     spec=S.config_c1(hilbert_mode="scan"), streams=1, frames=2_880_000, chunk=2_880_000,
@@ -374,7 +380,7 @@ def main():
     # FP64 thread-operations per frame (counted from the SASS of the sample loops) and the
     # measured issue rate of the FP64 pipe (tools/fp64_probe.cu): 64 lanes/clk/SM when an instruction reads two
     # vector registers (the third operand uniform), 42.7 when it reads three -- most of the modal DFMAs do
-    fp64_ops = {"c2": 164 + 82 + 105, "c5": 164 + 82 + 70, "c1": 164 + 82 + 70, "c4": 1124 + 70, "c3": 300}.get(wl["name"], 0)
+    fp64_ops = {"c2": 164 + 82 + 105, "c5": 164 + 82 + 70, "c1": 164 + 82 + 70, "c4": 1124 + 70, "c4ns": 1124 + 200, "c3": 300}.get(wl["name"], 0)
     roofline = dict(bound="hbm", kernel=dom, achieved=achieved, peak=pk["hbm_gbs"], unit="GB/s",
                     frac=achieved / pk["hbm_gbs"], traffic=traffic, peak_source=pk["source"],
                     algorithmic_bytes_per_frame=wl["bytes_per_frame"], frames_per_launch=units_per_launch,
