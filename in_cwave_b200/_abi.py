@@ -85,7 +85,7 @@ EXPORTS = [
     "icw_session_process_device", "icw_session_sync", "icw_session_stats", "icw_hilbert_device",
     "icw_mt_words_device", "icw_session_set_taps", "icw_debug_phase_device", "icw_mt_host_charpoly",
     "icw_mt_host_seq_state", "icw_mt_host_jump_state", "icw_mt_host_jump_state_family",
-    "icw_session_profile", "icw_session_profile_read", "icw_kernel_class_name",
+    "icw_session_profile", "icw_session_profile_read", "icw_kernel_class_name", "icw_crc32_device", "icw_crc32_host", "icw_crc32_combine",
 ]
 
 _lib = None
@@ -130,6 +130,10 @@ def lib() -> C.CDLL:
     L.icw_session_stats.argtypes = [vp, P(Stats)]
     L.icw_session_profile.argtypes = [vp, C.c_int]
     L.icw_session_profile_read.argtypes = [vp, P(Profile), C.c_int]
+    L.icw_crc32_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32)]
+    L.icw_crc32_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32)]
+    L.icw_crc32_combine.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64]
+    L.icw_crc32_combine.restype = C.c_uint32
     L.icw_kernel_class_name.argtypes = [C.c_int]
     L.icw_kernel_class_name.restype = C.c_char_p
     L.icw_hilbert_device.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i64, vp, vp, P(StreamState)]

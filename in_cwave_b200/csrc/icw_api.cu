@@ -16,6 +16,7 @@
 #include "icw_kernels.h"
 #include "icw_mt.h"
 #include "icw_scan.h"
+#include "icw_crc.h"
 #include "icw_hb_tables.inc"
 #include "icw_ns_tables.inc"
 
@@ -78,6 +79,7 @@ struct icw_engine {
     Scratch analytic, mtw[2], ckpt, io_in, io_out, leaf;
     bool unfused = false;               // ICW_UNFUSED=1: keep the two-kernel exact path (A/B measurements)
     Scratch scan_scratch;
+    Scratch crc_partial;                // per-tile CRC registers + the result word
     Scratch ns_pre;                     // noise shaping: (value, dither) pairs between chain_kernel and ns_render_kernel
     struct ScanPlan { bool ready = false; ModalCoef mc; double *d_pw = nullptr; };
     ScanPlan scan[ICW_HB_NTYPES][2];    // [filter_no][baseline]
@@ -391,7 +393,7 @@ static void engine_free(icw_engine *e)
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     e->analytic.release(); e->mtw[0].release(); e->mtw[1].release(); e->ckpt.release();
-    e->io_in.release(); e->io_out.release(); e->leaf.release(); e->scan_scratch.release(); e->ns_pre.release();
+    e->io_in.release(); e->io_out.release(); e->leaf.release(); e->scan_scratch.release(); e->ns_pre.release(); e->crc_partial.release();
     for (auto &row : e->scan) for (auto &pl : row) if (pl.d_pw) cudaFree(pl.d_pw);
     e->mt.release();
     cudaStreamSynchronize(e->aux);
@@ -594,6 +596,51 @@ extern "C" int icw_session_set_spec(icw_session *s, const icw_chain_spec *spec)
     s->ch = ch;
     s->coef = coef;
     return ICW_OK;
+}
+
+// CRC-32 of a device buffer with the reference's conventions (src/crc32.c:55-108: crc32init / update / final)
+extern "C" int icw_crc32_device(icw_engine *e, const void *d_data, size_t n_bytes, uint32_t *crc_out)
+{
+    if (!e || !crc_out || (!d_data && n_bytes)) return fail(ICW_E_ARG, "NULL argument");
+    CK(cudaSetDevice(e->device));
+    const size_t words = n_bytes / 32768 + 4;
+    int rc = e->crc_partial.reserve(words * sizeof(uint32_t));
+    if (rc) return rc;
+    uint32_t *d_part = (uint32_t *)e->crc_partial.p, *d_res = d_part + (words - 1);
+    int nl = 0;
+    CK(launch_crc32_raw((const uint8_t *)d_data, n_bytes, d_part, d_res, e->stream, &nl));
+    uint32_t raw = 0;
+    CK(cudaMemcpyAsync(&raw, d_res, sizeof raw, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    // start value 0xFFFFFFFF adds its own image after n bytes; then the final inversion
+    *crc_out = ~(raw ^ crc32_shift(0xFFFFFFFFu, n_bytes));
+    return ICW_OK;
+}
+
+// the same over host memory: blocks go through the engine's input staging and are joined with crc32_combine
+extern "C" int icw_crc32_host(icw_engine *e, const void *data, size_t n_bytes, uint32_t *crc_out)
+{
+    if (!e || !crc_out || (!data && n_bytes)) return fail(ICW_E_ARG, "NULL argument");
+    CK(cudaSetDevice(e->device));
+    const size_t block = (size_t)64 << 20;
+    int rc = e->io_in.reserve(n_bytes < block ? (n_bytes ? n_bytes : 16) : block);
+    if (rc) return rc;
+    uint32_t crc = 0;                                   // CRC of the empty message
+    for (size_t off = 0; off < n_bytes; off += block) {
+        const size_t n = n_bytes - off < block ? n_bytes - off : block;
+        uint32_t part;
+        CK(cudaMemcpyAsync(e->io_in.p, (const uint8_t *)data + off, n, cudaMemcpyHostToDevice, e->stream));
+        rc = icw_crc32_device(e, e->io_in.p, n, &part);
+        if (rc) return rc;
+        crc = off ? crc32_combine(crc, part, n) : part;
+    }
+    *crc_out = crc;
+    return ICW_OK;
+}
+
+extern "C" uint32_t icw_crc32_combine(uint32_t crc_a, uint32_t crc_b, uint64_t len_b)
+{
+    return crc32_combine(crc_a, crc_b, len_b);
 }
 
 // test-only taps: device buffers that receive the whole bus and the master output per frame

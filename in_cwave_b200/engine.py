@@ -61,6 +61,12 @@ class Engine:
         _abi.check(_abi.lib().icw_mt_words_device(self._h, seed, skip, n, out.data_ptr()))
         return out.cpu().numpy().view(np.uint32)
 
+    def crc32(self, data) -> int:
+        """CRC-32 of a CUDA uint8 tensor (the reference's CWAVE data check, src/crc32.c:55-108)."""
+        out = C.c_uint32(0)
+        _abi.check(_abi.lib().icw_crc32_device(self._h, data.data_ptr(), data.numel() * data.element_size(), C.byref(out)))
+        return int(out.value)
+
     def debug_phase(self, spec: dict, n0: int, n: int, freq_hz: float):
         import torch
         out = torch.empty((n, 2), dtype=torch.float64, device=f"cuda:{self.device}")

@@ -37,6 +37,8 @@ static struct {
     int64_t         pcm_have, pcm_taken;    /* bytes */
 } P;
 
+static void ensure_defaults(void);
+
 /* ---- little-endian field readers ---------------------------------------------------------------- */
 static unsigned rd16(const unsigned char *p) { return (unsigned)p[0] | ((unsigned)p[1] << 8); }
 static uint32_t rd32(const unsigned char *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
@@ -195,6 +197,49 @@ static FILE *open_and_parse(const char *name, const icwp_options *opt, icwp_file
         }
     }
     return fp;
+}
+
+/* CWAVE sample-data integrity (reference check_cwave, src/gui_cwave.c:82-130): CRC-32 over exactly
+ * n_samples frames from offset_data, compared with the header's n_CRC32 when the file is V2. */
+int icwp_check_cwave(const char *filename, uint32_t *crc_calc, uint32_t *crc_file, int *has_crc)
+{
+    icwp_fileinfo fi;
+    unsigned char h[48];
+    FILE *fp;
+    int64_t left;
+    uint32_t crc = 0, part;
+    int first = 1, ok = 1;
+    const size_t block = (size_t)32 << 20;
+    unsigned char *buf;
+
+    ensure_defaults();
+    fp = open_and_parse(filename, NULL, &fi);
+    if (!fp) return 0;
+    if (fi.fmt < ICW_FMT_CW_F64) { fclose(fp); return 0; }          /* WAV carries no CRC */
+    if (fseeko(fp, 0, SEEK_SET) || fread(h, 1, 48, fp) != 48) { fclose(fp); return 0; }
+    if (has_crc) *has_crc = rd32(h + 12) > 1;                        /* V1 headers have no CRC field */
+    if (crc_file) *crc_file = rd32(h + 36);
+    if (!P.engine && icw_engine_create(P.opt.device, &P.engine) != ICW_OK) { fclose(fp); return 0; }
+    {
+        icw_chain_spec sp;
+        icw_default_spec(&sp);
+        sp.fmt = fi.fmt; sp.n_channels = fi.n_channels;
+        left = fi.n_samples * (int64_t)icw_frame_bytes(&sp);
+    }
+    buf = malloc(block);
+    if (!buf || fseeko(fp, (off_t)fi.offset_data, SEEK_SET)) { free(buf); fclose(fp); return 0; }
+    while (left > 0 && ok) {
+        size_t n = left < (int64_t)block ? (size_t)left : block;
+        if (fread(buf, 1, n, fp) != n) { ok = 0; break; }           /* "Read error or file corrupted" */
+        if (icw_crc32_host(P.engine, buf, n, &part) != ICW_OK) { ok = 0; break; }
+        crc = first ? part : icw_crc32_combine(crc, part, n);
+        first = 0;
+        left -= (int64_t)n;
+    }
+    free(buf);
+    fclose(fp);
+    if (ok && crc_calc) *crc_calc = crc;
+    return ok;
 }
 
 int icwp_probe(const char *filename, const icwp_options *opt, icwp_fileinfo *out)

@@ -11,7 +11,7 @@ from . import _abi, spec as _spec
 PLUGIN_PATH = Path(__file__).resolve().parent / "libicw_plugin.so"
 EXPORTS = ["winampGetExtendedRead_open", "winampGetExtendedRead_getData", "winampGetExtendedRead_setTime",
            "winampGetExtendedRead_close", "icwp_configure", "icwp_reset", "icwp_stats", "icwp_probe",
-           "icwp_load_config", "icwp_save_config"]
+           "icwp_load_config", "icwp_save_config", "icwp_check_cwave"]
 
 
 class Options(C.Structure):
@@ -48,6 +48,7 @@ def lib() -> C.CDLL:
         L.icwp_reset.restype = None
         L.icwp_stats.argtypes = [C.POINTER(_abi.Stats)]
         L.icwp_probe.argtypes = [C.c_char_p, C.POINTER(Options), C.POINTER(FileInfo)]
+        L.icwp_check_cwave.argtypes = [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), ip]
         L.icwp_load_config.argtypes = [C.c_char_p, C.POINTER(_abi.ChainSpecC), C.POINTER(Options)]
         L.icwp_save_config.argtypes = [C.c_char_p, C.POINTER(_abi.ChainSpecC), C.POINTER(Options)]
         _lib = L
@@ -75,6 +76,13 @@ def load_config(path: str):
 def save_config(path: str, spec: dict, **opt) -> bool:
     o = Options(**opt)
     return bool(lib().icwp_save_config(str(path).encode(), _spec.to_c(spec), C.byref(o)))
+
+
+def check_cwave(path: str):
+    """(readable, crc_calculated, crc_in_header, header_has_crc) -- the reference's file-info CRC check."""
+    calc, filec, has = C.c_uint32(0), C.c_uint32(0), C.c_int(0)
+    ok = lib().icwp_check_cwave(str(path).encode(), C.byref(calc), C.byref(filec), C.byref(has))
+    return bool(ok), int(calc.value), int(filec.value), bool(has.value)
 
 
 def probe(path: str, **opt):

@@ -193,6 +193,13 @@ int  icw_hilbert_device(icw_engine *e, int filter_no, int is_kahan, int is_rejec
  * produced on the GPU through the jump-ahead path */
 int  icw_mt_words_device(icw_engine *e, uint32_t seed, uint64_t skip, int64_t n, uint32_t *d_out);
 
+/* CRC-32 of a device buffer, the reference's CWAVE data check (src/crc32.c:55-108 as driven by
+ * src/gui_cwave.c:82-130; == CRC-32/ISO-HDLC).  Synchronous.  icw_crc32_combine joins the CRCs of two
+ * consecutive pieces (crc of A, crc of B, length of B) so a file can be checked block by block. */
+int  icw_crc32_device(icw_engine *e, const void *d_data, size_t n_bytes, uint32_t *crc_out);
+int  icw_crc32_host(icw_engine *e, const void *data, size_t n_bytes, uint32_t *crc_out);   /* host memory, staged in blocks */
+uint32_t icw_crc32_combine(uint32_t crc_a, uint32_t crc_b, uint64_t len_b);
+
 /* ---- measurement: per-kernel device time from CUDA events on the launching stream ---------- */
 /* HILBERT: the exact recurrences (fused with the chain unless ICW_UNFUSED); SCAN_LOCAL / SCAN_APPLY: passes 1+2 and
  * pass 3 of the time-parallel converter; CHAIN: the pointwise kernel; MT: dither word generation incl. jump-ahead */

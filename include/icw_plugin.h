@@ -68,6 +68,10 @@ typedef struct icwp_fileinfo {
 } icwp_fileinfo;
 int  icwp_probe(const char *filename, const icwp_options *opt, icwp_fileinfo *out);
 
+/* CWAVE data check (reference check_cwave, src/gui_cwave.c:82-130): CRC-32 of the sample data on the GPU.
+ * Returns 1 when the data could be read; *has_crc = 0 for V1 files (no CRC in the header). */
+int  icwp_check_cwave(const char *filename, uint32_t *crc_calc, uint32_t *crc_file, int *has_crc);
+
 /* The reference's configuration file (text, "KEYWORD=values"; src/config.c:815-975, DSP-list lines
  * :562-774) -> chain + options, with the reference's acceptance rules: bounds clamped; an unknown
  * keyword, a line without '=' or version != 10 rejects the whole file (defaults left, returns 0) while a

@@ -328,14 +328,14 @@ def wav_bytes(d: dict, raw: np.ndarray, extensible: bool = False) -> bytes:
     return b"RIFF" + struct.pack("<I", len(body)) + body
 
 
-def cwave_bytes(d: dict, raw: np.ndarray, version: int = 2) -> bytes:
+def cwave_bytes(d: dict, raw: np.ndarray, version: int = 2, crc: int = 0) -> bytes:
     """CWAVE V2 header (reference src/cwave.h:47-59, 48 bytes packed) + raw I/Q sample bytes."""
     fmt = {"cw_f64": 0, "cw_i16": 1, "cw_i16f32": 2, "cw_f32": 3}[d["fmt"]]
     nch = int(d.get("n_channels", 2))
     data = np.ascontiguousarray(raw, dtype=np.uint8).tobytes()
     n = len(data) // frame_bytes(d)
     hdr = b"cPLXwAVE" + struct.pack("<IIIIIIiId", 48, version, fmt, nch, n,
-                                     int(d.get("sample_rate", 96000)), -1, 0, 0.0)
+                                     int(d.get("sample_rate", 96000)), -1, crc & 0xFFFFFFFF, 0.0)
     assert len(hdr) == 48
     return hdr + data
 

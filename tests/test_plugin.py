@@ -204,3 +204,26 @@ def test_state_survives_into_the_next_file(tmp_path):
     p1, _ = plugin.transcode(a)
     p2, _ = plugin.transcode(b)
     assert np.array_equal(p1, r1["pcm"]) and np.array_equal(p2, r2["pcm"])
+
+
+@pytest.mark.gpu
+def test_cwave_crc_check_like_the_reference_info_dialog(tmp_path):
+    """check_cwave (src/gui_cwave.c:82-130) -- CRC-32 of the sample data against the V2 header."""
+    import zlib
+    spec = S.config_c3()
+    raw = synth.stream_bytes(spec, 70001, stream_id=3)
+    good = zlib.crc32(np.ascontiguousarray(raw).tobytes())
+    f = tmp_path / "ok.cwave"
+    f.write_bytes(po.cwave_bytes(spec, raw, crc=good) + b"trailing bytes are not sample data")
+    assert plugin.check_cwave(f) == (True, good, good, True)
+    bad = bytearray(po.cwave_bytes(spec, raw, crc=good))
+    bad[48 + 12345] ^= 0x40
+    g = tmp_path / "bad.cwave"
+    g.write_bytes(bytes(bad))
+    ok, calc, filec, has = plugin.check_cwave(g)
+    assert ok and has and filec == good and calc != good
+    v1 = tmp_path / "v1.cwave"
+    v1.write_bytes(po.cwave_bytes(spec, raw, version=1))
+    ok, calc, filec, has = plugin.check_cwave(v1)
+    assert ok and not has and calc == good
+    assert plugin.check_cwave(tmp_path / "missing.cwave")[0] is False
