@@ -239,8 +239,8 @@ mt_words_kernel(const uint32_t *__restrict__ ckpt /* [unit][624] */, int n_units
     const int tail_blk = (tl >= 0 && tl < n_blk) ? (int)tl : -1;
     if (tail_blk >= 0 && tail_blk < e_hi) e_hi = tail_blk;
     uint32_t *o = out + (u0 - want_lo) + t;
-    int cur = 0;
-    for (int blk = 0; blk < n_blk; ++blk, o += ICW_MT_N) {
+    // one block with every special case: partial ranges, the tail states
+    auto step = [&](int blk, int cur) {
         const uint32_t *old = buf[cur];
         uint32_t *nw = buf[cur ^ 1];
         const bool is_tail = blk == tail_blk;
@@ -253,8 +253,19 @@ mt_words_kernel(const uint32_t *__restrict__ ckpt /* [unit][624] */, int n_units
         __syncthreads();
         if (is_tail)
             for (int i = t; i < ICW_MT_N; i += MT_WORDS_THREADS) tail[ICW_MT_N + i] = nw[i];
-        cur ^= 1;
+        o += ICW_MT_N;
+    };
+    int blk = 0;
+    for (; blk < n_blk && blk < e_lo; ++blk) step(blk, blk & 1);
+    // interior blocks two at a time: fixed buffer roles, no per-block case analysis
+    if (blk & 1) { if (blk < n_blk) { step(blk, 1); ++blk; } }
+    for (; blk + 2 <= e_hi; blk += 2, o += 2 * ICW_MT_N) {
+        if (active) mt_words_block<false>(buf[0], buf[1], t, s0, s1, s2, o, 0, 0, 0);
+        __syncthreads();
+        if (active) mt_words_block<false>(buf[1], buf[0], t, s0, s1, s2, o + ICW_MT_N, 0, 0, 0);
+        __syncthreads();
     }
+    for (; blk < n_blk; ++blk) step(blk, blk & 1);
 }
 
 cudaError_t launch_mt_words(const uint32_t *ckpt, int n_units, int blocks_per_unit, int64_t first_word,
@@ -273,7 +284,11 @@ cudaError_t launch_mt_words(const uint32_t *ckpt, int n_units, int blocks_per_un
 // one thread per frame, grid-stride inside a stream (blockIdx.y = stream).
 // src: raw file bytes (complex formats) or the analytic scratch written by hb_exact_kernel
 // (from_analytic: 4 doubles per frame, no fade -- it was applied before the Hilbert converter).
-__global__ void __launch_bounds__(256, 4)
+#ifndef ICW_CHAIN_THREADS
+#define ICW_CHAIN_THREADS 256
+#define ICW_CHAIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(ICW_CHAIN_THREADS, ICW_CHAIN_CTAS)
 chain_kernel(const __grid_constant__ DevChain ch, DevStream *__restrict__ streams, int64_t n_frames,
              const uint8_t *__restrict__ in, size_t in_stride, int from_analytic,
              const uint32_t *__restrict__ mtw_l, const uint32_t *__restrict__ mtw_r, size_t mt_stream_stride,
@@ -320,11 +335,11 @@ cudaError_t launch_chain(const DevChain &ch, DevStream *streams, int n_streams, 
                          uint8_t *out, size_t out_stride, double *tap_bus, double *tap_lr, double *pre,
                          int sm_count, cudaStream_t s)
 {
-    int threads = 256;
+    int threads = ICW_CHAIN_THREADS;
     int64_t need = (n_frames + threads - 1) / threads;
     int per_stream = (int)(need < 1 ? 1 : need);
     // keep the grid near a few waves of the machine
-    int cap = (sm_count * 8 + n_streams - 1) / n_streams;
+    int cap = (sm_count * 2 * ICW_CHAIN_CTAS + n_streams - 1) / n_streams;
     if (cap < 1) cap = 1;
     if (per_stream > cap) per_stream = cap;
     dim3 grid(per_stream, n_streams);
