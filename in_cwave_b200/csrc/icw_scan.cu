@@ -46,6 +46,7 @@ void scan_make_coef(int filter_no, bool baseline, double d0, ModalCoef &mc, std:
     memset(&mc, 0, sizeof mc);
     const int nm = ICW_HB_NMODES[filter_no];
     mc.nm = nm;
+    mc.real_last = ICW_HB_MODES[filter_no][nm - 1].is_real;
     mc.baseline = baseline;
     mc.d0 = d0;
     pw_table.assign((size_t)SCAN_CH * SCAN_NMAX * 2, 0.0);
@@ -142,6 +143,9 @@ __device__ __forceinline__ void cx_step(Cx &s, double mr, double mi, double u)
     s.re = nr; s.im = ni;
 }
 
+// the same for the real pole of an odd-order design: its state has no imaginary part, ever
+__device__ __forceinline__ void re_step(Cx &s, double mr, double u) { s.re = fma(mr, s.re, u); }
+
 // FMT is a compile-time constant: the format switch folds away inside the sample loops
 template <int FMT, bool FADE>
 __device__ __forceinline__ double scan_sample(const DevChain &ch, const uint8_t *row, int64_t frame, int chan_off,
@@ -181,7 +185,7 @@ __device__ __forceinline__ bool chunk_fades(const DevChain &ch, int64_t pos, int
 }
 
 // pass-1 inner loop: SCAN_L / 2 inputs of one filter from a zero state, sign-free form
-template <int NM, int FMT, bool FADE>
+template <int NM, bool RL, int FMT, bool FADE>
 __device__ __forceinline__ void local_run(Cx (&s)[NM], const double (&kpr)[NM], const double (&kpi)[NM], const DevChain &ch,
                                           const uint8_t *row, int64_t f0, int chan_off, int64_t pos0, const uint8_t *row_last)
 {
@@ -191,7 +195,10 @@ __device__ __forceinline__ void local_run(Cx (&s)[NM], const double (&kpr)[NM], 
         const double xn = scan_sample<FMT, FADE>(ch, row, f0 + kn, chan_off, pos0);
         scan_prefetch<FMT>(ch, row, f0 + kn, chan_off, row_last);
 #pragma unroll
-        for (int m = 0; m < NM; ++m) cx_step(s[m], kpr[m], kpi[m], -x);
+        for (int m = 0; m < NM; ++m) {
+            if (RL && m == NM - 1) re_step(s[m], kpr[m], -x);
+            else cx_step(s[m], kpr[m], kpi[m], -x);
+        }
         x = xn;
     }
 }
@@ -199,7 +206,7 @@ __device__ __forceinline__ void local_run(Cx (&s)[NM], const double (&kpr)[NM], 
 // pass-3 inner loop: one filter over one chunk from its true state S~, writing its half of every
 // frame.  The filter's inputs sit at frames off, off + 2, ...; the frame of an input gets
 // sum(2cp S~) (+ 2 d0 x) in its re slot, the frame after it sum(-2c S~') in its im slot.
-template <int NM, int FMT, bool FADE>
+template <int NM, bool RL, int FMT, bool FADE>
 __device__ __forceinline__ int apply_run(Cx (&S)[NM], const ModalCoef &mc, const double (*kshared)[SCAN_NMAX], bool direct, double d0x2, const DevChain &ch,
                                          const uint8_t *row, int64_t f0, int off, int len, int chan_off, int64_t pos0,
                                          const uint8_t *row_last, double *__restrict__ dst)
@@ -227,9 +234,15 @@ __device__ __forceinline__ int apply_run(Cx (&S)[NM], const ModalCoef &mc, const
         double y1 = direct ? d0x2 * x : 0.0, y2 = 0.0;
 #pragma unroll
         for (int m = 0; m < NM; ++m) {
-            y1 = fma(kcpr[m], S[m].re, fma(kcpi[m], S[m].im, y1));
-            cx_step(S[m], kpr[m], kpi[m], -x);
-            y2 = fma(kcr[m], S[m].re, fma(kci[m], S[m].im, y2));
+            if (RL && m == NM - 1) {                            // the real pole: im == 0 and its weights are 0
+                y1 = fma(kcpr[m], S[m].re, y1);
+                re_step(S[m], kpr[m], -x);
+                y2 = fma(kcr[m], S[m].re, y2);
+            } else {
+                y1 = fma(kcpr[m], S[m].re, fma(kcpi[m], S[m].im, y1));
+                cx_step(S[m], kpr[m], kpi[m], -x);
+                y2 = fma(kcr[m], S[m].re, fma(kci[m], S[m].im, y2));
+            }
         }
         dst[(size_t)j * 4] = y1;
         dst[(size_t)(j + 1) * 4 + 1] = y2;
@@ -257,7 +270,7 @@ __device__ __forceinline__ int apply_run(Cx (&S)[NM], const ModalCoef &mc, const
 // exactly one tile of 128 chunks -- the carry scan over chunks: warp shuffles (8 chunks per warp),
 // one shared-memory hop across the 16 warps.  Writes, per chunk, its carry-in from the tile start
 // (exclusive prefix) and, per tile, the tile's end state.
-template <int NM, int FMT>
+template <int NM, bool RL, int FMT>
 __global__ void __launch_bounds__(512, 1)
 scan_local_kernel(const __grid_constant__ ModalCoef mc, const __grid_constant__ DevChain ch,
                   const DevStream *__restrict__ streams, int64_t n_frames, int64_t n_chunks, int64_t n_tiles,
@@ -292,9 +305,9 @@ scan_local_kernel(const __grid_constant__ ModalCoef mc, const __grid_constant__ 
 #pragma unroll
         for (int m = 0; m < NM; ++m) { kpr[m] = kconst<LOCAL_UMASK>(mc, kshared, K_PR, m); kpi[m] = kconst<LOCAL_UMASK>(mc, kshared, K_PI, m); }
         if (chunk_fades(ch, st.pos + chunk * SCAN_L, SCAN_L))
-            local_run<NM, FMT, true>(s, kpr, kpi, ch, row, f0, chan_off, st.pos, row_last);
+            local_run<NM, RL, FMT, true>(s, kpr, kpi, ch, row, f0, chan_off, st.pos, row_last);
         else
-            local_run<NM, FMT, false>(s, kpr, kpi, ch, row, f0, chan_off, st.pos, row_last);
+            local_run<NM, RL, FMT, false>(s, kpr, kpi, ch, row, f0, chan_off, st.pos, row_last);
         // S~ -> S: SCAN_L / 2 inputs is an even count, the sign is the first input's
         const double sg = mixer_sign(filt, qf);
 #pragma unroll
@@ -399,7 +412,7 @@ scan_tile_carry_kernel(const __grid_constant__ ModalCoef mc, const DevStream *__
 
 // pass 3: every chunk again, from its true initial state, producing the analytic signal.
 // Each thread writes its own filter's half of every frame: re or im, alternating with the phase.
-template <int NM, int FMT>
+template <int NM, bool RL, int FMT>
 __global__ void __launch_bounds__(256, 1)
 scan_apply_kernel(const __grid_constant__ ModalCoef mc, const __grid_constant__ DevChain ch,
                   DevStream *__restrict__ streams, int64_t n_frames, int64_t n_chunks, int64_t n_tiles,
@@ -450,9 +463,9 @@ scan_apply_kernel(const __grid_constant__ ModalCoef mc, const __grid_constant__ 
     const double d0x2 = 2.0 * mc.d0;
     int n_in;
     if (chunk_fades(ch, st.pos + f0, len))
-        n_in = apply_run<NM, FMT, true>(S, mc, kshared, direct, d0x2, ch, row, f0, off, len, chan_off, st.pos, row_last, dst);
+        n_in = apply_run<NM, RL, FMT, true>(S, mc, kshared, direct, d0x2, ch, row, f0, off, len, chan_off, st.pos, row_last, dst);
     else
-        n_in = apply_run<NM, FMT, false>(S, mc, kshared, direct, d0x2, ch, row, f0, off, len, chan_off, st.pos, row_last, dst);
+        n_in = apply_run<NM, RL, FMT, false>(S, mc, kshared, direct, d0x2, ch, row, f0, off, len, chan_off, st.pos, row_last, dst);
     if (chunk == n_chunks - 1) {
         // state after the call's last sample: undo the sign (it flips with every input), and a filter
         // whose last input was not the last frame has idled one sample since
@@ -479,7 +492,7 @@ size_t scan_scratch_doubles(int n_streams, int64_t n_frames)
     return e + 2 * t;
 }
 
-template <int NM, int FMT>
+template <int NM, bool RL, int FMT>
 static cudaError_t scan_launch_nf(const ModalCoef &mc, const DevChain &ch, DevStream *streams, int n_streams,
                                   int64_t n_frames, const uint8_t *in, size_t in_stride, const double *pw,
                                   double *scratch, double *analytic, cudaStream_t s, int *launches,
@@ -491,25 +504,25 @@ static cudaError_t scan_launch_nf(const ModalCoef &mc, const DevChain &ch, DevSt
     double *Tend = E + (size_t)n_streams * (4 * SCAN_NMAX) * 2 * (size_t)n_chunks;
     double *Tin = Tend + (size_t)n_streams * (size_t)n_tiles * 2 * 2 * (SCAN_NMAX * 2);
     const unsigned cgrid = (unsigned)n_tiles;                   // one CTA = one tile: 128 chunks x 2 channels x 2 filters
-    scan_local_kernel<NM, FMT><<<dim3(cgrid, n_streams), 512, 0, s>>>(mc, ch, streams, n_frames, n_chunks, n_tiles, in, in_stride, E, Tend);
+    scan_local_kernel<NM, RL, FMT><<<dim3(cgrid, n_streams), 512, 0, s>>>(mc, ch, streams, n_frames, n_chunks, n_tiles, in, in_stride, E, Tend);
     const int64_t items = n_tiles * 2 * 2 * mc.nm;
     const unsigned tgrid = (unsigned)((items + 127) / 128);
     scan_tile_carry_kernel<<<dim3(tgrid, n_streams), 128, 0, s>>>(mc, streams, n_tiles, Tend, Tin);
     if (mid_end) { cudaEventRecord(mid_end, s); cudaEventRecord(mid_start, s); }
     const unsigned agrid = (unsigned)((n_chunks + 63) / 64);
-    scan_apply_kernel<NM, FMT><<<dim3(agrid, n_streams), 256, 0, s>>>(mc, ch, streams, n_frames, n_chunks, n_tiles, in, in_stride,
+    scan_apply_kernel<NM, RL, FMT><<<dim3(agrid, n_streams), 256, 0, s>>>(mc, ch, streams, n_frames, n_chunks, n_tiles, in, in_stride,
                                                                     E, Tin, pw, analytic);
     *launches += 3;
     return cudaGetLastError();
 }
 
-template <int NM>
+template <int NM, bool RL>
 static cudaError_t scan_launch_nm(const ModalCoef &mc, const DevChain &ch, DevStream *streams, int n_streams,
                                   int64_t n_frames, const uint8_t *in, size_t in_stride, const double *pw,
                                   double *scratch, double *analytic, cudaStream_t s, int *launches,
                                   cudaEvent_t mid_end, cudaEvent_t mid_start)
 {
-#define ICW_SCAN_FMT(F) case F: return scan_launch_nf<NM, F>(mc, ch, streams, n_streams, n_frames, in, in_stride, pw, scratch, analytic, s, launches, mid_end, mid_start)
+#define ICW_SCAN_FMT(F) case F: return scan_launch_nf<NM, RL, F>(mc, ch, streams, n_streams, n_frames, in, in_stride, pw, scratch, analytic, s, launches, mid_end, mid_start)
     switch (ch.fmt) {
         ICW_SCAN_FMT(ICW_FMT_WAV_U8);
         ICW_SCAN_FMT(ICW_FMT_WAV_I16);
@@ -527,9 +540,11 @@ cudaError_t launch_hb_scan(const ModalCoef &mc, const DevChain &ch, DevStream *s
                            double *scratch, double *analytic, cudaStream_t s, int *launches, cudaEvent_t mid_end, cudaEvent_t mid_start)
 {
     switch (mc.nm) {
-    case 8:  return scan_launch_nm<8>(mc, ch, streams, n_streams, n_frames, in, in_stride, pw, scratch, analytic, s, launches, mid_end, mid_start);
-    case 9:  return scan_launch_nm<9>(mc, ch, streams, n_streams, n_frames, in, in_stride, pw, scratch, analytic, s, launches, mid_end, mid_start);
-    case 10: return scan_launch_nm<10>(mc, ch, streams, n_streams, n_frames, in, in_stride, pw, scratch, analytic, s, launches, mid_end, mid_start);
+    // odd orders end with a real pole (15 -> 7 pairs + 1, 19 -> 9 + 1): its mode runs in scalar form
+    case 8:  return scan_launch_nm<8, true>(mc, ch, streams, n_streams, n_frames, in, in_stride, pw, scratch, analytic, s, launches, mid_end, mid_start);
+    case 9:  return scan_launch_nm<9, false>(mc, ch, streams, n_streams, n_frames, in, in_stride, pw, scratch, analytic, s, launches, mid_end, mid_start);
+    case 10: return mc.real_last ? scan_launch_nm<10, true>(mc, ch, streams, n_streams, n_frames, in, in_stride, pw, scratch, analytic, s, launches, mid_end, mid_start)
+                                : scan_launch_nm<10, false>(mc, ch, streams, n_streams, n_frames, in, in_stride, pw, scratch, analytic, s, launches, mid_end, mid_start);
     default: return cudaErrorInvalidValue;
     }
 }

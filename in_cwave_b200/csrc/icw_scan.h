@@ -16,6 +16,7 @@ constexpr int64_t SCAN_SEGMENT = 1 << 25;   // frames per launch group (bounds t
 // partial-fraction form of one half-band design, folded for the two-sample step (icw_scan.cu)
 struct ModalCoef {
     int    nm, baseline;
+    int    real_last, pad_;                         // the last mode is the real pole of an odd-order design
     double d0;
     double p_re[SCAN_NMAX], p_im[SCAN_NMAX];        // pole
     double p2_re[SCAN_NMAX], p2_im[SCAN_NMAX];      // pole^2
