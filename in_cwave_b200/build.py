@@ -16,7 +16,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libicw_b200.so"
-SOURCES = ["icw_api.cu", "icw_kernels.cu", "icw_fused.cu", "icw_scan.cu", "icw_mt.cu", "icw_crc.cu"]
+SOURCES = ["icw_api.cu", "icw_kernels.cu", "icw_fused.cu", "icw_scan.cu", "icw_mt.cu", "icw_crc.cu", "icw_chainmt.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17",
     "-gencode", "arch=compute_100a,code=sm_100a",

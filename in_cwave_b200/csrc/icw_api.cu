@@ -78,6 +78,7 @@ struct icw_engine {
     bool dying = false;                 // icw_engine_destroy was called while sessions were alive
     Scratch analytic, mtw[2], ckpt, io_in, io_out, leaf;
     bool unfused = false;               // ICW_UNFUSED=1: keep the two-kernel exact path (A/B measurements)
+    bool no_fuse_mt = false;            // ICW_NO_FUSE_MT=1: dither words through HBM even where chain_mt_kernel applies (A/B)
     Scratch scan_scratch;
     Scratch crc_partial;                // per-tile CRC registers + the result word
     Scratch ns_pre;                     // noise shaping: (value, dither) pairs between chain_kernel and ns_render_kernel
@@ -375,6 +376,7 @@ extern "C" int icw_engine_create(int device, icw_engine **out)
     CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
     { const char *u = getenv("ICW_UNFUSED"); e->unfused = u && *u == '1'; }
+    { const char *u = getenv("ICW_NO_FUSE_MT"); e->no_fuse_mt = u && *u == '1'; }
     *out = e;
     return ICW_OK;
 }
@@ -710,15 +712,17 @@ static int get_scan_plan(icw_engine *e, int filter_no, bool baseline, double d0,
 
 // one launch group: n_frames of every stream, state read from and left in the DevStream array
 // `pre`: dither words generated once for the whole call (pointing at this group's first frame), or NULL
+// `fuse_mt`: no word buffers at all -- chain_mt_kernel regenerates the dither inside the pointwise pass
 static int process_group(icw_session *s, int64_t n_frames, const uint8_t *d_in, size_t in_stride,
-                         uint8_t *d_out, size_t out_stride, cudaStream_t st, const DitherWords *pre)
+                         uint8_t *d_out, size_t out_stride, cudaStream_t st, const DitherWords *pre, bool fuse_mt)
 {
     icw_engine *e = s->e;
     const DevChain &ch = s->ch;
     const int K = s->n_streams;
     int rc;
     DitherWords dw;
-    if (pre) dw = *pre;
+    if (fuse_mt) { }
+    else if (pre) dw = *pre;
     else {
         ProfSpan ps(s, st, ICW_K_MT);
         rc = make_dither_words(s, n_frames, st, dw);
@@ -783,9 +787,24 @@ static int process_group(icw_session *s, int64_t n_frames, const uint8_t *d_in, 
             if (rc) return rc;
             pre = (double *)e->ns_pre.p;
         }
-        ProfSpan ps(s, st, ICW_K_CHAIN);
-        CK(launch_chain(ch, s->d_streams, K, n_frames, src, src_stride, from_analytic, wl, wr, mt_shared,
-                        d_out, out_stride, s->d_tap_bus, s->d_tap_lr, pre, e->sm_count, st));
+        if (fuse_mt) {
+            MtPlan pl[2];
+            {
+                ProfSpan ps(s, st, ICW_K_MT);
+                for (int c = 0; c < 2; ++c) {
+                    rc = e->mt.plan(c, s->mt_seed[c][0], s->mt_drawn[c][0], n_frames * ch.render.words_per_sample,
+                                    chain_mt_max_units(e->sm_count), e->sm_count, st, &s->launches, pl[c]);
+                    if (rc) return fail(rc, "%s", e->mt.error());
+                }
+            }
+            ProfSpan ps(s, st, ICW_K_CHAIN);
+            CK(launch_chain_mt(ch, s->d_streams, n_frames, src, from_analytic, pl[0], pl[1], d_out,
+                               s->d_tap_bus, s->d_tap_lr, pre, st));
+        } else {
+            ProfSpan ps(s, st, ICW_K_CHAIN);
+            CK(launch_chain(ch, s->d_streams, K, n_frames, src, src_stride, from_analytic, wl, wr, mt_shared,
+                            d_out, out_stride, s->d_tap_bus, s->d_tap_lr, pre, e->sm_count, st));
+        }
         s->launches++;
         if (shaped) {
             CK(launch_ns_render(ch, s->d_streams, K, n_frames, pre, d_out, out_stride, st));
@@ -807,12 +826,18 @@ static int process_group(icw_session *s, int64_t n_frames, const uint8_t *d_in, 
 struct CallCtx {
     DitherWords all;
     bool pre = false;
+    bool fuse_mt = false;   // dither regenerated inside the pointwise kernel: no word buffers
     int64_t step = 0;       // frames per launch group
     int mode = 0;
     bool real_in = false;
 };
 
-static int call_begin(icw_session *s, int64_t n_total, cudaStream_t st, CallCtx &cx)
+// frames per launch group when the group's dither comes from chain_mt_kernel: its CTAs are the
+// generator's jump-ahead units, so a group should be the whole call (analytic scratch: 32 B/frame)
+constexpr int64_t FUSE_MT_GROUP = (int64_t)1 << 30;
+
+// `one_range`: the caller hands the whole call over in a single call_range()
+static int call_begin(icw_session *s, int64_t n_total, cudaStream_t st, CallCtx &cx, bool one_range)
 {
     icw_engine *e = s->e;
     const DevChain &ch = s->ch;
@@ -830,8 +855,16 @@ static int call_begin(icw_session *s, int64_t n_total, cudaStream_t st, CallCtx 
     const bool scratchy = cx.real_in && (cx.mode == ICW_HILBERT_SCAN || e->unfused);
     const int64_t seg = scratchy ? SCAN_SEGMENT / (K > 64 ? 64 : K) / SCAN_L / SCAN_CH * (SCAN_L * SCAN_CH) : n_total;
     cx.step = seg < SCAN_L * SCAN_CH ? SCAN_L * SCAN_CH : seg;
-    // dither words for the whole call in one go when they fit (one jump tree instead of one per group)
     const int wps = ch.render.words_per_sample;
+    // the fused exact kernel reads word buffers; everything else that ends in chain_kernel can make its own
+    const bool hb_fused = cx.real_in && cx.mode == ICW_HILBERT_EXACT && !e->unfused && ch.render.ns_kind == 0;
+    if (wps && one_range && !hb_fused && !e->no_fuse_mt && K == 1 && chain_mt_supports(ch) &&
+        s->mt_drawn[0][0] == s->mt_drawn[1][0] && s->mt_drawn[0][0] % (uint64_t)wps == 0) {
+        cx.fuse_mt = true;
+        if (scratchy) cx.step = n_total < FUSE_MT_GROUP ? (n_total < cx.step ? cx.step : n_total) : FUSE_MT_GROUP;
+        return ICW_OK;
+    }
+    // dither words for the whole call in one go when they fit (one jump tree instead of one per group)
     if (wps && (double)n_total * wps * 4.0 * 2.0 * (K > 1 ? K : 1) <= 48e9) {
         // integer work on the aux stream next to the FP64-bound Hilbert kernels on `st`; the word
         // buffers may still be read by the previous call, so the aux stream first joins `st`
@@ -868,7 +901,7 @@ static int call_range(icw_session *s, CallCtx &cx, int64_t f0, int64_t n, const 
             cx.all.join = nullptr;
         }
         int rc = process_group(s, gn, d_in + (size_t)g0 * ch.frame_bytes, in_stride,
-                               d_out + (size_t)g0 * ch.out_frame_bytes, out_stride, st, cx.pre ? &here : nullptr);
+                               d_out + (size_t)g0 * ch.out_frame_bytes, out_stride, st, cx.pre ? &here : nullptr, cx.fuse_mt);
         if (rc) return rc;
     }
     return ICW_OK;
@@ -901,7 +934,7 @@ extern "C" int icw_session_process_device(icw_session *s, int64_t n_frames, cons
     CK(cudaSetDevice(e->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
     CallCtx cx;
-    int rc = call_begin(s, n_frames, st, cx);
+    int rc = call_begin(s, n_frames, st, cx, true);
     if (rc) return rc;
     rc = call_range(s, cx, 0, n_frames, (const uint8_t *)d_in, in_stride, (uint8_t *)d_out, out_stride, st);
     if (rc) return rc;
@@ -952,7 +985,7 @@ extern "C" int icw_session_process_host(icw_session *s, int64_t n_frames, const 
     note_alignment(s, e->io_in.p, din_stride);
     cudaStream_t st = e->stream;
     CallCtx cx;
-    rc = call_begin(s, n_frames, st, cx);
+    rc = call_begin(s, n_frames, st, cx, nbuf == 1);
     if (rc) return rc;
     int64_t k = 0;
     for (int64_t f0 = 0; f0 < n_frames; f0 += seg, ++k) {

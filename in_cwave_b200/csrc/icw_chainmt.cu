@@ -1,0 +1,228 @@
+// icw_chainmt.cu -- the pointwise chain with the dither generator inside it.
+//
+//   chain_mt_kernel   MT19937 block regeneration (both channels' generators) into shared memory,
+//                     then unpack -> oscillator -> DSP list -> dither + quantise -> PCM for the
+//                     frames those words belong to; tile after tile along the CTA's own span.
+//
+// chain_kernel reads its dither from a buffer that mt_words_kernel wrote: 8 (RPDF) or 16 (TPDF)
+// bytes per channel-sample go to HBM and come back, 64 of the ~140 bytes per frame the C2 workload
+// moved.  Here a CTA owns one "unit" of the generator's stream -- a run of 2^k consecutive
+// 624-word blocks that starts at a jump-ahead checkpoint (icw_mt.cu) -- and the frames whose draws
+// fall into it (the draw index is a closed form of the frame index: reference
+// src/sound_render.c:711-751 draws 2 or 4 words per channel-sample, in order).  The words never
+// leave the SM.  Block regeneration is mt_words_block (icw_mtdev.cuh), the frame arithmetic is
+// the same code chain_kernel runs (icw_frame.cuh): the bytes are identical by construction and
+// tests/test_gpu_parity.py compares both routes with the oracle.
+//
+// Straight-line DSP lists (Master alone, Shift -> Master) with plain PCM output get a lean frame
+// path: list shape and dither type are template parameters, no thread-private bus.
+#include "icw_dev.cuh"
+#include "icw_frame.cuh"
+#include "icw_kernels.h"
+#include "icw_mtdev.cuh"
+
+namespace icw {
+
+constexpr int CMT_THREADS = 256;
+constexpr int CMT_CTAS = 4;                         // resident per SM
+constexpr int CMT_TB = 8;                           // blocks per tile: 1248 TPDF frames, 2496 RPDF frames
+constexpr int CMT_STATE = ICW_MT_N + 8;             // + slack, see mt_words_kernel
+constexpr size_t CMT_SMEM = (size_t)(2 * 2 * CMT_STATE + 2 * CMT_TB * ICW_MT_N) * sizeof(uint32_t);   // 50 048 B
+
+int chain_mt_max_units(int sm_count) { return sm_count * CMT_CTAS; }
+
+struct CmtGeom {
+    int n_units, blocks_per_unit;
+    int64_t first_word, want_lo, want_hi, tail_block;
+};
+
+// dither value from the words of one channel-sample (reference src/sound_render.c:711-733)
+template <int RT>
+__device__ __forceinline__ double lean_dither(uint4 a, unsigned &redraws)
+{
+    if (RT == ICW_RENDER_TPDF) {
+        double v = dsopen2(make_uint2(a.x, a.y), redraws);
+        v += dsopen2(make_uint2(a.z, a.w), redraws);
+        return v * 0.5;                                         // /2.0, exact
+    }
+    return div_const(dsopen2(make_uint2(a.x, a.y), redraws), ICW_SQRT2, ICW_RSQRT2);
+}
+
+// one frame of a straight-line list, plain PCM out.  Operation for operation finish_frame()'s
+// ch.shape != GENERIC route with DITHER_GIVEN.
+template <int SHAPE, int RT>
+__device__ __forceinline__ void lean_frame(const DevChain &ch, DevStream &st, int64_t i, int64_t i_last, const double v[4],
+                                           uint4 wl, uint4 wr, uint8_t *dst, int dst_aligned, FrameAcc &acc, OscCounter &osc)
+{
+    const DevRender &rq = ch.render;
+    const double omega = norm_omega(ch, osc.at(ch, i));
+    double o[4], lo, ro;
+    run_shape<SHAPE>(ch, v, omega, o, lo, ro);
+    const double dl = lean_dither<RT>(wl, acc.redraws);
+    const double dr = lean_dither<RT>(wr, acc.redraws);
+    const RenderOut a = render_one(rq, lo, dl);
+    const RenderOut b = render_one(rq, ro, dr);
+    acc.clips_l += a.clipped; acc.clips_r += b.clipped;
+    acc.peak_l = fmax(acc.peak_l, a.level); acc.peak_r = fmax(acc.peak_r, b.level);
+    uint8_t *p = dst + i * ch.out_frame_bytes;
+    if (dst_aligned) store_frame_pcm(p, a.val, b.val, rq.bytes);
+    else { store_pcm(p, a.val, rq.bytes); store_pcm(p + rq.bytes, b.val, rq.bytes); }
+    if (i == i_last) {
+        // the context's bus after the call == the last frame's values (adv_modulator.c:634-751);
+        // plugs this list never writes keep what the context held
+        st.bus[0][0] = v[0]; st.bus[0][1] = v[1]; st.bus[0][2] = v[2]; st.bus[0][3] = v[3];
+        if (SHAPE == ICW_SHAPE_SHIFT_MASTER) {
+            const int k = ch.nodes[0].n_out;
+            st.bus[k][0] = o[0]; st.bus[k][1] = o[1]; st.bus[k][2] = o[2]; st.bus[k][3] = o[3];
+        }
+    }
+}
+
+// SHAPE == ICW_SHAPE_GENERIC: any list, taps, noise-shaping hand-off -- finish_frame() itself.
+template <int SHAPE, int RT>
+__global__ void __launch_bounds__(CMT_THREADS, CMT_CTAS)
+chain_mt_kernel(const __grid_constant__ DevChain ch, DevStream *__restrict__ streams, int64_t n_frames,
+                const uint8_t *__restrict__ in, int from_analytic, const __grid_constant__ CmtGeom g,
+                const uint32_t *__restrict__ ckpt_l, const uint32_t *__restrict__ ckpt_r,
+                uint32_t *__restrict__ tail_l, uint32_t *__restrict__ tail_r,
+                uint8_t *__restrict__ out, double *__restrict__ tap_bus, double *__restrict__ tap_lr, double *__restrict__ pre)
+{
+    constexpr int WPS = RT == ICW_RENDER_TPDF ? 4 : 2;
+    constexpr bool LEAN = SHAPE != ICW_SHAPE_GENERIC;
+    extern __shared__ __align__(16) uint32_t cmt_smem[];
+    uint32_t *sbuf = cmt_smem;                                  // [gen][2][CMT_STATE] untempered state, double-buffered
+    uint32_t *wd_l = cmt_smem + 4 * CMT_STATE;                  // [CMT_TB * 624] tempered words of the tile
+    uint32_t *wd_r = wd_l + CMT_TB * ICW_MT_N;
+    const int t = threadIdx.x;
+    const int unit = blockIdx.x;
+    DevStream &st = streams[0];
+
+    for (int i = t; i < ICW_MT_N; i += CMT_THREADS) {
+        sbuf[i] = ckpt_l[(size_t)unit * ICW_MT_N + i];
+        sbuf[2 * CMT_STATE + i] = ckpt_r[(size_t)unit * ICW_MT_N + i];
+    }
+    if (t < 32) sbuf[(t >> 3) * CMT_STATE + ICW_MT_N + (t & 7)] = 0u;
+    __syncthreads();
+    const bool active = t < 227;
+    uint32_t l0 = 0u, l1 = 0u, l2 = 0u, r0 = 0u, r1 = 0u, r2 = 0u;
+    if (active) {
+        l0 = sbuf[t]; l1 = sbuf[t + 227];
+        r0 = sbuf[2 * CMT_STATE + t]; r1 = sbuf[2 * CMT_STATE + t + 227];
+        if (t < 170) { l2 = sbuf[t + 454]; r2 = sbuf[2 * CMT_STATE + t + 454]; }
+    }
+    // block b of this unit holds stream words [u0 + 624 b, u0 + 624 (b + 1))
+    const int64_t u0 = g.first_word + (int64_t)unit * g.blocks_per_unit * ICW_MT_N;
+    int64_t nb64 = (g.want_hi - u0 + ICW_MT_N - 1) / ICW_MT_N;                      // blocks that start below want_hi
+    const int n_blk = (int)(nb64 < 0 ? 0 : nb64 > g.blocks_per_unit ? g.blocks_per_unit : nb64);
+    const int64_t tl = g.tail_block - (int64_t)unit * g.blocks_per_unit;
+    const int tail_blk = (tl >= 0 && tl < n_blk) ? (int)tl : -1;
+
+    FrameIO io;
+    io.mtw_l = io.mtw_r = nullptr;
+    io.dst = out;
+    io.dst_aligned = ((size_t)(uintptr_t)out & 3u) == 0;
+    io.tap_bus = tap_bus; io.tap_lr = tap_lr; io.pre = pre;
+    FrameAcc acc;
+    double bus[LEAN ? 1 : ICW_N_PLUGS][4];
+    if (!LEAN) load_bus(st, bus);
+    OscCounter osc;
+    {
+        int64_t f = (u0 - g.want_lo) / WPS;
+        f = (f < 0 ? 0 : f) + t;
+        osc.init(ch, st.n_frame, f < n_frames ? f : 0);
+    }
+    const int64_t pos0 = st.pos;
+
+    int cur = 0;
+    for (int b0 = 0; b0 < n_blk; b0 += CMT_TB) {
+        const int tb = n_blk - b0 < CMT_TB ? n_blk - b0 : CMT_TB;
+        // ---- the tile's words, both generators, one barrier per block ---------------------------------
+        for (int b = 0; b < tb; ++b) {
+            const uint32_t *ol = sbuf + cur * CMT_STATE, *orr = sbuf + (2 + cur) * CMT_STATE;
+            uint32_t *nl = sbuf + (cur ^ 1) * CMT_STATE, *nr = sbuf + (2 + (cur ^ 1)) * CMT_STATE;
+            const bool is_tail = b0 + b == tail_blk;
+            if (is_tail)
+                for (int i = t; i < ICW_MT_N; i += CMT_THREADS) { tail_l[i] = ol[i]; tail_r[i] = orr[i]; }
+            if (active) {
+                mt_words_block<false>(ol, nl, t, l0, l1, l2, wd_l + b * ICW_MT_N + t, 0, 0, 0);
+                mt_words_block<false>(orr, nr, t, r0, r1, r2, wd_r + b * ICW_MT_N + t, 0, 0, 0);
+            }
+            __syncthreads();
+            if (is_tail)
+                for (int i = t; i < ICW_MT_N; i += CMT_THREADS) { tail_l[ICW_MT_N + i] = nl[i]; tail_r[ICW_MT_N + i] = nr[i]; }
+            cur ^= 1;
+        }
+        // ---- the frames whose draws are those words -----------------------------------------------------
+        const int64_t w_lo = u0 + (int64_t)b0 * ICW_MT_N;       // stream word held by wd[0]
+        int64_t i_lo = w_lo - g.want_lo;
+        i_lo = i_lo < 0 ? 0 : i_lo / WPS;
+        int64_t i_hi = (w_lo + (int64_t)tb * ICW_MT_N - g.want_lo) / WPS;
+        if (i_hi > n_frames) i_hi = n_frames;
+        for (int64_t i = i_lo + t; i < i_hi; i += CMT_THREADS) {
+            const uint32_t off = (uint32_t)(g.want_lo + i * WPS - w_lo);
+            uint4 wl = make_uint4(0u, 0u, 0u, 0u), wr = wl;
+            if (WPS == 4) {
+                wl = *reinterpret_cast<const uint4 *>(wd_l + off);
+                wr = *reinterpret_cast<const uint4 *>(wd_r + off);
+            } else {
+                const uint2 a = *reinterpret_cast<const uint2 *>(wd_l + off), b = *reinterpret_cast<const uint2 *>(wd_r + off);
+                wl.x = a.x; wl.y = a.y; wr.x = b.x; wr.y = b.y;
+            }
+            double v[4];
+            if (from_analytic) {
+                const double2 *a = reinterpret_cast<const double2 *>(in) + i * 2;
+                const double2 a0 = a[0], a1 = a[1];
+                v[0] = a0.x; v[1] = a0.y; v[2] = a1.x; v[3] = a1.y;
+            } else {
+                unpack_frame(ch, in + i * ch.frame_bytes, pos0 + i, v);
+            }
+            if (LEAN) lean_frame<SHAPE, RT>(ch, st, i, n_frames - 1, v, wl, wr, io.dst, io.dst_aligned, acc, osc);
+            else finish_frame<DITHER_GIVEN>(ch, st, i, n_frames, v, bus, io, acc, osc, wl, wr);
+        }
+        __syncthreads();                                        // the next tile overwrites the words
+    }
+    commit_acc(&st, acc, 32);
+}
+
+template <int SHAPE, int RT>
+static cudaError_t launch_cmt(const DevChain &ch, DevStream *streams, int64_t n_frames, const uint8_t *in, int from_analytic,
+                              const CmtGeom &g, const MtPlan &pl, const MtPlan &pr, uint8_t *out, double *tap_bus, double *tap_lr,
+                              double *pre, cudaStream_t s)
+{
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(chain_mt_kernel<SHAPE, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CMT_SMEM);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    chain_mt_kernel<SHAPE, RT><<<g.n_units, CMT_THREADS, CMT_SMEM, s>>>(ch, streams, n_frames, in, from_analytic, g, pl.ckpt, pr.ckpt,
+                                                                      pl.tail, pr.tail, out, tap_bus, tap_lr, pre);
+    return cudaGetLastError();
+}
+
+bool chain_mt_supports(const DevChain &ch)
+{
+    return ch.render.render_type == ICW_RENDER_RPDF || ch.render.render_type == ICW_RENDER_TPDF;
+}
+
+cudaError_t launch_chain_mt(const DevChain &ch, DevStream *streams, int64_t n_frames, const uint8_t *in, int from_analytic,
+                            const MtPlan &pl, const MtPlan &pr, uint8_t *out, double *tap_bus, double *tap_lr, double *pre,
+                            cudaStream_t s)
+{
+    if (pl.n_units != pr.n_units || pl.blocks_per_unit != pr.blocks_per_unit || pl.first_word != pr.first_word ||
+        pl.want_lo != pr.want_lo || pl.want_hi != pr.want_hi)
+        return cudaErrorInvalidValue;                           // the two generators must stand at the same draw
+    CmtGeom g;
+    g.n_units = pl.n_units; g.blocks_per_unit = pl.blocks_per_unit;
+    g.first_word = pl.first_word; g.want_lo = pl.want_lo; g.want_hi = pl.want_hi; g.tail_block = pl.tail_block;
+    const bool lean = !tap_bus && !tap_lr && !pre && ch.shape != ICW_SHAPE_GENERIC && !ch.bypass;
+    const bool tpdf = ch.render.render_type == ICW_RENDER_TPDF;
+#define ICW_CMT(SH, RT) return launch_cmt<SH, RT>(ch, streams, n_frames, in, from_analytic, g, pl, pr, out, tap_bus, tap_lr, pre, s)
+    if (lean && ch.shape == ICW_SHAPE_SHIFT_MASTER) { if (tpdf) ICW_CMT(ICW_SHAPE_SHIFT_MASTER, ICW_RENDER_TPDF); ICW_CMT(ICW_SHAPE_SHIFT_MASTER, ICW_RENDER_RPDF); }
+    if (lean && ch.shape == ICW_SHAPE_MASTER) { if (tpdf) ICW_CMT(ICW_SHAPE_MASTER, ICW_RENDER_TPDF); ICW_CMT(ICW_SHAPE_MASTER, ICW_RENDER_RPDF); }
+    if (tpdf) ICW_CMT(ICW_SHAPE_GENERIC, ICW_RENDER_TPDF);
+    ICW_CMT(ICW_SHAPE_GENERIC, ICW_RENDER_RPDF);
+#undef ICW_CMT
+}
+
+}  // namespace icw

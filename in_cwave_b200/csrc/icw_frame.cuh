@@ -104,15 +104,19 @@ struct FrameIO {
 };
 
 // frame i of the call; v = (L.re, L.im, R.re, R.im) on plug 0; bus = thread-private plug values.
-// EARLY_DITHER: fetch the dither words before the DSP list (8 more live registers) or at their use.
-template <bool EARLY_DITHER = true>
+// DITHER_AT: where the dither words of the 2- and 4-word types come from -- fetched before the DSP
+// list (8 more live registers), fetched at their use, or handed in by the caller (chain_mt_kernel
+// makes them in shared memory; Gauss and sloped TPDF never take that route).
+enum { DITHER_EARLY = 1, DITHER_LATE = 0, DITHER_GIVEN = 2 };
+template <int DITHER_AT = DITHER_EARLY>
 __device__ __forceinline__ void finish_frame(const DevChain &ch, DevStream &st, int64_t i, int64_t n_frames,
                                              const double v[4], double (*bus)[4], const FrameIO &io, FrameAcc &acc,
-                                             OscCounter &osc)
+                                             OscCounter &osc, uint4 wl = make_uint4(0u, 0u, 0u, 0u),
+                                             uint4 wr = make_uint4(0u, 0u, 0u, 0u))
 {
     const DevRender &rq = ch.render;
     const int wps = rq.words_per_sample;
-    uint4 wl, wr;
+    constexpr bool EARLY_DITHER = DITHER_AT == DITHER_EARLY;
     if (EARLY_DITHER) { wl = dither_fetch(wps, io.mtw_l, i); wr = dither_fetch(wps, io.mtw_r, i); }
     double omega = norm_omega(ch, osc.at(ch, i));
     double lo, ro;
@@ -135,12 +139,12 @@ __device__ __forceinline__ void finish_frame(const DevChain &ch, DevStream &st, 
     double dl = 0.0, dr = 0.0;
     if (wps) {
         double prev_l = 0.0, prev_r = 0.0;
-        if (rq.render_type == ICW_RENDER_STPDF) {
+        if (DITHER_AT != DITHER_GIVEN && rq.render_type == ICW_RENDER_STPDF) {
             // the previous frame's draw, recomputed from that frame's words (frame 0: carried state)
             if (i == 0) { prev_l = st.prev_rnd[0]; prev_r = st.prev_rnd[1]; }
             else { prev_l = first_draw(io.mtw_l, i - 1); prev_r = first_draw(io.mtw_r, i - 1); }
         }
-        if (!EARLY_DITHER) { wl = dither_fetch(wps, io.mtw_l, i); wr = dither_fetch(wps, io.mtw_r, i); }
+        if (DITHER_AT == DITHER_LATE) { wl = dither_fetch(wps, io.mtw_l, i); wr = dither_fetch(wps, io.mtw_r, i); }
         dl = dither_sample(rq, wl, io.mtw_l, i, prev_l, acc.redraws);
         dr = dither_sample(rq, wr, io.mtw_r, i, prev_r, acc.redraws);
     }
@@ -164,7 +168,7 @@ __device__ __forceinline__ void finish_frame(const DevChain &ch, DevStream &st, 
     if (i == n_frames - 1) {
         // the context's bus after the call == the last frame's values (adv_modulator.c:634-751)
         for (int k = 0; k < ICW_N_PLUGS; ++k) { st.bus[k][0] = bus[k][0]; st.bus[k][1] = bus[k][1]; st.bus[k][2] = bus[k][2]; st.bus[k][3] = bus[k][3]; }
-        if (rq.render_type == ICW_RENDER_STPDF) {
+        if (DITHER_AT != DITHER_GIVEN && rq.render_type == ICW_RENDER_STPDF) {
             // frame 0 of this call may still be reading prev_rnd in another CTA: write the shadow copy
             st.prev_rnd_next[0] = first_draw(io.mtw_l, i);
             st.prev_rnd_next[1] = first_draw(io.mtw_r, i);

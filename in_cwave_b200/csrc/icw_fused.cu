@@ -160,7 +160,7 @@ hb_fused_kernel(const __grid_constant__ HbCoef coef, const __grid_constant__ Dev
                         double a = mix_up(0, q, y[2], slot); v[2 + slot] = a;
                         double c = mix_up(1, q, y[3], slot); v[2 + slot] = c;
                     }
-                    finish_frame<false>(ch, streams[stream0 + h_sl], f, n_frames, v, bus, io, acc, osc);
+                    finish_frame<DITHER_LATE>(ch, streams[stream0 + h_sl], f, n_frames, v, bus, io, acc, osc);
                 }
             }
         }

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "icw_internal.h"
+#include "icw_mt.h"
 
 namespace icw {
 
@@ -39,6 +40,13 @@ cudaError_t launch_chain(const DevChain &ch, DevStream *streams, int n_streams, 
                          const uint32_t *mtw_l, const uint32_t *mtw_r, size_t mt_stream_stride,
                          uint8_t *out, size_t out_stride, double *tap_bus, double *tap_lr, double *pre,
                          int sm_count, cudaStream_t s);
+// the pointwise chain with both dither generators regenerated inside it (icw_chainmt.cu): one stream,
+// RPDF / TPDF, both generators at the same draw.  The kernel fills pl.tail / pr.tail.
+bool chain_mt_supports(const DevChain &ch);
+int chain_mt_max_units(int sm_count);
+cudaError_t launch_chain_mt(const DevChain &ch, DevStream *streams, int64_t n_frames, const uint8_t *in, int from_analytic,
+                            const MtPlan &pl, const MtPlan &pr, uint8_t *out, double *tap_bus, double *tap_lr, double *pre,
+                            cudaStream_t s);
 // noise shaping on: chain_kernel leaves (value, dither) pairs in `pre`; one thread per (stream, channel) quantises
 cudaError_t launch_ns_render(const DevChain &ch, DevStream *streams, int n_streams, int64_t n_frames,
                              const double *pre, uint8_t *out, size_t out_stride, cudaStream_t s);

@@ -322,12 +322,11 @@ void MtJump::release()
     for (uint32_t *p : dev_poly_) if (p) cudaFree(p);
     dev_poly_.clear();
     host_poly_.clear();
-    if (d_ckpt_) cudaFree(d_ckpt_);
+    for (int l = 0; l < 2; ++l) { if (d_ckpt_[l]) cudaFree(d_ckpt_[l]); d_ckpt_[l] = nullptr; ckpt_cap_[l] = 0; }
     if (d_tmp_) cudaFree(d_tmp_);
     if (d_tail_) cudaFree(d_tail_);
-    d_ckpt_ = d_tmp_ = d_tail_ = nullptr;
+    d_tmp_ = d_tail_ = nullptr;
     for (auto &t : tails_) t.valid = false;
-    ckpt_cap_ = 0;
 }
 
 int MtJump::ensure_poly(int k)
@@ -388,26 +387,27 @@ int MtJump::state_at_block(uint32_t seed, uint64_t block, uint32_t *d_state, cud
     return ICW_OK;
 }
 
-int MtJump::generate(uint32_t seed, uint64_t skip, int64_t n, uint32_t *d_out, int sm_count,
-                     cudaStream_t stream, uint64_t *launches)
+int MtJump::plan(int lane, uint32_t seed, uint64_t skip, int64_t n, int max_units, int sm_count, cudaStream_t stream,
+                 uint64_t *launches, MtPlan &pl)
 {
+    pl = MtPlan();
     if (n <= 0) return ICW_OK;
     const uint64_t b0 = skip / MT_N, b1 = (skip + (uint64_t)n - 1) / MT_N;
     const uint64_t nb = b1 - b0 + 1;
-    // blocks per CTA = 2^kb so that every checkpoint distance has a polynomial in the x^(624*2^k) family
-    // one CTA of 256 threads per checkpoint (mt_words_kernel), eight of them resident per SM
-    const uint64_t max_cta = (uint64_t)sm_count * 8;
+    // blocks per unit = 2^kb so that every checkpoint distance has a polynomial in the x^(624*2^k) family
+    const uint64_t max_cta = (uint64_t)(max_units < 1 ? 1 : max_units);
     int kb = 0;
     while (((nb + (1ull << kb) - 1) >> kb) > max_cta) ++kb;
     const int n_cta = (int)((nb + (1ull << kb) - 1) >> kb);
-    if ((size_t)n_cta > ckpt_cap_) {
-        if (d_ckpt_) cudaFree(d_ckpt_);
-        d_ckpt_ = nullptr; ckpt_cap_ = 0;
+    uint32_t *&ck = d_ckpt_[lane];
+    if ((size_t)n_cta > ckpt_cap_[lane]) {
+        if (ck) cudaFree(ck);
+        ck = nullptr; ckpt_cap_[lane] = 0;
         size_t want = (size_t)std::max(n_cta, 64);
-        if (cudaMalloc(&d_ckpt_, want * MT_N * sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); err_ = "cudaMalloc(checkpoints) failed"; return ICW_E_NOMEM; }
-        ckpt_cap_ = want;
+        if (cudaMalloc(&ck, want * MT_N * sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); err_ = "cudaMalloc(checkpoints) failed"; return ICW_E_NOMEM; }
+        ckpt_cap_[lane] = want;
     }
-    int rc = state_at_block(seed, b0, d_ckpt_, stream, launches);
+    int rc = state_at_block(seed, b0, ck, stream, launches);
     if (rc) return rc;
     // doubling: checkpoints [2^j, 2^(j+1)) come from [0, 2^j) by a jump of 2^(kb+j) blocks
     for (int j = 0; (1 << j) < n_cta; ++j) {
@@ -416,18 +416,38 @@ int MtJump::generate(uint32_t seed, uint64_t skip, int64_t n, uint32_t *d_out, i
         const int first = 1 << j;
         const int count = std::min(n_cta, 2 << j) - first;
         const int sl = jump_slices(count, sm_count);
-        if (sl > 1) cudaMemsetAsync(d_ckpt_ + (size_t)first * MT_N, 0, (size_t)count * MT_N * sizeof(uint32_t), stream);
-        mt_jump_kernel<<<dim3(count, sl), JUMP_THREADS, JUMP_SMEM, stream>>>(d_ckpt_, nullptr, first, first, dev_poly_[kb + j]);
+        if (sl > 1) cudaMemsetAsync(ck + (size_t)first * MT_N, 0, (size_t)count * MT_N * sizeof(uint32_t), stream);
+        mt_jump_kernel<<<dim3(count, sl), JUMP_THREADS, JUMP_SMEM, stream>>>(ck, nullptr, first, first, dev_poly_[kb + j]);
         if (launches) ++*launches;
     }
+    if (cudaGetLastError() != cudaSuccess) { err_ = "mt_jump_kernel launch failed"; return ICW_E_CUDA; }
     if (!d_tail_ && cudaMalloc(&d_tail_, (size_t)NTAIL * 2 * MT_N * sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); err_ = "cudaMalloc(tail states) failed"; return ICW_E_NOMEM; }
     const int slot = tail_next_;
     tail_next_ = (tail_next_ + 1) % NTAIL;
-    tails_[2 * slot].valid = tails_[2 * slot + 1].valid = false;
-    cudaError_t e = launch_mt_words(d_ckpt_, n_cta, 1 << kb, (int64_t)(b0 * MT_N), (int64_t)skip, (int64_t)(skip + (uint64_t)n), d_out,
-                                    (int64_t)(b1 - b0), d_tail_ + (size_t)slot * 2 * MT_N, stream);
+    // the consumer of the plan fills the slot in stream order; lookups on the same stream come after it
     tails_[2 * slot] = { seed, b1, true, stream };          // state that regenerates into block b1
     tails_[2 * slot + 1] = { seed, b1 + 1, true, stream };  // state after block b1
+    pl.ckpt = ck;
+    pl.tail = d_tail_ + (size_t)slot * 2 * MT_N;
+    pl.n_units = n_cta;
+    pl.blocks_per_unit = 1 << kb;
+    pl.first_word = (int64_t)(b0 * MT_N);
+    pl.want_lo = (int64_t)skip;
+    pl.want_hi = (int64_t)(skip + (uint64_t)n);
+    pl.tail_block = (int64_t)(b1 - b0);
+    return ICW_OK;
+}
+
+int MtJump::generate(uint32_t seed, uint64_t skip, int64_t n, uint32_t *d_out, int sm_count,
+                     cudaStream_t stream, uint64_t *launches)
+{
+    if (n <= 0) return ICW_OK;
+    // one CTA of 256 threads per checkpoint (mt_words_kernel), eight of them resident per SM
+    MtPlan pl;
+    int rc = plan(0, seed, skip, n, sm_count * 8, sm_count, stream, launches, pl);
+    if (rc) return rc;
+    cudaError_t e = launch_mt_words(pl.ckpt, pl.n_units, pl.blocks_per_unit, pl.first_word, pl.want_lo, pl.want_hi, d_out,
+                                    pl.tail_block, pl.tail, stream);
     if (launches) ++*launches;
     if (e != cudaSuccess) { err_ = std::string("mt kernels: ") + cudaGetErrorString(e); return ICW_E_CUDA; }
     return ICW_OK;

@@ -34,8 +34,23 @@ void mt_poly_xpow(uint64_t e, MtPoly &out);                          // out = x^
 // target[m] = XOR_i g_i * seq[i+m], seq = the block sequence continued from base (host, slow)
 void mt_apply_host(const MtPoly &g, const uint32_t base[MT_N], uint32_t out[MT_N]);
 
+// where a kernel that regenerates the stream itself starts: one checkpoint per unit of
+// `blocks_per_unit` consecutive 624-word blocks; unit 0's first block starts at stream word `first_word`
+struct MtPlan {
+    const uint32_t *ckpt = nullptr;     // [n_units][624]: the state array that PRECEDES each unit's first block
+    uint32_t *tail = nullptr;           // [2][624]: to be filled with the state before and after block `tail_block`
+    int n_units = 0, blocks_per_unit = 0;
+    int64_t first_word = 0, want_lo = 0, want_hi = 0;   // wanted stream words [want_lo, want_hi)
+    int64_t tail_block = 0;             // relative index of the block holding the last wanted word
+};
+
 class MtJump {
 public:
+    // checkpoints for words [skip, skip + n) of the stream of `seed`, at most `max_units` of them.
+    // `lane` (0/1) selects one of two checkpoint buffers so that two generators can be live at once.
+    // The kernel that consumes the plan MUST write pl.tail (see mt_words_kernel).
+    int plan(int lane, uint32_t seed, uint64_t skip, int64_t n, int max_units, int sm_count, cudaStream_t stream,
+             uint64_t *launches, MtPlan &pl);
     // tempered words [skip, skip + n) of the stream of `seed` -> d_out (device), on `stream`
     int generate(uint32_t seed, uint64_t skip, int64_t n, uint32_t *d_out, int sm_count,
                  cudaStream_t stream, uint64_t *launches);
@@ -47,8 +62,8 @@ private:
     int state_at_block(uint32_t seed, uint64_t block, uint32_t *d_state, cudaStream_t stream, uint64_t *launches);
     std::vector<MtPoly> host_poly_;     // [k]
     std::vector<uint32_t *> dev_poly_;  // [k] -> 624 x uint32 on the device
-    uint32_t *d_ckpt_ = nullptr;        // checkpoint states [count][624]
-    size_t ckpt_cap_ = 0;
+    uint32_t *d_ckpt_[2] = { nullptr, nullptr };    // checkpoint states [lane][count][624]
+    size_t ckpt_cap_[2] = { 0, 0 };
     uint32_t *d_tmp_ = nullptr;         // ping-pong for sequential jumps
     // generator states left behind by earlier calls: a stream that continues where the last call
     // stopped finds its start state here instead of jumping there from the seed
