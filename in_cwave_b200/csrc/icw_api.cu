@@ -1160,6 +1160,16 @@ extern "C" int icw_mt_words_device(icw_engine *e, uint32_t seed, uint64_t skip, 
     return ICW_OK;
 }
 
+extern "C" int icw_debug_sincos_device(icw_engine *e, int64_t n, const double *d_x, double *d_out)
+{
+    if (!e || !d_x || !d_out || n < 0) return fail(ICW_E_ARG, "bad argument");
+    if (!n) return ICW_OK;
+    CK(cudaSetDevice(e->device));
+    CK(launch_sincos_leaf(n, d_x, d_out, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return ICW_OK;
+}
+
 // parity leaf for the oscillator: omega and fmod(omega*f, 2pi) for frames n0 .. n0+n-1 of a spec
 extern "C" int icw_debug_phase_device(icw_engine *e, const icw_chain_spec *spec, uint64_t n0, int64_t n,
                                       double freq_hz, double *d_out)

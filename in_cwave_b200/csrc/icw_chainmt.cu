@@ -45,7 +45,7 @@ __device__ __forceinline__ double lean_dither(uint4 a, unsigned &redraws)
         v += dsopen2(make_uint2(a.z, a.w), redraws);
         return v * 0.5;                                         // /2.0, exact
     }
-    return div_const(dsopen2(make_uint2(a.x, a.y), redraws), ICW_SQRT2, ICW_RSQRT2);
+    return div_const(dsopen2(make_uint2(a.x, a.y), redraws), ICW_KC[KC_SQRT2], ICW_KC[KC_RSQRT2]);
 }
 
 // one frame of a straight-line list, plain PCM out.  Operation for operation finish_frame()'s

@@ -35,7 +35,7 @@ __device__ __forceinline__ double dither_sample(const DevRender &r, uint4 a, con
 {
     switch (r.render_type) {
     case ICW_RENDER_RPDF:
-        return div_const(dsopen2(make_uint2(a.x, a.y), redraws), ICW_SQRT2, ICW_RSQRT2);
+        return div_const(dsopen2(make_uint2(a.x, a.y), redraws), ICW_KC[KC_SQRT2], ICW_KC[KC_RSQRT2]);
     case ICW_RENDER_TPDF: {
         double v = dsopen2(make_uint2(a.x, a.y), redraws);
         v += dsopen2(make_uint2(a.z, a.w), redraws);

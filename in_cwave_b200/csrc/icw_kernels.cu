@@ -442,6 +442,23 @@ __global__ void phase_leaf_kernel(const __grid_constant__ DevChain ch, uint64_t 
     out[i * 2 + 1] = fmod_2pi(om * f);
 }
 
+// debug / parity leaf: the modulator's sincos on [0, 2*pi) beside libdevice's
+__global__ void sincos_leaf_kernel(int64_t n, const double *__restrict__ x, double *__restrict__ out /* [n][4] */)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s, c, s2, c2;
+    sincos_2pi(x[i], s, c);
+    sincos(x[i], &s2, &c2);
+    out[i * 4] = s; out[i * 4 + 1] = c; out[i * 4 + 2] = s2; out[i * 4 + 3] = c2;
+}
+
+cudaError_t launch_sincos_leaf(int64_t n, const double *x, double *out, cudaStream_t s)
+{
+    sincos_leaf_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, x, out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_phase_leaf(const DevChain &ch, uint64_t n0, int64_t n, double f, double *out, cudaStream_t s)
 {
     phase_leaf_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ch, n0, n, f, out);

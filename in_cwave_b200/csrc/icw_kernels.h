@@ -52,6 +52,7 @@ cudaError_t launch_ns_render(const DevChain &ch, DevStream *streams, int n_strea
                              const double *pre, uint8_t *out, size_t out_stride, cudaStream_t s);
 cudaError_t launch_advance(const DevChain &ch, DevStream *streams, int n_streams, int64_t n_frames,
                            int advance_quad, cudaStream_t s);
+cudaError_t launch_sincos_leaf(int64_t n, const double *x, double *out, cudaStream_t s);
 cudaError_t launch_phase_leaf(const DevChain &ch, uint64_t n0, int64_t n, double f, double *out, cudaStream_t s);
 
 }  // namespace icw

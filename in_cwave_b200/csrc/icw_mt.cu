@@ -322,6 +322,8 @@ void MtJump::release()
     for (uint32_t *p : dev_poly_) if (p) cudaFree(p);
     dev_poly_.clear();
     host_poly_.clear();
+    for (auto &kv : any_poly_) if (kv.second.dev) cudaFree(kv.second.dev);
+    any_poly_.clear();
     for (int l = 0; l < 2; ++l) { if (d_ckpt_[l]) cudaFree(d_ckpt_[l]); d_ckpt_[l] = nullptr; ckpt_cap_[l] = 0; }
     if (d_tmp_) cudaFree(d_tmp_);
     if (d_tail_) cudaFree(d_tail_);
@@ -347,6 +349,41 @@ int MtJump::ensure_poly(int k)
         if (cudaFuncSetAttribute(mt_jump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JUMP_SMEM) != cudaSuccess) { err_ = "cudaFuncSetAttribute(mt_jump_kernel) failed"; return ICW_E_CUDA; }
         attr_set_ = true;
     }
+    return ICW_OK;
+}
+
+int MtJump::poly_for(uint64_t blocks, const uint32_t **d_poly)
+{
+    if (blocks && !(blocks & (blocks - 1))) {                       // a power of two: the family itself
+        int k = 0;
+        while ((blocks >> k) != 1u) ++k;
+        int rc = ensure_poly(k);
+        if (rc) return rc;
+        *d_poly = dev_poly_[k];
+        return ICW_OK;
+    }
+    auto it = any_poly_.find(blocks);
+    if (it == any_poly_.end()) {
+        AnyPoly ap;
+        ap.dev = nullptr;
+        auto half = (blocks & 1u) ? any_poly_.end() : any_poly_.find(blocks >> 1);
+        if (half != any_poly_.end()) {
+            mt_poly_square(half->second.host, ap.host);
+        } else {
+            bool first = true;
+            for (int k = 0; k < 64; ++k) {
+                if (!((blocks >> k) & 1u)) continue;
+                int rc = ensure_poly(k);
+                if (rc) return rc;
+                if (first) { ap.host = host_poly_[k]; first = false; }
+                else { MtPoly t; mt_poly_mul(ap.host, host_poly_[k], t); ap.host = t; }
+            }
+        }
+        if (cudaMalloc(&ap.dev, MT_N * sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); err_ = "cudaMalloc(jump polynomial) failed"; return ICW_E_NOMEM; }
+        if (cudaMemcpy(ap.dev, ap.host.w, MT_N * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) { err_ = "copy of jump polynomial failed"; return ICW_E_CUDA; }
+        it = any_poly_.emplace(blocks, ap).first;
+    }
+    *d_poly = it->second.dev;
     return ICW_OK;
 }
 
@@ -394,11 +431,16 @@ int MtJump::plan(int lane, uint32_t seed, uint64_t skip, int64_t n, int max_unit
     if (n <= 0) return ICW_OK;
     const uint64_t b0 = skip / MT_N, b1 = (skip + (uint64_t)n - 1) / MT_N;
     const uint64_t nb = b1 - b0 + 1;
-    // blocks per unit = 2^kb so that every checkpoint distance has a polynomial in the x^(624*2^k) family
+    // blocks per unit: the smallest m * 2^k (m < 16) that covers the range with max_units units -- a full
+    // wave of CTAs to within a few per cent, and a small set of jump distances to keep polynomials for
     const uint64_t max_cta = (uint64_t)(max_units < 1 ? 1 : max_units);
-    int kb = 0;
-    while (((nb + (1ull << kb) - 1) >> kb) > max_cta) ++kb;
-    const int n_cta = (int)((nb + (1ull << kb) - 1) >> kb);
+    uint64_t bpu = (nb + max_cta - 1) / max_cta;
+    {
+        int sh = 0;
+        while (bpu >= 16) { bpu = (bpu + 1) >> 1; ++sh; }
+        bpu <<= sh;
+    }
+    const int n_cta = (int)((nb + bpu - 1) / bpu);
     uint32_t *&ck = d_ckpt_[lane];
     if ((size_t)n_cta > ckpt_cap_[lane]) {
         if (ck) cudaFree(ck);
@@ -409,15 +451,17 @@ int MtJump::plan(int lane, uint32_t seed, uint64_t skip, int64_t n, int max_unit
     }
     int rc = state_at_block(seed, b0, ck, stream, launches);
     if (rc) return rc;
-    // doubling: checkpoints [2^j, 2^(j+1)) come from [0, 2^j) by a jump of 2^(kb+j) blocks
+    // doubling: checkpoints [2^j, 2^(j+1)) come from [0, 2^j) by a jump of bpu * 2^j blocks
+    if (n_cta > 1 && !attr_set_) { rc = ensure_poly(0); if (rc) return rc; }
     for (int j = 0; (1 << j) < n_cta; ++j) {
-        rc = ensure_poly(kb + j);
+        const uint32_t *d_poly = nullptr;
+        rc = poly_for(bpu << j, &d_poly);
         if (rc) return rc;
         const int first = 1 << j;
         const int count = std::min(n_cta, 2 << j) - first;
         const int sl = jump_slices(count, sm_count);
         if (sl > 1) cudaMemsetAsync(ck + (size_t)first * MT_N, 0, (size_t)count * MT_N * sizeof(uint32_t), stream);
-        mt_jump_kernel<<<dim3(count, sl), JUMP_THREADS, JUMP_SMEM, stream>>>(ck, nullptr, first, first, dev_poly_[kb + j]);
+        mt_jump_kernel<<<dim3(count, sl), JUMP_THREADS, JUMP_SMEM, stream>>>(ck, nullptr, first, first, d_poly);
         if (launches) ++*launches;
     }
     if (cudaGetLastError() != cudaSuccess) { err_ = "mt_jump_kernel launch failed"; return ICW_E_CUDA; }
@@ -430,7 +474,7 @@ int MtJump::plan(int lane, uint32_t seed, uint64_t skip, int64_t n, int max_unit
     pl.ckpt = ck;
     pl.tail = d_tail_ + (size_t)slot * 2 * MT_N;
     pl.n_units = n_cta;
-    pl.blocks_per_unit = 1 << kb;
+    pl.blocks_per_unit = (int)bpu;
     pl.first_word = (int64_t)(b0 * MT_N);
     pl.want_lo = (int64_t)skip;
     pl.want_hi = (int64_t)(skip + (uint64_t)n);
@@ -504,5 +548,30 @@ extern "C" int icw_mt_host_jump_state_family(uint32_t seed, uint64_t blocks, uin
         f = sq;
     }
     memcpy(out624, st, sizeof st);
+    return ICW_OK;
+}
+
+// same, as one polynomial: the product of the family over the set bits of the distance (MtJump::poly_for)
+extern "C" int icw_mt_host_jump_state_product(uint32_t seed, uint64_t blocks, uint32_t *out624)
+{
+    if (icw::mt_charpoly_terms().empty()) return ICW_E_ARG;
+    uint32_t st[icw::MT_N];
+    icw::mt_seed_state(seed, st);
+    if (blocks == 0) { memcpy(out624, st, sizeof st); return ICW_OK; }
+    icw::mt_regen_host(st);
+    const uint64_t rest = blocks - 1;
+    if (!rest) { memcpy(out624, st, sizeof st); return ICW_OK; }
+    icw::MtPoly f, sq, g, t;
+    icw::mt_poly_xpow(icw::MT_N, f);
+    bool first = true;
+    for (int k = 0; k < 64 && (rest >> k); ++k) {
+        if ((rest >> k) & 1u) {
+            if (first) { g = f; first = false; }
+            else { icw::mt_poly_mul(g, f, t); g = t; }
+        }
+        icw::mt_poly_square(f, sq);
+        f = sq;
+    }
+    icw::mt_apply_host(g, st, out624);
     return ICW_OK;
 }

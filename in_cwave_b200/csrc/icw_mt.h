@@ -10,6 +10,7 @@
 // generator's own output), the polynomials x^(624*2^k) mod phi lazily, and the GPU applies them.
 #pragma once
 #include <cstdint>
+#include <map>
 #include <string>
 #include <vector>
 #include <cuda_runtime.h>
@@ -59,6 +60,11 @@ public:
 
 private:
     int ensure_poly(int k);             // device copy of x^(624 * 2^k) mod phi
+    // device copy of x^(624 * blocks) mod phi for any distance: the product of the 2^k family over the
+    // set bits of `blocks`, or the square of the polynomial for blocks / 2 when that one is cached
+    int poly_for(uint64_t blocks, const uint32_t **d_poly);
+    struct AnyPoly { MtPoly host; uint32_t *dev; };
+    std::map<uint64_t, AnyPoly> any_poly_;
     int state_at_block(uint32_t seed, uint64_t block, uint32_t *d_state, cudaStream_t stream, uint64_t *launches);
     std::vector<MtPoly> host_poly_;     // [k]
     std::vector<uint32_t *> dev_poly_;  // [k] -> 624 x uint32 on the device

@@ -67,6 +67,13 @@ class Engine:
         _abi.check(_abi.lib().icw_crc32_device(self._h, data.data_ptr(), data.numel() * data.element_size(), C.byref(out)))
         return int(out.value)
 
+    def debug_sincos(self, x):
+        """x: torch float64 CUDA tensor -> [n, 4] = (sincos_2pi sin, cos, libdevice sin, cos)."""
+        import torch
+        out = torch.empty((x.numel(), 4), dtype=torch.float64, device=x.device)
+        _abi.check(_abi.lib().icw_debug_sincos_device(self._h, x.numel(), x.data_ptr(), out.data_ptr()))
+        return out.cpu().numpy()
+
     def debug_phase(self, spec: dict, n0: int, n: int, freq_hz: float):
         import torch
         out = torch.empty((n, 2), dtype=torch.float64, device=f"cuda:{self.device}")

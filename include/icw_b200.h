@@ -221,6 +221,9 @@ int  icw_session_set_taps(icw_session *s, double *d_tap_bus, double *d_tap_lr);
  * f = |freq_hz| on the spec's frequency grid (reference src/adv_modulator.c:36-38,537,611-625) */
 int  icw_debug_phase_device(icw_engine *e, const icw_chain_spec *spec, uint64_t n0, int64_t n,
                             double freq_hz, double *d_out);
+/* trig leaf: out[i] = { s, c, sin(x[i]), cos(x[i]) } with (s, c) from the modulator's own sincos for
+ * phases in [0, 2*pi) (icw_dev.cuh sincos_2pi) and the other two from CUDA's libdevice */
+int  icw_debug_sincos_device(icw_engine *e, int64_t n, const double *d_x, double *d_out);
 /* host-only checks of the MT19937 jump-ahead mathematics (no GPU is touched):
  * characteristic polynomial found by Berlekamp-Massey; the state array after `blocks` block
  * regenerations computed sequentially, through x^J mod phi, and through the x^(624*2^k) family */
@@ -228,6 +231,9 @@ int  icw_mt_host_charpoly(int *n_terms, int *degree);
 void icw_mt_host_seq_state(uint32_t seed, uint64_t blocks, uint32_t *out624);
 int  icw_mt_host_jump_state(uint32_t seed, uint64_t blocks, uint32_t *out624);
 int  icw_mt_host_jump_state_family(uint32_t seed, uint64_t blocks, uint32_t *out624);
+/* the same distance as ONE polynomial, the product of the x^(624*2^k) family over the set bits of the
+ * distance -- how the checkpoint tree reaches units of any length (MtJump::poly_for) */
+int  icw_mt_host_jump_state_product(uint32_t seed, uint64_t blocks, uint32_t *out624);
 
 #ifdef __cplusplus
 }

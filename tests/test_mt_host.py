@@ -21,11 +21,12 @@ def test_characteristic_polynomial():
 @pytest.mark.parametrize("blocks", [0, 1, 2, 3, 33, 34, 1000, 4097])
 def test_jump_lands_on_the_sequential_state(oracle, seed, blocks):
     L = _abi.lib()
-    seq, jmp, fam = (C.c_uint32 * 624)(), (C.c_uint32 * 624)(), (C.c_uint32 * 624)()
+    seq, jmp, fam, prod = (C.c_uint32 * 624)(), (C.c_uint32 * 624)(), (C.c_uint32 * 624)(), (C.c_uint32 * 624)()
     L.icw_mt_host_seq_state(seed, blocks, seq)
     assert L.icw_mt_host_jump_state(seed, blocks, jmp) == 0
     assert L.icw_mt_host_jump_state_family(seed, blocks, fam) == 0
-    assert list(seq) == list(jmp) == list(fam)
+    assert L.icw_mt_host_jump_state_product(seed, blocks, prod) == 0
+    assert list(seq) == list(jmp) == list(fam) == list(prod)
     # and the sequential state is the oracle's: draw 624*blocks words, then compare the next ones
     mt = oracle.Mt()
     P = oracle.port()
@@ -53,8 +54,9 @@ def test_far_jump_consistency():
     """2^33 blocks ahead (far beyond what can be generated sequentially here): the direct power and
     the squared-family composition must agree with each other."""
     L = _abi.lib()
-    a, b = (C.c_uint32 * 624)(), (C.c_uint32 * 624)()
+    a, b, c = (C.c_uint32 * 624)(), (C.c_uint32 * 624)(), (C.c_uint32 * 624)()
     blocks = (1 << 33) + 12345
     assert L.icw_mt_host_jump_state(0x13579BDF, blocks, a) == 0
     assert L.icw_mt_host_jump_state_family(0x13579BDF, blocks, b) == 0
-    assert list(a) == list(b)
+    assert L.icw_mt_host_jump_state_product(0x13579BDF, blocks, c) == 0
+    assert list(a) == list(b) == list(c)
