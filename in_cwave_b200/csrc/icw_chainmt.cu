@@ -36,48 +36,6 @@ struct CmtGeom {
     int64_t first_word, want_lo, want_hi, tail_block;
 };
 
-// dither value from the words of one channel-sample (reference src/sound_render.c:711-733)
-template <int RT>
-__device__ __forceinline__ double lean_dither(uint4 a, unsigned &redraws)
-{
-    if (RT == ICW_RENDER_TPDF) {
-        double v = dsopen2(make_uint2(a.x, a.y), redraws);
-        v += dsopen2(make_uint2(a.z, a.w), redraws);
-        return v * 0.5;                                         // /2.0, exact
-    }
-    return div_const(dsopen2(make_uint2(a.x, a.y), redraws), ICW_KC[KC_SQRT2], ICW_KC[KC_RSQRT2]);
-}
-
-// one frame of a straight-line list, plain PCM out.  Operation for operation finish_frame()'s
-// ch.shape != GENERIC route with DITHER_GIVEN.
-template <int SHAPE, int RT>
-__device__ __forceinline__ void lean_frame(const DevChain &ch, DevStream &st, int64_t i, int64_t i_last, const double v[4],
-                                           uint4 wl, uint4 wr, uint8_t *dst, int dst_aligned, FrameAcc &acc, OscCounter &osc)
-{
-    const DevRender &rq = ch.render;
-    const double omega = norm_omega(ch, osc.at(ch, i));
-    double o[4], lo, ro;
-    run_shape<SHAPE>(ch, v, omega, o, lo, ro);
-    const double dl = lean_dither<RT>(wl, acc.redraws);
-    const double dr = lean_dither<RT>(wr, acc.redraws);
-    const RenderOut a = render_one(rq, lo, dl);
-    const RenderOut b = render_one(rq, ro, dr);
-    acc.clips_l += a.clipped; acc.clips_r += b.clipped;
-    acc.peak_l = fmax(acc.peak_l, a.level); acc.peak_r = fmax(acc.peak_r, b.level);
-    uint8_t *p = dst + i * ch.out_frame_bytes;
-    if (dst_aligned) store_frame_pcm(p, a.val, b.val, rq.bytes);
-    else { store_pcm(p, a.val, rq.bytes); store_pcm(p + rq.bytes, b.val, rq.bytes); }
-    if (i == i_last) {
-        // the context's bus after the call == the last frame's values (adv_modulator.c:634-751);
-        // plugs this list never writes keep what the context held
-        st.bus[0][0] = v[0]; st.bus[0][1] = v[1]; st.bus[0][2] = v[2]; st.bus[0][3] = v[3];
-        if (SHAPE == ICW_SHAPE_SHIFT_MASTER) {
-            const int k = ch.nodes[0].n_out;
-            st.bus[k][0] = o[0]; st.bus[k][1] = o[1]; st.bus[k][2] = o[2]; st.bus[k][3] = o[3];
-        }
-    }
-}
-
 // SHAPE == ICW_SHAPE_GENERIC: any list, taps, noise-shaping hand-off -- finish_frame() itself.
 template <int SHAPE, int RT>
 __global__ void __launch_bounds__(CMT_THREADS, CMT_CTAS)
@@ -158,6 +116,9 @@ chain_mt_kernel(const __grid_constant__ DevChain ch, DevStream *__restrict__ str
         i_lo = i_lo < 0 ? 0 : i_lo / WPS;
         int64_t i_hi = (w_lo + (int64_t)tb * ICW_MT_N - g.want_lo) / WPS;
         if (i_hi > n_frames) i_hi = n_frames;
+        // (requesting a thread's next analytic frame one iteration ahead was measured slower: the eight
+        // extra live registers spill at 64 per thread)
+        const double2 *ana = reinterpret_cast<const double2 *>(in);
         for (int64_t i = i_lo + t; i < i_hi; i += CMT_THREADS) {
             const uint32_t off = (uint32_t)(g.want_lo + i * WPS - w_lo);
             uint4 wl = make_uint4(0u, 0u, 0u, 0u), wr = wl;
@@ -170,8 +131,7 @@ chain_mt_kernel(const __grid_constant__ DevChain ch, DevStream *__restrict__ str
             }
             double v[4];
             if (from_analytic) {
-                const double2 *a = reinterpret_cast<const double2 *>(in) + i * 2;
-                const double2 a0 = a[0], a1 = a[1];
+                const double2 a0 = ana[i * 2], a1 = ana[i * 2 + 1];
                 v[0] = a0.x; v[1] = a0.y; v[2] = a1.x; v[3] = a1.y;
             } else {
                 unpack_frame(ch, in + i * ch.frame_bytes, pos0 + i, v);

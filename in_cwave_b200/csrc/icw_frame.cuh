@@ -176,6 +176,52 @@ __device__ __forceinline__ void finish_frame(const DevChain &ch, DevStream &st, 
     }
 }
 
+// ---- lean frame path: straight-line DSP lists, plain PCM output ---------------------------------
+// List shape (ICW_SHAPE_MASTER / ICW_SHAPE_SHIFT_MASTER) and dither type (none, RPDF, TPDF) are
+// template parameters, the dither words arrive as values, there is no thread-private bus.
+// dither value from the words of one channel-sample (reference src/sound_render.c:711-733)
+template <int RT>
+__device__ __forceinline__ double lean_dither(uint4 a, unsigned &redraws)
+{
+    if (RT == ICW_RENDER_ROUND) return 0.0;
+    if (RT == ICW_RENDER_TPDF) {
+        double v = dsopen2(make_uint2(a.x, a.y), redraws);
+        v += dsopen2(make_uint2(a.z, a.w), redraws);
+        return v * 0.5;                                         // /2.0, exact
+    }
+    return div_const(dsopen2(make_uint2(a.x, a.y), redraws), ICW_KC[KC_SQRT2], ICW_KC[KC_RSQRT2]);
+}
+
+// one frame of a straight-line list, plain PCM out.  Operation for operation finish_frame()'s
+// ch.shape != GENERIC route with DITHER_GIVEN.
+template <int SHAPE, int RT>
+__device__ __forceinline__ void lean_frame(const DevChain &ch, DevStream &st, int64_t i, int64_t i_last, const double v[4],
+                                           uint4 wl, uint4 wr, uint8_t *dst, int dst_aligned, FrameAcc &acc, OscCounter &osc)
+{
+    const DevRender &rq = ch.render;
+    const double omega = norm_omega(ch, osc.at(ch, i));
+    double o[4], lo, ro;
+    run_shape<SHAPE>(ch, v, omega, o, lo, ro);
+    const double dl = lean_dither<RT>(wl, acc.redraws);
+    const double dr = lean_dither<RT>(wr, acc.redraws);
+    const RenderOut a = render_one(rq, lo, dl);
+    const RenderOut b = render_one(rq, ro, dr);
+    acc.clips_l += a.clipped; acc.clips_r += b.clipped;
+    acc.peak_l = fmax(acc.peak_l, a.level); acc.peak_r = fmax(acc.peak_r, b.level);
+    uint8_t *p = dst + i * ch.out_frame_bytes;
+    if (dst_aligned) store_frame_pcm(p, a.val, b.val, rq.bytes);
+    else { store_pcm(p, a.val, rq.bytes); store_pcm(p + rq.bytes, b.val, rq.bytes); }
+    if (i == i_last) {
+        // the context's bus after the call == the last frame's values (adv_modulator.c:634-751);
+        // plugs this list never writes keep what the context held
+        st.bus[0][0] = v[0]; st.bus[0][1] = v[1]; st.bus[0][2] = v[2]; st.bus[0][3] = v[3];
+        if (SHAPE == ICW_SHAPE_SHIFT_MASTER) {
+            const int k = ch.nodes[0].n_out;
+            st.bus[k][0] = o[0]; st.bus[k][1] = o[1]; st.bus[k][2] = o[2]; st.bus[k][3] = o[3];
+        }
+    }
+}
+
 // plugs nobody writes keep whatever the context held (normally 0.0)
 __device__ __forceinline__ void load_bus(const DevStream &st, double (*bus)[4])
 {

@@ -286,6 +286,43 @@ chain_kernel(const __grid_constant__ DevChain ch, DevStream *__restrict__ stream
     commit_acc(&st, acc, 32);
 }
 
+// The same pass for the straight-line lists with plain PCM output and no dither or a 2-/4-word one:
+// list shape and dither type fixed at compile time (lean_frame, icw_frame.cuh), no thread-private bus.
+template <int SHAPE, int RT>
+__global__ void __launch_bounds__(ICW_CHAIN_THREADS, ICW_CHAIN_CTAS)
+chain_lean_kernel(const __grid_constant__ DevChain ch, DevStream *__restrict__ streams, int64_t n_frames,
+                  const uint8_t *__restrict__ in, size_t in_stride, int from_analytic,
+                  const uint32_t *__restrict__ mtw_l, const uint32_t *__restrict__ mtw_r, size_t mt_stream_stride,
+                  uint8_t *__restrict__ out, size_t out_stride)
+{
+    constexpr int WPS = RT == ICW_RENDER_TPDF ? 4 : RT == ICW_RENDER_RPDF ? 2 : 0;
+    const int stream = blockIdx.y;
+    DevStream &st = streams[stream];
+    const uint8_t *src = in + (size_t)stream * in_stride;
+    const size_t mt_off = (size_t)stream * mt_stream_stride;
+    const uint32_t *wl_p = WPS ? mtw_l + mt_off : nullptr, *wr_p = WPS ? mtw_r + mt_off : nullptr;
+    uint8_t *dst = out + (size_t)stream * out_stride;
+    const int dst_aligned = ((size_t)(uintptr_t)dst & 3u) == 0;
+    const int64_t pos0 = st.pos;
+    FrameAcc acc;
+    OscCounter osc;
+    osc.init(ch, st.n_frame, (int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_frames;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 wl = dither_fetch(WPS, wl_p, i), wr = dither_fetch(WPS, wr_p, i);
+        double v[4];
+        if (from_analytic) {
+            const double2 *a = reinterpret_cast<const double2 *>(src) + i * 2;
+            const double2 a0 = a[0], a1 = a[1];
+            v[0] = a0.x; v[1] = a0.y; v[2] = a1.x; v[3] = a1.y;
+        } else {
+            unpack_frame(ch, src + i * ch.frame_bytes, pos0 + i, v);
+        }
+        lean_frame<SHAPE, RT>(ch, st, i, n_frames - 1, v, wl, wr, dst, dst_aligned, acc, osc);
+    }
+    commit_acc(&st, acc, 32);
+}
+
 cudaError_t launch_chain(const DevChain &ch, DevStream *streams, int n_streams, int64_t n_frames,
                          const uint8_t *in, size_t in_stride, int from_analytic,
                          const uint32_t *mtw_l, const uint32_t *mtw_r, size_t mt_stream_stride,
@@ -300,6 +337,23 @@ cudaError_t launch_chain(const DevChain &ch, DevStream *streams, int n_streams, 
     if (cap < 1) cap = 1;
     if (per_stream > cap) per_stream = cap;
     dim3 grid(per_stream, n_streams);
+    const int rt = ch.render.render_type;
+    if (!tap_bus && !tap_lr && !pre && !ch.bypass && (ch.shape == ICW_SHAPE_MASTER || ch.shape == ICW_SHAPE_SHIFT_MASTER) &&
+        (rt == ICW_RENDER_ROUND || rt == ICW_RENDER_RPDF || rt == ICW_RENDER_TPDF)) {
+#define ICW_LEAN(SH, RT) chain_lean_kernel<SH, RT><<<grid, threads, 0, s>>>(ch, streams, n_frames, in, in_stride, from_analytic, \
+                                                                            mtw_l, mtw_r, mt_stream_stride, out, out_stride)
+        if (ch.shape == ICW_SHAPE_MASTER) {
+            if (rt == ICW_RENDER_ROUND) ICW_LEAN(ICW_SHAPE_MASTER, ICW_RENDER_ROUND);
+            else if (rt == ICW_RENDER_RPDF) ICW_LEAN(ICW_SHAPE_MASTER, ICW_RENDER_RPDF);
+            else ICW_LEAN(ICW_SHAPE_MASTER, ICW_RENDER_TPDF);
+        } else {
+            if (rt == ICW_RENDER_ROUND) ICW_LEAN(ICW_SHAPE_SHIFT_MASTER, ICW_RENDER_ROUND);
+            else if (rt == ICW_RENDER_RPDF) ICW_LEAN(ICW_SHAPE_SHIFT_MASTER, ICW_RENDER_RPDF);
+            else ICW_LEAN(ICW_SHAPE_SHIFT_MASTER, ICW_RENDER_TPDF);
+        }
+#undef ICW_LEAN
+        return cudaGetLastError();
+    }
     chain_kernel<<<grid, threads, 0, s>>>(ch, streams, n_frames, in, in_stride, from_analytic, mtw_l, mtw_r,
                                           mt_stream_stride, out, out_stride, tap_bus, tap_lr, pre);
     return cudaGetLastError();
