@@ -146,29 +146,29 @@ __device__ __forceinline__ void cx_step(Cx &s, double mr, double mi, double u)
 // the same for the real pole of an odd-order design: its state has no imaginary part, ever
 __device__ __forceinline__ void re_step(Cx &s, double mr, double u) { s.re = fma(mr, s.re, u); }
 
-// FMT is a compile-time constant: the format switch folds away inside the sample loops
+// FMT is a compile-time constant: the format switch folds away inside the sample loops.
+// A thread walks its filter's samples by POINTER (p advances two frames a step): forming the address
+// from the frame index costs a 64-bit multiply-add chain per sample, a quarter of the loop's
+// instructions before this form.
 template <int FMT, bool FADE>
-__device__ __forceinline__ double scan_sample(const DevChain &ch, const uint8_t *row, int64_t frame, int chan_off,
-                                              int64_t pos0)
+__device__ __forceinline__ double scan_sample_at(const DevChain &ch, const uint8_t *p, int64_t file_pos)
 {
-    double x = unpack_real(FMT, row + frame * ch.frame_bytes + chan_off, ch.aligned);
+    double x = unpack_real(FMT, p, ch.aligned);
     if (FADE) {
-        double g = fade_gain(ch, pos0 + frame);
+        double g = fade_gain(ch, file_pos);
         if (g >= 0.0) x *= g;
     }
     return x;
 }
 
-// A thread walks its chunk's bytes front to back with only one or two warps per scheduler to hide a
-// miss: ask for the line two ahead of the one being read, every sample (the clamp keeps the request
-// inside the row).
-template <int FMT>
-__device__ __forceinline__ void scan_prefetch(const DevChain &ch, const uint8_t *row, int64_t frame, int chan_off,
-                                              const uint8_t *row_last)
+// With only one or two warps per scheduler to hide a miss, ask for the line two ahead of the one
+// being read (the clamp keeps the request inside the row); once every fourth step is enough, a
+// 128-byte line holds five to sixteen steps.
+__device__ __forceinline__ void scan_prefetch_at(const uint8_t *p, const uint8_t *row_last)
 {
-    const uint8_t *p = row + frame * ch.frame_bytes + chan_off + 256;
-    if (p > row_last) p = row_last;
-    asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+    const uint8_t *q = p + 256;
+    if (q > row_last) q = row_last;
+    asm volatile("prefetch.global.L1 [%0];" :: "l"(q));
 }
 
 // E layout: [stream][comp][chan][chunk], comp = (filter * SCAN_NMAX + mode) * 2 + {re, im}
@@ -189,18 +189,27 @@ template <int NM, bool RL, int FMT, bool FADE>
 __device__ __forceinline__ void local_run(Cx (&s)[NM], const double (&kpr)[NM], const double (&kpi)[NM], const DevChain &ch,
                                           const uint8_t *row, int64_t f0, int chan_off, int64_t pos0, const uint8_t *row_last)
 {
-    double x = scan_sample<FMT, FADE>(ch, row, f0, chan_off, pos0);
-    for (int k = 0; k < SCAN_L; k += 2) {
-        const int kn = k + 2 < SCAN_L ? k + 2 : k;              // fetched one pair ahead
-        const double xn = scan_sample<FMT, FADE>(ch, row, f0 + kn, chan_off, pos0);
-        scan_prefetch<FMT>(ch, row, f0 + kn, chan_off, row_last);
+    const uint8_t *p = row + f0 * ch.frame_bytes + chan_off;
+    const int step_bytes = 2 * ch.frame_bytes;
+    int64_t fpos = pos0 + f0;
+    double x = scan_sample_at<FMT, FADE>(ch, p, fpos);
+    auto advance = [&](double xin) {
 #pragma unroll
         for (int m = 0; m < NM; ++m) {
-            if (RL && m == NM - 1) re_step(s[m], kpr[m], -x);
-            else cx_step(s[m], kpr[m], kpi[m], -x);
+            if (RL && m == NM - 1) re_step(s[m], kpr[m], -xin);
+            else cx_step(s[m], kpr[m], kpi[m], -xin);
         }
+    };
+#pragma unroll 4
+    for (int k = 0; k < SCAN_L / 2 - 1; ++k) {                  // the next input is fetched one step ahead
+        p += step_bytes;
+        if (FADE) fpos += 2;
+        const double xn = scan_sample_at<FMT, FADE>(ch, p, fpos);
+        if ((k & 3) == 0) scan_prefetch_at(p, row_last);
+        advance(x);
         x = xn;
     }
+    advance(x);
 }
 
 // pass-3 inner loop: one filter over one chunk from its true state S~, writing its half of every
@@ -224,41 +233,54 @@ __device__ __forceinline__ int apply_run(Cx (&S)[NM], const ModalCoef &mc, const
         for (int m = 0; m < NM; ++m) y2 = fma(kcr[m], S[m].re, fma(kci[m], S[m].im, y2));
         dst[1] = y2;
     }
-    int j = off, n_in = 0;
-    double x = j < len ? scan_sample<FMT, FADE>(ch, row, f0 + j, chan_off, pos0) : 0.0;
-    double xn = j + 2 < len ? scan_sample<FMT, FADE>(ch, row, f0 + j + 2, chan_off, pos0) : x;
-    for (; j + 1 < len; j += 2, ++n_in) {
-        const int jn = j + 4 < len ? j + 4 : j;                 // this filter's input after next, fetched two steps ahead
-        const double xnn = scan_sample<FMT, FADE>(ch, row, f0 + jn, chan_off, pos0);
-        scan_prefetch<FMT>(ch, row, f0 + jn, chan_off, row_last);
-        double y1 = direct ? d0x2 * x : 0.0, y2 = 0.0;
+    // this filter's inputs in the chunk: n_s of them, the first n_full followed by a frame of the chunk
+    const int n_s = len > off ? (len - off + 1) >> 1 : 0, n_full = len > off ? (len - off) >> 1 : 0;
+    const uint8_t *p = row + (f0 + off) * ch.frame_bytes + chan_off;
+    const int step_bytes = 2 * ch.frame_bytes;
+    int64_t fpos = pos0 + f0 + off;
+    double *dp = dst + (size_t)off * 4;
+    double x = 0.0, xn = 0.0;
+    if (n_s > 0) x = scan_sample_at<FMT, FADE>(ch, p, fpos);
+    if (n_s > 1) { p += step_bytes; fpos += 2; xn = scan_sample_at<FMT, FADE>(ch, p, fpos); }
+    auto one = [&](double xin) {                                // one input: both outputs it shapes
+        double y1 = direct ? d0x2 * xin : 0.0, y2 = 0.0;
 #pragma unroll
         for (int m = 0; m < NM; ++m) {
             if (RL && m == NM - 1) {                            // the real pole: im == 0 and its weights are 0
                 y1 = fma(kcpr[m], S[m].re, y1);
-                re_step(S[m], kpr[m], -x);
+                re_step(S[m], kpr[m], -xin);
                 y2 = fma(kcr[m], S[m].re, y2);
             } else {
                 y1 = fma(kcpr[m], S[m].re, fma(kcpi[m], S[m].im, y1));
-                cx_step(S[m], kpr[m], kpi[m], -x);
+                cx_step(S[m], kpr[m], kpi[m], -xin);
                 y2 = fma(kcr[m], S[m].re, fma(kci[m], S[m].im, y2));
             }
         }
-        dst[(size_t)j * 4] = y1;
-        dst[(size_t)(j + 1) * 4 + 1] = y2;
+        dp[0] = y1;
+        dp[5] = y2;
+        dp += 8;
+    };
+    int i = 0;
+#pragma unroll 2
+    for (; i + 2 < n_s; ++i) {                                  // the input after next is fetched two steps ahead
+        p += step_bytes;
+        if (FADE) fpos += 2;
+        const double xnn = scan_sample_at<FMT, FADE>(ch, p, fpos);
+        if ((i & 1) == 0) scan_prefetch_at(p, row_last);
+        one(x);
         x = xn; xn = xnn;
     }
-    if (j < len) {                                              // an input on the call's very last frame
+    for (; i < n_full; ++i) { one(x); x = xn; }                 // the last one or two, nothing left to fetch
+    if (n_s > n_full) {                                         // an input on the call's very last frame
         double y1 = direct ? d0x2 * x : 0.0;
 #pragma unroll
         for (int m = 0; m < NM; ++m) {
             y1 = fma(kcpr[m], S[m].re, fma(kcpi[m], S[m].im, y1));
             cx_step(S[m], kpr[m], kpi[m], -x);
         }
-        dst[(size_t)j * 4] = y1;
-        ++n_in;
+        dp[0] = y1;
     }
-    return n_in;
+    return n_s;
 }
 
 // Thread = one recurrence set: (chunk, channel, filter I/Q) with the filter's NM modal states in
