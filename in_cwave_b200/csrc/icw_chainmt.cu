@@ -130,13 +130,14 @@ chain_mt_kernel(const __grid_constant__ DevChain ch, DevStream *__restrict__ str
                 wl.x = a.x; wl.y = a.y; wr.x = b.x; wr.y = b.y;
             }
             double v[4];
-            if (from_analytic) {
+            if (SHAPE == ICW_SHAPE_SHIFT_MASTER_FAST || from_analytic) {
                 const double2 a0 = ana[i * 2], a1 = ana[i * 2 + 1];
                 v[0] = a0.x; v[1] = a0.y; v[2] = a1.x; v[3] = a1.y;
             } else {
                 unpack_frame(ch, in + i * ch.frame_bytes, pos0 + i, v);
             }
-            if (LEAN) lean_frame<SHAPE, RT>(ch, st, i, n_frames - 1, v, wl, wr, io.dst, io.dst_aligned, acc, osc);
+            if (SHAPE == ICW_SHAPE_SHIFT_MASTER_FAST) lean_frame_fast<RT>(ch, st, i, n_frames - 1, v, wl, wr, io.dst, acc, osc);
+            else if (LEAN) lean_frame<SHAPE, RT>(ch, st, i, n_frames - 1, v, wl, wr, io.dst, io.dst_aligned, acc, osc);
             else finish_frame<DITHER_GIVEN>(ch, st, i, n_frames, v, bus, io, acc, osc, wl, wr);
         }
         __syncthreads();                                        // the next tile overwrites the words
@@ -178,6 +179,10 @@ cudaError_t launch_chain_mt(const DevChain &ch, DevStream *streams, int64_t n_fr
     const bool lean = !tap_bus && !tap_lr && !pre && ch.shape != ICW_SHAPE_GENERIC && !ch.bypass;
     const bool tpdf = ch.render.render_type == ICW_RENDER_TPDF;
 #define ICW_CMT(SH, RT) return launch_cmt<SH, RT>(ch, streams, n_frames, in, from_analytic, g, pl, pr, out, tap_bus, tap_lr, pre, s)
+    if (lean && from_analytic && lean_fast_ok(ch) && ((size_t)(uintptr_t)out & 3u) == 0) {
+        if (tpdf) ICW_CMT(ICW_SHAPE_SHIFT_MASTER_FAST, ICW_RENDER_TPDF);
+        ICW_CMT(ICW_SHAPE_SHIFT_MASTER_FAST, ICW_RENDER_RPDF);
+    }
     if (lean && ch.shape == ICW_SHAPE_SHIFT_MASTER) { if (tpdf) ICW_CMT(ICW_SHAPE_SHIFT_MASTER, ICW_RENDER_TPDF); ICW_CMT(ICW_SHAPE_SHIFT_MASTER, ICW_RENDER_RPDF); }
     if (lean && ch.shape == ICW_SHAPE_MASTER) { if (tpdf) ICW_CMT(ICW_SHAPE_MASTER, ICW_RENDER_TPDF); ICW_CMT(ICW_SHAPE_MASTER, ICW_RENDER_RPDF); }
     if (tpdf) ICW_CMT(ICW_SHAPE_GENERIC, ICW_RENDER_TPDF);

@@ -222,6 +222,68 @@ __device__ __forceinline__ void lean_frame(const DevChain &ch, DevStream &st, in
     }
 }
 
+// The commonest chain of all -- Shift(In -> X) at one |frequency| on both channels, Master(X) with
+// I+Q or I-Q outputs, scaled oscillator, 24-bit PCM into a 4-byte aligned row -- with every one of
+// those facts known at compile time (the host checks them: lean_fast_ok).  Same operations in the
+// same order as run_shape<ICW_SHAPE_SHIFT_MASTER> + master_out + render_one; x - y is computed as
+// x + (-y), which is the same IEEE operation.
+#define ICW_SHAPE_SHIFT_MASTER_FAST 3
+__host__ __device__ inline bool lean_fast_ok(const DevChain &ch)
+{
+    if (ch.shape != ICW_SHAPE_SHIFT_MASTER || !ch.is_frmod_scaled || ch.render.bytes != 3) return false;
+    const DevNode &sh = ch.nodes[0], &ms = ch.nodes[ch.n_nodes - 1];
+    if (!sh.l_on || !sh.r_on || sh.l_f != sh.r_f || !(sh.l_f < 1.0e8)) return false;
+    const bool lt = ms.l_tout == ICW_OUT_ADD_REIM || ms.l_tout == ICW_OUT_SUB_REIM;
+    const bool rt = ms.r_tout == ICW_OUT_ADD_REIM || ms.r_tout == ICW_OUT_SUB_REIM;
+    return lt && rt;
+}
+
+template <int RT>
+__device__ __forceinline__ void lean_frame_fast(const DevChain &ch, DevStream &st, int64_t i, int64_t i_last, const double v[4],
+                                                uint4 wl, uint4 wr, uint8_t *dst, FrameAcc &acc, OscCounter &osc)
+{
+    const DevRender &rq = ch.render;
+    const DevNode &sh = ch.nodes[0], &ms = ch.nodes[1];
+    // oscillator, scaled counter (adv_modulator.c:611-625)
+    uint64_t d = (uint64_t)(i - osc.frame);
+    osc.frame = i;
+    if (d >= ch.scale_sr) d %= ch.scale_sr;
+    osc.value += d;
+    if (osc.value >= ch.scale_sr) osc.value -= ch.scale_sr;
+    const double omega = norm_omega(ch, osc.value);
+    // shift node: mix from +0.0, gain, one phase for both channels (:519-550)
+    double d0 = (0.0 + v[0]) * sh.l_gain, d1 = (0.0 + v[1]) * sh.l_gain;
+    double d2 = (0.0 + v[2]) * sh.r_gain, d3 = (0.0 + v[3]) * sh.r_gain;
+    const double x = omega * sh.l_f;                            // < 2*pi * 1e8: the quotient below is exact enough
+    const double q = floor(x * ICW_KC[KC_INV_TWO_PI]);
+    double ph = fma(-q, ICW_KC[KC_TWO_PI], x);
+    if (ph < 0.0) ph += ICW_KC[KC_TWO_PI];
+    else if (ph >= ICW_KC[KC_TWO_PI]) ph -= ICW_KC[KC_TWO_PI];
+    double s, c;
+    sincos_2pi(ph, s, c);
+    const double sl = sh.l_neg ? -s : s, sr = sh.r_neg ? -s : s;
+    double o[4];
+    rotate(c, sl, d0, d1, o[0], o[1]);
+    rotate(c, sr, d2, d3, o[2], o[3]);
+    // master (:485-507)
+    d0 = (0.0 + o[0]) * ms.l_gain; d1 = (0.0 + o[1]) * ms.l_gain;
+    d2 = (0.0 + o[2]) * ms.r_gain; d3 = (0.0 + o[3]) * ms.r_gain;
+    const double lo = div_const(d0 + (ms.l_tout == ICW_OUT_SUB_REIM ? -d1 : d1), ICW_KC[KC_SQRT2], ICW_KC[KC_RSQRT2]);
+    const double ro = div_const(d2 + (ms.r_tout == ICW_OUT_SUB_REIM ? -d3 : d3), ICW_KC[KC_SQRT2], ICW_KC[KC_RSQRT2]);
+    const double dl = lean_dither<RT>(wl, acc.redraws);
+    const double dr = lean_dither<RT>(wr, acc.redraws);
+    const RenderOut a = render_one(rq, lo, dl);
+    const RenderOut b = render_one(rq, ro, dr);
+    acc.clips_l += a.clipped; acc.clips_r += b.clipped;
+    acc.peak_l = fmax(acc.peak_l, a.level); acc.peak_r = fmax(acc.peak_r, b.level);
+    store_frame_pcm(dst + i * 6, a.val, b.val, 3);
+    if (i == i_last) {
+        st.bus[0][0] = v[0]; st.bus[0][1] = v[1]; st.bus[0][2] = v[2]; st.bus[0][3] = v[3];
+        const int k = sh.n_out;
+        st.bus[k][0] = o[0]; st.bus[k][1] = o[1]; st.bus[k][2] = o[2]; st.bus[k][3] = o[3];
+    }
+}
+
 // plugs nobody writes keep whatever the context held (normally 0.0)
 __device__ __forceinline__ void load_bus(const DevStream &st, double (*bus)[4])
 {
