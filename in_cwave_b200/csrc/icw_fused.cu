@@ -34,7 +34,8 @@ hb_fused_kernel(const __grid_constant__ HbCoef coef, const __grid_constant__ Dev
                 const uint8_t *__restrict__ in, size_t in_stride,
                 const uint32_t *__restrict__ mtw_l, const uint32_t *__restrict__ mtw_r, size_t mt_stream_stride,
                 uint8_t *__restrict__ out, size_t out_stride,
-                double *__restrict__ tap_bus, double *__restrict__ tap_lr)
+                double *__restrict__ tap_bus, double *__restrict__ tap_lr,
+                int fast /* Shift -> Master, no dither, no taps, aligned rows: lean_frame_fast (icw_frame.cuh) */)
 {
     using Chain = typename ChainSel<ORD, KAHAN>::type;
     constexpr int LAG = Chain::LAG;
@@ -160,7 +161,12 @@ hb_fused_kernel(const __grid_constant__ HbCoef coef, const __grid_constant__ Dev
                         double a = mix_up(0, q, y[2], slot); v[2 + slot] = a;
                         double c = mix_up(1, q, y[3], slot); v[2 + slot] = c;
                     }
-                    finish_frame<DITHER_LATE>(ch, streams[stream0 + h_sl], f, n_frames, v, bus, io, acc, osc);
+                    if (fast) {
+                        const uint4 nw = make_uint4(0u, 0u, 0u, 0u);
+                        lean_frame_fast<ICW_RENDER_ROUND>(ch, streams[stream0 + h_sl], f, n_frames - 1, v, nw, nw, io.dst, acc, osc);
+                    } else {
+                        finish_frame<DITHER_LATE>(ch, streams[stream0 + h_sl], f, n_frames, v, bus, io, acc, osc);
+                    }
                 }
             }
         }
@@ -184,6 +190,8 @@ static cudaError_t launch_fused_ord(bool kahan, const HbCoef &coef, const DevCha
                                     uint8_t *out, size_t out_stride, double *tap_bus, double *tap_lr, cudaStream_t s)
 {
     const int blocks = (n_streams + FUSED_STREAMS - 1) / FUSED_STREAMS;
+    const int fast = !tap_bus && !tap_lr && ch.render.render_type == ICW_RENDER_ROUND && lean_fast_ok(ch) &&
+                     ((size_t)(uintptr_t)out & 3u) == 0 && (n_streams == 1 || (out_stride & 3u) == 0);
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e1 = cudaFuncSetAttribute(hb_fused_kernel<ORD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUSED_SMEM);
@@ -194,10 +202,10 @@ static cudaError_t launch_fused_ord(bool kahan, const HbCoef &coef, const DevCha
     }
     if (kahan)
         hb_fused_kernel<ORD, true><<<blocks, FUSED_THREADS, FUSED_SMEM, s>>>(coef, ch, streams, n_streams, n_frames, in, in_stride,
-                                                          mtw_l, mtw_r, mt_stream_stride, out, out_stride, tap_bus, tap_lr);
+                                                          mtw_l, mtw_r, mt_stream_stride, out, out_stride, tap_bus, tap_lr, fast);
     else
         hb_fused_kernel<ORD, false><<<blocks, FUSED_THREADS, FUSED_SMEM, s>>>(coef, ch, streams, n_streams, n_frames, in, in_stride,
-                                                           mtw_l, mtw_r, mt_stream_stride, out, out_stride, tap_bus, tap_lr);
+                                                           mtw_l, mtw_r, mt_stream_stride, out, out_stride, tap_bus, tap_lr, fast);
     return cudaGetLastError();
 }
 

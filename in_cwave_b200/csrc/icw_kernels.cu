@@ -311,14 +311,15 @@ chain_lean_kernel(const __grid_constant__ DevChain ch, DevStream *__restrict__ s
          i += (int64_t)gridDim.x * blockDim.x) {
         const uint4 wl = dither_fetch(WPS, wl_p, i), wr = dither_fetch(WPS, wr_p, i);
         double v[4];
-        if (from_analytic) {
+        if (SHAPE == ICW_SHAPE_SHIFT_MASTER_FAST || from_analytic) {
             const double2 *a = reinterpret_cast<const double2 *>(src) + i * 2;
             const double2 a0 = a[0], a1 = a[1];
             v[0] = a0.x; v[1] = a0.y; v[2] = a1.x; v[3] = a1.y;
         } else {
             unpack_frame(ch, src + i * ch.frame_bytes, pos0 + i, v);
         }
-        lean_frame<SHAPE, RT>(ch, st, i, n_frames - 1, v, wl, wr, dst, dst_aligned, acc, osc);
+        if (SHAPE == ICW_SHAPE_SHIFT_MASTER_FAST) lean_frame_fast<RT>(ch, st, i, n_frames - 1, v, wl, wr, dst, acc, osc);
+        else lean_frame<SHAPE, RT>(ch, st, i, n_frames - 1, v, wl, wr, dst, dst_aligned, acc, osc);
     }
     commit_acc(&st, acc, 32);
 }
@@ -342,7 +343,13 @@ cudaError_t launch_chain(const DevChain &ch, DevStream *streams, int n_streams, 
         (rt == ICW_RENDER_ROUND || rt == ICW_RENDER_RPDF || rt == ICW_RENDER_TPDF)) {
 #define ICW_LEAN(SH, RT) chain_lean_kernel<SH, RT><<<grid, threads, 0, s>>>(ch, streams, n_frames, in, in_stride, from_analytic, \
                                                                             mtw_l, mtw_r, mt_stream_stride, out, out_stride)
-        if (ch.shape == ICW_SHAPE_MASTER) {
+        // every stream's row must be 4-byte aligned for the fast path's 16-bit PCM stores
+        const bool fast = from_analytic && lean_fast_ok(ch) && ((size_t)(uintptr_t)out & 3u) == 0 && (n_streams == 1 || (out_stride & 3u) == 0);
+        if (fast) {
+            if (rt == ICW_RENDER_ROUND) ICW_LEAN(ICW_SHAPE_SHIFT_MASTER_FAST, ICW_RENDER_ROUND);
+            else if (rt == ICW_RENDER_RPDF) ICW_LEAN(ICW_SHAPE_SHIFT_MASTER_FAST, ICW_RENDER_RPDF);
+            else ICW_LEAN(ICW_SHAPE_SHIFT_MASTER_FAST, ICW_RENDER_TPDF);
+        } else if (ch.shape == ICW_SHAPE_MASTER) {
             if (rt == ICW_RENDER_ROUND) ICW_LEAN(ICW_SHAPE_MASTER, ICW_RENDER_ROUND);
             else if (rt == ICW_RENDER_RPDF) ICW_LEAN(ICW_SHAPE_MASTER, ICW_RENDER_RPDF);
             else ICW_LEAN(ICW_SHAPE_MASTER, ICW_RENDER_TPDF);
