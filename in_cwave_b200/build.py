@@ -47,7 +47,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         if not PLUGIN.exists() or PLUGIN.stat().st_mtime < (PKG / "host" / "icw_plugin.c").stat().st_mtime:
             build_plugin()
         return LIB
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", str(LIB)] + [str(CSRC / s) for s in SOURCES]
+    extra = os.environ.get("ICW_NVCC_EXTRA", "").split()      # A/B experiments: -DICW_APPLY_THREADS=384 ...
+    cmd = [nvcc_path(), *NVCC_FLAGS, *extra, "-o", str(LIB)] + [str(CSRC / s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr
     (PKG / "build.log").write_text(" ".join(cmd) + "\n" + log)

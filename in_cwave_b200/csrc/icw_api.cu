@@ -83,7 +83,7 @@ struct icw_engine {
     Scratch crc_partial;                // per-tile CRC registers + the result word
     Scratch ns_pre;                     // noise shaping: (value, dither) pairs between chain_kernel and ns_render_kernel
     struct ScanPlan { bool ready = false; ModalCoef mc; double *d_pw = nullptr; };
-    ScanPlan scan[ICW_HB_NTYPES][2];    // [filter_no][baseline]
+    ScanPlan scan[ICW_HB_NTYPES][2][3]; // [filter_no][baseline][chunk length: 256, 1024, 2048 (or the forced one)]
     MtJump mt;                          // MT19937 checkpoint service (icw_mt.cu)
 };
 
@@ -396,7 +396,7 @@ static void engine_free(icw_engine *e)
     cudaStreamSynchronize(e->stream);
     e->analytic.release(); e->mtw[0].release(); e->mtw[1].release(); e->ckpt.release();
     e->io_in.release(); e->io_out.release(); e->leaf.release(); e->scan_scratch.release(); e->ns_pre.release(); e->crc_partial.release();
-    for (auto &row : e->scan) for (auto &pl : row) if (pl.d_pw) cudaFree(pl.d_pw);
+    for (auto &row : e->scan) for (auto &col : row) for (auto &pl : col) if (pl.d_pw) cudaFree(pl.d_pw);
     e->mt.release();
     cudaStreamSynchronize(e->aux);
     if (e->h2d) {
@@ -696,12 +696,18 @@ static int make_dither_words(icw_session *s, int64_t n_frames, cudaStream_t st, 
     return ICW_OK;
 }
 
-static int get_scan_plan(icw_engine *e, int filter_no, bool baseline, double d0, icw_engine::ScanPlan **out)
+static int get_scan_plan(icw_engine *e, int filter_no, bool baseline, double d0, int L, icw_engine::ScanPlan **out)
 {
-    icw_engine::ScanPlan &pl = e->scan[filter_no][baseline ? 1 : 0];
+    icw_engine::ScanPlan &pl = e->scan[filter_no][baseline ? 1 : 0][L <= SCAN_L ? 0 : L <= 4 * SCAN_L ? 1 : 2];
+    if (pl.ready && pl.mc.L != L) {             // only when ICW_SCAN_L forces odd lengths: rebuild in place
+        CK(cudaStreamSynchronize(e->stream));
+        cudaFree(pl.d_pw);
+        pl.d_pw = nullptr;
+        pl.ready = false;
+    }
     if (!pl.ready) {
         std::vector<double> pw;
-        scan_make_coef(filter_no, baseline, d0, pl.mc, pw);
+        scan_make_coef(filter_no, baseline, d0, L, pl.mc, pw);
         if (cudaMalloc(&pl.d_pw, pw.size() * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return fail(ICW_E_NOMEM, "cudaMalloc(scan power table) failed"); }
         CK(cudaMemcpy(pl.d_pw, pw.data(), pw.size() * sizeof(double), cudaMemcpyHostToDevice));
         pl.ready = true;
@@ -750,10 +756,11 @@ static int process_group(icw_session *s, int64_t n_frames, const uint8_t *d_in, 
             if (scan) {
                 // time-parallel modal scan (icw_scan.cu): chunk end states -> carries -> apply
                 icw_engine::ScanPlan *plp;
-                rc = get_scan_plan(e, s->spec.filter_no, !s->spec.is_kahan, s->coef.d0, &plp);
+                const int L = scan_chunk_len(K, n_frames, e->sm_count);
+                rc = get_scan_plan(e, s->spec.filter_no, !s->spec.is_kahan, s->coef.d0, L, &plp);
                 if (rc) return rc;
                 icw_engine::ScanPlan &pl = *plp;
-                rc = e->scan_scratch.reserve(scan_scratch_doubles(K, n_frames) * sizeof(double));
+                rc = e->scan_scratch.reserve(scan_scratch_doubles(K, n_frames, L) * sizeof(double));
                 if (rc) return rc;
                 int nl = 0;
                 // profiling: one span for passes 1 + 2, one for pass 3 (two events recorded between them)
@@ -835,6 +842,7 @@ struct CallCtx {
 // frames per launch group when the group's dither comes from chain_mt_kernel: its CTAs are the
 // generator's jump-ahead units, so a group should be the whole call (analytic scratch: 32 B/frame)
 constexpr int64_t FUSE_MT_GROUP = (int64_t)1 << 30;
+constexpr int64_t BIG_GROUP = (int64_t)1 << 30;     // frames per launch group of one long stream (34 GB of analytic scratch)
 
 // `one_range`: the caller hands the whole call over in a single call_range()
 static int call_begin(icw_session *s, int64_t n_total, cudaStream_t st, CallCtx &cx, bool one_range)
@@ -853,7 +861,10 @@ static int call_begin(icw_session *s, int64_t n_total, cudaStream_t st, CallCtx 
     }
     // scan mode and the unfused path go through per-frame scratch: bound it by walking the call in groups
     const bool scratchy = cx.real_in && (cx.mode == ICW_HILBERT_SCAN || e->unfused);
-    const int64_t seg = scratchy ? SCAN_SEGMENT / (K > 64 ? 64 : K) / SCAN_L / SCAN_CH * (SCAN_L * SCAN_CH) : n_total;
+    // one stream: groups as long as the analytic scratch may grow (32 B/frame) -- long groups let the scan use
+    // long chunks (scan_chunk_len); many streams: 2^25 frames over all of them
+    const int64_t seg = !scratchy ? n_total
+                      : K == 1 ? BIG_GROUP : SCAN_SEGMENT / (K > 64 ? 64 : K) / SCAN_L / SCAN_CH * (SCAN_L * SCAN_CH);
     cx.step = seg < SCAN_L * SCAN_CH ? SCAN_L * SCAN_CH : seg;
     const int wps = ch.render.words_per_sample;
     // the fused exact kernel reads word buffers; everything else that ends in chain_kernel can make its own
@@ -1083,7 +1094,8 @@ extern "C" int icw_hilbert_device(icw_engine *e, int filter_no, int is_kahan, in
         const double a0 = word_as_double(ICW_HB_A[filter_no][0]);
         const double d0 = word_as_double(ICW_HB_B[filter_no][0]) / a0;
         icw_engine::ScanPlan *pl;
-        int rc = get_scan_plan(e, filter_no, !is_kahan, d0, &pl);
+        const int L = scan_chunk_len(n_chan, n, e->sm_count);
+        int rc = get_scan_plan(e, filter_no, !is_kahan, d0, L, &pl);
         if (rc) return rc;
         DevChain ch;
         memset(&ch, 0, sizeof ch);
@@ -1100,7 +1112,7 @@ extern "C" int icw_hilbert_device(icw_engine *e, int filter_no, int is_kahan, in
         if (rc) return rc;
         rc = e->analytic.reserve((size_t)n_chan * (size_t)n * 4 * sizeof(double));
         if (rc) return rc;
-        rc = e->scan_scratch.reserve(scan_scratch_doubles(n_chan, n) * sizeof(double));
+        rc = e->scan_scratch.reserve(scan_scratch_doubles(n_chan, n, L) * sizeof(double));
         if (rc) return rc;
         CK(cudaMemcpyAsync(e->leaf.p, ds.data(), sizeof(DevStream) * ds.size(), cudaMemcpyHostToDevice, e->stream));
         int nl = 0;

@@ -150,12 +150,9 @@ static cudaError_t launch_cmt(const DevChain &ch, DevStream *streams, int64_t n_
                               const CmtGeom &g, const MtPlan &pl, const MtPlan &pr, uint8_t *out, double *tap_bus, double *tap_lr,
                               double *pre, cudaStream_t s)
 {
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(chain_mt_kernel<SHAPE, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CMT_SMEM);
-        if (e != cudaSuccess) return e;
-        attr = true;
-    }
+    // per device, not per process: set on every launch (a few microseconds) rather than cached in a static
+    cudaError_t e = cudaFuncSetAttribute(chain_mt_kernel<SHAPE, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CMT_SMEM);
+    if (e != cudaSuccess) return e;
     chain_mt_kernel<SHAPE, RT><<<g.n_units, CMT_THREADS, CMT_SMEM, s>>>(ch, streams, n_frames, in, from_analytic, g, pl.ckpt, pr.ckpt,
                                                                       pl.tail, pr.tail, out, tap_bus, tap_lr, pre);
     return cudaGetLastError();

@@ -192,13 +192,10 @@ static cudaError_t launch_fused_ord(bool kahan, const HbCoef &coef, const DevCha
     const int blocks = (n_streams + FUSED_STREAMS - 1) / FUSED_STREAMS;
     const int fast = !tap_bus && !tap_lr && ch.render.render_type == ICW_RENDER_ROUND && lean_fast_ok(ch) &&
                      ((size_t)(uintptr_t)out & 3u) == 0 && (n_streams == 1 || (out_stride & 3u) == 0);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e1 = cudaFuncSetAttribute(hb_fused_kernel<ORD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUSED_SMEM);
-        cudaError_t e2 = cudaFuncSetAttribute(hb_fused_kernel<ORD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUSED_SMEM);
+    {   // per device, not per process: set on every launch rather than cached in a static
+        cudaError_t e1 = kahan ? cudaFuncSetAttribute(hb_fused_kernel<ORD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUSED_SMEM)
+                               : cudaFuncSetAttribute(hb_fused_kernel<ORD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUSED_SMEM);
         if (e1 != cudaSuccess) return e1;
-        if (e2 != cudaSuccess) return e2;
-        attr_done = true;
     }
     if (kahan)
         hb_fused_kernel<ORD, true><<<blocks, FUSED_THREADS, FUSED_SMEM, s>>>(coef, ch, streams, n_streams, n_frames, in, in_stride,

@@ -17,6 +17,7 @@
 // (1e-9 .. 1e-3 of RMS depending on the design) and ignores the |w|<1
 // state zeroing.  Exact mode (icw_fused.cu) is the bit-exact path.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -25,6 +26,12 @@
 #include "icw_kernels.h"
 #include "icw_scan.h"
 #include "icw_hb_modal.inc"
+
+// 384 threads at 168 registers (12 warps per SM, ~100 B of spill per thread outside the sample loop's
+// steady state) beat 256 at 207-224 (8 warps): 10.3 against 11.0 ms per C2 step; 320 and 512 lose
+#ifndef ICW_APPLY_THREADS
+#define ICW_APPLY_THREADS 384
+#endif
 
 namespace icw {
 
@@ -41,11 +48,25 @@ static inline cld cpowi(cld a, long long e)
     return r;
 }
 
-void scan_make_coef(int filter_no, bool baseline, double d0, ModalCoef &mc, std::vector<double> &pw_table)
+int scan_chunk_len(int n_streams, int64_t n_frames, int sm_count)
+{
+    const char *f = getenv("ICW_SCAN_L");                       // tests force a length on short inputs
+    if (f && *f) { const int v = atoi(f); if (v >= SCAN_L && v % SCAN_L == 0 && v <= 16384) return v; }
+    const double chunks256 = (double)n_streams * (double)n_frames / SCAN_L;
+    const double wave = (double)sm_count * (ICW_APPLY_THREADS / 4);    // pass-3 chunks resident at once
+    // measured on C2 (i24, 691 M frames): 256 -> 5.0 + 10.3 ms (pass 1 + pass 3), 1024 -> 4.3 + 10.2,
+    // 2048 -> 4.2 + 10.3, 4096 -> 4.2 + 10.5, 8192 -> 4.5 + 10.5; on the C5 shape (f32) 2048 is within 1 % of 4096
+    if (chunks256 / 8 >= 8 * wave) return 8 * SCAN_L;
+    if (chunks256 / 4 >= 8 * wave) return 4 * SCAN_L;
+    return SCAN_L;
+}
+
+void scan_make_coef(int filter_no, bool baseline, double d0, int L, ModalCoef &mc, std::vector<double> &pw_table)
 {
     memset(&mc, 0, sizeof mc);
     const int nm = ICW_HB_NMODES[filter_no];
     mc.nm = nm;
+    mc.L = L;
     mc.real_last = ICW_HB_MODES[filter_no][nm - 1].is_real;
     mc.baseline = baseline;
     mc.d0 = d0;
@@ -59,8 +80,8 @@ void scan_make_coef(int filter_no, bool baseline, double d0, ModalCoef &mc, std:
         ld n2 = p.re * p.re + p.im * p.im;
         cld pinv = { p.re / n2, -p.im / n2 };
         cld rp = cmul(r, p);
-        cld pl = cpowi(p, SCAN_L);
-        cld pt = cpowi(p, (long long)SCAN_L * SCAN_CH);
+        cld pl = cpowi(p, L);
+        cld pt = cpowi(p, (long long)L * SCAN_CH);
         mc.p_re[m] = (double)p.re;       mc.p_im[m] = (double)p.im;
         mc.p2_re[m] = (double)p2.re;     mc.p2_im[m] = (double)p2.im;
         mc.pinv_re[m] = (double)pinv.re; mc.pinv_im[m] = (double)pinv.im;
@@ -82,6 +103,25 @@ void scan_make_coef(int filter_no, bool baseline, double d0, ModalCoef &mc, std:
             pw_table[((size_t)j * SCAN_NMAX + m) * 2 + 1] = (double)acc.im;
             acc = cmul(acc, pl);
         }
+    }
+    // pass 1 wants a chunk's END state from zero: a mode whose pole has radius r has forgotten an input after
+    // log(1e-18)/log(r) samples, so it may start that many samples before the chunk end.  Ranks: the slowest
+    // mode first; the table lists conjugate pairs by ascending radius and the real pole (the fastest) last.
+    {
+        const bool rl = mc.real_last != 0;
+        int prev = 0;
+        for (int r = 0; r < nm; ++r) {
+            const int m = rl ? (r == nm - 1 ? nm - 1 : nm - 2 - r) : nm - 1 - r;
+            const double rad = std::sqrt(mc.p_re[m] * mc.p_re[m] + mc.p_im[m] * mc.p_im[m]);
+            const double forget = rad > 0.0 && rad < 1.0 ? std::log(1e-18) / std::log(rad) : 1e30;   // samples
+            int j = 0;
+            if (forget < (double)L) j = (int)(((double)L - forget) / 2.0) - 2;       // steps of two samples
+            j = (j < 0 || r == 0) ? 0 : (j / 4) * 4;                                // the slowest mode walks the whole chunk
+            if (j < prev) j = prev;                                                 // ranks join in order
+            mc.join[r] = j;
+            prev = j;
+        }
+        for (int r = nm; r <= SCAN_NMAX; ++r) mc.join[r] = L / 2;
     }
 }
 
@@ -118,6 +158,19 @@ __device__ __forceinline__ void stage_constants(double (*k)[SCAN_NMAX], const Mo
 #define ICW_LOCAL_UMASK 0x03
 #endif
 constexpr int APPLY_UMASK = ICW_APPLY_UMASK, LOCAL_UMASK = ICW_LOCAL_UMASK;
+#ifndef ICW_APPLY_UNROLL
+#define ICW_APPLY_UNROLL 1
+#endif
+constexpr int APPLY_UNROLL = ICW_APPLY_UNROLL;      // steps of the pass-3 sample loop per trip
+#ifndef ICW_LOCAL_UNROLL
+#define ICW_LOCAL_UNROLL 4
+#endif
+#ifndef ICW_SCAN_PF_BYTES
+#define ICW_SCAN_PF_BYTES 256
+#endif
+constexpr int LOCAL_UNROLL = ICW_LOCAL_UNROLL;      // steps of the pass-1 sample loop per trip (one prefetch per trip)
+// (re-reading the residue constants from shared memory at every use -- a broadcast LDS each, 80 registers
+// freed, 512 threads per SM -- was measured slower: 13.7 ms against 10.3 per C2 step)
 template <int UMASK>
 __device__ __forceinline__ double kconst(const ModalCoef &mc, const double (*kshared)[SCAN_NMAX], int a, int m)
 {
@@ -166,7 +219,7 @@ __device__ __forceinline__ double scan_sample_at(const DevChain &ch, const uint8
 // 128-byte line holds five to sixteen steps.
 __device__ __forceinline__ void scan_prefetch_at(const uint8_t *p, const uint8_t *row_last)
 {
-    const uint8_t *q = p + 256;
+    const uint8_t *q = p + ICW_SCAN_PF_BYTES;
     if (q > row_last) q = row_last;
     asm volatile("prefetch.global.L1 [%0];" :: "l"(q));
 }
@@ -184,32 +237,61 @@ __device__ __forceinline__ bool chunk_fades(const DevChain &ch, int64_t pos, int
     return pos < ch.n_fade_in || pos + n > ch.n_samples - ch.n_fade_out;
 }
 
-// pass-1 inner loop: SCAN_L / 2 inputs of one filter from a zero state, sign-free form
+// pass-1 inner loop: L / 2 inputs of one filter from a zero state, sign-free form.  The slowest mode runs
+// over the whole chunk; the mode of rank r joins at step mc.join[r] with a zero state (what it would hold by
+// then has decayed below 1e-18 by the chunk end).  ACT = modes running in the current phase.
+template <int NM, bool RL> __device__ __forceinline__ constexpr int mode_rank(int m)
+{
+    return RL ? (m == NM - 1 ? NM - 1 : NM - 2 - m) : NM - 1 - m;
+}
+template <int ACT, int NM, bool RL>
+__device__ __forceinline__ void local_advance(Cx (&s)[NM], const double (&kpr)[NM], const double (&kpi)[NM], double xin)
+{
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+        if (mode_rank<NM, RL>(m) >= ACT) continue;
+        if (RL && m == NM - 1) re_step(s[m], kpr[m], -xin);
+        else cx_step(s[m], kpr[m], kpi[m], -xin);
+    }
+}
+template <int ACT, int NM, bool RL, int FMT, bool FADE>
+__device__ __forceinline__ void local_phase(Cx (&s)[NM], const double (&kpr)[NM], const double (&kpi)[NM], const DevChain &ch,
+                                            const uint8_t *&p, int step_bytes, int64_t &fpos, const uint8_t *row_last,
+                                            double &x, int k0, int k1)
+{
+#pragma unroll LOCAL_UNROLL
+    for (int k = k0; k < k1; ++k) {                             // the next input is fetched one step ahead
+        p += step_bytes;
+        if (FADE) fpos += 2;
+        const double xn = scan_sample_at<FMT, FADE>(ch, p, fpos);
+        if ((k & (LOCAL_UNROLL - 1)) == 0) scan_prefetch_at(p, row_last);
+        local_advance<ACT, NM, RL>(s, kpr, kpi, x);
+        x = xn;
+    }
+}
+template <int ACT, int NM, bool RL, int FMT, bool FADE>
+struct LocalPhases {
+    static __device__ __forceinline__ void run(Cx (&s)[NM], const double (&kpr)[NM], const double (&kpi)[NM], const DevChain &ch,
+                                               const ModalCoef &mc, const uint8_t *&p, int step_bytes, int64_t &fpos,
+                                               const uint8_t *row_last, double &x, int last)
+    {
+        // phase ACT: steps [join[ACT-1], join[ACT]) -- never the chunk's last step, which has nothing to fetch
+        const int k0 = mc.join[ACT - 1], k1 = mc.join[ACT] < last ? mc.join[ACT] : last;
+        local_phase<ACT, NM, RL, FMT, FADE>(s, kpr, kpi, ch, p, step_bytes, fpos, row_last, x, k0, k1);
+        if (ACT < NM) LocalPhases<(ACT < NM ? ACT + 1 : NM), NM, RL, FMT, FADE>::run(s, kpr, kpi, ch, mc, p, step_bytes, fpos, row_last, x, last);
+    }
+};
 template <int NM, bool RL, int FMT, bool FADE>
 __device__ __forceinline__ void local_run(Cx (&s)[NM], const double (&kpr)[NM], const double (&kpi)[NM], const DevChain &ch,
-                                          const uint8_t *row, int64_t f0, int chan_off, int64_t pos0, const uint8_t *row_last)
+                                          const ModalCoef &mc, const uint8_t *row, int64_t f0, int chan_off, int64_t pos0,
+                                          const uint8_t *row_last)
 {
     const uint8_t *p = row + f0 * ch.frame_bytes + chan_off;
     const int step_bytes = 2 * ch.frame_bytes;
     int64_t fpos = pos0 + f0;
     double x = scan_sample_at<FMT, FADE>(ch, p, fpos);
-    auto advance = [&](double xin) {
-#pragma unroll
-        for (int m = 0; m < NM; ++m) {
-            if (RL && m == NM - 1) re_step(s[m], kpr[m], -xin);
-            else cx_step(s[m], kpr[m], kpi[m], -xin);
-        }
-    };
-#pragma unroll 4
-    for (int k = 0; k < SCAN_L / 2 - 1; ++k) {                  // the next input is fetched one step ahead
-        p += step_bytes;
-        if (FADE) fpos += 2;
-        const double xn = scan_sample_at<FMT, FADE>(ch, p, fpos);
-        if ((k & 3) == 0) scan_prefetch_at(p, row_last);
-        advance(x);
-        x = xn;
-    }
-    advance(x);
+    LocalPhases<1, NM, RL, FMT, FADE>::run(s, kpr, kpi, ch, mc, p, step_bytes, fpos, row_last, x, mc.L / 2 - 1);
+    local_advance<NM, NM, RL>(s, kpr, kpi, x);                  // the chunk's last input: every mode is in by now
 }
 
 // pass-3 inner loop: one filter over one chunk from its true state S~, writing its half of every
@@ -261,7 +343,7 @@ __device__ __forceinline__ int apply_run(Cx (&S)[NM], const ModalCoef &mc, const
         dp += 8;
     };
     int i = 0;
-#pragma unroll 2
+#pragma unroll APPLY_UNROLL
     for (; i + 2 < n_s; ++i) {                                  // the input after next is fetched two steps ahead
         p += step_bytes;
         if (FADE) fpos += 2;
@@ -321,16 +403,16 @@ scan_local_kernel(const __grid_constant__ ModalCoef mc, const __grid_constant__ 
         const uint8_t *row = in + (size_t)stream * in_stride;
         const int chan_off = (ch.n_channels > 1 ? chan : 0) * ch.chan_bytes;
         const uint8_t *row_last = row + n_frames * ch.frame_bytes - 1;
-        const int64_t f0 = chunk * SCAN_L + (is_x ? 0 : 1);     // this filter's first input sample
+        const int64_t f0 = chunk * mc.L + (is_x ? 0 : 1);       // this filter's first input sample
         const unsigned qf = (q0 + (is_x ? 0u : 1u)) & 3u;       // its mixer phase (chunks start on a multiple of 4)
         double kpr[NM], kpi[NM];
 #pragma unroll
         for (int m = 0; m < NM; ++m) { kpr[m] = kconst<LOCAL_UMASK>(mc, kshared, K_PR, m); kpi[m] = kconst<LOCAL_UMASK>(mc, kshared, K_PI, m); }
-        if (chunk_fades(ch, st.pos + chunk * SCAN_L, SCAN_L))
-            local_run<NM, RL, FMT, true>(s, kpr, kpi, ch, row, f0, chan_off, st.pos, row_last);
+        if (chunk_fades(ch, st.pos + chunk * mc.L, mc.L))
+            local_run<NM, RL, FMT, true>(s, kpr, kpi, ch, mc, row, f0, chan_off, st.pos, row_last);
         else
-            local_run<NM, RL, FMT, false>(s, kpr, kpi, ch, row, f0, chan_off, st.pos, row_last);
-        // S~ -> S: SCAN_L / 2 inputs is an even count, the sign is the first input's
+            local_run<NM, RL, FMT, false>(s, kpr, kpi, ch, mc, row, f0, chan_off, st.pos, row_last);
+        // S~ -> S: L / 2 inputs is an even count, the sign is the first input's
         const double sg = mixer_sign(filt, qf);
 #pragma unroll
         for (int m = 0; m < NM; ++m) { s[m].re *= sg; s[m].im *= sg; }
@@ -435,7 +517,7 @@ scan_tile_carry_kernel(const __grid_constant__ ModalCoef mc, const DevStream *__
 // pass 3: every chunk again, from its true initial state, producing the analytic signal.
 // Each thread writes its own filter's half of every frame: re or im, alternating with the phase.
 template <int NM, bool RL, int FMT>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(ICW_APPLY_THREADS, 1)
 scan_apply_kernel(const __grid_constant__ ModalCoef mc, const __grid_constant__ DevChain ch,
                   DevStream *__restrict__ streams, int64_t n_frames, int64_t n_chunks, int64_t n_tiles,
                   const uint8_t *__restrict__ in, size_t in_stride,
@@ -453,8 +535,8 @@ scan_apply_kernel(const __grid_constant__ ModalCoef mc, const __grid_constant__ 
     const bool is_x = filt == (int)(q0 & 1);
     const uint8_t *row = in + (size_t)stream * in_stride;
     const int chan_off = (ch.n_channels > 1 ? chan : 0) * ch.chan_bytes;
-    const int64_t f0 = chunk * SCAN_L;
-    const int len = (int)((n_frames - f0 < SCAN_L) ? n_frames - f0 : SCAN_L);
+    const int64_t f0 = chunk * mc.L;
+    const int len = (int)((n_frames - f0 < mc.L) ? n_frames - f0 : mc.L);
     const int64_t tile = chunk / SCAN_CH;
     const int jl = (int)(chunk % SCAN_CH);
     double *dst = analytic + ((size_t)stream * (size_t)n_frames + (size_t)f0) * 4 + chan * 2;
@@ -505,9 +587,9 @@ scan_apply_kernel(const __grid_constant__ ModalCoef mc, const __grid_constant__ 
 // ---------------------------------------------------------------------------------------------
 // launch sequence
 // ---------------------------------------------------------------------------------------------
-size_t scan_scratch_doubles(int n_streams, int64_t n_frames)
+size_t scan_scratch_doubles(int n_streams, int64_t n_frames, int L)
 {
-    const int64_t n_chunks = (n_frames + SCAN_L - 1) / SCAN_L;
+    const int64_t n_chunks = (n_frames + L - 1) / L;
     const int64_t n_tiles = (n_chunks + SCAN_CH - 1) / SCAN_CH;
     const size_t e = (size_t)n_streams * (4 * SCAN_NMAX) * 2 * (size_t)n_chunks;
     const size_t t = (size_t)n_streams * (size_t)n_tiles * 2 * 2 * (SCAN_NMAX * 2);
@@ -520,7 +602,7 @@ static cudaError_t scan_launch_nf(const ModalCoef &mc, const DevChain &ch, DevSt
                                   double *scratch, double *analytic, cudaStream_t s, int *launches,
                                   cudaEvent_t mid_end, cudaEvent_t mid_start)
 {
-    const int64_t n_chunks = (n_frames + SCAN_L - 1) / SCAN_L;
+    const int64_t n_chunks = (n_frames + mc.L - 1) / mc.L;
     const int64_t n_tiles = (n_chunks + SCAN_CH - 1) / SCAN_CH;
     double *E = scratch;
     double *Tend = E + (size_t)n_streams * (4 * SCAN_NMAX) * 2 * (size_t)n_chunks;
@@ -531,8 +613,8 @@ static cudaError_t scan_launch_nf(const ModalCoef &mc, const DevChain &ch, DevSt
     const unsigned tgrid = (unsigned)((items + 127) / 128);
     scan_tile_carry_kernel<<<dim3(tgrid, n_streams), 128, 0, s>>>(mc, streams, n_tiles, Tend, Tin);
     if (mid_end) { cudaEventRecord(mid_end, s); cudaEventRecord(mid_start, s); }
-    const unsigned agrid = (unsigned)((n_chunks + 63) / 64);
-    scan_apply_kernel<NM, RL, FMT><<<dim3(agrid, n_streams), 256, 0, s>>>(mc, ch, streams, n_frames, n_chunks, n_tiles, in, in_stride,
+    const unsigned agrid = (unsigned)((n_chunks + ICW_APPLY_THREADS / 4 - 1) / (ICW_APPLY_THREADS / 4));
+    scan_apply_kernel<NM, RL, FMT><<<dim3(agrid, n_streams), ICW_APPLY_THREADS, 0, s>>>(mc, ch, streams, n_frames, n_chunks, n_tiles, in, in_stride,
                                                                     E, Tin, pw, analytic);
     *launches += 3;
     return cudaGetLastError();

@@ -180,3 +180,46 @@ def test_time_sharding_stitches_on_one_gpu(engine, oracle):
     rep = pcm_report(np.concatenate([p0, p1]), whole, 3)
     print(f"[time shards] {rep}")
     assert rep["max_lsb"] <= 1 and rep["mismatches"] <= 2
+
+
+@pytest.mark.parametrize("L", [1024, 4096])
+@pytest.mark.parametrize("ft", [0, 1, 5])
+def test_scan_long_chunks_late_starting_modes(engine, oracle, monkeypatch, ft, L):
+    """Long streams use chunks of 1024 / 4096 frames and pass 1 starts the fast modes late (a mode of
+    pole radius r has forgotten an input after log(1e-18)/log(r) samples).  Forced here on a short
+    input (ICW_SCAN_L): same bar against the binary128 truth, split calls included."""
+    import torch
+    monkeypatch.setenv("ICW_SCAN_L", str(L))
+    rng = np.random.default_rng(900 + ft)
+    n = 3 * 128 * L // 2 + 12345                     # two tiles and a ragged tail
+    n = min(n, 800_000)
+    x = (rng.random((2, n)) - 0.5) * 30000.0
+    x[1] += 12000.0 * np.sin(2 * np.pi * 0.2499 * np.arange(n))
+    xa = torch.from_numpy(x).cuda()
+    out, st = engine.hilbert(xa, ft, 1, 0, "scan")
+    out = out.cpu().numpy()
+    cut = 5 * L + 3
+    o1, s1 = engine.hilbert(xa[:, :cut].contiguous(), ft, 1, 0, "scan")
+    o2, _ = engine.hilbert(xa[:, cut:].contiguous(), ft, 1, 0, "scan", states=s1)
+    both = np.concatenate([o1.cpu().numpy(), o2.cpu().numpy()], axis=1)
+    for c in range(2):
+        ti, tq = truth_iq(oracle, x[c], ft, 1)
+        scale = np.sqrt(np.mean(ti ** 2 + tq ** 2))
+        for name, got in (("one call", out), ("two calls", both)):
+            err = max(np.max(np.abs(got[c, :, 0] - ti)), np.max(np.abs(got[c, :, 1] - tq))) / scale
+            print(f"[scan L={L}] type {ft} ch {c} {name}: max err / rms = {err:.2e}")
+            assert err <= TOL
+
+
+def test_scan_long_chunks_whole_chain(engine, oracle, monkeypatch):
+    """The C2 chain with 4096-frame chunks gives the bytes of the 256-frame chunks up to the scan's
+    own rounding (carries differ at the 1e-16 level)."""
+    spec = S.config_c2(hilbert_mode="scan")
+    n = 700_001
+    raw = rand_bytes(spec, n, 71)
+    base = engine.session(spec, 1).process_host(raw)[0]
+    monkeypatch.setenv("ICW_SCAN_L", "4096")
+    long_ = engine.session(spec, 1).process_host(raw)[0]
+    rep = pcm_report(long_, base, 3)
+    print(f"[scan L=4096 vs 256] {rep}")
+    assert rep["max_lsb"] <= 1 and rep["mismatches"] <= 4
