@@ -221,7 +221,11 @@ __device__ __forceinline__ void scan_prefetch_at(const uint8_t *p, const uint8_t
 {
     const uint8_t *q = p + ICW_SCAN_PF_BYTES;
     if (q > row_last) q = row_last;
+#ifdef ICW_SCAN_PF_L2
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(q));
+#else
     asm volatile("prefetch.global.L1 [%0];" :: "l"(q));
+#endif
 }
 
 // E layout: [stream][comp][chan][chunk], comp = (filter * SCAN_NMAX + mode) * 2 + {re, im}
