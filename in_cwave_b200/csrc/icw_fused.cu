@@ -21,7 +21,10 @@
 
 namespace icw {
 
-constexpr int FUSED_T = 32;                 // frames per tile
+#ifndef ICW_FUSED_T
+#define ICW_FUSED_T 32
+#endif
+constexpr int FUSED_T = ICW_FUSED_T;        // frames per tile
 constexpr int FUSED_STREAMS = 32;           // streams per CTA
 constexpr int FUSED_ROWS = FUSED_T + 2;     // output window: T frames + the Kahan lag
 constexpr int FUSED_HPS = 8;                // helper threads per stream (8 helper warps per CTA)
