@@ -45,6 +45,7 @@ class ChainSpecC(C.Structure):
         ("quantz_type", C.c_uint32), ("render_type", C.c_uint32), ("nshape_type", C.c_uint32),
         ("sign_bits16", C.c_uint32), ("sign_bits24", C.c_uint32),
         ("bypass", C.c_int32), ("n_nodes", C.c_int32), ("nodes", Node * MAX_NODES),
+        ("is_fp_check", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 
@@ -82,7 +83,7 @@ EXPORTS = [
     "icw_out_frame_bytes", "icw_peak_db", "icw_engine_create", "icw_engine_destroy",
     "icw_session_create", "icw_session_destroy", "icw_session_set_spec", "icw_session_get_state",
     "icw_session_set_state", "icw_session_reset", "icw_session_process_host",
-    "icw_session_process_device", "icw_session_sync", "icw_session_stats", "icw_hilbert_device",
+    "icw_session_process_device", "icw_session_sync", "icw_session_stats", "icw_session_fp_stats", "icw_hilbert_device",
     "icw_mt_words_device", "icw_session_set_taps", "icw_debug_phase_device", "icw_debug_sincos_device", "icw_mt_host_charpoly",
     "icw_mt_host_seq_state", "icw_mt_host_jump_state", "icw_mt_host_jump_state_family", "icw_mt_host_jump_state_product",
     "icw_session_profile", "icw_session_profile_read", "icw_kernel_class_name", "icw_crc32_device", "icw_crc32_host", "icw_crc32_combine",
@@ -128,6 +129,7 @@ def lib() -> C.CDLL:
     L.icw_session_process_device.argtypes = [vp, i64, vp, sz, vp, sz, vp]
     L.icw_session_sync.argtypes = [vp]
     L.icw_session_stats.argtypes = [vp, P(Stats)]
+    L.icw_session_fp_stats.argtypes = [vp, C.c_int, P((C.c_uint32 * 7) * 4)]
     L.icw_session_profile.argtypes = [vp, C.c_int]
     L.icw_session_profile_read.argtypes = [vp, P(Profile), C.c_int]
     L.icw_crc32_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32)]

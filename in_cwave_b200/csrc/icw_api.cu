@@ -251,6 +251,7 @@ static int fold_spec(const icw_chain_spec &sp, DevChain &ch, HbCoef &coef)
     ch.hb_ord = ICW_HB_ORDER[sp.filter_no];
     ch.is_kahan = sp.is_kahan != 0;
     ch.reject_flag = sp.is_subnorm_reject;
+    ch.fp_check = sp.is_fp_check != 0;
     {
         double a0 = word_as_double(ICW_HB_A[sp.filter_no][0]);
         coef.d0 = word_as_double(ICW_HB_B[sp.filter_no][0]) / a0;
@@ -738,7 +739,7 @@ static int process_group(icw_session *s, int64_t n_frames, const uint8_t *d_in, 
     const size_t mt_shared = dw.stream_stride;      // words between consecutive streams' dither (0 = shared)
     const bool scan = !ch.is_complex && s->spec.hilbert_mode == ICW_HILBERT_SCAN;
     const bool shaped = ch.render.ns_kind != 0;     // error feedback through the quantiser: serial per channel
-    if (!ch.is_complex && !scan && !e->unfused && !shaped) {
+    if (!ch.is_complex && !scan && !e->unfused && !shaped && !ch.fp_check) {
         // real input, reference-exact Hilbert: the whole chain in one kernel
         if (dw.join) CK(cudaStreamWaitEvent(st, dw.join, 0));
         ProfSpan ps(s, st, ICW_K_HILBERT);
@@ -859,8 +860,11 @@ static int call_begin(icw_session *s, int64_t n_total, cudaStream_t st, CallCtx 
                                            "needs icw_session_reset(ICW_RESET_HILBERT) first (state conversion is not built)",
                         s->hb_basis ? "modal (scan)" : "delay-line (exact)", cx.mode ? "scan" : "exact");
     }
+    if (cx.real_in && cx.mode == ICW_HILBERT_SCAN && ch.fp_check)
+        return fail(ICW_E_UNSUPPORTED, "FP_CHECK counts exceptional intermediates of the reference's own recurrences: "
+                                       "exact Hilbert mode only (the modal scan has different intermediates)");
     // scan mode and the unfused path go through per-frame scratch: bound it by walking the call in groups
-    const bool scratchy = cx.real_in && (cx.mode == ICW_HILBERT_SCAN || e->unfused);
+    const bool scratchy = cx.real_in && (cx.mode == ICW_HILBERT_SCAN || e->unfused || ch.fp_check);
     // one stream: groups as long as the analytic scratch may grow (32 B/frame) -- long groups let the scan use
     // long chunks (scan_chunk_len); many streams: 2^25 frames over all of them
     const int64_t seg = !scratchy ? n_total
@@ -868,7 +872,7 @@ static int call_begin(icw_session *s, int64_t n_total, cudaStream_t st, CallCtx 
     cx.step = seg < SCAN_L * SCAN_CH ? SCAN_L * SCAN_CH : seg;
     const int wps = ch.render.words_per_sample;
     // the fused exact kernel reads word buffers; everything else that ends in chain_kernel can make its own
-    const bool hb_fused = cx.real_in && cx.mode == ICW_HILBERT_EXACT && !e->unfused && ch.render.ns_kind == 0;
+    const bool hb_fused = cx.real_in && cx.mode == ICW_HILBERT_EXACT && !e->unfused && ch.render.ns_kind == 0 && !ch.fp_check;
     if (wps && one_range && !hb_fused && !e->no_fuse_mt && K == 1 && chain_mt_supports(ch) &&
         s->mt_drawn[0][0] == s->mt_drawn[1][0] && s->mt_drawn[0][0] % (uint64_t)wps == 0) {
         cx.fuse_mt = true;
@@ -1074,6 +1078,16 @@ extern "C" int icw_session_stats(icw_session *s, icw_stats *out)
     out->peak_db[0] = icw_peak_db(pk[0]);
     out->peak_db[1] = icw_peak_db(pk[1]);
     out->kernel_launches = s->launches;
+    return ICW_OK;
+}
+
+extern "C" int icw_session_fp_stats(icw_session *s, int stream, uint32_t out[4][7])
+{
+    if (!s || !out) return fail(ICW_E_ARG, "NULL argument");
+    if (stream < 0 || stream >= s->n_streams) return fail(ICW_E_ARG, "stream index out of range");
+    CK(cudaStreamSynchronize(s->e->stream));
+    CK(cudaMemcpy(out, (const uint8_t *)(s->d_streams + stream) + offsetof(DevStream, fp_cnt), sizeof(uint32_t) * 4 * 7,
+                  cudaMemcpyDeviceToHost));
     return ICW_OK;
 }
 

@@ -173,7 +173,7 @@ cudaError_t launch_chain_mt(const DevChain &ch, DevStream *streams, int64_t n_fr
     CmtGeom g;
     g.n_units = pl.n_units; g.blocks_per_unit = pl.blocks_per_unit;
     g.first_word = pl.first_word; g.want_lo = pl.want_lo; g.want_hi = pl.want_hi; g.tail_block = pl.tail_block;
-    const bool lean = !tap_bus && !tap_lr && !pre && ch.shape != ICW_SHAPE_GENERIC && !ch.bypass;
+    const bool lean = !tap_bus && !tap_lr && !pre && ch.shape != ICW_SHAPE_GENERIC && !ch.bypass && !ch.fp_check;
     const bool tpdf = ch.render.render_type == ICW_RENDER_TPDF;
 #define ICW_CMT(SH, RT) return launch_cmt<SH, RT>(ch, streams, n_frames, in, from_analytic, g, pl, pr, out, tap_bus, tap_lr, pre, s)
     if (lean && from_analytic && lean_fast_ok(ch) && ((size_t)(uintptr_t)out & 3u) == 0) {

@@ -35,7 +35,7 @@ __device__ __forceinline__ double dither_sample(const DevRender &r, uint4 a, con
 {
     switch (r.render_type) {
     case ICW_RENDER_RPDF:
-        return div_const(dsopen2(make_uint2(a.x, a.y), redraws), ICW_KC[KC_SQRT2], ICW_KC[KC_RSQRT2]);
+        return div_const_finite(dsopen2(make_uint2(a.x, a.y), redraws), ICW_KC[KC_SQRT2], ICW_KC[KC_RSQRT2]);
     case ICW_RENDER_TPDF: {
         double v = dsopen2(make_uint2(a.x, a.y), redraws);
         v += dsopen2(make_uint2(a.z, a.w), redraws);
@@ -54,7 +54,7 @@ __device__ __forceinline__ double dither_sample(const DevRender &r, uint4 a, con
             v += dsopen2(make_uint2(a.z, a.w), redraws);
         }
         const double d = 2.0 * ICW_SQRT6;
-        return div_const(v, d, 1.0 / d);
+        return div_const_finite(v, d, 1.0 / d);
     }
     default:
         return 0.0;
@@ -152,8 +152,9 @@ __device__ __forceinline__ void finish_frame(const DevChain &ch, DevStream &st, 
         double4 *q = reinterpret_cast<double4 *>(io.pre) + i;
         *q = make_double4(lo, dl, ro, dr);
     } else {
-        RenderOut a = render_one(rq, lo, dl);
-        RenderOut b = render_one(rq, ro, dr);
+        // FP_CHECK: the checked twin, counters fes_sr_left / _right (adv_modulator.c:757-758)
+        RenderOut a = ch.fp_check ? render_one_checked(rq, lo, dl, st.fp_cnt[2]) : render_one(rq, lo, dl);
+        RenderOut b = ch.fp_check ? render_one_checked(rq, ro, dr, st.fp_cnt[3]) : render_one(rq, ro, dr);
         acc.clips_l += a.clipped; acc.clips_r += b.clipped;
         acc.peak_l = fmax(acc.peak_l, a.level); acc.peak_r = fmax(acc.peak_r, b.level);
         uint8_t *p = io.dst + i * ch.out_frame_bytes;
@@ -189,7 +190,7 @@ __device__ __forceinline__ double lean_dither(uint4 a, unsigned &redraws)
         v += dsopen2(make_uint2(a.z, a.w), redraws);
         return v * 0.5;                                         // /2.0, exact
     }
-    return div_const(dsopen2(make_uint2(a.x, a.y), redraws), ICW_KC[KC_SQRT2], ICW_KC[KC_RSQRT2]);
+    return div_const_finite(dsopen2(make_uint2(a.x, a.y), redraws), ICW_KC[KC_SQRT2], ICW_KC[KC_RSQRT2]);
 }
 
 // one frame of a straight-line list, plain PCM out.  Operation for operation finish_frame()'s

@@ -179,19 +179,88 @@ struct PlainChain {
     __device__ __forceinline__ void drain(const HbCoef &, double &, double &) {}
 };
 
-template <int ORD, bool KAHAN> struct ChainSel { using type = KahanChain<ORD>; };
-template <int ORD> struct ChainSel<ORD, false> { using type = PlainChain<ORD>; };
+// The FP-exception-checked twins (reference src/hblpf.c:928-950 baseline, :1059-1096 Kahan): the same sums
+// with FC() around every product and every partial sum, written the way the reference walks them (no lag, no
+// interleaving -- a diagnostic mode).  cnt = the FP_EXCEPT_STATS block of this channel's converter.
+template <int ORD, bool KAHAN>
+struct CheckedChain {
+    static constexpr int LAG = 0;
+    double z[ORD];
+    uint32_t *cnt = nullptr;
+    __device__ __forceinline__ void load(const double *zs)
+    {
+#pragma unroll
+        for (int i = 0; i < ORD; ++i) z[i] = zs[i];
+    }
+    __device__ __forceinline__ void store(double *zs) const
+    {
+#pragma unroll
+        for (int i = 0; i < ORD; ++i) zs[i] = z[i];
+    }
+    __device__ __forceinline__ void kadd(Comp &a, double x)
+    {
+        // kahan_step_fes, hblpf.c:995-1003
+        const double y = fc(__dsub_rn(x, a.c), cnt);
+        const double t = fc(__dadd_rn(a.s, y), cnt);
+        a.c = fc(__dsub_rn(fc(__dsub_rn(t, a.s), cnt), y), cnt);
+        a.s = t;
+    }
+    __device__ __forceinline__ double step(double x, const HbCoef &k, int reject, double thr, unsigned long long &rejects)
+    {
+        double w, y = 0.0, acc_out = 0.0;
+        if (KAHAN) {
+            Comp in, out;
+            in.s = x; in.c = 0.0;
+            out.s = 0.0; out.c = 0.0;
+#pragma unroll
+            for (int j = 0; j < ORD; ++j) {
+                const double t = fc(__dmul_rn(z[j], k.fb[j]), cnt);
+                kadd(in, t);
+                const double f = fc(__dmul_rn(z[j], k.ff[j]), cnt);
+                if (j == 0) { out.s = f; out.c = 0.0; } else kadd(out, f);
+                kadd(out, fc(__dmul_rn(t, k.d0), cnt));
+            }
+            w = in.s;
+            y = out.s;                                          // no d0*x term: bug-for-bug (hblpf.c:1095)
+        } else {
+            double acc_in = x;
+#pragma unroll
+            for (int j = 0; j < ORD; ++j) {
+                acc_in = fc(__dadd_rn(acc_in, fc(__dmul_rn(z[j], k.fb[j]), cnt)), cnt);
+                acc_out = fc(__dadd_rn(acc_out, fc(__dmul_rn(z[j], k.ff[j]), cnt)), cnt);
+            }
+            w = acc_in;
+        }
+        const bool rj = (reject != 0) & (fabs(w) < thr);
+        w = rj ? 0.0 : w;
+        rejects += rj ? 1ull : 0ull;
+        if (!KAHAN) y = fc(__dadd_rn(fc(__dmul_rn(w, k.d0), cnt), acc_out), cnt);      // hblpf.c:949
+#pragma unroll
+        for (int j = ORD - 1; j > 0; --j) z[j] = z[j - 1];
+        z[0] = w;
+        return y;
+    }
+    __device__ __forceinline__ void drain(const HbCoef &, double &, double &) {}
+};
+
+template <int ORD, bool KAHAN, bool CHECK = false> struct ChainSel { using type = KahanChain<ORD>; };
+template <int ORD> struct ChainSel<ORD, false, false> { using type = PlainChain<ORD>; };
+template <int ORD, bool KAHAN> struct ChainSel<ORD, KAHAN, true> { using type = CheckedChain<ORD, KAHAN>; };
 
 // One half-band recurrence over n samples: `in(i)` gives the mixed-down input of sample i,
 // `out(i, y)` receives the filter output of sample i.
-template <int ORD, bool KAHAN, class In, class Out>
+template <class Chain> __device__ __forceinline__ void chain_set_counters(Chain &, uint32_t *) {}
+template <int ORD, bool KAHAN> __device__ __forceinline__ void chain_set_counters(CheckedChain<ORD, KAHAN> &c, uint32_t *cnt) { c.cnt = cnt; }
+
+template <int ORD, bool KAHAN, bool CHECK = false, class In, class Out>
 __device__ __forceinline__ void hb_run(double *zstate, unsigned long long &rejects, const HbCoef &k,
-                                       int reject, int64_t n, In in, Out out)
+                                       int reject, int64_t n, In in, Out out, uint32_t *fp_cnt = nullptr)
 {
-    using Chain = typename ChainSel<ORD, KAHAN>::type;
+    using Chain = typename ChainSel<ORD, KAHAN, CHECK>::type;
     const double thr = (double)reject;
     if (n <= 0) return;
     Chain c;
+    chain_set_counters(c, fp_cnt);
     c.load(zstate);
     double xc = in(0);
     for (int64_t i = 0; i < n; ++i) {

@@ -57,6 +57,7 @@ struct DevChain {
     int32_t  bypass, n_nodes;
     int32_t  shape;                     // ICW_SHAPE_*: DSP lists common enough to get straight-line code
     int32_t  filter_no, hb_ord, is_kahan, reject_flag;
+    int32_t  fp_check, pad_fp;          // the FP-exception-checked twins (reference src/fp_check.c:52-99)
     int64_t  n_samples, n_fade_in, n_fade_out;
     uint64_t scale_sr;                  // sample_rate * 1000 (scaled) or 0
     double   osc_div, osc_rdiv;         // divisor of the oscillator phase and RN(1/divisor)
@@ -84,6 +85,9 @@ struct DevStream {
     double   prev_rnd_next[2];          // written by the last frame of a call, committed by advance
     uint32_t hb_basis, pad0;            // 0 = hb[] is the DF-II delay line, 1 = modal states
     double   ns_e[2][ICW_NS_MAX_TAPS], ns_o[2][ICW_NS_MAX_TAPS], ns_prev_err[2];   // age-ordered shaper memory
+    // FP_EXCEPT_STATS x 4: [hilbert L, hilbert R, render L, render R][total, snan, qnan, ninf, nden, pden, pinf]
+    uint32_t fp_cnt[4][7];
+    uint32_t pad_fp[4];
 };
 
 }  // namespace icw

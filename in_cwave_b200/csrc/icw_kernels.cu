@@ -23,7 +23,7 @@ namespace icw {
 // chain id = ((stream * 2 + channel) * 2 + iq).  Output: analytic frames as 4 doubles
 // (L.re, L.im, R.re, R.im) == the layout of ICW_FMT_CW_F64 stereo, so chain_kernel reads it back
 // as complex input.
-template <int ORD, bool KAHAN>
+template <int ORD, bool KAHAN, bool CHECK>
 __global__ void __launch_bounds__(128)
 hb_exact_kernel(const __grid_constant__ HbCoef coef, const __grid_constant__ DevChain ch,
                 DevStream *__restrict__ streams, int n_streams, int64_t n_frames,
@@ -46,7 +46,7 @@ hb_exact_kernel(const __grid_constant__ HbCoef coef, const __grid_constant__ Dev
     double *dst = analytic + (size_t)stream * (size_t)n_frames * 4 + chan * 2;
     const bool fading = (ch.n_fade_in | ch.n_fade_out) != 0;
 
-    hb_run<ORD, KAHAN>(z, rejects, coef, ch.reject_flag, n_frames,
+    hb_run<ORD, KAHAN, CHECK>(z, rejects, coef, ch.reject_flag, n_frames,
         [&](int64_t i) {
             double x = unpack_real(ch.fmt, src + i * ch.frame_bytes);
             if (fading) {
@@ -59,7 +59,7 @@ hb_exact_kernel(const __grid_constant__ HbCoef coef, const __grid_constant__ Dev
             int slot;
             double v = mix_up(iq, (q0 + (unsigned)i) & 3u, y, slot);
             dst[i * 4 + slot] = v;
-        });
+        }, st.fp_cnt[chan]);                                    // fes_hilb_left / _right (xwave_reader.c:980,998)
 #pragma unroll
     for (int i = 0; i < ORD; ++i) st.hb[chan][iq][i] = z[i];
     st.hb_rejects[chan][iq] = rejects;
@@ -73,10 +73,13 @@ static cudaError_t launch_hb_ord(bool kahan, const HbCoef &coef, const DevChain 
 {
     int threads = 128;
     int blocks = (n_streams * 4 + threads - 1) / threads;
-    if (kahan)
-        hb_exact_kernel<ORD, true><<<blocks, threads, 0, s>>>(coef, ch, streams, n_streams, n_frames, in, in_stride, analytic);
+    if (ch.fp_check) {
+        if (kahan) hb_exact_kernel<ORD, true, true><<<blocks, threads, 0, s>>>(coef, ch, streams, n_streams, n_frames, in, in_stride, analytic);
+        else       hb_exact_kernel<ORD, false, true><<<blocks, threads, 0, s>>>(coef, ch, streams, n_streams, n_frames, in, in_stride, analytic);
+    } else if (kahan)
+        hb_exact_kernel<ORD, true, false><<<blocks, threads, 0, s>>>(coef, ch, streams, n_streams, n_frames, in, in_stride, analytic);
     else
-        hb_exact_kernel<ORD, false><<<blocks, threads, 0, s>>>(coef, ch, streams, n_streams, n_frames, in, in_stride, analytic);
+        hb_exact_kernel<ORD, false, false><<<blocks, threads, 0, s>>>(coef, ch, streams, n_streams, n_frames, in, in_stride, analytic);
     return cudaGetLastError();
 }
 
@@ -339,7 +342,7 @@ cudaError_t launch_chain(const DevChain &ch, DevStream *streams, int n_streams, 
     if (per_stream > cap) per_stream = cap;
     dim3 grid(per_stream, n_streams);
     const int rt = ch.render.render_type;
-    if (!tap_bus && !tap_lr && !pre && !ch.bypass && (ch.shape == ICW_SHAPE_MASTER || ch.shape == ICW_SHAPE_SHIFT_MASTER) &&
+    if (!tap_bus && !tap_lr && !pre && !ch.bypass && !ch.fp_check && (ch.shape == ICW_SHAPE_MASTER || ch.shape == ICW_SHAPE_SHIFT_MASTER) &&
         (rt == ICW_RENDER_ROUND || rt == ICW_RENDER_RPDF || rt == ICW_RENDER_TPDF)) {
 #define ICW_LEAN(SH, RT) chain_lean_kernel<SH, RT><<<grid, threads, 0, s>>>(ch, streams, n_frames, in, in_stride, from_analytic, \
                                                                             mtw_l, mtw_r, mt_stream_stride, out, out_stride)
@@ -374,7 +377,7 @@ cudaError_t launch_chain(const DevChain &ch, DevStream *streams, int n_streams, 
 // chain_kernel stops before the quantiser (FrameIO::pre) when a shaper is on.  The error memory is a
 // register array ordered by age (static indices after unrolling), the reference's circular buffer
 // read newest-first is the same sum.  ORD is the shaper's order; plain mul + add as in the reference.
-template <int ORD, bool IIR>
+template <int ORD, bool IIR, bool CHECK>
 __global__ void __launch_bounds__(64)
 ns_render_kernel(const __grid_constant__ DevChain ch, DevStream *__restrict__ streams, int n_streams, int64_t n_frames,
                  const double *__restrict__ pre, uint8_t *__restrict__ out, size_t out_stride)
@@ -399,30 +402,33 @@ ns_render_kernel(const __grid_constant__ DevChain ch, DevStream *__restrict__ st
     double2 cur = n_frames > 0 ? src[0] : make_double2(0.0, 0.0);
     for (int64_t i = 0; i < n_frames; ++i) {
         const double2 nxt = src[2 * (i + 1 < n_frames ? i + 1 : i)];       // (value, dither) of the next frame
-        const double v = cur.x * q.norm_mul - prev_err;
-        double qv = v + cur.y * q.dth_mul;
+        // CHECK: the FP-exception-checked twins (src/sound_render.c:846-897, :415-441, :458-489)
+        uint32_t *cnt = st.fp_cnt[2 + c];
+        auto F = [&](double x) { return CHECK ? fc(x, cnt) : x; };
+        const double v = F(F(cur.x * q.norm_mul) - prev_err);
+        double qv = F(v + F(cur.y * q.dth_mul));
         int delta;
-        if (qv < 0.0) { qv -= q.round_off; delta = q.neg_delta; }
-        else          { qv += q.round_off; delta = 0; }
+        if (qv < 0.0) { qv = F(qv - q.round_off); delta = q.neg_delta; }
+        else          { qv = F(qv + q.round_off); delta = 0; }
         peak = fmax(peak, fabs(qv) * q.inv_hi);
         if (qv >= q.hi) { qv = q.hi - 1.0; ++clips; }
         if (qv <= q.lo) { qv = q.lo + 1.0; ++clips; }
         int val = __double2int_rz(qv) + delta;
         // the error of this sample through the shaper
-        const double err = (double)val - v;
+        const double err = F((double)val - v);
 #pragma unroll
         for (int k = ORD - 1; k > 0; --k) e[k] = e[k - 1];
-        e[0] = err;
+        e[0] = F(err);
         double res = 0.0;
         if (IIR) {
 #pragma unroll
-            for (int k = 0; k < ORD; ++k) res = res + (ce[k] * e[k] - co[k] * o[k]);
+            for (int k = 0; k < ORD; ++k) res = F(res + F(F(ce[k] * e[k]) - F(co[k] * o[k])));
 #pragma unroll
             for (int k = ORD - 1; k > 0; --k) o[k] = o[k - 1];
             o[0] = res;
         } else {
 #pragma unroll
-            for (int k = 0; k < ORD; ++k) res = res + ce[k] * e[k];
+            for (int k = 0; k < ORD; ++k) res = F(res + F(ce[k] * e[k]));
         }
         prev_err = res;
         val = (int)((unsigned)val << q.shift);
@@ -445,7 +451,8 @@ cudaError_t launch_ns_render(const DevChain &ch, DevStream *streams, int n_strea
 {
     const int threads = 64;
     const int grid = (n_streams * 2 + threads - 1) / threads;
-#define ICW_NS_CASE(O, I) ns_render_kernel<O, I><<<grid, threads, 0, s>>>(ch, streams, n_streams, n_frames, pre, out, out_stride); break
+#define ICW_NS_CASE(O, I) if (ch.fp_check) ns_render_kernel<O, I, true><<<grid, threads, 0, s>>>(ch, streams, n_streams, n_frames, pre, out, out_stride); \
+                          else ns_render_kernel<O, I, false><<<grid, threads, 0, s>>>(ch, streams, n_streams, n_frames, pre, out, out_stride); break
     if (ch.render.ns_kind == 2) {
         switch (ch.render.ns_order) {
         case 4: ICW_NS_CASE(4, true);

@@ -132,6 +132,13 @@ class Session:
                     hb_rejects=int(s.hb_rejects), mt_redraws=int(s.mt_redraws),
                     kernel_launches=int(s.kernel_launches))
 
+    def fp_stats(self, k: int = 0):
+        """FP exception counters of stream k: [hilbert L, hilbert R, render L, render R] x
+        [total, snan, qnan, ninf, nden, pden, pinf] (reference fecs_getcnts)."""
+        out = ((C.c_uint32 * 7) * 4)()
+        _abi.check(_abi.lib().icw_session_fp_stats(self._h, int(k), out))
+        return [list(r) for r in out]
+
     def profile(self, on: bool = True) -> None:
         _abi.check(_abi.lib().icw_session_profile(self._h, int(on)))
 

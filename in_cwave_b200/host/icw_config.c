@@ -239,9 +239,10 @@ int icwp_load_config(const char *path, icw_chain_spec *chain, icwp_options *opt)
              * character or an over-long line reject the file. */
             if      (KW("VER_CONFIG"))    { if (get_unsigned(&c, &u)) version = u; }
             else if (KW("WAV_SUPPORT") || KW("RWAVE_SUPPORT") || KW("LAST_CHANCE") || KW("DISABLE_SLEEP") ||
-                     KW("SHOW_LONGNUMB") || KW("FP_CHECK") || KW("IBOX_PARENT") || KW("PLAY_SLEEP") ||
+                     KW("SHOW_LONGNUMB") || KW("IBOX_PARENT") || KW("PLAY_SLEEP") ||
                      KW("IIR_SUBN_THR"))
                                           { /* GUI / player plumbing, or never reaches the arithmetic (src/hblpf.c:915) */ }
+            else if (KW("FP_CHECK"))      { if (get_bool(&c, &b)) chain->is_fp_check = b; }      /* src/config.c:180 */
             else if (KW("SEC_ALIGN"))     { if (get_unsigned(&c, &u)) opt->sec_align = clampu(u, 0, 20); }
             else if (KW("FADE_IN"))       { if (get_unsigned(&c, &u)) opt->fade_in_ms = clampu(u, 0, 10000); }
             else if (KW("FADE_OUT"))      { if (get_unsigned(&c, &u)) opt->fade_out_ms = clampu(u, 0, 10000); }
@@ -315,8 +316,8 @@ int icwp_save_config(const char *path, const icw_chain_spec *chain, const icwp_o
     fprintf(fp, "FRMOD_SCALED=%d\nIIR_HBLPF_IX=%u\nIIR_SUM_KAHAN=%d\nIIR_SUBN_ZERO=%d\n", chain->is_frmod_scaled ? 1 : 0,
             (unsigned)chain->filter_no, chain->is_kahan ? 1 : 0, chain->is_subnorm_reject ? 1 : 0);
     fprintf(fp, "IIR_SUBN_THR="); { uint64_t b; double t = 1.0e-150; memcpy(&b, &t, 8); fprintf(fp, "0x%08" PRIX64 "\n", b); }
-    fprintf(fp, "CLR_NFRAME_PT=%d\nCLR_HILB_PT=%d\nSHOW_LONGNUMB=0\nFP_CHECK=0\nNEED24BITS=%d\n",
-            opt->clr_nframe_trk ? 1 : 0, opt->clr_hilb_trk ? 1 : 0, chain->need24bits ? 1 : 0);
+    fprintf(fp, "CLR_NFRAME_PT=%d\nCLR_HILB_PT=%d\nSHOW_LONGNUMB=0\nFP_CHECK=%d\nNEED24BITS=%d\n",
+            opt->clr_nframe_trk ? 1 : 0, opt->clr_hilb_trk ? 1 : 0, chain->is_fp_check ? 1 : 0, chain->need24bits ? 1 : 0);
     fprintf(fp, "DITHER_BITS="); { uint64_t b; memcpy(&b, &chain->dth_bits, 8); fprintf(fp, "0x%08" PRIX64 "\n", b); }
     fprintf(fp, "QUANTIZE_TYPE=%u\nRENDER_TYPE=%u\nNOISE_SHAPING=%u\nSIGNBITS16=%u\nSIGNBITS24=%u\n",
             chain->quantz_type, chain->render_type, chain->nshape_type, chain->sign_bits16, chain->sign_bits24);

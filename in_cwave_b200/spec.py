@@ -19,7 +19,7 @@ def default_spec(**over) -> dict:
         fmt="wav_f32", n_channels=2, sample_rate=48000, n_samples=0, n_fade_in=0, n_fade_out=0,
         filter_no=1, is_kahan=1, is_subnorm_reject=1, hilbert_mode="exact", is_frmod_scaled=1,
         need24bits=1, dth_bits=1.0, quantz_type=1, render_type=0, nshape_type=0,
-        sign_bits16=16, sign_bits24=24, bypass=0, nodes=[copy.deepcopy(DEFAULT_MASTER)],
+        sign_bits16=16, sign_bits24=24, bypass=0, is_fp_check=0, nodes=[copy.deepcopy(DEFAULT_MASTER)],
     )
     d.update(over)
     return d
@@ -75,6 +75,7 @@ def to_c(d: dict) -> _abi.ChainSpecC:
     sp.sign_bits16 = int(full["sign_bits16"])
     sp.sign_bits24 = int(full["sign_bits24"])
     sp.bypass = int(full["bypass"])
+    sp.is_fp_check = int(full.get("is_fp_check", 0))
     nodes = full["nodes"]
     if len(nodes) > _abi.MAX_NODES:
         raise ValueError("too many nodes")

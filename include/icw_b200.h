@@ -100,6 +100,12 @@ typedef struct icw_chain_spec {
     int32_t  bypass;            /* src/adv_modulator.c:637,644 */
     int32_t  n_nodes;
     icw_node nodes[ICW_MAX_NODES];
+    int32_t  is_fp_check;       /* FP_CHECK (src/config.c:180, off by default): the FP-exception-checked twins of the
+                                   half-band filters, the renderer and the noise shapers (src/fp_check.c:52-99,
+                                   src/hblpf.c:928-950,1059-1096, src/sound_render.c:811-913): NaN and denormal
+                                   intermediates become 0, +-Inf becomes +-65535, every event counted.  Exact Hilbert
+                                   mode only (scan mode refuses it) */
+    int32_t  reserved_;
 } icw_chain_spec;
 
 /* What persists from frame to frame for one stream: the reference's MOD_CONTEXT
@@ -182,6 +188,10 @@ typedef struct icw_stats {
     uint64_t kernel_launches;   /* our kernels launched by this session so far */
 } icw_stats;
 int  icw_session_stats(icw_session *s, icw_stats *out);
+/* FP exception counters of one stream (reference fecs_getcnts, src/in_cwave.c:383-440; FP_EXCEPT_STATS,
+ * src/fp_check.h:66-76): out[block][class], block = hilbert L, hilbert R, render L, render R; class = total,
+ * snan, qnan, ninf, nden, pden, pinf.  Arithmetic never yields a signalling NaN: snan stays 0. */
+int  icw_session_fp_stats(icw_session *s, int stream, uint32_t out[4][7]);
 
 /* leaf entry points (device buffers in, device buffers out) for stage-wise parity:
  * hq_rp_process (src/lpf_hilbert_quad.c:129-156) over n samples of n_chan independent channels,

@@ -203,6 +203,22 @@ static void hb_load(int type, hb_design *h)
     }
 }
 
+/* ---- FP-exception-checked twins (reference src/fp_check.c:52-99; used when cfg.is_fp_check) ----
+ * FC(v): NaN and denormals become 0.0, +-Inf becomes +-65535.0, each event counted by class.  The
+ * counter block in force is file-scope state of this (single-threaded, test-only) oracle: NULL = the
+ * unchecked code paths. */
+static unsigned *g_fpc = NULL;
+static double fc(double v)
+{
+    unsigned *c = g_fpc;
+    switch (fpclassify(v)) {
+    case FP_NAN:       c[0]++; c[2]++; return 0.0;              /* every NaN counts as quiet: arithmetic results are */
+    case FP_SUBNORMAL: c[0]++; c[signbit(v) ? 4 : 5]++; return 0.0;
+    case FP_INFINITE:  c[0]++; if (signbit(v)) { c[3]++; return -65535.0; } c[6]++; return 65535.0;
+    default:           return v;
+    }
+}
+
 /* the "reject" test compares |w| with the FLAG VALUE, not with the configured threshold
  * (hblpf.c:915,1046; SURVEY.md finding 4) */
 static inline double hb_reject(double w, int flag, uint64_t *count)
@@ -263,8 +279,59 @@ static double hb_step_kahan(const hb_design *h, icwo_iir *f, double x, int flag)
     return out.s;
 }
 
+static double hb_step_plain_fc(const hb_design *h, icwo_iir *f, double x, int flag)
+{
+    /* hblpf.c:928-950 */
+    double acc_in = x, acc_out = 0.0;
+    int k = f->ix;
+    for (int i = 0; i < h->ord; ++i) {
+        k = (k == 0 ? h->ord : k) - 1;
+        acc_in  = fc(acc_in  + fc(f->z[k] * h->fb[i]));
+        acc_out = fc(acc_out + fc(f->z[k] * h->ff[i]));
+    }
+    acc_in = hb_reject(acc_in, flag, &f->rejects);
+    f->z[f->ix] = acc_in;
+    if (++f->ix >= h->ord) f->ix = 0;
+    return fc(fc(acc_in * h->d0) + acc_out);
+}
+
+static inline void comp_add_fc(comp_sum *a, double x)
+{
+    /* hblpf.c:995-1003 */
+    double y = fc(x - a->c);
+    double t = fc(a->s + y);
+    a->c = fc(fc(t - a->s) - y);
+    a->s = t;
+}
+
+static double hb_step_kahan_fc(const hb_design *h, icwo_iir *f, double x, int flag)
+{
+    /* hblpf.c:1059-1096 */
+    comp_sum in = { x, 0.0 }, out;
+    int k = f->ix;
+
+    k = (k == 0 ? h->ord : k) - 1;
+    double t = fc(f->z[k] * h->fb[0]);
+    comp_add_fc(&in, t);
+    out.s = fc(f->z[k] * h->ff[0]);
+    out.c = 0.0;
+    comp_add_fc(&out, fc(t * h->d0));
+    for (int i = 1; i < h->ord; ++i) {
+        k = (k == 0 ? h->ord : k) - 1;
+        t = fc(f->z[k] * h->fb[i]);
+        comp_add_fc(&in, t);
+        comp_add_fc(&out, fc(f->z[k] * h->ff[i]));
+        comp_add_fc(&out, fc(t * h->d0));
+    }
+    in.s = hb_reject(in.s, flag, &f->rejects);
+    f->z[f->ix] = in.s;
+    if (++f->ix >= h->ord) f->ix = 0;
+    return out.s;
+}
+
 static inline double hb_step(const hb_design *h, icwo_iir *f, double x, int kahan, int flag)
 {
+    if (g_fpc) return kahan ? hb_step_kahan_fc(h, f, x, flag) : hb_step_plain_fc(h, f, x, flag);
     return kahan ? hb_step_kahan(h, f, x, flag) : hb_step_plain(h, f, x, flag);
 }
 
@@ -434,6 +501,25 @@ static double ns_step(unsigned type, icwo_ns *ns, double err)
     return res;
 }
 
+static double ns_step_fc(unsigned type, icwo_ns *ns, double err)
+{
+    /* src/sound_render.c:415-441 (FIR), :458-489 (IIR), checked halves */
+    const int kind = ICW_NS_KIND[type], ord = ICW_NS_ORDER[type];
+    const double *c = (const double *)ICW_NS_COEF[type];
+    double res = 0.0;
+    if (!kind) return 0.0;
+    for (int i = ord - 1; i > 0; --i) ns->e[i] = ns->e[i - 1];
+    ns->e[0] = fc(err);
+    if (kind == 1) {
+        for (int i = 0; i < ord; ++i) res = fc(res + fc(c[i] * ns->e[i]));
+    } else {
+        for (int i = 0; i < ord; ++i) res = fc(res + fc(fc(c[i] * ns->e[i]) - fc(c[i + ord] * ns->o[i])));
+        for (int i = ord - 1; i > 0; --i) ns->o[i] = ns->o[i - 1];
+        ns->o[0] = res;
+    }
+    return res;
+}
+
 int64_t icwo_render(const icwo_spec *sp, icwo_mt *mt, double *prev_rnd, icwo_ns *ns, const double *in, int64_t n,
                     uint8_t *out, unsigned *clips, double *peak_db)
 {
@@ -442,12 +528,22 @@ int64_t icwo_render(const icwo_spec *sp, icwo_mt *mt, double *prev_rnd, icwo_ns 
     const unsigned nst = sp->nshape_type < ICW_NS_COUNT ? sp->nshape_type : 0;   /* src/sound_render.c:546 */
     quant_setup(sp, &q);
     for (int64_t k = 0; k < n; ++k) {
+        /* the dither draws are sums of a few values in (-1, 1) on a 2^-52 grid: FC() can never fire on
+         * them (src/sound_render.c:821-845), so the checked twin shares dither_draw() */
         double rnd = dither_draw(sp->render_type, mt, prev_rnd);
-        double v = in[k] * q.norm_mul - (nst ? ns->prev_err : 0.0);
-        double qv = v + rnd * q.dth_mul;
+        double v, qv;
         int delta;
-        if (qv < 0.0) { qv -= q.round_off; delta = q.neg_delta; }
-        else          { qv += q.round_off; delta = 0; }
+        if (g_fpc) {                                    /* src/sound_render.c:848-861 */
+            v = fc(fc(in[k] * q.norm_mul) - (nst ? ns->prev_err : 0.0));
+            qv = fc(v + fc(rnd * q.dth_mul));
+            if (qv < 0.0) { qv = fc(qv - q.round_off); delta = q.neg_delta; }
+            else          { qv = fc(qv + q.round_off); delta = 0; }
+        } else {
+            v = in[k] * q.norm_mul - (nst ? ns->prev_err : 0.0);
+            qv = v + rnd * q.dth_mul;
+            if (qv < 0.0) { qv -= q.round_off; delta = q.neg_delta; }
+            else          { qv += q.round_off; delta = 0; }
+        }
 
         double lvl = fabs(qv) / q.hi;                   /* peak: after rounding offset, before clip */
         lvl = lvl ? 20.0 * log10(lvl) : ICWO_SILENCE_DB;
@@ -457,7 +553,8 @@ int64_t icwo_render(const icwo_spec *sp, icwo_mt *mt, double *prev_rnd, icwo_ns 
         if (qv <= q.lo) { qv = q.lo + 1.0; ++*clips; }
 
         int val = (int)qv + delta;
-        if (nst) ns->prev_err = ns_step(nst, ns, (double)val - v);      /* src/sound_render.c:800 */
+        if (nst) ns->prev_err = g_fpc ? ns_step_fc(nst, ns, fc((double)val - v))   /* src/sound_render.c:897 */
+                                      : ns_step(nst, ns, (double)val - v);          /* src/sound_render.c:800 */
         val = (int)((unsigned)val << q.shift);          /* same bits as the reference's signed << */
         *p++ = (uint8_t)val;
         *p++ = (uint8_t)(val >> 8);
@@ -659,8 +756,10 @@ int icwo_process(const icwo_spec *sp, icwo_state *st, const uint8_t *in, int64_t
         if (!is_complex) {
             for (int ch = 0; ch < 2; ++ch) {
                 for (int k = 0; k < m; ++k) xr[k] = x4[k][2 * ch];
+                g_fpc = sp->is_fp_check ? st->fp_cnt[ch] : NULL;        /* fes_hilb_left / _right (xwave_reader.c:980,998) */
                 icwo_hilbert(sp->filter_no, sp->is_kahan, sp->is_subnorm_reject, st->lpf[ch],
                              &st->quad[ch], xr, m, ai, aq);
+                g_fpc = NULL;
                 for (int k = 0; k < m; ++k) { x4[k][2 * ch] = ai[k]; x4[k][2 * ch + 1] = aq[k]; }
             }
         }
@@ -691,8 +790,11 @@ int icwo_process(const icwo_spec *sp, icwo_state *st, const uint8_t *in, int64_t
         if (pcm) {
             uint8_t tmpl[BLK * 3], tmpr[BLK * 3];
             int sb = ob / 2;
+            g_fpc = sp->is_fp_check ? st->fp_cnt[2] : NULL;             /* fes_sr_left / _right (adv_modulator.c:757-758) */
             icwo_render(sp, &st->mt[0], &st->prev_rnd[0], &st->ns[0], lo, m, tmpl, &st->clips[0], &st->peak_db[0]);
+            g_fpc = sp->is_fp_check ? st->fp_cnt[3] : NULL;
             icwo_render(sp, &st->mt[1], &st->prev_rnd[1], &st->ns[1], ro, m, tmpr, &st->clips[1], &st->peak_db[1]);
+            g_fpc = NULL;
             for (int k = 0; k < m; ++k) {
                 memcpy(pcm + (base + k) * ob, tmpl + k * sb, sb);
                 memcpy(pcm + (base + k) * ob + sb, tmpr + k * sb, sb);

@@ -71,6 +71,7 @@ typedef struct icwo_spec {
     int      bypass;
     int      n_nodes;
     icwo_node nodes[ICWO_MAX_NODES];
+    int      is_fp_check;       /* FP_CHECK: the FP-exception-checked twins (src/fp_check.c:52-99) */
 } icwo_spec;
 
 typedef struct icwo_iir {
@@ -106,6 +107,9 @@ typedef struct icwo_state {
     unsigned clips[2];
     double   peak_db[2];
     icwo_ns  ns[2];
+    /* FP_EXCEPT_STATS of the context (src/in_cwave.h:418-421): [hilbert L, hilbert R, render L, render R]
+     * x [total, snan, qnan, ninf, nden, pden, pinf] (src/fp_check.h:66-76) */
+    unsigned fp_cnt[4][7];
 } icwo_state;
 
 void    icwo_default_spec(icwo_spec *sp);

@@ -54,6 +54,7 @@ class Spec(C.Structure):
         ("quantz_type", C.c_uint), ("render_type", C.c_uint), ("nshape_type", C.c_uint),
         ("sign_bits16", C.c_uint), ("sign_bits24", C.c_uint),
         ("bypass", C.c_int), ("n_nodes", C.c_int), ("nodes", Node * MAX_NODES),
+        ("is_fp_check", C.c_int),
     ]
 
 
@@ -80,6 +81,7 @@ class State(C.Structure):
         ("mt", Mt * 2), ("prev_rnd", C.c_double * 2),
         ("clips", C.c_uint * 2), ("peak_db", C.c_double * 2),
         ("ns", Ns * 2),
+        ("fp_cnt", (C.c_uint * 7) * 4),
     ]
 
 
@@ -251,6 +253,7 @@ def make_spec(d: dict) -> Spec:
     sp.sign_bits16 = int(d.get("sign_bits16", 16))
     sp.sign_bits24 = int(d.get("sign_bits24", 24))
     sp.bypass = int(d.get("bypass", 0))
+    sp.is_fp_check = int(d.get("is_fp_check", 0))
     nodes = d.get("nodes")
     if nodes is not None:
         sp.n_nodes = len(nodes)
@@ -381,7 +384,9 @@ def ref_process(d: dict, raw: np.ndarray, taps: list[int] | None = None, read_qu
         raise RuntimeError(f"reference refused the file (rc={got})")
     st = RefStats()
     L.icwref_get_stats(C.byref(st), 0)
-    return dict(pcm=pcm[: got * ob], bus=bus, frames=int(got), stats=st)
+    fp = ((C.c_uint * 7) * 4)()
+    L.icwref_fp_stats(fp)
+    return dict(pcm=pcm[: got * ob], bus=bus, frames=int(got), stats=st, fp_cnt=[list(r) for r in fp])
 
 
 # ---------------------------------------------------------------------------------------------

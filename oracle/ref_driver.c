@@ -373,6 +373,19 @@ void icwref_get_stats(icwref_stats *st, int reset)
     }
 }
 
+/* FP exception counters of the transcode context: [hilbert L, hilbert R, render L, render R] x
+ * [total, snan, qnan, ninf, nden, pden, pinf] (the reference's own getter, src/in_cwave.c:383-440) */
+void icwref_fp_stats(unsigned out[4][7])
+{
+    FP_EXCEPT_STATS s[4];
+    memset(s, 0, sizeof s);
+    fecs_getcnts(&s[0], &s[1], &s[2], &s[3]);
+    for (int i = 0; i < 4; ++i) {
+        out[i][0] = s[i].cnt_total; out[i][1] = s[i].cnt_snan; out[i][2] = s[i].cnt_qnan; out[i][3] = s[i].cnt_ninf;
+        out[i][4] = s[i].cnt_nden;  out[i][5] = s[i].cnt_pden; out[i][6] = s[i].cnt_pinf;
+    }
+}
+
 /* ---- leaf taps ------------------------------------------------------------------------- */
 
 /* real -> analytic for one channel from a fresh converter; returns the subnorm-reject count */

@@ -189,3 +189,54 @@ def test_transcode_entry_points_agree():
     assert got == n * 6
     assert list(info) == [n * 6, 24, 2, 48000]
     assert np.array_equal(pcm, direct["pcm"])
+
+
+def _exceptional(spec, n, seed):
+    """Seeded input with NaN, +-Inf and values that make denormal intermediates scattered through it."""
+    from in_cwave_b200 import synth
+    raw = synth.stream_bytes(spec, n, stream_id=seed).copy()
+    f64 = spec["fmt"] == "cw_f64"
+    f = raw.view(np.float64 if f64 else np.float32).copy()
+    idx = np.random.default_rng(seed).choice(f.size, 60, replace=False)
+    vals = [np.nan, np.inf, -np.inf, 3e-312 if f64 else 1e-42, -2e-311 if f64 else -1e-43, 1e300 if f64 else 3e38]
+    for j, i in enumerate(idx):
+        f[i] = vals[j % len(vals)]
+    return f.view(np.uint8)
+
+
+FP_CHECK_CASES = {
+    "hilbert_kahan_tpdf": lambda S: S.config_c1(is_fp_check=1, render_type=2),
+    "hilbert_plain_noreject": lambda S: S.config_c1(is_fp_check=1, is_kahan=0, is_subnorm_reject=0),
+    "hilbert_type5_mono": lambda S: S.config_c1(is_fp_check=1, filter_no=5, n_channels=1),
+    "render_denormals_fir_shaper": lambda S: S.default_spec(
+        fmt="cw_f64", is_fp_check=1, render_type=2, nshape_type=6, sample_rate=44100,
+        nodes=[dict(mode="master", inputs=[0], l_gain=1.0, r_gain=1.0, l_tout=2, r_tout=3)]),
+    # (no trig in the graphs of the shaper cases: a 1-ulp sin/cos difference between libm and libdevice flips an
+    # LSB now and then, and error feedback turns one flip into a different sequence)
+    "render_iir_shaper_16bit": lambda S: S.default_spec(
+        fmt="cw_f32", is_fp_check=1, nshape_type=16, sample_rate=44100, need24bits=0,
+        nodes=[dict(mode="master", inputs=[0], l_gain=0.9, r_gain=0.7, l_tout=0, r_tout=1)]),
+    "render_flat_gauss": lambda S: S.default_spec(
+        fmt="cw_f64", is_fp_check=1, render_type=4,
+        nodes=[dict(mode="master", inputs=[0], l_gain=1.0, r_gain=1.0, l_tout=2, r_tout=3)]),
+}
+
+
+@pytest.mark.parametrize("case", sorted(FP_CHECK_CASES))
+def test_fp_checked_twins_port_equals_reference(oracle, case):
+    """FP_CHECK=1: the checked twins of the half-band filters, the renderer and the shapers flush
+    NaN / denormals to 0 and +-Inf to +-65535 and count every event -- same PCM and the same four counter
+    blocks as the compiled reference, on inputs full of exceptional values."""
+    from in_cwave_b200 import spec as S
+    spec = FP_CHECK_CASES[case](S)
+    raw = _exceptional(spec, 12000, 11)
+    ref = oracle.ref_process(spec, raw)
+    port = oracle.port_process(spec, raw)
+    assert np.array_equal(ref["pcm"], port["pcm"])
+    cnt = [list(r) for r in port["state"].fp_cnt]
+    print(case, cnt)
+    assert cnt == ref["fp_cnt"]
+    assert sum(r[0] for r in cnt) > 0
+    # and with the check off the same input is processed unchecked: no counters move
+    off = oracle.port_process(dict(spec, is_fp_check=0), raw)
+    assert all(v == 0 for r in off["state"].fp_cnt for v in r)
