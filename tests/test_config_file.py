@@ -23,13 +23,13 @@ pytestmark = pytest.mark.skipif(not po.have_ref(), reason="oracle/_ref not built
 def _cfg_tuple_ref(c):
     return (c.filter_no, c.is_kahan, c.is_subnorm_reject, c.is_frmod_scaled, c.need24bits, c.dth_bits,
             c.quantz_type, c.render_type, c.nshape_type, c.sign_bits16, c.sign_bits24,
-            c.sec_align, c.fade_in, c.fade_out, c.clr_nframe_trk, c.clr_hilb_trk)
+            c.sec_align, c.fade_in, c.fade_out, c.clr_nframe_trk, c.clr_hilb_trk, c.is_fp_check)
 
 
 def _cfg_tuple_ours(sp, o):
     return (sp.filter_no, sp.is_kahan, sp.is_subnorm_reject, sp.is_frmod_scaled, sp.need24bits, sp.dth_bits,
             sp.quantz_type, sp.render_type, sp.nshape_type, sp.sign_bits16, sp.sign_bits24,
-            o.sec_align, o.fade_in_ms, o.fade_out_ms, o.clr_nframe_trk, o.clr_hilb_trk)
+            o.sec_align, o.fade_in_ms, o.fade_out_ms, o.clr_nframe_trk, o.clr_hilb_trk, sp.is_fp_check)
 
 
 CASES = {
@@ -38,6 +38,7 @@ CASES = {
     "c3": S.config_c3(),
     "plain": S.default_spec(filter_no=4, is_kahan=0, is_subnorm_reject=0, is_frmod_scaled=0, need24bits=0,
                             quantz_type=0, render_type=4, sign_bits16=12),
+    "fp_check": S.config_c1(is_fp_check=1, render_type=2),
 }
 
 
