@@ -563,7 +563,10 @@ extern "C" int icw_session_reset(icw_session *s, unsigned what)
             d.quad[0] = d.quad[1] = 0;
         }
         if (w & ICW_RESET_FRAMECNT) d.n_frame = 0;
-        if (w & ICW_RESET_COUNTERS) { d.clips[0] = d.clips[1] = 0; d.peak[0] = d.peak[1] = 0.0; }
+        if (w & ICW_RESET_COUNTERS) {
+            d.clips[0] = d.clips[1] = 0; d.peak[0] = d.peak[1] = 0.0;
+            memset(d.fp_cnt, 0, sizeof d.fp_cnt);               // except_stats_reset, reference src/fp_check.c:37-47
+        }
         if (w & ICW_RESET_FILEPOS) d.pos = 0;
     }, &what);
 }
@@ -582,11 +585,14 @@ extern "C" int icw_session_set_spec(icw_session *s, const icw_chain_spec *spec)
     if (memcmp(&ch.render, &s->ch.render, sizeof ch.render) != 0) flags |= 2;
     // iir_rp_setcfg clears the reject counters (reference src/hblpf.c:1114-1125)
     if (spec->is_kahan != s->spec.is_kahan || spec->is_subnorm_reject != s->spec.is_subnorm_reject) flags |= 4;
+    // switching FP_CHECK on or off clears its counters (reference mod_context_fpcheck_endis, src/in_cwave.c:325-379)
+    if ((spec->is_fp_check != 0) != (s->spec.is_fp_check != 0)) flags |= 8;
     if (flags) {
         rc = rewrite_states(s, [](DevStream &d, void *a) {
             unsigned f = *(unsigned *)a;
             if (f & 1) { memset(d.hb, 0, sizeof d.hb); d.quad[0] = d.quad[1] = 0; }
             if (f & (1 | 4)) memset(d.hb_rejects, 0, sizeof d.hb_rejects);
+            if (f & 8) memset(d.fp_cnt, 0, sizeof d.fp_cnt);
             if (f & 2) {            // sound_render_recalc also clears the shaper memory (src/sound_render.c:546-571)
                 d.prev_rnd[0] = d.prev_rnd[1] = 0.0;
                 memset(d.ns_e, 0, sizeof d.ns_e); memset(d.ns_o, 0, sizeof d.ns_o);
