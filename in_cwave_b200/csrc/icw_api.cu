@@ -805,11 +805,10 @@ static int process_group(icw_session *s, int64_t n_frames, const uint8_t *d_in, 
             MtPlan pl[2];
             {
                 ProfSpan ps(s, st, ICW_K_MT);
-                for (int c = 0; c < 2; ++c) {
-                    rc = e->mt.plan(c, s->mt_seed[c][0], s->mt_drawn[c][0], n_frames * ch.render.words_per_sample,
-                                    chain_mt_max_units(e->sm_count), e->sm_count, st, &s->launches, pl[c]);
-                    if (rc) return fail(rc, "%s", e->mt.error());
-                }
+                const uint32_t seeds[2] = { s->mt_seed[0][0], s->mt_seed[1][0] };
+                rc = e->mt.plan_pair(seeds, s->mt_drawn[0][0], n_frames * ch.render.words_per_sample,
+                                     chain_mt_max_units(e->sm_count), e->sm_count, st, &s->launches, pl);
+                if (rc) return fail(rc, "%s", e->mt.error());
             }
             ProfSpan ps(s, st, ICW_K_CHAIN);
             CK(launch_chain_mt(ch, s->d_streams, n_frames, src, from_analytic, pl[0], pl[1], d_out,

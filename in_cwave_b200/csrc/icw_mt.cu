@@ -244,8 +244,10 @@ __device__ __forceinline__ void mt_next_block(const uint32_t *old, uint32_t *nw,
 // that bounded the word-per-XOR version is out of the picture; the bound is the ALU pipe.
 __global__ void __launch_bounds__(JUMP_THREADS, 2)
 mt_jump_kernel(uint32_t *__restrict__ states, const uint32_t *__restrict__ src_states, int dst_first, int span,
-               const uint32_t *__restrict__ poly)
+               const uint32_t *__restrict__ poly, uint32_t *__restrict__ states_b = nullptr /* blockIdx.z == 1: a second
+               generator's checkpoint array, same geometry (both channels' trees in one launch) */)
 {
+    if (blockIdx.z) states = states_b;
     extern __shared__ __align__(16) uint32_t sm[];
     uint32_t *seq = sm;
     uint32_t *pw = sm + JUMP_SEQ_PAD;
@@ -424,10 +426,12 @@ int MtJump::state_at_block(uint32_t seed, uint64_t block, uint32_t *d_state, cud
     return ICW_OK;
 }
 
-int MtJump::plan(int lane, uint32_t seed, uint64_t skip, int64_t n, int max_units, int sm_count, cudaStream_t stream,
-                 uint64_t *launches, MtPlan &pl)
+// geometry + checkpoint 0 of one lane; the doubling tree is run by the caller (alone or for both lanes at once)
+int MtJump::plan_prepare(int lane, uint32_t seed, uint64_t skip, int64_t n, int max_units, cudaStream_t stream,
+                         uint64_t *launches, MtPlan &pl, uint64_t &bpu_out)
 {
     pl = MtPlan();
+    bpu_out = 0;
     if (n <= 0) return ICW_OK;
     const uint64_t b0 = skip / MT_N, b1 = (skip + (uint64_t)n - 1) / MT_N;
     const uint64_t nb = b1 - b0 + 1;
@@ -451,20 +455,6 @@ int MtJump::plan(int lane, uint32_t seed, uint64_t skip, int64_t n, int max_unit
     }
     int rc = state_at_block(seed, b0, ck, stream, launches);
     if (rc) return rc;
-    // doubling: checkpoints [2^j, 2^(j+1)) come from [0, 2^j) by a jump of bpu * 2^j blocks
-    if (n_cta > 1 && !attr_set_) { rc = ensure_poly(0); if (rc) return rc; }
-    for (int j = 0; (1 << j) < n_cta; ++j) {
-        const uint32_t *d_poly = nullptr;
-        rc = poly_for(bpu << j, &d_poly);
-        if (rc) return rc;
-        const int first = 1 << j;
-        const int count = std::min(n_cta, 2 << j) - first;
-        const int sl = jump_slices(count, sm_count);
-        if (sl > 1) cudaMemsetAsync(ck + (size_t)first * MT_N, 0, (size_t)count * MT_N * sizeof(uint32_t), stream);
-        mt_jump_kernel<<<dim3(count, sl), JUMP_THREADS, JUMP_SMEM, stream>>>(ck, nullptr, first, first, d_poly);
-        if (launches) ++*launches;
-    }
-    if (cudaGetLastError() != cudaSuccess) { err_ = "mt_jump_kernel launch failed"; return ICW_E_CUDA; }
     if (!d_tail_ && cudaMalloc(&d_tail_, (size_t)NTAIL * 2 * MT_N * sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); err_ = "cudaMalloc(tail states) failed"; return ICW_E_NOMEM; }
     const int slot = tail_next_;
     tail_next_ = (tail_next_ + 1) % NTAIL;
@@ -479,7 +469,53 @@ int MtJump::plan(int lane, uint32_t seed, uint64_t skip, int64_t n, int max_unit
     pl.want_lo = (int64_t)skip;
     pl.want_hi = (int64_t)(skip + (uint64_t)n);
     pl.tail_block = (int64_t)(b1 - b0);
+    bpu_out = bpu;
     return ICW_OK;
+}
+
+// doubling: checkpoints [2^j, 2^(j+1)) come from [0, 2^j) by a jump of bpu * 2^j blocks; ck_b != NULL runs a second
+// checkpoint array of the same geometry in the same launches (blockIdx.z)
+int MtJump::plan_tree(uint32_t *ck_a, uint32_t *ck_b, int n_cta, uint64_t bpu, int sm_count, cudaStream_t stream, uint64_t *launches)
+{
+    if (n_cta > 1 && !attr_set_) { int rc = ensure_poly(0); if (rc) return rc; }
+    const int nz = ck_b ? 2 : 1;
+    for (int j = 0; (1 << j) < n_cta; ++j) {
+        const uint32_t *d_poly = nullptr;
+        int rc = poly_for(bpu << j, &d_poly);
+        if (rc) return rc;
+        const int first = 1 << j;
+        const int count = std::min(n_cta, 2 << j) - first;
+        const int sl = jump_slices(count * nz, sm_count);
+        if (sl > 1) {
+            cudaMemsetAsync(ck_a + (size_t)first * MT_N, 0, (size_t)count * MT_N * sizeof(uint32_t), stream);
+            if (ck_b) cudaMemsetAsync(ck_b + (size_t)first * MT_N, 0, (size_t)count * MT_N * sizeof(uint32_t), stream);
+        }
+        mt_jump_kernel<<<dim3(count, sl, nz), JUMP_THREADS, JUMP_SMEM, stream>>>(ck_a, nullptr, first, first, d_poly, ck_b);
+        if (launches) ++*launches;
+    }
+    if (cudaGetLastError() != cudaSuccess) { err_ = "mt_jump_kernel launch failed"; return ICW_E_CUDA; }
+    return ICW_OK;
+}
+
+int MtJump::plan(int lane, uint32_t seed, uint64_t skip, int64_t n, int max_units, int sm_count, cudaStream_t stream,
+                 uint64_t *launches, MtPlan &pl)
+{
+    uint64_t bpu = 0;
+    int rc = plan_prepare(lane, seed, skip, n, max_units, stream, launches, pl, bpu);
+    if (rc || n <= 0) return rc;
+    return plan_tree(d_ckpt_[lane], nullptr, pl.n_units, bpu, sm_count, stream, launches);
+}
+
+int MtJump::plan_pair(const uint32_t seed[2], uint64_t skip, int64_t n, int max_units, int sm_count, cudaStream_t stream,
+                      uint64_t *launches, MtPlan pl[2])
+{
+    uint64_t bpu[2] = { 0, 0 };
+    for (int c = 0; c < 2; ++c) {
+        int rc = plan_prepare(c, seed[c], skip, n, max_units, stream, launches, pl[c], bpu[c]);
+        if (rc) return rc;
+    }
+    if (n <= 0) return ICW_OK;
+    return plan_tree(d_ckpt_[0], d_ckpt_[1], pl[0].n_units, bpu[0], sm_count, stream, launches);
 }
 
 int MtJump::generate(uint32_t seed, uint64_t skip, int64_t n, uint32_t *d_out, int sm_count,

@@ -52,6 +52,10 @@ public:
     // The kernel that consumes the plan MUST write pl.tail (see mt_words_kernel).
     int plan(int lane, uint32_t seed, uint64_t skip, int64_t n, int max_units, int sm_count, cudaStream_t stream,
              uint64_t *launches, MtPlan &pl);
+    // the same for two generators standing at the same draw (the two channels' dither): one doubling tree
+    // of launches for both (lanes 0 and 1)
+    int plan_pair(const uint32_t seed[2], uint64_t skip, int64_t n, int max_units, int sm_count, cudaStream_t stream,
+                  uint64_t *launches, MtPlan pl[2]);
     // tempered words [skip, skip + n) of the stream of `seed` -> d_out (device), on `stream`
     int generate(uint32_t seed, uint64_t skip, int64_t n, uint32_t *d_out, int sm_count,
                  cudaStream_t stream, uint64_t *launches);
@@ -59,6 +63,9 @@ public:
     void release();
 
 private:
+    int plan_prepare(int lane, uint32_t seed, uint64_t skip, int64_t n, int max_units, cudaStream_t stream,
+                     uint64_t *launches, MtPlan &pl, uint64_t &bpu_out);
+    int plan_tree(uint32_t *ck_a, uint32_t *ck_b, int n_cta, uint64_t bpu, int sm_count, cudaStream_t stream, uint64_t *launches);
     int ensure_poly(int k);             // device copy of x^(624 * 2^k) mod phi
     // device copy of x^(624 * blocks) mod phi for any distance: the product of the 2^k family over the
     // set bits of `blocks`, or the square of the polynomial for blocks / 2 when that one is cached
