@@ -85,7 +85,7 @@ EXPORTS = [
     "icw_session_set_state", "icw_session_reset", "icw_session_process_host",
     "icw_session_process_device", "icw_session_sync", "icw_session_stats", "icw_session_fp_stats", "icw_hilbert_device",
     "icw_mt_words_device", "icw_session_set_taps", "icw_debug_phase_device", "icw_debug_sincos_device", "icw_mt_host_charpoly",
-    "icw_mt_host_seq_state", "icw_mt_host_jump_state", "icw_mt_host_jump_state_family", "icw_mt_host_jump_state_product",
+    "icw_mt_host_seq_state", "icw_mt_host_jump_state", "icw_mt_host_jump_state_family", "icw_mt_host_jump_state_product", "icw_mt_host_unit_blocks", "icw_host_scan_chunk_len",
     "icw_session_profile", "icw_session_profile_read", "icw_kernel_class_name", "icw_crc32_device", "icw_crc32_host", "icw_crc32_combine",
 ]
 
@@ -149,6 +149,9 @@ def lib() -> C.CDLL:
     L.icw_mt_host_jump_state.argtypes = [C.c_uint32, u64, P(C.c_uint32)]
     L.icw_mt_host_jump_state_family.argtypes = [C.c_uint32, u64, P(C.c_uint32)]
     L.icw_mt_host_jump_state_product.argtypes = [C.c_uint32, u64, P(C.c_uint32)]
+    L.icw_mt_host_unit_blocks.argtypes = [u64, C.c_int]
+    L.icw_mt_host_unit_blocks.restype = u64
+    L.icw_host_scan_chunk_len.argtypes = [C.c_int, i64, C.c_int]
     _lib = L
     return L
 

@@ -426,6 +426,15 @@ int MtJump::state_at_block(uint32_t seed, uint64_t block, uint32_t *d_state, cud
     return ICW_OK;
 }
 
+uint64_t mt_unit_blocks(uint64_t nb, int max_units)
+{
+    const uint64_t max_cta = (uint64_t)(max_units < 1 ? 1 : max_units);
+    uint64_t bpu = (nb + max_cta - 1) / max_cta;
+    int sh = 0;
+    while (bpu >= 16) { bpu = (bpu + 1) >> 1; ++sh; }
+    return (bpu ? bpu : 1) << sh;
+}
+
 // geometry + checkpoint 0 of one lane; the doubling tree is run by the caller (alone or for both lanes at once)
 int MtJump::plan_prepare(int lane, uint32_t seed, uint64_t skip, int64_t n, int max_units, cudaStream_t stream,
                          uint64_t *launches, MtPlan &pl, uint64_t &bpu_out)
@@ -437,13 +446,7 @@ int MtJump::plan_prepare(int lane, uint32_t seed, uint64_t skip, int64_t n, int 
     const uint64_t nb = b1 - b0 + 1;
     // blocks per unit: the smallest m * 2^k (m < 16) that covers the range with max_units units -- a full
     // wave of CTAs to within a few per cent, and a small set of jump distances to keep polynomials for
-    const uint64_t max_cta = (uint64_t)(max_units < 1 ? 1 : max_units);
-    uint64_t bpu = (nb + max_cta - 1) / max_cta;
-    {
-        int sh = 0;
-        while (bpu >= 16) { bpu = (bpu + 1) >> 1; ++sh; }
-        bpu <<= sh;
-    }
+    const uint64_t bpu = mt_unit_blocks(nb, max_units);
     const int n_cta = (int)((nb + bpu - 1) / bpu);
     uint32_t *&ck = d_ckpt_[lane];
     if ((size_t)n_cta > ckpt_cap_[lane]) {
@@ -611,3 +614,6 @@ extern "C" int icw_mt_host_jump_state_product(uint32_t seed, uint64_t blocks, ui
     icw::mt_apply_host(g, st, out624);
     return ICW_OK;
 }
+
+// unit length (blocks) the checkpoint planner picks for nb blocks and at most max_units units
+extern "C" uint64_t icw_mt_host_unit_blocks(uint64_t nb, int max_units) { return icw::mt_unit_blocks(nb, max_units); }

@@ -45,6 +45,9 @@ struct MtPlan {
     int64_t tail_block = 0;             // relative index of the block holding the last wanted word
 };
 
+// blocks per jump-ahead unit for a range of nb blocks and at most max_units units: the smallest m * 2^k, m < 16
+uint64_t mt_unit_blocks(uint64_t nb, int max_units);
+
 class MtJump {
 public:
     // checkpoints for words [skip, skip + n) of the stream of `seed`, at most `max_units` of them.

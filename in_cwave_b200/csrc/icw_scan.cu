@@ -658,3 +658,9 @@ cudaError_t launch_hb_scan(const ModalCoef &mc, const DevChain &ch, DevStream *s
 }
 
 }  // namespace icw
+
+// host-only hook for the CPU tests: the chunk length the scan picks for a launch group
+extern "C" int icw_host_scan_chunk_len(int n_streams, int64_t n_frames, int sm_count)
+{
+    return icw::scan_chunk_len(n_streams, n_frames, sm_count);
+}

@@ -244,6 +244,10 @@ int  icw_mt_host_jump_state_family(uint32_t seed, uint64_t blocks, uint32_t *out
 /* the same distance as ONE polynomial, the product of the x^(624*2^k) family over the set bits of the
  * distance -- how the checkpoint tree reaches units of any length (MtJump::poly_for) */
 int  icw_mt_host_jump_state_product(uint32_t seed, uint64_t blocks, uint32_t *out624);
+/* planning arithmetic, host only: blocks per jump-ahead unit for nb blocks over at most max_units CTAs (m * 2^k,
+ * m < 16); frames per scan chunk for a launch group (256, 1024 or 2048; ICW_SCAN_L overrides) */
+uint64_t icw_mt_host_unit_blocks(uint64_t nb, int max_units);
+int  icw_host_scan_chunk_len(int n_streams, int64_t n_frames, int sm_count);
 
 #ifdef __cplusplus
 }

@@ -60,3 +60,34 @@ def test_far_jump_consistency():
     assert L.icw_mt_host_jump_state_family(0x13579BDF, blocks, b) == 0
     assert L.icw_mt_host_jump_state_product(0x13579BDF, blocks, c) == 0
     assert list(a) == list(b) == list(c)
+
+
+def test_unit_length_covers_the_range_with_one_wave():
+    """Jump-ahead units are m * 2^k blocks with m < 16: never more units than CTAs, and the wave at least
+    8/9 full once there is more than one block per CTA."""
+    L = _abi.lib()
+    for max_units in (1, 8, 592, 1184):
+        for nb in (1, 2, 15, 16, 17, 591, 592, 593, 2565, 107_000, 4_430_770, 10 ** 9 + 7):
+            u = int(L.icw_mt_host_unit_blocks(nb, max_units))
+            m = u
+            while m % 2 == 0 and m >= 16:
+                m //= 2
+            assert m < 16 and u >= 1
+            units = -(-nb // u)
+            assert units <= max_units
+            if nb >= 16 * max_units:
+                assert units * 9 >= max_units * 8 - 9, (nb, max_units, u, units)
+    assert int(L.icw_mt_host_unit_blocks(4_430_770, 592)) == 7680        # the C2 call: 577 units of 15 * 512 blocks
+
+
+def test_scan_chunk_length_policy(monkeypatch):
+    L = _abi.lib()
+    monkeypatch.delenv("ICW_SCAN_L", raising=False)
+    assert L.icw_host_scan_chunk_len(1, 50_000, 148) == 256
+    assert L.icw_host_scan_chunk_len(1, 138_240_000, 148) == 1024
+    assert L.icw_host_scan_chunk_len(1, 691_200_000, 148) == 2048
+    assert L.icw_host_scan_chunk_len(4096, 480_000, 148) == 2048          # many streams count like one long one
+    monkeypatch.setenv("ICW_SCAN_L", "4096")
+    assert L.icw_host_scan_chunk_len(1, 1000, 148) == 4096
+    monkeypatch.setenv("ICW_SCAN_L", "300")                                # not a multiple of 256: ignored
+    assert L.icw_host_scan_chunk_len(1, 1000, 148) == 256
