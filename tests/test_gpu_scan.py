@@ -223,3 +223,17 @@ def test_scan_long_chunks_whole_chain(engine, oracle, monkeypatch):
     rep = pcm_report(long_, base, 3)
     print(f"[scan L=4096 vs 256] {rep}")
     assert rep["max_lsb"] <= 1 and rep["mismatches"] <= 4
+
+
+def test_scan_long_chunks_many_streams(engine, oracle, monkeypatch):
+    """Several streams in one launch group with 1024-frame chunks: same bytes as with 256-frame chunks up to
+    the scan's own rounding, stream by stream."""
+    spec = S.config_c1(hilbert_mode="scan")
+    K, n = 5, 300_001
+    raws = np.stack([rand_bytes(spec, n, 700 + k) for k in range(K)])
+    base = engine.session(spec, K).process_host(raws)
+    monkeypatch.setenv("ICW_SCAN_L", "1024")
+    long_ = engine.session(spec, K).process_host(raws)
+    for k in range(K):
+        rep = pcm_report(long_[k], base[k], 3)
+        assert rep["max_lsb"] <= 1 and rep["mismatches"] <= 4, (k, rep)
