@@ -115,16 +115,10 @@ static void reduce_wide(uint64_t *wide)
 
 void mt_poly_square(const MtPoly &a, MtPoly &out)
 {
-    static uint16_t spread[256];
-    static bool init = false;
-    if (!init) {
-        for (int v = 0; v < 256; ++v) {
-            uint16_t s = 0;
-            for (int b = 0; b < 8; ++b) if (v & (1 << b)) s |= (uint16_t)(1u << (2 * b));
-            spread[v] = s;
-        }
-        init = true;
-    }
+    // bit-spreading table, built once (function-local static: initialisation is thread-safe)
+    struct Spread { uint16_t t[256]; Spread() { for (int v = 0; v < 256; ++v) { uint16_t s = 0; for (int b = 0; b < 8; ++b) if (v & (1 << b)) s |= (uint16_t)(1u << (2 * b)); t[v] = s; } } };
+    static const Spread table;
+    const uint16_t *spread = table.t;
     uint64_t wide[2 * MT_PW];
     for (int i = 0; i < MT_PW; ++i) {
         uint64_t v = a.w[i], lo = 0, hi = 0;
