@@ -209,6 +209,11 @@ def cpu_model() -> str:
     return "unknown"
 
 
+def base_config(wl: dict) -> dict:
+    """The keys both arms print under `config`: what the workload IS (the arms differ in how they run it)."""
+    return dict(workload=wl["desc"], streams=wl["streams"], frames_per_stream=wl["frames"])
+
+
 def reference_arm(args, wl):
     """--impl reference: the reference's CPU implementation of the path, all host threads."""
     rank = int(os.environ.get("RANK", "0"))
@@ -236,7 +241,8 @@ def reference_arm(args, wl):
     line = dict(impl="reference", metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f64", data="synthetic",
-                config=dict(workload=wl["desc"], hilbert=wl["hilbert"]),
+                config=base_config(wl),
+                parity=dict(hilbert="reference: serial DF-II recurrences on the CPU (the definition of bit-exact)"),
                 cpu_baseline=dict(value=val, unit=UNIT, cores=cores, kind=kind, sample=sample, cpu=cpu_model()),
                 e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
@@ -257,6 +263,287 @@ class _NoDist:
 
 
 # ---------------------------------------------------------------------------------------------
+# in-run parity: the bytes this run produced against the reference's own code on the same input
+# ---------------------------------------------------------------------------------------------
+def _oracle_pcm(spec: dict, raw: np.ndarray):
+    """PCM of a FRESH reference context over raw (oracle/_ref when it travelled with the repo, else the port)."""
+    from oracle import pyoracle as po
+    if po.have_ref():
+        return po.ref_process(spec, raw, read_quant=4096, tmpdir=os.environ.get("ICW_TMPDIR"))["pcm"], "reference"
+    return po.port_process(spec, raw)["pcm"], "port"
+
+
+def _pcm_ints(pcm: np.ndarray, bps: int) -> np.ndarray:
+    b = np.asarray(pcm, dtype=np.uint8).reshape(-1, bps).astype(np.int64)
+    v = b[:, 0] | (b[:, 1] << 8)
+    if bps == 3:
+        v |= b[:, 2] << 16
+        return np.where(v >= 1 << 23, v - (1 << 24), v)
+    return np.where(v >= 1 << 15, v - (1 << 16), v)
+
+
+def pcm_distance(got: np.ndarray, want: np.ndarray, bps: int) -> dict:
+    g, w = _pcm_ints(got, bps), _pcm_ints(want, bps)
+    d = np.abs(g - w)
+    rms_w = float(np.sqrt(np.mean(w.astype(np.float64) ** 2))) or 1.0
+    return dict(samples=int(g.size), mismatches=int(np.count_nonzero(d)), max_lsb=int(d.max() if d.size else 0),
+                rms_vs_reference=float(np.sqrt(np.mean(d.astype(np.float64) ** 2))) / rms_w)
+
+
+def parity_check(wl: dict, d_in, d_out, K: int, N: int) -> dict:
+    """Sampled windows of the LAST timed step's output (every step starts from fresh contexts) against the reference:
+    one long stream -> its first 2^18 frames; a batch -> three whole streams."""
+    spec = wl["spec"]
+    fb, ob = S.frame_bytes(spec), S.out_frame_bytes(spec)
+    bps = ob // 2
+    # the reference's Hilbert is always its own serial recurrence: compare against the exact-mode spec
+    ref_spec = dict(spec, hilbert_mode="exact")
+    t0 = time.perf_counter()
+    if K == 1:
+        W = min(N, 1 << 18)
+        picks = [(0, W)]
+    else:
+        W = min(N, 480_000)
+        picks = [(k, W) for k in sorted({0, K // 3, K - 1})]
+    tot = dict(samples=0, mismatches=0, max_lsb=0)
+    sq, kind = 0.0, "port"
+    for k, w in picks:
+        raw = d_in[k, : w * fb].cpu().numpy()
+        got = d_out[k, : w * ob].cpu().numpy()
+        want, kind = _oracle_pcm(ref_spec, raw)
+        r = pcm_distance(got, want, bps)
+        tot["samples"] += r["samples"]; tot["mismatches"] += r["mismatches"]; tot["max_lsb"] = max(tot["max_lsb"], r["max_lsb"])
+        sq += r["rms_vs_reference"] ** 2 * r["samples"]
+    tot["rms_vs_reference"] = float(np.sqrt(sq / max(1, tot["samples"])))
+    tot["against"] = f"oracle/{'_ref (the compiled reference)' if kind == 'reference' else 'port'}, fresh context per stream"
+    tot["window"] = (f"first {picks[0][1]} frames of the stream" if K == 1 else
+                     f"streams {[k for k, _ in picks]} x {W} frames (whole streams)")
+    tot["hilbert"] = wl["hilbert"]
+    tot["seconds"] = round(time.perf_counter() - t0, 2)
+    if wl["hilbert"] == "scan":
+        tot["note"] = ("scan mode evaluates the filter exactly (3e-15 of binary128); the reference's serial FP64 recurrence carries "
+                       "its own rounding noise (about 5e-5 of RMS for the default design), which is the distance counted here")
+    return tot
+
+
+# ---------------------------------------------------------------------------------------------
+# one workload on this rank: resident timing, per-kernel roofline, e2e, parity
+# ---------------------------------------------------------------------------------------------
+FP64_OPS = {"c2": 164 + 82 + 105, "c5": 164 + 82 + 70, "c1": 164 + 82 + 70, "c4": 1124 + 70, "c4ns": 1124 + 200, "c3": 300}
+
+
+def measure(ctx, name: str, steps: int, warmup: int, want_e2e: bool, want_parity: bool, args=None) -> dict:
+    import torch
+    from in_cwave_b200 import dist as D
+    dist, world, rank, local, dev, eng = ctx["dist"], ctx["world"], ctx["rank"], ctx["local"], ctx["dev"], ctx["eng"]
+    wl = workload(name)
+    if args is not None and args.streams:
+        wl["streams"] = args.streams
+    if args is not None and args.frames:
+        wl["frames"] = args.frames
+        wl["chunk"] = min(wl["chunk"], args.frames)
+    spec, N, chunk = wl["spec"], wl["frames"], wl["chunk"]
+    K_all = wl["streams"]
+    # how the workload spreads over the ranks (SURVEY.md 8e): a batch is cut by stream (fixed total: strong scaling);
+    # one long stream is cut in time (c5) or, having nothing to cut, replicated (weak scaling, no collective)
+    if K_all > 1 and world > 1:
+        lo, hi = D.shard_streams(K_all, rank, world)
+        K, scaling, sharding = hi - lo, "strong", f"by stream: {K_all} streams / {world} ranks, no collective"
+        frames_step = K_all * N
+    elif wl.get("time_sharded"):
+        K, scaling = 1, "weak"
+        sharding = f"by time: rank r plays frames [r*{N}, (r+1)*{N}) of ONE stream of {world * N} frames; NCCL hand-off of the Hilbert state"
+        frames_step = N * world
+    else:
+        K, scaling = K_all, "weak"
+        sharding = "replicas: one independent stream per rank, no collective" if world > 1 else "single GPU"
+        frames_step = K * N * world
+    fb, ob = S.frame_bytes(spec), S.out_frame_bytes(spec)
+    ses = eng.session(spec, K)
+    d_in = synth.device_fill(spec, K, N, dev)
+    in_stride = d_in.stride(0)
+    out_stride = (N * ob + 15) // 16 * 16
+    d_out = torch.empty((K, out_stride), dtype=torch.uint8, device=dev)
+    cs = torch.cuda.current_stream().cuda_stream
+    shard_be = None
+    if wl.get("time_sharded"):
+        shard_be = D.CudaBackend(eng, spec)
+        shard_be.ses.close()
+        shard_be.ses = ses                            # profile / count launches on the session bench reads
+    handoff_ms = []
+
+    def one_step():
+        ses.reset()                                   # every step = the same fresh streams
+        if shard_be is not None:
+            info = D.run_time_sharded(shard_be, dist if world > 1 else _NoDist(), spec, d_in[0, : N * fb], rank * N, rank, world,
+                                      device=dev, d_out=d_out[0])
+            if isinstance(info, tuple) and len(info) > 3 and info[3] is not None:
+                handoff_ms.append(info[3])
+            return
+        for f0 in range(0, N, chunk):
+            n = min(chunk, N - f0)
+            ses.process_device(d_in.data_ptr() + f0 * fb, n, d_out.data_ptr() + f0 * ob,
+                               in_stride=in_stride, out_stride=out_stride, stream=cs)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        one_step()
+    barrier()
+    handoff_ms.clear()
+    launches0 = ses.stats()["kernel_launches"]
+    ses.profile(True)
+    ses.profile_read(reset=True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(steps):
+        one_step()
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    prof = ses.profile_read(reset=True)
+    ses.profile(False)
+    launches = ses.stats()["kernel_launches"] - launches0
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / steps
+    value = frames_step / (ms_step * 1e-3) / 1e6
+
+    # ---- roofline of the dominant kernel (this rank's launches) -----------------------------------------
+    pk = peaks()
+    dom = max(prof, key=lambda k: prof[k]["ms"])
+    spans = max(1, prof[dom]["launches"])
+    dom_ms = prof[dom]["ms"] / spans                         # one span = the class's kernels over one launch group
+    units_per_launch = K * N * steps / spans                 # frames one such span processes
+    algo_bytes = units_per_launch * wl["bytes_per_frame"]
+    achieved = algo_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    traffic = None
+    for tf in ("r2_traffic.json", "r1_traffic.json"):        # dram bytes per frame from the ncu --set full captures
+        tfile = ROOT / "profiles" / tf
+        if tfile.exists():
+            tt = json.loads(tfile.read_text()).get(wl["name"], {}).get(dom)
+            if tt:
+                traffic = tt["dram_bytes_per_frame"] * units_per_launch
+                break
+    fp64_ops = FP64_OPS.get(wl["name"], 0)
+    total_ms = max(1e-9, sum(x["ms"] for x in prof.values()))
+    roofline = dict(bound="hbm", kernel=dom, achieved=achieved, peak=pk["hbm_gbs"], unit="GB/s",
+                    frac=achieved / pk["hbm_gbs"], traffic=traffic, peak_source=pk["source"],
+                    algorithmic_bytes_per_frame=wl["bytes_per_frame"], frames_per_launch=units_per_launch,
+                    avg_launch_ms=dom_ms,
+                    whole_step_frac=(K * N * wl["bytes_per_frame"] / (ms_step * 1e-3) / 1e9) / pk["hbm_gbs"],
+                    kernel_share={k: v["ms"] / total_ms for k, v in prof.items()},
+                    binding_bound=dict(kind="fp64 pipe / instruction issue (not HBM)", peak_tops=18.55, peak_tops_3_vector_operands=12.37,
+                                       peak_source="tools/fp64_probe.cu on this pool's B200 (profiles/r1_fp64_probe_b200.txt)",
+                                       approx_ops_per_frame=fp64_ops,
+                                       whole_step_frac=(K * N) * fp64_ops / (ms_step * 1e-3) / 18.55e12))
+
+    res = dict(desc=wl["desc"], value=value, unit=UNIT, ms_per_step=ms_step, steps=steps, warmup=warmup, scaling=scaling,
+               sharding=sharding, hilbert=wl["hilbert"], streams_this_rank=K, frames_per_stream=N, frames_per_step=frames_step,
+               roofline=roofline, gpu_launches=int(launches), kernel_ms={k: v["ms"] / steps for k, v in prof.items()},
+               clocks=clocks, l2="inputs larger than L2 (per-step input %.2f GB on this rank)" % (K * N * fb / 1e9),
+               config=base_config(wl))
+    if handoff_ms:
+        hm = torch.tensor([float(np.mean(handoff_ms))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(hm, op=dist.ReduceOp.MAX)
+        res["handoff_ms"] = float(hm.item())
+
+    # ---- parity of what the timed steps wrote ---------------------------------------------------------
+    if want_parity:
+        pc = None
+        if rank == 0:
+            try:
+                pc = parity_check(wl, d_in, d_out, K, N)
+            except Exception as ex:                           # the bench line must still appear
+                pc = dict(error=f"{type(ex).__name__}: {ex}"[:300])
+        if shard_be is not None and world > 1:
+            st = stitch_check(ctx, wl, d_in, d_out, N)
+            if rank == 0:
+                pc = dict(pc or {}, stitch=st)
+        res["parity_check"] = pc
+
+    # ---- end to end through the host entry point --------------------------------------------------------
+    if want_e2e and shard_be is None:
+        try:
+            h_in = torch.empty((K, N * fb), dtype=torch.uint8, pin_memory=True)
+            h_out = torch.empty((K, N * ob), dtype=torch.uint8, pin_memory=True)
+            h_in.copy_(d_in[:, : N * fb])
+            torch.cuda.synchronize()
+
+            def e2e_step():
+                ses.reset()
+                for f0 in range(0, N, chunk):
+                    n = min(chunk, N - f0)
+                    ses.process_host_into(h_in.data_ptr() + f0 * fb, N * fb, n, h_out.data_ptr() + f0 * ob, N * ob)
+
+            e2e_step()
+            barrier()
+            t0 = time.perf_counter()
+            reps = max(1, min(steps, 2))
+            for _ in range(reps):
+                e2e_step()
+            barrier()
+            dt = (time.perf_counter() - t0) / reps
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            same = bool(torch.equal(h_out[0, : min(N, 1 << 16) * ob].to(dev), d_out[0, : min(N, 1 << 16) * ob]))
+            res["e2e"] = dict(value=frames_step / float(tt.item()) / 1e6, unit=UNIT, h2d_bytes_per_step=K * N * fb,
+                              d2h_bytes_per_step=K * N * ob, ms_per_step=float(tt.item()) * 1e3, steps=reps,
+                              how="icw_session_process_host on pinned host buffers; H2D + kernels + D2H inside the timed region",
+                              host_affinity=ctx["numa_note"], same_bytes_as_resident_run=same)
+            del h_in, h_out
+        except RuntimeError as ex:
+            res["e2e"] = dict(value=None, unit=UNIT, error=str(ex)[:200])
+    res["_spec"] = spec
+    ses.close()
+    del d_in, d_out
+    torch.cuda.empty_cache()
+    return res
+
+
+def stitch_check(ctx, wl: dict, d_in, d_out, N: int) -> dict:
+    """c5: is the cut invisible?  Every rank r > 0 replays, alone, the 2^19 frames before its cut from a zero filter
+    state (the input is periodic over the ranks, so those are the last frames of its own buffer) and then the first
+    2^16 frames of its shard, and compares them with what the time-sharded run wrote there after the NCCL hand-off."""
+    import torch
+    from in_cwave_b200 import dist as D
+    dist, world, rank, dev, eng = ctx["dist"], ctx["world"], ctx["rank"], ctx["dev"], ctx["eng"]
+    spec = wl["spec"]
+    fb, ob = S.frame_bytes(spec), S.out_frame_bytes(spec)
+    W, C = min(N, D.WARMUP_FRAMES), min(N, 1 << 16)
+    stats = torch.zeros(3, dtype=torch.float64, device=dev)     # mismatching samples, max LSB, samples
+    if rank > 0:
+        be = D.CudaBackend(eng, spec)
+        a = rank * N
+        be.start_at(D.closed_form_state(spec, a - W), np.zeros(D.STATE_DOUBLES))
+        scratch = torch.empty(W * ob + 16, dtype=torch.uint8, device=dev)
+        be.process(d_in[0, (N - W) * fb: N * fb], scratch)
+        again = torch.empty(C * ob + 16, dtype=torch.uint8, device=dev)
+        be.process(d_in[0, : C * fb], again)
+        torch.cuda.synchronize()
+        r = pcm_distance(again[: C * ob].cpu().numpy(), d_out[0, : C * ob].cpu().numpy(), ob // 2)
+        stats = torch.tensor([r["mismatches"], r["max_lsb"], r["samples"]], dtype=torch.float64, device=dev)
+        be.ses.close()
+    mx = stats.clone()
+    dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    return dict(cuts=world - 1, samples=int(stats[2].item()), mismatches=int(stats[0].item()), max_lsb=int(mx[1].item()),
+                how=f"each rank > 0: single-GPU replay of {W} warm-up frames + the first {C} frames of its shard vs the sharded run's bytes")
+
+
+# ---------------------------------------------------------------------------------------------
 # the GPU arm
 # ---------------------------------------------------------------------------------------------
 def main():
@@ -270,17 +557,18 @@ def main():
     ap.add_argument("--frames", type=int, default=0, help="override frames per stream")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-workloads", action="store_true", help="only the headline workload, no `workloads` object")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     wl = workload(args.workload)
-    if args.streams:
-        wl["streams"] = args.streams
-    if args.frames:
-        wl["frames"] = args.frames
-        wl["chunk"] = min(wl["chunk"], args.frames)
     if args.warmup < 3:
         args.warmup = 3
 
     if args.impl == "reference":
+        if args.streams:
+            wl["streams"] = args.streams
+        if args.frames:
+            wl["frames"] = args.frames
         reference_arm(args, wl)
         return
 
@@ -297,133 +585,24 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     numa_note = bind_near_gpu(local) if world > 1 else "single rank: not bound"
-
-    spec, K, N, chunk = wl["spec"], wl["streams"], wl["frames"], wl["chunk"]
-    fb, ob = S.frame_bytes(spec), S.out_frame_bytes(spec)
     eng = icw.Engine(local)
-    ses = eng.session(spec, K)
+    ctx = dict(dist=dist, world=world, rank=rank, local=local, dev=dev, eng=eng, numa_note=numa_note)
 
-    # resident synthetic input, one row per stream (rows padded to 16 B)
-    d_in = synth.device_fill(spec, K, N, dev)
-    in_stride = d_in.stride(0)
-    out_stride = (N * ob + 15) // 16 * 16
-    d_out = torch.empty((K, out_stride), dtype=torch.uint8, device=dev)
-    cs = torch.cuda.current_stream().cuda_stream
+    # ---- the headline workload: full treatment --------------------------------------------------------
+    head = measure(ctx, args.workload, args.steps, args.warmup, want_e2e=not args.no_e2e, want_parity=not args.no_parity, args=args)
+    spec = head.pop("_spec")
 
-    shard_be = None
-    if wl.get("time_sharded"):
-        from in_cwave_b200 import dist as D
-        shard_be = D.CudaBackend(eng, spec)
-        shard_be.ses.close()
-        shard_be.ses = ses                            # profile / count launches on the session bench reads
-
-    def one_step():
-        ses.reset()                                   # every step = the same fresh streams
-        if shard_be is not None:
-            # rank r plays frames [r*N, (r+1)*N) of one stream of world*N frames
-            D.run_time_sharded(shard_be, dist if world > 1 else _NoDist(), spec, d_in[0, : N * fb], rank * N, rank, world,
-                               device=dev, d_out=d_out[0])
-            return
-        for f0 in range(0, N, chunk):
-            n = min(chunk, N - f0)
-            ses.process_device(d_in.data_ptr() + f0 * fb, n, d_out.data_ptr() + f0 * ob,
-                               in_stride=in_stride, out_stride=out_stride, stream=cs)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        one_step()
-    barrier()
-    launches0 = ses.stats()["kernel_launches"]
-    ses.profile(True)
-    ses.profile_read(reset=True)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        one_step()
-    ev1.record()
-    barrier()
-    ms_total = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
-    prof = ses.profile_read(reset=True)
-    ses.profile(False)
-    launches = ses.stats()["kernel_launches"] - launches0
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
-    frames_step = K * N * world
-    value = frames_step / (ms_step * 1e-3) / 1e6
-
-    # ---- roofline of the dominant kernel --------------------------------------------------------
-    pk = peaks()
-    dom = max(prof, key=lambda k: prof[k]["ms"])
-    spans = max(1, prof[dom]["launches"])
-    dom_ms = prof[dom]["ms"] / spans                         # one span = the class's kernels over one launch group
-    units_per_launch = K * N * args.steps / spans            # frames one such span processes
-    algo_bytes = units_per_launch * wl["bytes_per_frame"]
-    achieved = algo_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-    traffic = None
-    tfile = ROOT / "profiles" / "r1_traffic.json"            # dram bytes per frame from the ncu --set full captures
-    if tfile.exists():
-        t = json.loads(tfile.read_text()).get(wl["name"], {}).get(dom)
-        if t:
-            traffic = t["dram_bytes_per_frame"] * units_per_launch
-    # FP64 thread-operations per frame (counted from the SASS of the sample loops) and the
-    # measured issue rate of the FP64 pipe (tools/fp64_probe.cu): 64 lanes/clk/SM when an instruction reads two
-    # vector registers (the third operand uniform), 42.7 when it reads three -- most of the modal DFMAs do
-    fp64_ops = {"c2": 164 + 82 + 105, "c5": 164 + 82 + 70, "c1": 164 + 82 + 70, "c4": 1124 + 70, "c4ns": 1124 + 200, "c3": 300}.get(wl["name"], 0)
-    roofline = dict(bound="hbm", kernel=dom, achieved=achieved, peak=pk["hbm_gbs"], unit="GB/s",
-                    frac=achieved / pk["hbm_gbs"], traffic=traffic, peak_source=pk["source"],
-                    algorithmic_bytes_per_frame=wl["bytes_per_frame"], frames_per_launch=units_per_launch,
-                    avg_launch_ms=dom_ms,
-                    kernel_share={k: v["ms"] / max(1e-9, sum(x["ms"] for x in prof.values())) for k, v in prof.items()},
-                    binding_bound=dict(kind="fp64 pipe / instruction issue (not HBM)", peak_tops=18.55, peak_tops_3_vector_operands=12.37,
-                                       peak_source="tools/fp64_probe.cu on this pool's B200 (profiles/r1_fp64_probe_b200.txt)",
-                                       approx_ops_per_frame=fp64_ops,
-                                       whole_step_frac=(frames_step / world) * fp64_ops / (ms_step * 1e-3) / 18.55e12))
-
-    # ---- end to end through the host entry point ----------------------------------------------------
-    e2e = None
-    if not args.no_e2e and not wl.get("time_sharded"):
-        try:
-            h_in = torch.empty((K, N * fb), dtype=torch.uint8, pin_memory=True)
-            h_out = torch.empty((K, N * ob), dtype=torch.uint8, pin_memory=True)
-            h_in.copy_(d_in[:, : N * fb])
-            torch.cuda.synchronize()
-
-            def e2e_step():
-                ses.reset()
-                for f0 in range(0, N, chunk):
-                    n = min(chunk, N - f0)
-                    ses.process_host_into(h_in.data_ptr() + f0 * fb, N * fb, n, h_out.data_ptr() + f0 * ob, N * ob)
-
-            e2e_step()
-            barrier()
-            t0 = time.perf_counter()
-            reps = max(1, min(args.steps, 2))
-            for _ in range(reps):
-                e2e_step()
-            barrier()
-            dt = (time.perf_counter() - t0) / reps
-            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            e2e = dict(value=frames_step / float(tt.item()) / 1e6, unit=UNIT, h2d_bytes_per_step=K * N * fb,
-                       d2h_bytes_per_step=K * N * ob, ms_per_step=float(tt.item()) * 1e3, steps=reps,
-                       how="icw_session_process_host on pinned host buffers; H2D + kernels + D2H inside the timed region",
-                       host_affinity=numa_note)
-            del h_in, h_out
-        except RuntimeError as ex:
-            e2e = dict(value=None, unit=UNIT, error=str(ex)[:200])
+    # ---- the other named configs, same run, same box: the bit-exact batch sharded by stream, the full
+    # graph, and -- where there is more than one GPU -- the time-sharded stream with its NCCL hand-off timed ------------
+    others = {}
+    if not args.no_workloads and args.workload == "c2" and not args.streams and not args.frames:
+        for name in ["c4", "c3"] + (["c5"] if world > 1 else []):
+            try:
+                r = measure(ctx, name, max(3, min(args.steps, 10)), 3, want_e2e=not args.no_e2e, want_parity=not args.no_parity)
+                r.pop("_spec", None)
+                others[name] = r
+            except Exception as ex:
+                others[name] = dict(error=f"{type(ex).__name__}: {ex}"[:300])
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) ------------------------------------
     cpu = None
@@ -431,25 +610,33 @@ def main():
         args.no_cpu = True
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = host_cores()
-        fr = min(N, 480_000)
+        fr = min(head["frames_per_stream"], 480_000)
         spc = max(1, int(12.0e6 // fr))               # ~12 s of single-core work per process
         f, busy, wall, kind = cpu_run(spec, fr, spc, cores)
         cpu = dict(value=f / busy / 1e6, unit=UNIT, cores=cores, kind=kind, cpu=cpu_model(),
                    sample=f"{cores} processes x {spc} fresh streams x {fr} frames of the same chain ({busy:.1f} s busy)")
 
     if rank == 0:
-        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-                    ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+        hil = head["hilbert"]
+        line = dict(metric=METRIC, value=head["value"], unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=head["ms_per_step"], higher_is_better=True, scaling=head["scaling"], vs_baseline=None, dtype="f64",
                     data="synthetic",
-                    parity=dict(hilbert=wl["hilbert"],
-                                note=("exact: bit-exact with the reference (tests/test_gpu_parity.py)" if wl["hilbert"] != "scan" else
+                    parity=dict(hilbert=hil,
+                                note=("exact: bit-exact with the reference (tests/test_gpu_parity.py)" if hil != "scan" else
                                       "scan: analytic signal within 1e-12 of the binary128 evaluation of the reference's filter; "
                                       "everything downstream byte-exact; the reference's own FP64 rounding noise (5e-5 of RMS for the "
-                                      "default design) separates its PCM from ours (tests/test_gpu_scan.py)")),
-                    config=dict(workload=wl["desc"], streams_per_gpu=K, frames_per_stream=N, frames_per_launch=units_per_launch,
-                                hilbert=wl["hilbert"], l2="inputs larger than L2 (per-step input %.1f GB)" % (K * N * fb / 1e9)),
-                    roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks,
-                    kernel_ms={k: v["ms"] / args.steps for k, v in prof.items()})
+                                      "default design) separates its PCM from ours -- counted in parity_check; the bit-exact mode is "
+                                      "workloads.c4 (tests/test_gpu_scan.py)")),
+                    parity_check=head.get("parity_check"),
+                    config=head["config"],
+                    timing=dict(streams_per_gpu=head["streams_this_rank"], frames_per_launch=head["roofline"]["frames_per_launch"],
+                                sharding=head["sharding"], l2=head["l2"]),
+                    roofline=head["roofline"], cpu_baseline=cpu, e2e=head.get("e2e"), gpu_launches=head["gpu_launches"],
+                    clocks=head["clocks"], kernel_ms=head["kernel_ms"])
+        if "handoff_ms" in head:
+            line["handoff_ms"] = head["handoff_ms"]
+        if others:
+            line["workloads"] = others
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -87,7 +87,12 @@ EXPORTS = [
     "icw_mt_words_device", "icw_session_set_taps", "icw_debug_phase_device", "icw_debug_sincos_device", "icw_mt_host_charpoly",
     "icw_mt_host_seq_state", "icw_mt_host_jump_state", "icw_mt_host_jump_state_family", "icw_mt_host_jump_state_product", "icw_mt_host_unit_blocks", "icw_host_scan_chunk_len",
     "icw_session_profile", "icw_session_profile_read", "icw_kernel_class_name", "icw_crc32_device", "icw_crc32_host", "icw_crc32_combine",
+    "icw_pinned_alloc", "icw_pinned_free",
+    "icw_session_boundary_export", "icw_session_boundary_import", "icw_session_seek_closed_form", "icw_comm_unique_id", "icw_comm_init",
+    "icw_comm_destroy", "icw_nccl_version", "icw_session_handoff", "icw_session_reduce_counters", "icw_host_hb_convert",
 ]
+BOUNDARY_DOUBLES = 2 * 2 * MAX_ORD
+COMM_ID_BYTES = 128
 
 _lib = None
 
@@ -152,6 +157,18 @@ def lib() -> C.CDLL:
     L.icw_mt_host_unit_blocks.argtypes = [u64, C.c_int]
     L.icw_mt_host_unit_blocks.restype = u64
     L.icw_host_scan_chunk_len.argtypes = [C.c_int, i64, C.c_int]
+    L.icw_pinned_alloc.argtypes = [sz, P(vp)]
+    L.icw_pinned_free.argtypes = [vp]
+    L.icw_pinned_free.restype = None
+    L.icw_session_boundary_export.argtypes = [vp, C.c_int, vp, P(C.c_int), vp]
+    L.icw_session_boundary_import.argtypes = [vp, C.c_int, vp, C.c_int, vp]
+    L.icw_session_seek_closed_form.argtypes = [vp, C.c_int, i64, P(StreamState)]
+    L.icw_comm_unique_id.argtypes = [C.c_char_p]
+    L.icw_comm_init.argtypes = [C.c_char_p, C.c_int, C.c_int, P(vp)]
+    L.icw_comm_destroy.argtypes = [vp]
+    L.icw_session_handoff.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp]
+    L.icw_session_reduce_counters.argtypes = [vp, vp, vp, P(C.c_uint64 * 2), P(C.c_double * 2)]
+    L.icw_host_hb_convert.argtypes = [C.c_int, C.c_int, P(C.c_double), P(C.c_double)]
     _lib = L
     return L
 

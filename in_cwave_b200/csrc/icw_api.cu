@@ -17,6 +17,7 @@
 #include "icw_mt.h"
 #include "icw_scan.h"
 #include "icw_crc.h"
+#include "icw_comm.h"
 #include "icw_hb_tables.inc"
 #include "icw_ns_tables.inc"
 
@@ -74,6 +75,11 @@ struct icw_engine {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t h2d = nullptr, d2h = nullptr;      // copy streams of the host entry point's pipeline
     cudaEvent_t ev_in[2] = { nullptr, nullptr }, ev_comp[2] = { nullptr, nullptr }, ev_out[2] = { nullptr, nullptr };
+    // engine-wide scratch (analytic, mtw, scan_scratch, ns_pre, checkpoints) is shared by all sessions: a call on a
+    // stream other than the one that used it last first waits for that stream's work (event below)
+    cudaStream_t last_stream = nullptr;
+    bool last_stream_valid = false;
+    cudaEvent_t ev_scratch = nullptr;
     int n_sessions = 0;
     bool dying = false;                 // icw_engine_destroy was called while sessions were alive
     Scratch analytic, mtw[2], ckpt, io_in, io_out, leaf;
@@ -98,6 +104,7 @@ struct icw_session {
     std::vector<uint32_t> mt_seed[2];
     std::vector<uint64_t> mt_drawn[2];
     uint64_t launches = 0;
+    cudaStream_t last_stream = nullptr; // the stream of the most recent process call (NULL: none yet / engine stream)
     int hb_basis = 0;                   // basis of the Hilbert state on the device
     bool hb_live = false;               // that state is not all-zero / has been used
     double *d_tap_bus = nullptr;        // test taps, set through icw_session_set_taps
@@ -295,7 +302,13 @@ static int fold_spec(const icw_chain_spec &sp, DevChain &ch, HbCoef &coef)
     if (q.ns_kind == 2)     // IIR: [order, 2*order) of the table weigh the filter's own outputs
         for (int i = 0; i < q.ns_order; ++i) { q.ns_coef[ICW_NS_MAX_TAPS + i] = q.ns_coef[q.ns_order + i]; }
 
-    // DSP list
+    // DSP list.  First pass: every output plug in range (the feedback analysis below shifts by it)
+    for (int i = 0; i < sp.n_nodes; ++i) {
+        const icw_node &s = sp.nodes[i];
+        if (s.mode < ICW_MODE_MASTER || s.mode > ICW_MODE_MIX) return fail(ICW_E_ARG, "node %d: bad mode %d", i, s.mode);
+        if (s.mode != ICW_MODE_MASTER && (s.n_out < 1 || s.n_out >= ICW_N_PLUGS))
+            return fail(ICW_E_ARG, "node %d: output plug %d out of range", i, s.n_out);
+    }
     uint32_t written = 1u;                                // plug 0 is written by the unpacker
     for (int i = 0; i < sp.n_nodes; ++i) {
         const icw_node &s = sp.nodes[i];
@@ -376,6 +389,7 @@ extern "C" int icw_engine_create(int device, icw_engine **out)
     CK(cudaStreamCreateWithFlags(&e->aux, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->ev_scratch, cudaEventDisableTiming));
     { const char *u = getenv("ICW_UNFUSED"); e->unfused = u && *u == '1'; }
     { const char *u = getenv("ICW_NO_FUSE_MT"); e->no_fuse_mt = u && *u == '1'; }
     *out = e;
@@ -405,7 +419,7 @@ static void engine_free(icw_engine *e)
         for (int i = 0; i < 2; ++i) { cudaEventDestroy(e->ev_in[i]); cudaEventDestroy(e->ev_comp[i]); cudaEventDestroy(e->ev_out[i]); }
         cudaStreamDestroy(e->h2d); cudaStreamDestroy(e->d2h);
     }
-    cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_join);
+    cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_join); cudaEventDestroy(e->ev_scratch);
     cudaStreamDestroy(e->aux);
     cudaStreamDestroy(e->stream);
     delete e;
@@ -491,11 +505,12 @@ extern "C" int icw_session_create(icw_engine *e, const icw_chain_spec *spec, int
     return ICW_OK;
 }
 
+static int quiesce(icw_session *s);
+
 extern "C" void icw_session_destroy(icw_session *s)
 {
     if (!s) return;
-    cudaSetDevice(s->e->device);
-    cudaStreamSynchronize(s->e->stream);
+    quiesce(s);
     if (s->d_streams) cudaFree(s->d_streams);
     for (auto &sp : s->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto ev : s->ev_pool) cudaEventDestroy(ev);
@@ -504,18 +519,28 @@ extern "C" void icw_session_destroy(icw_session *s)
     if (--e->n_sessions == 0 && e->dying) engine_free(e);
 }
 
+// Everything that may still read or write this session's stream states: the engine's own stream and the caller's
+// stream of the last icw_session_process_device (which may be a non-blocking stream that nothing else orders).
+static int quiesce(icw_session *s)
+{
+    CK(cudaSetDevice(s->e->device));
+    if (s->last_stream && s->last_stream != s->e->stream) CK(cudaStreamSynchronize(s->last_stream));
+    CK(cudaStreamSynchronize(s->e->stream));
+    return ICW_OK;
+}
+
 extern "C" int icw_session_sync(icw_session *s)
 {
     if (!s) return fail(ICW_E_ARG, "NULL session");
-    CK(cudaStreamSynchronize(s->e->stream));
-    return ICW_OK;
+    return quiesce(s);
 }
 
 extern "C" int icw_session_get_state(icw_session *s, int k, icw_stream_state *out)
 {
     if (!s || !out || k < 0 || k >= s->n_streams) return fail(ICW_E_ARG, "bad stream index");
     DevStream d;
-    CK(cudaStreamSynchronize(s->e->stream));
+    int rc = quiesce(s);
+    if (rc) return rc;
     CK(cudaMemcpy(&d, s->d_streams + k, sizeof d, cudaMemcpyDeviceToHost));
     from_dev(d, *out);
     out->hb_basis = (uint32_t)s->hb_basis;
@@ -525,16 +550,25 @@ extern "C" int icw_session_get_state(icw_session *s, int k, icw_stream_state *ou
 extern "C" int icw_session_set_state(icw_session *s, int k, const icw_stream_state *in)
 {
     if (!s || !in || k < 0 || k >= s->n_streams) return fail(ICW_E_ARG, "bad stream index");
-    DevStream d;
-    to_dev(*in, d);
-    CK(cudaStreamSynchronize(s->e->stream));
-    CK(cudaMemcpy(s->d_streams + k, &d, sizeof d, cudaMemcpyHostToDevice));
-    for (int c = 0; c < 2; ++c) { s->mt_seed[c][k] = in->mt_seed[c]; s->mt_drawn[c][k] = in->mt_drawn[c]; }
+    // validate before anything is touched: a refused call leaves the stream as it was
     bool any = false;
     for (int c = 0; c < 2 && !any; ++c) for (int f = 0; f < 2 && !any; ++f) for (int i = 0; i < ICW_MAX_ORD; ++i) if (in->hb[c][f][i] != 0.0) { any = true; break; }
     if (any) {
-        if (s->hb_live && s->hb_basis != (int)in->hb_basis)
+        if (in->hb_basis > 1u) return fail(ICW_E_ARG, "stream %d: hb_basis %u is neither 0 (delay line) nor 1 (modal)", k, in->hb_basis);
+        if (s->hb_live && s->hb_basis != (int)in->hb_basis && s->n_streams > 1)
             return fail(ICW_E_ARG, "stream %d: hb_basis %u differs from the session's live Hilbert state basis %d", k, in->hb_basis, s->hb_basis);
+    }
+    int rc = quiesce(s);
+    if (rc) return rc;
+    // what only the kernels keep (re-draw flags, FP_CHECK counters) is not part of the ABI state and stays
+    DevStream d, old;
+    CK(cudaMemcpy(&old, s->d_streams + k, sizeof old, cudaMemcpyDeviceToHost));
+    to_dev(*in, d);
+    d.mt_redraws = old.mt_redraws;
+    memcpy(d.fp_cnt, old.fp_cnt, sizeof d.fp_cnt);
+    CK(cudaMemcpy(s->d_streams + k, &d, sizeof d, cudaMemcpyHostToDevice));
+    for (int c = 0; c < 2; ++c) { s->mt_seed[c][k] = in->mt_seed[c]; s->mt_drawn[c][k] = in->mt_drawn[c]; }
+    if (any) {
         s->hb_basis = (int)in->hb_basis;
         s->hb_live = true;
     }
@@ -544,7 +578,8 @@ extern "C" int icw_session_set_state(icw_session *s, int k, const icw_stream_sta
 static int rewrite_states(icw_session *s, void (*fn)(DevStream &, void *), void *arg)
 {
     std::vector<DevStream> all((size_t)s->n_streams);
-    CK(cudaStreamSynchronize(s->e->stream));
+    int rc = quiesce(s);
+    if (rc) return rc;
     CK(cudaMemcpy(all.data(), s->d_streams, sizeof(DevStream) * all.size(), cudaMemcpyDeviceToHost));
     for (auto &d : all) fn(d, arg);
     CK(cudaMemcpy(s->d_streams, all.data(), sizeof(DevStream) * all.size(), cudaMemcpyHostToDevice));
@@ -606,6 +641,21 @@ extern "C" int icw_session_set_spec(icw_session *s, const icw_chain_spec *spec)
     s->coef = coef;
     return ICW_OK;
 }
+
+// page-locked host memory for the layers above this ABI (they are plain C and do not link the CUDA runtime)
+extern "C" int icw_pinned_alloc(size_t bytes, void **out)
+{
+    if (!out) return fail(ICW_E_ARG, "out is NULL");
+    *out = nullptr;
+    if (!bytes) return ICW_OK;
+    if (cudaHostAlloc(out, bytes, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        *out = nullptr;
+        return fail(ICW_E_NOMEM, "cudaHostAlloc(%zu) failed", bytes);
+    }
+    return ICW_OK;
+}
+extern "C" void icw_pinned_free(void *p) { if (p) cudaFreeHost(p); }
 
 // CRC-32 of a device buffer with the reference's conventions (src/crc32.c:55-108: crc32init / update / final)
 extern "C" int icw_crc32_device(icw_engine *e, const void *d_data, size_t n_bytes, uint32_t *crc_out)
@@ -835,6 +885,23 @@ static int process_group(icw_session *s, int64_t n_frames, const uint8_t *d_in, 
     return ICW_OK;
 }
 
+// every stream's Hilbert memory from the session's live basis to `to_basis` (0 delay line, 1 modal)
+static int convert_basis(icw_session *s, int to_basis)
+{
+    struct Arg { int ft, to, bad; } arg = { s->spec.filter_no, to_basis, 0 };
+    int rc = rewrite_states(s, [](DevStream &d, void *a) {
+        Arg &g = *(Arg *)a;
+        for (int c = 0; c < 2; ++c)
+            for (int f = 0; f < 2; ++f)
+                if (icw_host_hb_convert(g.ft, g.to, d.hb[c][f], d.hb[c][f]) != 0) g.bad = 1;
+        d.hb_basis = (uint32_t)g.to;
+    }, &arg);
+    if (rc) return rc;
+    if (arg.bad) return fail(ICW_E_ARG, "filter state conversion failed for design %d", s->spec.filter_no);
+    s->hb_basis = to_basis;
+    return ICW_OK;
+}
+
 // ---- one API call = begin (checks, dither words for the whole call) + ranges + end ------------------
 struct CallCtx {
     DitherWords all;
@@ -858,22 +925,29 @@ static int call_begin(icw_session *s, int64_t n_total, cudaStream_t st, CallCtx 
     const int K = s->n_streams;
     cx.real_in = !ch.is_complex;
     cx.mode = s->spec.hilbert_mode;
+    if (e->last_stream_valid && e->last_stream != st) CK(cudaStreamWaitEvent(st, e->ev_scratch, 0));
+    if (s->last_stream && s->last_stream != st && s->last_stream != e->last_stream) CK(cudaStreamSynchronize(s->last_stream));
     if (cx.real_in) {
         if (cx.mode != ICW_HILBERT_EXACT && cx.mode != ICW_HILBERT_SCAN) return fail(ICW_E_ARG, "hilbert_mode out of range");
-        if (s->hb_live && s->hb_basis != cx.mode)
-            return fail(ICW_E_UNSUPPORTED, "the streams' Hilbert state is in the %s basis; switching a live stream to %s mode "
-                                           "needs icw_session_reset(ICW_RESET_HILBERT) first (state conversion is not built)",
-                        s->hb_basis ? "modal (scan)" : "delay-line (exact)", cx.mode ? "scan" : "exact");
+        if (s->hb_live && s->hb_basis != cx.mode) {
+            // the filter memory goes over to the other basis (icw_hbconv.cpp: binary128 on the host); the reference
+            // changes filter settings on a live stream as well (src/in_cwave.c:135-191)
+            int rc = convert_basis(s, cx.mode);
+            if (rc) return rc;
+        }
     }
     if (cx.real_in && cx.mode == ICW_HILBERT_SCAN && ch.fp_check)
         return fail(ICW_E_UNSUPPORTED, "FP_CHECK counts exceptional intermediates of the reference's own recurrences: "
                                        "exact Hilbert mode only (the modal scan has different intermediates)");
     // scan mode and the unfused path go through per-frame scratch: bound it by walking the call in groups
-    const bool scratchy = cx.real_in && (cx.mode == ICW_HILBERT_SCAN || e->unfused || ch.fp_check);
-    // one stream: groups as long as the analytic scratch may grow (32 B/frame) -- long groups let the scan use
-    // long chunks (scan_chunk_len); many streams: 2^25 frames over all of them
+    // per-frame scratch: the analytic signal (real input unless the fused exact kernel runs) and, with a noise
+    // shaper, the (value, dither) pairs between the pointwise pass and the serial quantiser -- 32 B/frame each
+    const bool shaped = ch.render.ns_kind != 0;
+    const bool scratchy = (cx.real_in && (cx.mode == ICW_HILBERT_SCAN || e->unfused || ch.fp_check || shaped)) || shaped;
+    // one stream: groups as long as the scratch may grow -- long groups let the scan use long chunks
+    // (scan_chunk_len); many streams: 2^25 frames over ALL of them, never less than one scan tile per stream
     const int64_t seg = !scratchy ? n_total
-                      : K == 1 ? BIG_GROUP : SCAN_SEGMENT / (K > 64 ? 64 : K) / SCAN_L / SCAN_CH * (SCAN_L * SCAN_CH);
+                      : K == 1 ? BIG_GROUP : SCAN_SEGMENT / K / (SCAN_L * SCAN_CH) * (SCAN_L * SCAN_CH);
     cx.step = seg < SCAN_L * SCAN_CH ? SCAN_L * SCAN_CH : seg;
     const int wps = ch.render.words_per_sample;
     // the fused exact kernel reads word buffers; everything else that ends in chain_kernel can make its own
@@ -927,9 +1001,13 @@ static int call_range(icw_session *s, CallCtx &cx, int64_t f0, int64_t n, const 
     return ICW_OK;
 }
 
-static void call_end(icw_session *s, const CallCtx &cx)
+static void call_end(icw_session *s, const CallCtx &cx, cudaStream_t st)
 {
     if (cx.real_in) { s->hb_basis = cx.mode; s->hb_live = true; }
+    icw_engine *e = s->e;
+    cudaEventRecord(e->ev_scratch, st);
+    e->last_stream = st; e->last_stream_valid = true;
+    s->last_stream = st;
 }
 
 static void note_alignment(icw_session *s, const void *d_in, size_t in_stride)
@@ -958,7 +1036,7 @@ extern "C" int icw_session_process_device(icw_session *s, int64_t n_frames, cons
     if (rc) return rc;
     rc = call_range(s, cx, 0, n_frames, (const uint8_t *)d_in, in_stride, (uint8_t *)d_out, out_stride, st);
     if (rc) return rc;
-    call_end(s, cx);
+    call_end(s, cx, st);
     return ICW_OK;
 }
 
@@ -1030,7 +1108,7 @@ extern "C" int icw_session_process_host(icw_session *s, int64_t n_frames, const 
     }
     CK(cudaStreamSynchronize(e->d2h));
     CK(cudaStreamSynchronize(st));
-    call_end(s, cx);
+    call_end(s, cx, st);
     return ICW_OK;
 }
 
@@ -1068,7 +1146,8 @@ extern "C" int icw_session_stats(icw_session *s, icw_stats *out)
 {
     if (!s || !out) return fail(ICW_E_ARG, "NULL argument");
     std::vector<DevStream> all((size_t)s->n_streams);
-    CK(cudaStreamSynchronize(s->e->stream));
+    int rc = quiesce(s);
+    if (rc) return rc;
     CK(cudaMemcpy(all.data(), s->d_streams, sizeof(DevStream) * all.size(), cudaMemcpyDeviceToHost));
     memset(out, 0, sizeof *out);
     double pk[2] = { 0.0, 0.0 };
@@ -1090,7 +1169,7 @@ extern "C" int icw_session_fp_stats(icw_session *s, int stream, uint32_t out[4][
 {
     if (!s || !out) return fail(ICW_E_ARG, "NULL argument");
     if (stream < 0 || stream >= s->n_streams) return fail(ICW_E_ARG, "stream index out of range");
-    CK(cudaStreamSynchronize(s->e->stream));
+    { int rc = quiesce(s); if (rc) return rc; }
     CK(cudaMemcpy(out, (const uint8_t *)(s->d_streams + stream) + offsetof(DevStream, fp_cnt), sizeof(uint32_t) * 4 * 7,
                   cudaMemcpyDeviceToHost));
     return ICW_OK;
@@ -1214,5 +1293,151 @@ extern "C" int icw_debug_phase_device(icw_engine *e, const icw_chain_spec *spec,
     CK(cudaSetDevice(e->device));
     CK(launch_phase_leaf(ch, n0, n, scaled_freq(fabs(freq_hz), ch.is_frmod_scaled), d_out, e->stream));
     CK(cudaStreamSynchronize(e->stream));
+    return ICW_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// time-sharded streams: boundary state on the device, NCCL hand-off (icw_comm.cu)
+// ---------------------------------------------------------------------------------------------
+static cudaStream_t pick_stream(icw_session *s, void *cuda_stream) { return cuda_stream ? (cudaStream_t)cuda_stream : s->e->stream; }
+
+extern "C" int icw_session_boundary_export(icw_session *s, int stream, double *d_state, int *basis_out, void *cuda_stream)
+{
+    if (!s || !d_state || stream < 0 || stream >= s->n_streams) return fail(ICW_E_ARG, "bad argument");
+    CK(cudaSetDevice(s->e->device));
+    cudaStream_t st = pick_stream(s, cuda_stream);
+    if (s->last_stream && s->last_stream != st) CK(cudaStreamSynchronize(s->last_stream));
+    CK(cudaMemcpyAsync(d_state, (const uint8_t *)(s->d_streams + stream) + offsetof(DevStream, hb), sizeof(double) * ICW_BOUNDARY_DOUBLES,
+                       cudaMemcpyDeviceToDevice, st));
+    if (basis_out) *basis_out = s->hb_basis;
+    s->last_stream = st;
+    return ICW_OK;
+}
+
+extern "C" int icw_session_boundary_import(icw_session *s, int stream, const double *d_state, int basis, void *cuda_stream)
+{
+    if (!s || !d_state || stream < 0 || stream >= s->n_streams || (basis != 0 && basis != 1)) return fail(ICW_E_ARG, "bad argument");
+    if (s->hb_live && s->hb_basis != basis && s->n_streams > 1)
+        return fail(ICW_E_ARG, "basis %d differs from the session's live Hilbert state basis %d", basis, s->hb_basis);
+    CK(cudaSetDevice(s->e->device));
+    cudaStream_t st = pick_stream(s, cuda_stream);
+    if (s->last_stream && s->last_stream != st) CK(cudaStreamSynchronize(s->last_stream));
+    CK(cudaMemcpyAsync((uint8_t *)(s->d_streams + stream) + offsetof(DevStream, hb), d_state, sizeof(double) * ICW_BOUNDARY_DOUBLES,
+                       cudaMemcpyDeviceToDevice, st));
+    s->hb_basis = basis;
+    s->hb_live = true;
+    s->last_stream = st;
+    return ICW_OK;
+}
+
+extern "C" int icw_session_seek_closed_form(icw_session *s, int k, int64_t frames, const icw_stream_state *base)
+{
+    if (!s || k < 0 || k >= s->n_streams || frames < 0) return fail(ICW_E_ARG, "bad argument");
+    icw_stream_state b;
+    if (base) b = *base; else icw_default_state(&b);
+    int rc = quiesce(s);
+    if (rc) return rc;
+    DevStream d;
+    CK(cudaMemcpy(&d, s->d_streams + k, sizeof d, cudaMemcpyDeviceToHost));
+    const uint64_t wps = (uint64_t)s->ch.render.words_per_sample;
+    if (s->ch.is_frmod_scaled) d.n_frame = (b.n_frame + (uint64_t)frames % s->ch.scale_sr) % s->ch.scale_sr;
+    else d.n_frame = b.n_frame + (uint64_t)frames;
+    d.pos = b.pos + frames;
+    for (int c = 0; c < 2; ++c) {
+        d.quad[c] = (uint32_t)((b.quad[c] + (uint64_t)frames) & 3u);
+        d.mt_seed[c] = b.mt_seed[c];
+        d.mt_drawn[c] = b.mt_drawn[c] + (uint64_t)frames * wps;
+        s->mt_seed[c][k] = d.mt_seed[c];
+        s->mt_drawn[c][k] = d.mt_drawn[c];
+    }
+    if (s->ch.render.render_type == ICW_RENDER_STPDF && frames > 0) {
+        // sloped TPDF carries the previous sample's first draw (src/sound_render.c:729): regenerate it from the
+        // generator at draw (frames - 1) * wps
+        for (int c = 0; c < 2; ++c) {
+            rc = s->e->leaf.reserve(2 * sizeof(uint32_t));
+            if (rc) return rc;
+            uint64_t launches = 0;
+            rc = s->e->mt.generate(d.mt_seed[c], d.mt_drawn[c] - wps, 2, (uint32_t *)s->e->leaf.p, s->e->sm_count, s->e->stream, &launches);
+            if (rc) return fail(rc, "%s", s->e->mt.error());
+            uint32_t w[2];
+            CK(cudaMemcpyAsync(w, s->e->leaf.p, sizeof w, cudaMemcpyDeviceToHost, s->e->stream));
+            CK(cudaStreamSynchronize(s->e->stream));
+            const uint32_t a = w[0] >> 5, bb = w[1] >> 6;             // mtrnd_gen_dsemi / dsopen, src/mt_jrnd.c:218-256
+            d.prev_rnd[c] = ((double)a * 67108864.0 + (double)bb) * (1.0 / 9007199254740992.0) * 2.0 - 1.0;
+        }
+    }
+    CK(cudaMemcpy(s->d_streams + k, &d, sizeof d, cudaMemcpyHostToDevice));
+    return ICW_OK;
+}
+
+extern "C" int icw_comm_unique_id(unsigned char id[ICW_COMM_ID_BYTES])
+{
+    std::string err;
+    int rc = comm_unique_id(id, err);
+    return rc ? fail(rc == -3 ? ICW_E_UNSUPPORTED : ICW_E_CUDA, "%s", err.c_str()) : ICW_OK;
+}
+extern "C" int icw_comm_init(const unsigned char id[ICW_COMM_ID_BYTES], int rank, int world, void **comm_out)
+{
+    if (!comm_out || world < 1 || rank < 0 || rank >= world) return fail(ICW_E_ARG, "bad argument");
+    std::string err;
+    int rc = comm_init(id, rank, world, comm_out, err);
+    return rc ? fail(rc == -3 ? ICW_E_UNSUPPORTED : ICW_E_CUDA, "%s", err.c_str()) : ICW_OK;
+}
+extern "C" int icw_comm_destroy(void *comm)
+{
+    std::string err;
+    int rc = comm_destroy(comm, err);
+    return rc ? fail(rc == -3 ? ICW_E_UNSUPPORTED : ICW_E_CUDA, "%s", err.c_str()) : ICW_OK;
+}
+extern "C" int icw_nccl_version(void) { return nccl_version(); }
+
+extern "C" int icw_session_handoff(icw_session *from, icw_session *to, void *comm, int rank, int world, void *cuda_stream)
+{
+    if (!comm || world < 1 || rank < 0 || rank >= world) return fail(ICW_E_ARG, "bad argument");
+    if (rank + 1 < world && !from) return fail(ICW_E_ARG, "rank %d of %d has a right neighbour but no state to send", rank, world);
+    if (rank > 0 && !to) return fail(ICW_E_ARG, "rank %d has a left neighbour but no session to receive into", rank);
+    icw_session *any = from ? from : to;
+    if (!any) return ICW_OK;                                // world == 1
+    if (from && from->hb_live && from->hb_basis != ICW_HILBERT_SCAN) {
+        int rc = convert_basis(from, ICW_HILBERT_SCAN);     // a shard may have been run in exact mode: send modal states
+        if (rc) return rc;
+    }
+    CK(cudaSetDevice(any->e->device));
+    cudaStream_t st = pick_stream(any, cuda_stream);
+    for (icw_session *x : { from, to })
+        if (x && x->last_stream && x->last_stream != st) CK(cudaStreamSynchronize(x->last_stream));
+    const double *snd = (from && rank + 1 < world) ? (const double *)((const uint8_t *)from->d_streams + offsetof(DevStream, hb)) : nullptr;
+    double *rcv = (to && rank > 0) ? (double *)((uint8_t *)to->d_streams + offsetof(DevStream, hb)) : nullptr;
+    std::string err;
+    int rc = comm_shift_right(comm, rank, world, snd, rcv, ICW_BOUNDARY_DOUBLES, st, err);
+    if (rc) return fail(rc == -3 ? ICW_E_UNSUPPORTED : ICW_E_CUDA, "%s", err.c_str());
+    if (rcv) { to->hb_basis = ICW_HILBERT_SCAN; to->hb_live = true; to->last_stream = st; }
+    if (from) from->last_stream = st;
+    return ICW_OK;
+}
+
+extern "C" int icw_session_reduce_counters(icw_session *s, void *comm, void *cuda_stream, uint64_t clips_out[2], double peak_db_out[2])
+{
+    if (!s || !comm || !clips_out || !peak_db_out) return fail(ICW_E_ARG, "bad argument");
+    icw_stats mine;
+    int rc = icw_session_stats(s, &mine);                   // sums / maxima over this rank's streams (synchronises)
+    if (rc) return rc;
+    std::vector<DevStream> all((size_t)s->n_streams);
+    CK(cudaMemcpy(all.data(), s->d_streams, sizeof(DevStream) * all.size(), cudaMemcpyDeviceToHost));
+    struct { unsigned long long clips[2]; double peak[2]; } h;
+    h.clips[0] = mine.clips[0]; h.clips[1] = mine.clips[1];
+    h.peak[0] = h.peak[1] = 0.0;
+    for (const auto &d : all) { h.peak[0] = std::max(h.peak[0], d.peak[0]); h.peak[1] = std::max(h.peak[1], d.peak[1]); }
+    rc = s->e->leaf.reserve(sizeof h);
+    if (rc) return rc;
+    cudaStream_t st = pick_stream(s, cuda_stream);
+    CK(cudaMemcpyAsync(s->e->leaf.p, &h, sizeof h, cudaMemcpyHostToDevice, st));
+    std::string err;
+    rc = comm_reduce(comm, (unsigned long long *)s->e->leaf.p, 2, (double *)((uint8_t *)s->e->leaf.p + 16), 2, st, err);
+    if (rc) return fail(rc == -3 ? ICW_E_UNSUPPORTED : ICW_E_CUDA, "%s", err.c_str());
+    CK(cudaMemcpyAsync(&h, s->e->leaf.p, sizeof h, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    clips_out[0] = h.clips[0]; clips_out[1] = h.clips[1];
+    peak_db_out[0] = icw_peak_db(h.peak[0]); peak_db_out[1] = icw_peak_db(h.peak[1]);
     return ICW_OK;
 }

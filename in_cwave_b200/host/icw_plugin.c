@@ -3,13 +3,16 @@
 #define _FILE_OFFSET_BITS 64
 #define _POSIX_C_SOURCE 200809L
 #define _DEFAULT_SOURCE
+#include <time.h>
 #include "icw_plugin.h"
 
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <strings.h>
 #include <sys/types.h>
+#include <unistd.h>
 
 #define MIN_FILE_SAMPLES 2              /* reference src/in_cwave.h:315 */
 #define MAX_FS_SRC 2000000u             /* reference src/in_cwave.h:160 */
@@ -22,6 +25,18 @@ typedef struct reader {
     int64_t  pos_samples, pos_tail;     /* like XWAVE_READER, reference src/in_cwave.h:394-395 */
 } reader;
 
+/* One read-ahead block: `to_read` frames from the file at byte offset `file_off`, then `to_fill` frames of
+ * virtual silence, in a page-locked buffer (so the H2D copy of icw_session_process_host is a real
+ * asynchronous DMA).  Two of them: while the GPU renders one, the reader thread fills the other. */
+typedef struct block {
+    unsigned char *buf;
+    size_t         cap;
+    int64_t        pos_samples, pos_tail;   /* reader position the block starts at */
+    int64_t        to_read, to_fill;
+    int64_t        file_off;
+    int            ok;                       /* the file gave every byte asked for */
+} block;
+
 static struct {
     int             configured;
     icw_chain_spec  chain;
@@ -31,11 +46,25 @@ static struct {
     reader          rd;
     int             open;
     int             out_frame_bytes;
-    /* read-ahead: rendered PCM not yet handed to the host */
-    unsigned char  *in_buf, *pcm_buf;
-    size_t          in_cap, pcm_cap;
-    int64_t         pcm_have, pcm_taken;    /* bytes */
-} P;
+    /* read-ahead.  The DSP state on the device stands at the END of the rendered block; `snap` is the state
+     * at its START, so that a seek or an early close can put the stream back to exactly the frames the host
+     * took (the reference advances its MOD_CONTEXT only by what each getData asked for, src/transcode.c:82-100) */
+    block           blk[2];
+    int             cur;                     /* block whose PCM is being served */
+    int             pf_valid;                /* blk[cur ^ 1] holds (or is receiving) the block after `cur` */
+    unsigned char  *pcm_buf;
+    size_t          pcm_cap;
+    int64_t         pcm_have, pcm_taken;     /* bytes */
+    int64_t         blk_frames;              /* frames rendered from blk[cur] */
+    icw_stream_state snap;
+    /* reader thread */
+    pthread_t       th;
+    int             th_up, th_quit;
+    pthread_mutex_t mu;
+    pthread_cond_t  cv_req, cv_done;
+    int             req_pending, req_blk, req_fd;
+    icwp_iostats    io;
+} P = { .mu = PTHREAD_MUTEX_INITIALIZER, .cv_req = PTHREAD_COND_INITIALIZER, .cv_done = PTHREAD_COND_INITIALIZER };
 
 static void ensure_defaults(void);
 
@@ -272,10 +301,23 @@ int icwp_configure(const icw_chain_spec *chain, const icwp_options *opt)
     return ICW_OK;
 }
 
+static void reader_stop(void);
+static void settle(void);
+
 void icwp_reset(void)
 {
     if (P.open) winampGetExtendedRead_close((intptr_t)&P);
     if (P.session) { icw_session_destroy(P.session); P.session = NULL; }
+    reader_stop();
+    for (int i = 0; i < 2; ++i) { icw_pinned_free(P.blk[i].buf); P.blk[i].buf = NULL; P.blk[i].cap = 0; }
+    icw_pinned_free(P.pcm_buf); P.pcm_buf = NULL; P.pcm_cap = 0;
+}
+
+int icwp_io_stats(icwp_iostats *out, int reset)
+{
+    if (out) *out = P.io;
+    if (reset) memset(&P.io, 0, sizeof P.io);
+    return ICW_OK;
 }
 
 int icwp_stats(icw_stats *out)
@@ -315,9 +357,9 @@ intptr_t winampGetExtendedRead_open(const char *filename, int *size, int *bps, i
     if (P.opt.clr_nframe_trk) reset |= ICW_RESET_FRAMECNT;      /* src/in_cwave.c:226-229 */
     if (P.opt.clr_hilb_trk) reset |= ICW_RESET_HILBERT;
     if (icw_session_reset(P.session, reset) != ICW_OK) goto fail;
-    if (fseeko(P.rd.fp, (off_t)P.rd.fi.offset_data, SEEK_SET)) goto fail;
     P.rd.pos_samples = P.rd.pos_tail = 0;
     P.pcm_have = P.pcm_taken = 0;
+    P.pf_valid = 0; P.cur = 0; P.blk_frames = 0;
     P.open = 1;
     *nch = 2;
     *srate = (int)P.rd.fi.sample_rate;
@@ -330,39 +372,197 @@ fail:
     return 0;
 }
 
-/* read up to `want` frames (file, then virtual silence) and render them; returns frames rendered */
-static int64_t refill(int64_t want)
+/* ---- overlapped file I/O (the step before the path: reference src/xwave_reader.c:838-904) ----------------
+ * The reference reads read_quant frames with one ReadFile, then computes them, in series.  Here a reader
+ * thread preads block k+1 into page-locked memory while block k is on the GPU and its PCM is being handed
+ * to the host; only the main thread ever touches the DSP state. */
+static double now_s(void)
 {
-    reader *r = &P.rd;
-    int64_t to_read = 0, to_fill = 0, n;
-    size_t need_in, need_out;
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
 
-    if (r->pos_samples < r->fi.n_samples) {
-        to_read = r->fi.n_samples - r->pos_samples;
+static int fill_block(block *b, int fd, int silence_byte, int frame_bytes)
+{
+    size_t want = (size_t)b->to_read * (size_t)frame_bytes, got = 0;
+    while (got < want) {
+        ssize_t r = pread(fd, b->buf + got, want - got, (off_t)(b->file_off + (int64_t)got));
+        if (r <= 0) return 0;                       /* short read == broken file == end, as in the reference */
+        got += (size_t)r;
+    }
+    if (b->to_fill)     /* silence: 0x80 for unsigned 8-bit, zero bits otherwise (src/xwave_reader.c:100-105) */
+        memset(b->buf + want, silence_byte, (size_t)b->to_fill * (size_t)frame_bytes);
+    return 1;
+}
+
+static void *reader_main(void *arg)
+{
+    (void)arg;
+    pthread_mutex_lock(&P.mu);
+    for (;;) {
+        while (!P.req_pending && !P.th_quit) pthread_cond_wait(&P.cv_req, &P.mu);
+        if (P.th_quit) break;
+        block *b = &P.blk[P.req_blk];
+        int fd = P.req_fd, sil = P.rd.fi.fmt == ICW_FMT_WAV_U8 ? 0x80 : 0, fb = P.rd.frame_bytes;
+        pthread_mutex_unlock(&P.mu);
+        double t0 = now_s();
+        int ok = fill_block(b, fd, sil, fb);
+        double dt = now_s() - t0;
+        pthread_mutex_lock(&P.mu);
+        b->ok = ok;
+        P.io.read_s += dt;
+        P.io.read_bytes += (uint64_t)b->to_read * (uint64_t)fb;
+        P.req_pending = 0;
+        pthread_cond_broadcast(&P.cv_done);
+    }
+    pthread_mutex_unlock(&P.mu);
+    return NULL;
+}
+
+static void reader_wait(void)
+{
+    pthread_mutex_lock(&P.mu);
+    while (P.req_pending) pthread_cond_wait(&P.cv_done, &P.mu);
+    pthread_mutex_unlock(&P.mu);
+}
+
+static void reader_stop(void)
+{
+    if (!P.th_up) return;
+    reader_wait();
+    pthread_mutex_lock(&P.mu);
+    P.th_quit = 1;
+    pthread_cond_broadcast(&P.cv_req);
+    pthread_mutex_unlock(&P.mu);
+    pthread_join(P.th, NULL);
+    P.th_up = 0; P.th_quit = 0;
+}
+
+/* what xwave_read_samples would take next from position (ps, pt): frames from the file, then silence */
+static int64_t plan_block(block *b, int64_t ps, int64_t pt, int64_t want)
+{
+    const reader *r = &P.rd;
+    int64_t to_read = 0, to_fill = 0;
+    if (ps < r->fi.n_samples) {
+        to_read = r->fi.n_samples - ps;
         if (to_read > want) to_read = want;
     }
     if (to_read < want && r->fi.n_tail) {
-        to_fill = r->fi.n_tail - r->pos_tail;
+        to_fill = r->fi.n_tail - pt;
         if (to_fill > want - to_read) to_fill = want - to_read;
     }
-    n = to_read + to_fill;
-    if (n <= 0) return 0;
-    need_in = (size_t)n * r->frame_bytes;
-    need_out = (size_t)n * P.out_frame_bytes;
-    if (need_in > P.in_cap) { free(P.in_buf); P.in_buf = malloc(need_in); P.in_cap = P.in_buf ? need_in : 0; }
-    if (need_out > P.pcm_cap) { free(P.pcm_buf); P.pcm_buf = malloc(need_out); P.pcm_cap = P.pcm_buf ? need_out : 0; }
-    if (!P.in_buf || !P.pcm_buf) return 0;
-    if (to_read && fread(P.in_buf, (size_t)r->frame_bytes, (size_t)to_read, r->fp) != (size_t)to_read)
-        return 0;                                   /* short read == broken file == end, as in the reference */
-    if (to_fill) {
-        /* silence: 0x80 for unsigned 8-bit, zero bits otherwise (src/xwave_reader.c:100-105) */
-        memset(P.in_buf + (size_t)to_read * r->frame_bytes, r->fi.fmt == ICW_FMT_WAV_U8 ? 0x80 : 0,
-               (size_t)to_fill * r->frame_bytes);
+    b->pos_samples = ps; b->pos_tail = pt;
+    b->to_read = to_read; b->to_fill = to_fill;
+    b->file_off = r->fi.offset_data + ps * r->frame_bytes;
+    b->ok = 0;
+    return to_read + to_fill;
+}
+
+static int block_reserve(block *b, size_t need)
+{
+    if (need <= b->cap) return 1;
+    icw_pinned_free(b->buf);
+    b->buf = NULL; b->cap = 0;
+    if (icw_pinned_alloc(need, (void **)&b->buf) != ICW_OK) return 0;
+    b->cap = need;
+    return 1;
+}
+
+/* hand blk[i] to the reader thread (started on first use) */
+static int reader_submit(int i)
+{
+    if (!P.th_up) {
+        if (pthread_create(&P.th, NULL, reader_main, NULL)) return 0;
+        P.th_up = 1;
     }
-    if (icw_session_process_host(P.session, n, P.in_buf, 0, P.pcm_buf, 0) != ICW_OK) return 0;
-    r->pos_samples += to_read;
-    r->pos_tail += to_fill;
+    pthread_mutex_lock(&P.mu);
+    P.req_blk = i; P.req_fd = fileno(P.rd.fp); P.req_pending = 1;
+    pthread_cond_broadcast(&P.cv_req);
+    pthread_mutex_unlock(&P.mu);
+    return 1;
+}
+
+/* render the next block of up to `want` frames from the reader position; returns frames rendered */
+static int64_t refill(int64_t want)
+{
+    reader *r = &P.rd;
+    block *b;
+    int64_t n, n_next;
+    size_t need_out;
+    double t0;
+
+    if (P.pf_valid && P.blk[P.cur ^ 1].pos_samples == r->pos_samples && P.blk[P.cur ^ 1].pos_tail == r->pos_tail) {
+        t0 = now_s();
+        reader_wait();                              /* usually done long ago */
+        P.io.wait_s += now_s() - t0;
+        P.cur ^= 1;
+        b = &P.blk[P.cur];
+        n = b->to_read + b->to_fill;
+        P.io.blocks_prefetched++;
+    } else {
+        reader_wait();                              /* a prefetch for another position (seek): let it finish, drop it */
+        b = &P.blk[P.cur];
+        n = plan_block(b, r->pos_samples, r->pos_tail, want);
+        if (n <= 0) { P.pf_valid = 0; return 0; }
+        if (!block_reserve(b, (size_t)n * r->frame_bytes)) return 0;
+        t0 = now_s();
+        b->ok = fill_block(b, fileno(r->fp), r->fi.fmt == ICW_FMT_WAV_U8 ? 0x80 : 0, r->frame_bytes);
+        P.io.read_s += now_s() - t0;
+        P.io.read_bytes += (uint64_t)b->to_read * (uint64_t)r->frame_bytes;
+        P.io.blocks_sync++;
+    }
+    P.pf_valid = 0;
+    if (n <= 0 || !b->ok) return 0;
+    /* the block after this one goes to the reader thread before the GPU gets this one */
+    {
+        block *nb = &P.blk[P.cur ^ 1];
+        n_next = plan_block(nb, b->pos_samples + b->to_read, b->pos_tail + b->to_fill, want);
+        if (n_next > 0 && nb->to_read > 0 && block_reserve(nb, (size_t)n_next * r->frame_bytes) && reader_submit(P.cur ^ 1))
+            P.pf_valid = 1;
+        else if (n_next > 0 && nb->to_read == 0 && block_reserve(nb, (size_t)n_next * r->frame_bytes)) {
+            nb->ok = fill_block(nb, -1, r->fi.fmt == ICW_FMT_WAV_U8 ? 0x80 : 0, r->frame_bytes);   /* silence only */
+            P.pf_valid = 1;
+        }
+    }
+    need_out = (size_t)n * P.out_frame_bytes;
+    if (need_out > P.pcm_cap) {
+        icw_pinned_free(P.pcm_buf);
+        P.pcm_buf = NULL; P.pcm_cap = 0;
+        if (icw_pinned_alloc(need_out, (void **)&P.pcm_buf) != ICW_OK) return 0;
+        P.pcm_cap = need_out;
+    }
+    if (icw_session_get_state(P.session, 0, &P.snap) != ICW_OK) return 0;
+    t0 = now_s();
+    if (icw_session_process_host(P.session, n, b->buf, 0, P.pcm_buf, 0) != ICW_OK) return 0;
+    P.io.gpu_s += now_s() - t0;
+    P.io.frames += (uint64_t)n;
+    r->pos_samples += b->to_read;
+    r->pos_tail += b->to_fill;
+    P.blk_frames = n;
     return n;
+}
+
+/* Put the DSP state where the HOST is: rendered-but-unserved frames are un-done by restoring the state the
+ * block started from and running only the frames that were handed out again (their input is still in
+ * blk[cur]).  The reference never runs ahead of getData (src/transcode.c:82-100), so after this the frame
+ * counter, Hilbert memory, dither stream and clip/peak counters are the reference's. */
+static void settle(void)
+{
+    int64_t served;
+    if (!P.session || P.pcm_taken >= P.pcm_have) { P.pcm_have = P.pcm_taken = 0; return; }
+    served = P.pcm_taken / P.out_frame_bytes;
+    if (icw_session_set_state(P.session, 0, &P.snap) == ICW_OK && served > 0)
+        icw_session_process_host(P.session, served, P.blk[P.cur].buf, 0, P.pcm_buf, 0);
+    /* the reader stands after the served frames too */
+    {
+        const block *b = &P.blk[P.cur];
+        int64_t from_file = served < b->to_read ? served : b->to_read;
+        P.rd.pos_samples = b->pos_samples + from_file;
+        P.rd.pos_tail = b->pos_tail + (served - from_file);
+    }
+    P.io.resettles++;
+    P.pcm_have = P.pcm_taken = 0;
 }
 
 intptr_t winampGetExtendedRead_getData(intptr_t handle, char *dest, int len, int *killswitch)
@@ -394,15 +594,15 @@ int winampGetExtendedRead_setTime(intptr_t handle, int decode_pos_ms)
     int64_t total, pos;
     icw_stream_state st;
     if ((void *)handle != (void *)&P || !P.open) return 0;
+    settle();                                       /* un-served read-ahead is dropped, like the reader's buffer */
     total = r->fi.n_samples + r->fi.n_tail;
     pos = (int64_t)decode_pos_ms * (int64_t)r->fi.sample_rate / 1000;
     if (pos > total) pos = total;
     if (pos < 0) pos = 0;
     if (pos <= r->fi.n_samples) { r->pos_samples = pos; r->pos_tail = 0; }
     else { r->pos_samples = r->fi.n_samples; r->pos_tail = pos - r->fi.n_samples; }
-    if (fseeko(r->fp, (off_t)(r->fi.offset_data + r->pos_samples * r->frame_bytes), SEEK_SET)) return 0;
-    P.pcm_have = P.pcm_taken = 0;                   /* un-served read-ahead is dropped, like the reader's buffer */
-    /* the fades follow the absolute file position (src/xwave_reader.c:923) */
+    /* the fades follow the absolute file position (src/xwave_reader.c:923); nothing else of the context moves
+     * (xwave_seek_samples, src/xwave_reader.c:782-808) */
     if (icw_session_get_state(P.session, 0, &st) != ICW_OK) return 0;
     st.pos = pos;
     return icw_session_set_state(P.session, 0, &st) == ICW_OK;
@@ -411,6 +611,9 @@ int winampGetExtendedRead_setTime(intptr_t handle, int decode_pos_ms)
 void winampGetExtendedRead_close(intptr_t handle)
 {
     if ((void *)handle != (void *)&P || !P.open) return;
+    settle();                                       /* the next file continues from what the host took */
+    reader_wait();
+    P.pf_valid = 0;
     fclose(P.rd.fp);
     P.rd.fp = NULL;
     P.open = 0;

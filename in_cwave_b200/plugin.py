@@ -11,13 +11,19 @@ from . import _abi, spec as _spec
 PLUGIN_PATH = Path(__file__).resolve().parent / "libicw_plugin.so"
 EXPORTS = ["winampGetExtendedRead_open", "winampGetExtendedRead_getData", "winampGetExtendedRead_setTime",
            "winampGetExtendedRead_close", "icwp_configure", "icwp_reset", "icwp_stats", "icwp_probe",
-           "icwp_load_config", "icwp_save_config", "icwp_check_cwave"]
+           "icwp_load_config", "icwp_save_config", "icwp_check_cwave", "icwp_io_stats"]
 
 
 class Options(C.Structure):
     _fields_ = [("sec_align", C.c_uint), ("fade_in_ms", C.c_uint), ("fade_out_ms", C.c_uint),
                 ("clr_nframe_trk", C.c_int), ("clr_hilb_trk", C.c_int), ("device", C.c_int),
                 ("readahead_frames", C.c_int64)]
+
+
+class IoStats(C.Structure):
+    _fields_ = [("read_s", C.c_double), ("wait_s", C.c_double), ("gpu_s", C.c_double), ("read_bytes", C.c_uint64),
+                ("frames", C.c_uint64), ("blocks_prefetched", C.c_uint64), ("blocks_sync", C.c_uint64),
+                ("resettles", C.c_uint64)]
 
 
 class FileInfo(C.Structure):
@@ -47,6 +53,7 @@ def lib() -> C.CDLL:
         L.icwp_configure.argtypes = [C.POINTER(_abi.ChainSpecC), C.POINTER(Options)]
         L.icwp_reset.restype = None
         L.icwp_stats.argtypes = [C.POINTER(_abi.Stats)]
+        L.icwp_io_stats.argtypes = [C.POINTER(IoStats), C.c_int]
         L.icwp_probe.argtypes = [C.c_char_p, C.POINTER(Options), C.POINTER(FileInfo)]
         L.icwp_check_cwave.argtypes = [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), ip]
         L.icwp_load_config.argtypes = [C.c_char_p, C.POINTER(_abi.ChainSpecC), C.POINTER(Options)]
@@ -83,6 +90,13 @@ def check_cwave(path: str):
     calc, filec, has = C.c_uint32(0), C.c_uint32(0), C.c_int(0)
     ok = lib().icwp_check_cwave(str(path).encode(), C.byref(calc), C.byref(filec), C.byref(has))
     return bool(ok), int(calc.value), int(filec.value), bool(has.value)
+
+
+def io_stats(reset: bool = False) -> dict:
+    """How the overlapped reader did since the last reset (include/icw_plugin.h icwp_iostats)."""
+    st = IoStats()
+    lib().icwp_io_stats(C.byref(st), int(reset))
+    return {k: getattr(st, k) for k, _ in IoStats._fields_}
 
 
 def probe(path: str, **opt):

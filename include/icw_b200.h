@@ -12,6 +12,10 @@
  * DSP LIST is the modulator graph; a STREAM is one file played through one fresh MOD_CONTEXT.
  *
  * Threading: one icw_engine per process and GPU; calls on one session must not overlap.
+ * Streams: icw_session_process_device is asynchronous on the caller's stream.  Every state accessor
+ * (get/set_state, reset, set_spec, stats, fp_stats, sync, destroy) first waits for the engine's own stream
+ * AND for the stream of the session's last process call; scratch shared between sessions of one engine is
+ * ordered across streams by an event, so sessions may use different streams.
  * Errors: every int-returning call gives ICW_OK (0) or a negative ICW_E_* code and leaves a
  * message in icw_last_error().  There is NO CPU fallback anywhere behind this header.
  */
@@ -59,7 +63,8 @@ enum { ICW_RENDER_ROUND = 0, ICW_RENDER_RPDF = 1, ICW_RENDER_TPDF = 2, ICW_RENDE
 enum {
     ICW_HILBERT_EXACT = 0,      /* the reference's own operation order; bit-exact; serial per stream */
     ICW_HILBERT_SCAN = 1        /* modal block scan; time-parallel; differs from the reference by
-                                   the reference's own rounding noise (DESIGN.md "numerics") */
+                                   the reference's own rounding noise (DESIGN.md "numerics").  A live stream may
+                                   switch modes: its filter memory is converted between the bases (icw_host_hb_convert) */
 };
 
 /* One DSP-list node in EXECUTION order (the reference walks its list tail -> head, so the
@@ -149,6 +154,11 @@ double icw_peak_db(double peak_linear);
 
 int  icw_engine_create(int device, icw_engine **out);
 void icw_engine_destroy(icw_engine *e);
+/* page-locked host memory (cudaHostAlloc) for callers that are plain C: buffers handed to
+ * icw_session_process_host from it move by asynchronous DMA and overlap the kernels; stands where the
+ * reference's reader mallocs its read buffer (src/xwave_reader.c:822-835) */
+int  icw_pinned_alloc(size_t bytes, void **out);
+void icw_pinned_free(void *p);
 
 /* K independent streams sharing one spec; stands in for K fresh MOD_CONTEXTs
  * (src/in_cwave.c:46-80) plus amod_init (src/adv_modulator.c:216-331). */
@@ -209,6 +219,40 @@ int  icw_mt_words_device(icw_engine *e, uint32_t seed, uint64_t skip, int64_t n,
 int  icw_crc32_device(icw_engine *e, const void *d_data, size_t n_bytes, uint32_t *crc_out);
 int  icw_crc32_host(icw_engine *e, const void *data, size_t n_bytes, uint32_t *crc_out);   /* host memory, staged in blocks */
 uint32_t icw_crc32_combine(uint32_t crc_a, uint32_t crc_b, uint64_t len_b);
+
+/* ---- time-sharded streams: the block-boundary hand-off ---------------------------------------
+ * One long stream cut in time over several GPUs: everything a frame needs except the Hilbert filter memory is a
+ * closed form of its index, so rank r only has to receive the four half-band filters' state at its first frame.
+ * That state is the reference's IIR_RAT_POLY delay line x 4 plus the mixer phase (src/hblpf.h:115-127,
+ * src/lpf_hilbert_quad.h:52-57); here it is hb[2][2][ICW_MAX_ORD] of the stream, in the session's current basis,
+ * and it never leaves device memory: */
+#define ICW_BOUNDARY_DOUBLES (2 * 2 * ICW_MAX_ORD)
+/* stream's hb[] -> d_state[ICW_BOUNDARY_DOUBLES] (device memory), asynchronous on cuda_stream; *basis_out (optional)
+ * receives the basis it is in (0 delay line, 1 modal) */
+int  icw_session_boundary_export(icw_session *s, int stream, double *d_state, int *basis_out, void *cuda_stream);
+/* d_state (device memory, `basis` as exported) -> stream's hb[]; asynchronous on cuda_stream */
+int  icw_session_boundary_import(icw_session *s, int stream, const double *d_state, int basis, void *cuda_stream);
+/* closed-form part of a segment start: what frame counter, file position, mixer phase and dither offset a stream
+ * that began fresh (or at `base`, if not NULL) holds `frames` frames later (src/adv_modulator.c:611-625,
+ * src/lpf_hilbert_quad.c:155, src/sound_render.c:711-751); the Hilbert memory, counters and bus are left alone */
+int  icw_session_seek_closed_form(icw_session *s, int stream, int64_t frames, const icw_stream_state *base);
+/* a communicator of our own: rank 0 makes an id, the caller distributes its ICW_COMM_ID_BYTES bytes, every rank inits.
+ * NCCL is loaded at run time (the copy already in the process, e.g. torch's); ICW_E_UNSUPPORTED if there is none. */
+#define ICW_COMM_ID_BYTES 128
+int  icw_comm_unique_id(unsigned char id[ICW_COMM_ID_BYTES]);
+int  icw_comm_init(const unsigned char id[ICW_COMM_ID_BYTES], int rank, int world, void **comm_out);
+int  icw_comm_destroy(void *comm);
+int  icw_nccl_version(void);                    /* 0 when NCCL cannot be loaded */
+/* THE collective of the path: `from` (stream 0's filter state; NULL on the last rank) goes to rank + 1 and rank - 1's
+ * arrives in `to` (NULL on rank 0), device to device over NVLink by ncclSend / ncclRecv on cuda_stream; `to` is then
+ * in the modal basis.  comm: an ncclComm_t (icw_comm_init or the caller's own).  Both sessions must be scan-mode. */
+int  icw_session_handoff(icw_session *from, icw_session *to, void *comm, int rank, int world, void *cuda_stream);
+/* clip counters summed and peaks maximised over the shards (the reference keeps ONE pair of accumulators,
+ * src/adv_modulator.c:54-55): ncclAllReduce on cuda_stream, results to the host (synchronises) */
+int  icw_session_reduce_counters(icw_session *s, void *comm, void *cuda_stream, uint64_t clips_out[2], double peak_db_out[2]);
+/* one filter's state between the two bases, on the host in binary128 (icw_hbconv.cpp): to_basis 1 = delay line ->
+ * modal, 0 = modal -> delay line.  A live stream whose hilbert_mode changes is converted with this automatically. */
+int  icw_host_hb_convert(int filter_no, int to_basis, const double *in, double *out);
 
 /* ---- measurement: per-kernel device time from CUDA events on the launching stream ---------- */
 /* HILBERT: the exact recurrences (fused with the chain unless ICW_UNFUSED); SCAN_LOCAL / SCAN_APPLY: passes 1+2 and

@@ -17,7 +17,9 @@
  * CWAVE V1/V2) follows reference src/xwave_reader.c:243-585 and src/cwave.h:47-84; the virtual
  * silence tail (sec_align) and the fades follow src/xwave_reader.c:593-728,838-904.
  * Hosts ask for 4-64 KB at a time (src/transcode.c:94); this layer reads ahead in large blocks and
- * runs them through libicw_b200.so, so a GPU launch is not paid per host call.
+ * runs them through libicw_b200.so, so a GPU launch is not paid per host call.  Read-ahead is invisible:
+ * a seek or an early close puts the DSP state (frame counter, Hilbert memory, dither stream, counters)
+ * back to exactly the frames the host took, which is all the reference ever advances it by.
  *
  * Configuration: icwp_load_config() reads the reference's own config file format; icwp_configure()
  * takes the chain description (filter, summation, DSP list, render settings; the per-file fields
@@ -54,6 +56,18 @@ int  icwp_configure(const icw_chain_spec *chain, const icwp_options *opt);
 void icwp_reset(void);
 /* clips / peaks / reject counters of the transcode context (src/adv_modulator.c:445-465) */
 int  icwp_stats(icw_stats *out);
+
+/* how the overlapped reader did (N1: the step before the path, reference src/xwave_reader.c:838-904): file reads run
+ * on a reader thread into page-locked blocks while the previous block is on the GPU */
+typedef struct icwp_iostats {
+    double   read_s;            /* time spent inside pread (reader thread, or the caller for the first block / after a seek) */
+    double   wait_s;            /* time getData waited for a prefetched block that was not ready yet */
+    double   gpu_s;             /* time inside icw_session_process_host */
+    uint64_t read_bytes, frames;
+    uint64_t blocks_prefetched, blocks_sync;
+    uint64_t resettles;         /* seeks / early closes that had to put the DSP state back to what the host took */
+} icwp_iostats;
+int  icwp_io_stats(icwp_iostats *out, int reset);
 
 /* header parsing alone (no GPU touched): what xwave_reader_create (src/xwave_reader.c:593-728)
  * would accept and report.  Returns 1 if the file is playable, 0 otherwise. */

@@ -227,3 +227,132 @@ def test_cwave_crc_check_like_the_reference_info_dialog(tmp_path):
     ok, calc, filec, has = plugin.check_cwave(v1)
     assert ok and not has and calc == good
     assert plugin.check_cwave(tmp_path / "missing.cwave")[0] is False
+
+
+# ---- read-ahead must be invisible: seek and early close (reference src/transcode.c:82-118) --------------------
+def _bind_transcode(L):
+    ip = C.POINTER(C.c_int)
+    L.winampGetExtendedRead_open.argtypes = [C.c_char_p, ip, ip, ip, ip]
+    L.winampGetExtendedRead_open.restype = C.c_ssize_t
+    L.winampGetExtendedRead_getData.argtypes = [C.c_ssize_t, C.c_void_p, C.c_int, ip]
+    L.winampGetExtendedRead_getData.restype = C.c_ssize_t
+    L.winampGetExtendedRead_setTime.argtypes = [C.c_ssize_t, C.c_int]
+    L.winampGetExtendedRead_setTime.restype = C.c_int
+    L.winampGetExtendedRead_close.argtypes = [C.c_ssize_t]
+    L.winampGetExtendedRead_close.restype = None
+    return L
+
+
+def _run_script(L, script):
+    """script: list of ("open", path) / ("get", bytes, times) / ("seek", ms) / ("drain", bytes) / ("close",).
+    The same four exported symbols on either library; returns every byte served, in order."""
+    out = bytearray()
+    h, kill = 0, C.c_int(0)
+    info = (C.c_int * 4)()
+    for op in script:
+        if op[0] == "open":
+            h = L.winampGetExtendedRead_open(str(op[1]).encode(), *[C.byref(C.c_int.from_buffer(info, 4 * i)) for i in range(4)])
+            assert h, f"open failed: {op[1]}"
+        elif op[0] == "get":
+            buf = (C.c_char * op[1])()
+            for _ in range(op[2]):
+                got = L.winampGetExtendedRead_getData(h, buf, op[1], C.byref(kill))
+                out += buf.raw[:got]
+        elif op[0] == "seek":
+            assert L.winampGetExtendedRead_setTime(h, op[1])
+        elif op[0] == "drain":
+            buf = (C.c_char * op[1])()
+            while True:
+                got = L.winampGetExtendedRead_getData(h, buf, op[1], C.byref(kill))
+                if got <= 0:
+                    break
+                out += buf.raw[:got]
+        elif op[0] == "close":
+            L.winampGetExtendedRead_close(h)
+            h = 0
+    return np.frombuffer(bytes(out), dtype=np.uint8)
+
+
+def _both(spec, script, readahead, opts=None, over=None):
+    from util import pcm_report
+    d = dict(spec); d.update(over or {})
+    cfg = po.make_refcfg(d)
+    po.ref().icwref_reset(C.byref(cfg))
+    arr = (po.Node * len(spec["nodes"]))()
+    for i, nd in enumerate(spec["nodes"]):
+        po.fill_node(arr[i], nd)
+    assert po.ref().icwref_set_graph(arr, len(spec["nodes"]), 0) == 0
+    want = _run_script(_bind_transcode(po.ref()), script)
+    plugin.lib().icwp_reset()
+    plugin.configure(spec, readahead_frames=readahead, **(opts or {}))
+    got = _run_script(plugin.lib(), script)
+    assert got.size == want.size and got.size > 0
+    rep = pcm_report(got, want, 3 if spec.get("need24bits", 1) else 2)
+    ref_stats = po.ref_stats() if hasattr(po, "ref_stats") else None
+    return rep, ref_stats
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not po.have_ref(), reason="oracle/_ref/libicw_ref.so not built")
+@pytest.mark.parametrize("readahead", [7001, 0])
+@pytest.mark.parametrize("mode", ["exact_tpdf", "cwave_graph", "fade_tail"])
+def test_seek_in_the_middle_of_a_read_ahead_block(tmp_path, readahead, mode):
+    """getData x k -> setTime -> getData ...: the reference moves only the reader (src/xwave_reader.c:782-808), its
+    oscillator counter, Hilbert memory and dither stream stand at the frames actually served.  Our read-ahead
+    renders up to a block beyond that; the seek must undo it."""
+    opts, over = {}, {}
+    if mode == "exact_tpdf":
+        spec = S.config_c2(sample_rate=48000)
+    elif mode == "cwave_graph":
+        spec = S.config_c3(render_type=2, need24bits=1)
+    else:
+        spec = S.config_c1(sample_rate=8000, render_type=1)
+        opts = dict(sec_align=3, fade_in_ms=500, fade_out_ms=1000)
+        over = dict(sec_align=3, fade_in=500, fade_out=1000)
+    n = 30000
+    raw = synth.stream_bytes(spec, n, stream_id=11)
+    is_cw = spec["fmt"].startswith("cw_")
+    path = tmp_path / ("x.cwave" if is_cw else "x.wav")
+    path.write_bytes(po.cwave_bytes(spec, raw) if is_cw else po.wav_bytes(spec, raw))
+    ms = lambda fr: fr * 1000 // spec["sample_rate"]
+    script = [("open", path), ("get", 4998, 5), ("seek", ms(20000)), ("get", 6000, 3), ("seek", ms(1000)), ("get", 600, 7),
+              ("seek", ms(29000)), ("drain", 4096), ("close",)]
+    rep, _ = _both(spec, script, readahead, opts, over)
+    print(f"[seek {mode} ra={readahead}] {rep}")
+    assert rep["max_lsb"] <= 1 and rep["mismatches"] <= 2
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not po.have_ref(), reason="oracle/_ref/libicw_ref.so not built")
+@pytest.mark.parametrize("readahead", [5000, 0])
+def test_cancelled_transcode_then_the_next_file(tmp_path, readahead):
+    """getData x k -> close -> open the next file: the context survives across files (src/config.c:171,174), so the
+    second file's bytes depend on exactly how many frames of the first were rendered."""
+    spec = S.config_c2(sample_rate=48000)
+    fb = S.frame_bytes(spec)
+    raw = synth.stream_bytes(spec, 24000, stream_id=12)
+    a, b = tmp_path / "a.wav", tmp_path / "b.wav"
+    a.write_bytes(po.wav_bytes(spec, raw[: 14000 * fb]))
+    b.write_bytes(po.wav_bytes(spec, raw[14000 * fb:]))
+    script = [("open", a), ("get", 4092, 4), ("close",), ("open", b), ("drain", 8190), ("close",)]
+    rep, _ = _both(spec, script, readahead)
+    print(f"[cancel ra={readahead}] {rep}")
+    assert rep["mismatches"] == 0
+
+
+@pytest.mark.gpu
+def test_overlapped_reader_prefetches_blocks(tmp_path):
+    """N1: block k+1 is read by the reader thread while block k is rendered; only the first block of a file
+    (and the first after a seek) is read by the caller."""
+    spec = S.config_c2(sample_rate=48000, hilbert_mode="scan")
+    raw = synth.stream_bytes(spec, 200_000, stream_id=13)
+    path = tmp_path / "long.wav"
+    path.write_bytes(po.wav_bytes(spec, raw))
+    plugin.lib().icwp_reset()
+    plugin.configure(spec, readahead_frames=32768)
+    plugin.io_stats(reset=True)
+    pcm, _ = plugin.transcode(path, chunk=65536)
+    st = plugin.io_stats()
+    assert pcm.size == 200_000 * 6
+    assert st["blocks_sync"] == 1 and st["blocks_prefetched"] == (200_000 + 32767) // 32768 - 1
+    assert st["frames"] == 200_000 and st["read_bytes"] == raw.size and st["resettles"] == 0
