@@ -367,7 +367,9 @@ def measure(ctx, name: str, steps: int, warmup: int, want_e2e: bool, want_parity
     cs = torch.cuda.current_stream().cuda_stream
     shard_be = None
     if wl.get("time_sharded"):
-        shard_be = D.CudaBackend(eng, spec)
+        if world > 1 and ctx.get("comm") is None:
+            ctx["comm"] = D.make_comm(dist, rank, world, dev)     # our own ncclComm_t; the id travels over torch.distributed
+        shard_be = D.CudaBackend(eng, spec, comm=ctx.get("comm"))
         shard_be.ses.close()
         shard_be.ses = ses                            # profile / count launches on the session bench reads
     handoff_ms = []
@@ -458,6 +460,8 @@ def measure(ctx, name: str, steps: int, warmup: int, want_e2e: bool, want_parity
         if world > 1:
             dist.all_reduce(hm, op=dist.ReduceOp.MAX)
         res["handoff_ms"] = float(hm.item())
+        res["handoff"] = ("icw_session_handoff (C ABI): ncclSend/ncclRecv of the %d-double filter state, device to device, inside the "
+                          "timed region; NCCL %s" % (4 * 20, _abi_nccl_version()))
 
     # ---- parity of what the timed steps wrote ---------------------------------------------------------
     if want_parity:
@@ -511,6 +515,12 @@ def measure(ctx, name: str, steps: int, warmup: int, want_e2e: bool, want_parity
     del d_in, d_out
     torch.cuda.empty_cache()
     return res
+
+
+def _abi_nccl_version() -> str:
+    from in_cwave_b200 import _abi
+    v = _abi.lib().icw_nccl_version()
+    return f"{v // 10000}.{v // 100 % 100}.{v % 100}" if v else "unavailable"
 
 
 def stitch_check(ctx, wl: dict, d_in, d_out, N: int) -> dict:
@@ -616,6 +626,9 @@ def main():
         cpu = dict(value=f / busy / 1e6, unit=UNIT, cores=cores, kind=kind, cpu=cpu_model(),
                    sample=f"{cores} processes x {spc} fresh streams x {fr} frames of the same chain ({busy:.1f} s busy)")
 
+    if ctx.get("comm") is not None:
+        from in_cwave_b200 import dist as D
+        D.free_comm(ctx["comm"])
     if rank == 0:
         hil = head["hilbert"]
         line = dict(metric=METRIC, value=head["value"], unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,

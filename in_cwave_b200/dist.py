@@ -52,6 +52,7 @@ class SegmentStart:
     pos: int
     quad: int
     mt_drawn: int
+    frames: int = 0         # the offset these were computed for
 
 
 def closed_form_state(spec: dict, a: int, base: _abi.StreamState | None = None) -> SegmentStart:
@@ -66,20 +67,103 @@ def closed_form_state(spec: dict, a: int, base: _abi.StreamState | None = None) 
         n_frame = (n0 + a) % (int(spec.get("sample_rate", 48000)) * 1000)
     else:
         n_frame = n0 + a
-    return SegmentStart(n_frame=n_frame, pos=p0 + a, quad=(q0 + a) & 3, mt_drawn=d0 + a * wps)
+    return SegmentStart(n_frame=n_frame, pos=p0 + a, quad=(q0 + a) & 3, mt_drawn=d0 + a * wps, frames=a)
+
+
+def make_comm(dist, rank: int, world: int, device="cpu"):
+    """Our own NCCL communicator for the hand-off (include/icw_b200.h icw_comm_*): rank 0 makes the 128-byte id,
+    torch.distributed -- the plumbing -- broadcasts it, every rank joins.  Returns an opaque handle (int) or None
+    for world == 1."""
+    import torch
+    if world <= 1:
+        return None
+    L = _abi.lib()
+    buf = C.create_string_buffer(_abi.COMM_ID_BYTES)
+    if rank == 0:
+        _abi.check(L.icw_comm_unique_id(buf))
+    t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).to(device)
+    dist.broadcast(t, src=0)
+    idb = bytes(t.cpu().numpy().tobytes())
+    comm = C.c_void_p()
+    _abi.check(L.icw_comm_init(idb, rank, world, C.byref(comm)))
+    return comm
+
+
+def free_comm(comm) -> None:
+    if comm:
+        _abi.check(_abi.lib().icw_comm_destroy(comm))
 
 
 class CudaBackend:
-    """The CUDA session as the compute engine of a time shard (scan mode)."""
+    """The CUDA session as the compute engine of a time shard (scan mode).
 
-    def __init__(self, engine, spec: dict):
+    With a communicator (``make_comm``) the whole step runs through the C ABI and the filter state never leaves
+    device memory: icw_session_seek_closed_form + a warm-up run on a second session, icw_session_handoff
+    (ncclSend / ncclRecv straight out of / into the sessions' device-resident state), the shard itself,
+    icw_session_reduce_counters (``native_step``).  Without one (single GPU, CPU tests with a stand-in backend)
+    ``run_time_sharded`` drives the generic numpy path below."""
+
+    def __init__(self, engine, spec: dict, comm=None):
         if spec.get("hilbert_mode", "exact") not in ("scan", 1):
             raise ValueError("time sharding needs hilbert_mode='scan': the exact recurrences are serial in time")
         if int(spec.get("nshape_type", 0)):
             raise ValueError("time sharding needs FLAT noise shaping: the error feedback is serial in time (SURVEY.md 8e)")
         self.engine, self.spec = engine, dict(spec)
         self.ses = engine.session(spec, 1)
+        self.comm = comm
+        self._warm = None
+        self.last_handoff_ms = None
 
+    def close(self) -> None:
+        if self._warm is not None:
+            self._warm.close()
+            self._warm = None
+        self.ses.close()
+
+    def warm_session(self):
+        if self._warm is None:
+            self._warm = self.engine.session(self.spec, 1)
+        return self._warm
+
+    # ---- the native path: everything through the C entry points ------------------------------------------
+    def native_step(self, my_raw, a: int, rank: int, world: int, d_out, warmup: int = WARMUP_FRAMES):
+        """Frames [a, a + n) of the long stream on this rank; returns (d_out, clips, peak_db, handoff_ms)."""
+        import torch
+        L = _abi.lib()
+        cs = torch.cuda.current_stream().cuda_stream or 1
+        fb = self.ses.frame_bytes
+        n = my_raw.numel() // fb
+        warm = None
+        if rank + 1 < world:
+            if n < warmup:
+                raise ValueError(f"shard of {n} frames is shorter than the {warmup}-frame warm-up the hand-off state needs; "
+                                 "use fewer ranks or pass the left neighbours' frames")
+            warm = self.warm_session()
+            warm.reset()
+            _abi.check(L.icw_session_seek_closed_form(warm._h, 0, a + n - warmup, None))
+            tail = my_raw[(n - warmup) * fb: n * fb]
+            scratch = self._scratch(warmup * self.ses.out_frame_bytes + 16, my_raw.device)
+            warm.process_device(tail, warmup, scratch, stream=cs)
+        self.ses.reset()
+        _abi.check(L.icw_session_seek_closed_form(self.ses._h, 0, a, None))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _abi.check(L.icw_session_handoff(warm._h if warm is not None else None, self.ses._h if rank > 0 else None,
+                                         self.comm, rank, world, cs))
+        e1.record()
+        self.ses.process_device(my_raw, n, d_out, stream=cs)
+        clips, peak = (C.c_uint64 * 2)(), (C.c_double * 2)()
+        _abi.check(L.icw_session_reduce_counters(self.ses._h, self.comm, cs, C.byref(clips), C.byref(peak)))
+        self.last_handoff_ms = e0.elapsed_time(e1)
+        return d_out, [int(clips[0]), int(clips[1])], [float(peak[0]), float(peak[1])], self.last_handoff_ms
+
+    def _scratch(self, nbytes: int, device):
+        import torch
+        if getattr(self, "_scr", None) is None or self._scr.numel() < nbytes:
+            self._scr = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        return self._scr
+
+    # ---- the generic path (single GPU emulation of the split; tests) ---------------------------------------
     def hilbert_state_after(self, raw_tail, quad0: int) -> np.ndarray:
         """Filter state after running the converter over raw_tail (uint8 bytes, host or CUDA tensor) from zero."""
         import torch
@@ -102,10 +186,11 @@ class CudaBackend:
         return hb.reshape(-1)
 
     def start_at(self, start: SegmentStart, hb: np.ndarray) -> None:
+        L = _abi.lib()
+        _abi.check(L.icw_session_seek_closed_form(self.ses._h, 0, start.frames, None))
         st = self.ses.get_state(0)
-        st.n_frame, st.pos = start.n_frame, start.pos
-        st.quad[0] = st.quad[1] = start.quad
-        st.mt_drawn[0] = st.mt_drawn[1] = start.mt_drawn
+        assert (int(st.n_frame), int(st.pos), int(st.quad[0]), int(st.mt_drawn[0])) == \
+            (start.n_frame, start.pos, start.quad, start.mt_drawn), "closed forms of dist.py and the C ABI disagree"
         hb = np.asarray(hb, dtype=np.float64).reshape(2, 2, _abi.MAX_ORD)
         for c in range(2):
             for f in range(2):
@@ -159,13 +244,20 @@ def run_time_sharded(backend, dist, spec: dict, my_raw, a: int, rank: int, world
                      warmup: int = WARMUP_FRAMES, d_out=None, group=None):
     """Process this rank's frames [a, a + len(my_raw)/frame_bytes) of one long stream.
 
-    my_raw: this rank's input bytes (numpy uint8 or CUDA uint8 tensor).  Returns (pcm, clips, peaks)
-    with the counters already reduced over all ranks."""
+    my_raw: this rank's input bytes (numpy uint8 or CUDA uint8 tensor).  Returns (pcm, clips, peaks, handoff_ms):
+    the counters already reduced over all ranks (peaks LINEAR on the generic path, dB on the native one -- see
+    ``CudaBackend.native_step``), handoff_ms the device time of the collective or None."""
+    if getattr(backend, "comm", None) is not None and not isinstance(my_raw, np.ndarray):
+        return backend.native_step(my_raw, a, rank, world, d_out, warmup=min(warmup, WARMUP_FRAMES))
     fb = _spec.frame_bytes(spec)
     n = (my_raw.size if isinstance(my_raw, np.ndarray) else my_raw.numel()) // fb
+    if int(spec.get("render_type", 0)) == 3 and rank > 0 and not hasattr(backend, "ses"):
+        raise ValueError("sloped TPDF carries the previous sample's draw: only the CUDA backend regenerates it at a cut")
     # 1. state at my segment end, from a warm-up over my own last frames -> right neighbour
     state_out = None
     if rank + 1 < world:
+        if n < warmup and warmup <= WARMUP_FRAMES:
+            raise ValueError(f"shard of {n} frames is shorter than the {warmup}-frame warm-up the hand-off state needs")
         w = min(warmup, n)
         tail = my_raw[(n - w) * fb: n * fb]
         state_out = backend.hilbert_state_after(tail, (closed_form_state(spec, a + n - w).quad))
@@ -175,4 +267,4 @@ def run_time_sharded(backend, dist, spec: dict, my_raw, a: int, rank: int, world
     pcm = backend.process(my_raw, d_out)
     clips, peaks = backend.counters()
     clips, peaks = reduce_counters(dist, clips, peaks, device=device, group=group)
-    return pcm, clips, peaks
+    return pcm, clips, peaks, None

@@ -93,7 +93,7 @@ def _worker(rank, world, port, spec, n, level, outdir):
     raw = synth.stream_bytes(spec, n, stream_id=77, level=level)
     a, b = D.shard_time(n, rank, world)
     be = OracleBackend(pyoracle, spec)
-    pcm, clips, peaks = D.run_time_sharded(be, dist, spec, raw[a * fb:b * fb], a, rank, world, warmup=1 << 30)
+    pcm, clips, peaks, _ = D.run_time_sharded(be, dist, spec, raw[a * fb:b * fb], a, rank, world, warmup=1 << 30)
     np.save(os.path.join(outdir, f"pcm{rank}.npy"), pcm)
     np.save(os.path.join(outdir, f"cnt{rank}.npy"), np.array(clips + peaks, dtype=np.float64))
     dist.barrier()
