@@ -70,7 +70,7 @@ class Stats(C.Structure):
     ]
 
 
-K_NAMES = ["hilbert", "chain", "mt", "misc", "scan_local", "scan_apply"]
+K_NAMES = ["hilbert", "chain", "mt", "misc", "scan_local", "scan_apply", "scan_fused"]
 
 
 class Profile(C.Structure):

@@ -18,6 +18,7 @@
 #include "icw_scan.h"
 #include "icw_crc.h"
 #include "icw_comm.h"
+#include "icw_sfused.h"
 #include "icw_hb_tables.inc"
 #include "icw_ns_tables.inc"
 
@@ -89,7 +90,8 @@ struct icw_engine {
     Scratch crc_partial;                // per-tile CRC registers + the result word
     Scratch ns_pre;                     // noise shaping: (value, dither) pairs between chain_kernel and ns_render_kernel
     struct ScanPlan { bool ready = false; ModalCoef mc; double *d_pw = nullptr; };
-    ScanPlan scan[ICW_HB_NTYPES][2][3]; // [filter_no][baseline][chunk length: 256, 1024, 2048 (or the forced one)]
+    ScanPlan scan[ICW_HB_NTYPES][2][4]; // [filter_no][baseline][chunk length: 256, 1024, 2048 (or the forced one); 3 = the one-kernel path's]
+    int sfused = -1;                    // ICW_SFUSED: 1 = the one-kernel scan path wherever it applies, 0 = never, unset = where it pays
     MtJump mt;                          // MT19937 checkpoint service (icw_mt.cu)
 };
 
@@ -392,6 +394,7 @@ extern "C" int icw_engine_create(int device, icw_engine **out)
     CK(cudaEventCreateWithFlags(&e->ev_scratch, cudaEventDisableTiming));
     { const char *u = getenv("ICW_UNFUSED"); e->unfused = u && *u == '1'; }
     { const char *u = getenv("ICW_NO_FUSE_MT"); e->no_fuse_mt = u && *u == '1'; }
+    { const char *u = getenv("ICW_SFUSED"); e->sfused = (u && *u) ? atoi(u) : -1; }
     *out = e;
     return ICW_OK;
 }
@@ -755,7 +758,7 @@ static int make_dither_words(icw_session *s, int64_t n_frames, cudaStream_t st, 
 
 static int get_scan_plan(icw_engine *e, int filter_no, bool baseline, double d0, int L, icw_engine::ScanPlan **out)
 {
-    icw_engine::ScanPlan &pl = e->scan[filter_no][baseline ? 1 : 0][L <= SCAN_L ? 0 : L <= 4 * SCAN_L ? 1 : 2];
+    icw_engine::ScanPlan &pl = e->scan[filter_no][baseline ? 1 : 0][L == SF_LC ? 3 : L <= SCAN_L ? 0 : L <= 4 * SCAN_L ? 1 : 2];
     if (pl.ready && pl.mc.L != L) {             // only when ICW_SCAN_L forces odd lengths: rebuild in place
         CK(cudaStreamSynchronize(e->stream));
         cudaFree(pl.d_pw);
@@ -776,13 +779,46 @@ static int get_scan_plan(icw_engine *e, int filter_no, bool baseline, double d0,
 // one launch group: n_frames of every stream, state read from and left in the DevStream array
 // `pre`: dither words generated once for the whole call (pointing at this group's first frame), or NULL
 // `fuse_mt`: no word buffers at all -- chain_mt_kernel regenerates the dither inside the pointwise pass
+// scan mode, one long stream: the whole chain in one kernel (icw_sfused.cu)
+static int process_sfused(icw_session *s, int64_t n_frames, const uint8_t *d_in, uint8_t *d_out, cudaStream_t st)
+{
+    icw_engine *e = s->e;
+    const DevChain &ch = s->ch;
+    icw_engine::ScanPlan *plp;
+    int rc = get_scan_plan(e, s->spec.filter_no, !s->spec.is_kahan, s->coef.d0, SF_LC, &plp);
+    if (rc) return rc;
+    const int wps = ch.render.words_per_sample;
+    MtPlan pl[2];
+    if (wps) {
+        ProfSpan ps(s, st, ICW_K_MT);
+        const uint32_t seeds[2] = { s->mt_seed[0][0], s->mt_seed[1][0] };
+        rc = e->mt.plan_pair(seeds, s->mt_drawn[0][0], n_frames * wps, e->sm_count, e->sm_count, st, &s->launches, pl);
+        if (rc) return fail(rc, "%s", e->mt.error());
+    }
+    {
+        ProfSpan ps(s, st, ICW_K_SCAN_FUSED);
+        CK(launch_scan_fused(plp->mc, ch, s->d_streams, n_frames, d_in, d_out, wps ? &pl[0] : nullptr, wps ? &pl[1] : nullptr,
+                             e->sm_count, sfused_warm_frames(plp->mc), st));
+    }
+    s->launches++;
+    {
+        ProfSpan ps(s, st, ICW_K_MISC);
+        CK(launch_advance(ch, s->d_streams, 1, n_frames, 1, st));
+    }
+    s->launches++;
+    const uint64_t words = (uint64_t)n_frames * (uint64_t)wps;
+    for (int c = 0; c < 2; ++c) s->mt_drawn[c][0] += words;
+    return ICW_OK;
+}
+
 static int process_group(icw_session *s, int64_t n_frames, const uint8_t *d_in, size_t in_stride,
-                         uint8_t *d_out, size_t out_stride, cudaStream_t st, const DitherWords *pre, bool fuse_mt)
+                         uint8_t *d_out, size_t out_stride, cudaStream_t st, const DitherWords *pre, bool fuse_mt, bool sfused = false)
 {
     icw_engine *e = s->e;
     const DevChain &ch = s->ch;
     const int K = s->n_streams;
     int rc;
+    if (sfused) return process_sfused(s, n_frames, d_in, d_out, st);
     DitherWords dw;
     if (fuse_mt) { }
     else if (pre) dw = *pre;
@@ -907,6 +943,7 @@ struct CallCtx {
     DitherWords all;
     bool pre = false;
     bool fuse_mt = false;   // dither regenerated inside the pointwise kernel: no word buffers
+    bool sfused = false;    // scan mode in one kernel (icw_sfused.cu): no scratch at all, the call is one launch
     int64_t step = 0;       // frames per launch group
     int mode = 0;
     bool real_in = false;
@@ -950,6 +987,20 @@ static int call_begin(icw_session *s, int64_t n_total, cudaStream_t st, CallCtx 
                       : K == 1 ? BIG_GROUP : SCAN_SEGMENT / K / (SCAN_L * SCAN_CH) * (SCAN_L * SCAN_CH);
     cx.step = seg < SCAN_L * SCAN_CH ? SCAN_L * SCAN_CH : seg;
     const int wps = ch.render.words_per_sample;
+    // scan mode, one stream, straight-line list: everything in one kernel.  A unit (one CTA) first runs the filters over
+    // `warm` frames before its own: that only pays on streams long enough to give every SM a unit many times that long
+    if (cx.real_in && cx.mode == ICW_HILBERT_SCAN && one_range && e->sfused != 0 && !e->unfused &&
+        sfused_supports(ch, K, s->d_tap_bus || s->d_tap_lr) &&
+        (!wps || (s->mt_drawn[0][0] == s->mt_drawn[1][0] && s->mt_drawn[0][0] % (uint64_t)wps == 0))) {
+        bool go = e->sfused == 1;
+        if (!go) {
+            icw_engine::ScanPlan *plp;
+            int rc = get_scan_plan(e, s->spec.filter_no, !s->spec.is_kahan, s->coef.d0, SF_LC, &plp);
+            if (rc) return rc;
+            go = n_total / e->sm_count >= 4 * sfused_warm_frames(plp->mc);
+        }
+        if (go) { cx.sfused = true; cx.step = n_total; return ICW_OK; }
+    }
     // the fused exact kernel reads word buffers; everything else that ends in chain_kernel can make its own
     const bool hb_fused = cx.real_in && cx.mode == ICW_HILBERT_EXACT && !e->unfused && ch.render.ns_kind == 0 && !ch.fp_check;
     if (wps && one_range && !hb_fused && !e->no_fuse_mt && K == 1 && chain_mt_supports(ch) &&
@@ -995,7 +1046,7 @@ static int call_range(icw_session *s, CallCtx &cx, int64_t f0, int64_t n, const 
             cx.all.join = nullptr;
         }
         int rc = process_group(s, gn, d_in + (size_t)g0 * ch.frame_bytes, in_stride,
-                               d_out + (size_t)g0 * ch.out_frame_bytes, out_stride, st, cx.pre ? &here : nullptr, cx.fuse_mt);
+                               d_out + (size_t)g0 * ch.out_frame_bytes, out_stride, st, cx.pre ? &here : nullptr, cx.fuse_mt, cx.sfused);
         if (rc) return rc;
     }
     return ICW_OK;
@@ -1138,7 +1189,7 @@ extern "C" int icw_session_profile_read(icw_session *s, icw_profile *out, int re
 
 extern "C" const char *icw_kernel_class_name(int k)
 {
-    static const char *names[ICW_K_COUNT] = { "hilbert", "chain", "mt", "misc", "scan_local", "scan_apply" };
+    static const char *names[ICW_K_COUNT] = { "hilbert", "chain", "mt", "misc", "scan_local", "scan_apply", "scan_fused" };
     return (k >= 0 && k < ICW_K_COUNT) ? names[k] : "?";
 }
 

@@ -16,6 +16,8 @@
 //
 // Straight-line DSP lists (Master alone, Shift -> Master) with plain PCM output get a lean frame
 // path: list shape and dither type are template parameters, no thread-private bus.
+#include <type_traits>
+
 #include "icw_dev.cuh"
 #include "icw_frame.cuh"
 #include "icw_kernels.h"
@@ -26,8 +28,8 @@ namespace icw {
 constexpr int CMT_THREADS = 256;
 constexpr int CMT_CTAS = 4;                         // resident per SM
 constexpr int CMT_TB = 8;                           // blocks per tile: 1248 TPDF frames, 2496 RPDF frames
-constexpr int CMT_STATE = ICW_MT_N + 8;             // + slack, see mt_words_kernel
-constexpr size_t CMT_SMEM = (size_t)(2 * 2 * CMT_STATE + 2 * CMT_TB * ICW_MT_N) * sizeof(uint32_t);   // 50 048 B
+constexpr int CMT_GEN_WORDS = (CMT_TB + 1) * ICW_MT_N;     // per generator: 624 words of history + the tile's new words, untempered
+constexpr size_t CMT_SMEM = (size_t)(2 * CMT_GEN_WORDS) * sizeof(uint32_t);   // 44 928 B
 
 int chain_mt_max_units(int sm_count) { return sm_count * CMT_CTAS; }
 
@@ -48,25 +50,18 @@ chain_mt_kernel(const __grid_constant__ DevChain ch, DevStream *__restrict__ str
     constexpr int WPS = RT == ICW_RENDER_TPDF ? 4 : 2;
     constexpr bool LEAN = SHAPE != ICW_SHAPE_GENERIC;
     extern __shared__ __align__(16) uint32_t cmt_smem[];
-    uint32_t *sbuf = cmt_smem;                                  // [gen][2][CMT_STATE] untempered state, double-buffered
-    uint32_t *wd_l = cmt_smem + 4 * CMT_STATE;                  // [CMT_TB * 624] tempered words of the tile
-    uint32_t *wd_r = wd_l + CMT_TB * ICW_MT_N;
+    uint32_t *ub_l = cmt_smem;                                  // [624 history + CMT_TB * 624] the left generator's stream, untempered
+    uint32_t *ub_r = cmt_smem + CMT_GEN_WORDS;                  // the right generator's
     const int t = threadIdx.x;
     const int unit = blockIdx.x;
     DevStream &st = streams[0];
+    // threads 0..127 make the left generator's words, 128..255 the right one's: 128 words of each per pass (icw_mtdev.cuh)
+    const int gen = t >> 7, lane_w = t & 127;
+    uint32_t *my_ub = gen ? ub_r : ub_l;
 
-    for (int i = t; i < ICW_MT_N; i += CMT_THREADS) {
-        sbuf[i] = ckpt_l[(size_t)unit * ICW_MT_N + i];
-        sbuf[2 * CMT_STATE + i] = ckpt_r[(size_t)unit * ICW_MT_N + i];
-    }
-    if (t < 32) sbuf[(t >> 3) * CMT_STATE + ICW_MT_N + (t & 7)] = 0u;
-    __syncthreads();
-    const bool active = t < 227;
-    uint32_t l0 = 0u, l1 = 0u, l2 = 0u, r0 = 0u, r1 = 0u, r2 = 0u;
-    if (active) {
-        l0 = sbuf[t]; l1 = sbuf[t + 227];
-        r0 = sbuf[2 * CMT_STATE + t]; r1 = sbuf[2 * CMT_STATE + t + 227];
-        if (t < 170) { l2 = sbuf[t + 454]; r2 = sbuf[2 * CMT_STATE + t + 454]; }
+    for (int i = t; i < ICW_MT_N; i += CMT_THREADS) {           // history of the first tile = the unit's checkpoint
+        ub_l[i] = ckpt_l[(size_t)unit * ICW_MT_N + i];
+        ub_r[i] = ckpt_r[(size_t)unit * ICW_MT_N + i];
     }
     // block b of this unit holds stream words [u0 + 624 b, u0 + 624 (b + 1))
     const int64_t u0 = g.first_word + (int64_t)unit * g.blocks_per_unit * ICW_MT_N;
@@ -74,6 +69,7 @@ chain_mt_kernel(const __grid_constant__ DevChain ch, DevStream *__restrict__ str
     const int n_blk = (int)(nb64 < 0 ? 0 : nb64 > g.blocks_per_unit ? g.blocks_per_unit : nb64);
     const int64_t tl = g.tail_block - (int64_t)unit * g.blocks_per_unit;
     const int tail_blk = (tl >= 0 && tl < n_blk) ? (int)tl : -1;
+    __syncthreads();
 
     FrameIO io;
     io.mtw_l = io.mtw_r = nullptr;
@@ -91,24 +87,29 @@ chain_mt_kernel(const __grid_constant__ DevChain ch, DevStream *__restrict__ str
     }
     const int64_t pos0 = st.pos;
 
-    int cur = 0;
     for (int b0 = 0; b0 < n_blk; b0 += CMT_TB) {
         const int tb = n_blk - b0 < CMT_TB ? n_blk - b0 : CMT_TB;
-        // ---- the tile's words, both generators, one barrier per block ---------------------------------
-        for (int b = 0; b < tb; ++b) {
-            const uint32_t *ol = sbuf + cur * CMT_STATE, *orr = sbuf + (2 + cur) * CMT_STATE;
-            uint32_t *nl = sbuf + (cur ^ 1) * CMT_STATE, *nr = sbuf + (2 + (cur ^ 1)) * CMT_STATE;
-            const bool is_tail = b0 + b == tail_blk;
-            if (is_tail)
-                for (int i = t; i < ICW_MT_N; i += CMT_THREADS) { tail_l[i] = ol[i]; tail_r[i] = orr[i]; }
-            if (active) {
-                mt_words_block<false>(ol, nl, t, l0, l1, l2, wd_l + b * ICW_MT_N + t, 0, 0, 0);
-                mt_words_block<false>(orr, nr, t, r0, r1, r2, wd_r + b * ICW_MT_N + t, 0, 0, 0);
+        // ---- the tile's words: both generators, 128 words each per pass, one barrier per pass ----------------
+        {
+            uint32_t *u = my_ub + ICW_MT_N + lane_w;
+            const int n_new = tb * ICW_MT_N;
+            const int full = n_new >> 7, rag = n_new & 127;      // 624 tb is not a multiple of 128: one ragged pass
+            for (int k = 0; k < full; ++k, u += 128) {
+                mt_window_word(u);
+                __syncthreads();
             }
-            __syncthreads();
-            if (is_tail)
-                for (int i = t; i < ICW_MT_N; i += CMT_THREADS) { tail_l[ICW_MT_N + i] = nl[i]; tail_r[ICW_MT_N + i] = nr[i]; }
-            cur ^= 1;
+            if (rag) {
+                if (lane_w < rag) mt_window_word(u);
+                __syncthreads();
+            }
+            // (a barrier per generator -- bar.sync over its 128 threads -- and 227 words between barriers were both
+            // measured: 13.4 and 14.6 ms per C2 step against 13.3 for this form; the phase is not barrier-bound)
+        }
+        // the states around the call's last block go back to the host's bookkeeping (MtPlan::tail): the block before
+        // it (or the history, when it is the tile's first) and the block itself
+        if (tail_blk >= b0 && tail_blk < b0 + tb) {
+            const uint32_t *sl = ub_l + (tail_blk - b0) * ICW_MT_N, *sr = ub_r + (tail_blk - b0) * ICW_MT_N;
+            for (int i = t; i < 2 * ICW_MT_N; i += CMT_THREADS) { tail_l[i] = sl[i]; tail_r[i] = sr[i]; }
         }
         // ---- the frames whose draws are those words -----------------------------------------------------
         const int64_t w_lo = u0 + (int64_t)b0 * ICW_MT_N;       // stream word held by wd[0]
@@ -119,16 +120,20 @@ chain_mt_kernel(const __grid_constant__ DevChain ch, DevStream *__restrict__ str
         // (requesting a thread's next analytic frame one iteration ahead was measured slower: the eight
         // extra live registers spill at 64 per thread)
         const double2 *ana = reinterpret_cast<const double2 *>(in);
-        for (int64_t i = i_lo + t; i < i_hi; i += CMT_THREADS) {
+        // one frame from the tile's words; LAST as in icw_frame.cuh (the call's last frame leaves the bus state behind)
+        auto frame = [&](int64_t i, auto last_tag) {
+            constexpr int LAST = decltype(last_tag)::value;
             const uint32_t off = (uint32_t)(g.want_lo + i * WPS - w_lo);
             uint4 wl = make_uint4(0u, 0u, 0u, 0u), wr = wl;
             if (WPS == 4) {
-                wl = *reinterpret_cast<const uint4 *>(wd_l + off);
-                wr = *reinterpret_cast<const uint4 *>(wd_r + off);
+                wl = *reinterpret_cast<const uint4 *>(ub_l + ICW_MT_N + off);
+                wr = *reinterpret_cast<const uint4 *>(ub_r + ICW_MT_N + off);
+                wl.z = mt_temper_mul(wl.z); wl.w = mt_temper_mul(wl.w); wr.z = mt_temper_mul(wr.z); wr.w = mt_temper_mul(wr.w);
             } else {
-                const uint2 a = *reinterpret_cast<const uint2 *>(wd_l + off), b = *reinterpret_cast<const uint2 *>(wd_r + off);
+                const uint2 a = *reinterpret_cast<const uint2 *>(ub_l + ICW_MT_N + off), b = *reinterpret_cast<const uint2 *>(ub_r + ICW_MT_N + off);
                 wl.x = a.x; wl.y = a.y; wr.x = b.x; wr.y = b.y;
             }
+            wl.x = mt_temper_mul(wl.x); wl.y = mt_temper_mul(wl.y); wr.x = mt_temper_mul(wr.x); wr.y = mt_temper_mul(wr.y);
             double v[4];
             if (SHAPE == ICW_SHAPE_SHIFT_MASTER_FAST || from_analytic) {
                 const double2 a0 = ana[i * 2], a1 = ana[i * 2 + 1];
@@ -136,11 +141,22 @@ chain_mt_kernel(const __grid_constant__ DevChain ch, DevStream *__restrict__ str
             } else {
                 unpack_frame(ch, in + i * ch.frame_bytes, pos0 + i, v);
             }
-            if (SHAPE == ICW_SHAPE_SHIFT_MASTER_FAST) lean_frame_fast<RT>(ch, st, i, n_frames - 1, v, wl, wr, io.dst, acc, osc);
-            else if (LEAN) lean_frame<SHAPE, RT>(ch, st, i, n_frames - 1, v, wl, wr, io.dst, io.dst_aligned, acc, osc);
-            else finish_frame<DITHER_GIVEN>(ch, st, i, n_frames, v, bus, io, acc, osc, wl, wr);
+            if (SHAPE == ICW_SHAPE_SHIFT_MASTER_FAST) lean_frame_fast<RT, LAST>(ch, st, i, n_frames - 1, v, wl, wr, io.dst, acc, osc);
+            else if (LEAN) lean_frame<SHAPE, RT, LAST>(ch, st, i, n_frames - 1, v, wl, wr, io.dst, io.dst_aligned, acc, osc);
+            else if (LAST != FRAME_LAST_ONLY) finish_frame<DITHER_GIVEN>(ch, st, i, n_frames, v, bus, io, acc, osc, wl, wr);
+        };
+        for (int64_t i = i_lo + t; i < i_hi; i += CMT_THREADS) frame(i, std::integral_constant<int, LEAN ? FRAME_NO_LAST : FRAME_CHECK_LAST>());
+        // the call's last frame again, for the bus state it leaves in the context (the words are still in the tile)
+        if (LEAN && i_hi == n_frames && i_lo < i_hi && t == (int)((n_frames - 1 - i_lo) % CMT_THREADS))
+            frame(n_frames - 1, std::integral_constant<int, FRAME_LAST_ONLY>());
+        __syncthreads();                                        // every frame of the tile has its words
+        if (b0 + CMT_TB < n_blk) {                              // the tile's last block becomes the next tile's history
+            for (int i = t; i < ICW_MT_N; i += CMT_THREADS) {
+                ub_l[i] = ub_l[tb * ICW_MT_N + i];
+                ub_r[i] = ub_r[tb * ICW_MT_N + i];
+            }
+            __syncthreads();
         }
-        __syncthreads();                                        // the next tile overwrites the words
     }
     commit_acc(&st, acc, 32);
 }

@@ -195,7 +195,11 @@ __device__ __forceinline__ double lean_dither(uint4 a, unsigned &redraws)
 
 // one frame of a straight-line list, plain PCM out.  Operation for operation finish_frame()'s
 // ch.shape != GENERIC route with DITHER_GIVEN.
-template <int SHAPE, int RT>
+// LAST: FRAME_CHECK_LAST = render, and leave the bus state behind if i == i_last; FRAME_NO_LAST = render only (the
+// caller revisits the call's last frame); FRAME_LAST_ONLY = that revisit: the bus state alone, nothing rendered.
+// The eight predicated stores of the check are issue slots on every frame of an issue-bound loop.
+enum { FRAME_CHECK_LAST = 0, FRAME_NO_LAST = 1, FRAME_LAST_ONLY = 2 };
+template <int SHAPE, int RT, int LAST = FRAME_CHECK_LAST>
 __device__ __forceinline__ void lean_frame(const DevChain &ch, DevStream &st, int64_t i, int64_t i_last, const double v[4],
                                            uint4 wl, uint4 wr, uint8_t *dst, int dst_aligned, FrameAcc &acc, OscCounter &osc)
 {
@@ -203,20 +207,22 @@ __device__ __forceinline__ void lean_frame(const DevChain &ch, DevStream &st, in
     const double omega = norm_omega(ch, osc.at(ch, i));
     double o[4], lo, ro;
     run_shape<SHAPE>(ch, v, omega, o, lo, ro);
-    const double dl = lean_dither<RT>(wl, acc.redraws);
-    const double dr = lean_dither<RT>(wr, acc.redraws);
-    const RenderOut a = render_one(rq, lo, dl);
-    const RenderOut b = render_one(rq, ro, dr);
-    acc.clips_l += a.clipped; acc.clips_r += b.clipped;
-    acc.peak_l = fmax(acc.peak_l, a.level); acc.peak_r = fmax(acc.peak_r, b.level);
-    uint8_t *p = dst + i * ch.out_frame_bytes;
-    if (dst_aligned) store_frame_pcm(p, a.val, b.val, rq.bytes);
-    else { store_pcm(p, a.val, rq.bytes); store_pcm(p + rq.bytes, b.val, rq.bytes); }
-    if (i == i_last) {
+    if (LAST != FRAME_LAST_ONLY) {
+        const double dl = lean_dither<RT>(wl, acc.redraws);
+        const double dr = lean_dither<RT>(wr, acc.redraws);
+        const RenderOut a = render_one(rq, lo, dl);
+        const RenderOut b = render_one(rq, ro, dr);
+        acc.clips_l += a.clipped; acc.clips_r += b.clipped;
+        acc.peak_l = fmax(acc.peak_l, a.level); acc.peak_r = fmax(acc.peak_r, b.level);
+        uint8_t *p = dst + i * ch.out_frame_bytes;
+        if (dst_aligned) store_frame_pcm(p, a.val, b.val, rq.bytes);
+        else { store_pcm(p, a.val, rq.bytes); store_pcm(p + rq.bytes, b.val, rq.bytes); }
+    }
+    if (LAST == FRAME_LAST_ONLY || (LAST == FRAME_CHECK_LAST && i == i_last)) {
         // the context's bus after the call == the last frame's values (adv_modulator.c:634-751);
         // plugs this list never writes keep what the context held
         st.bus[0][0] = v[0]; st.bus[0][1] = v[1]; st.bus[0][2] = v[2]; st.bus[0][3] = v[3];
-        if (SHAPE == ICW_SHAPE_SHIFT_MASTER) {
+        if (SHAPE == ICW_SHAPE_SHIFT_MASTER || (SHAPE == ICW_SHAPE_GENERIC && ch.shape == ICW_SHAPE_SHIFT_MASTER)) {
             const int k = ch.nodes[0].n_out;
             st.bus[k][0] = o[0]; st.bus[k][1] = o[1]; st.bus[k][2] = o[2]; st.bus[k][3] = o[3];
         }
@@ -239,7 +245,7 @@ __host__ __device__ inline bool lean_fast_ok(const DevChain &ch)
     return lt && rt;
 }
 
-template <int RT>
+template <int RT, int LAST = FRAME_CHECK_LAST>
 __device__ __forceinline__ void lean_frame_fast(const DevChain &ch, DevStream &st, int64_t i, int64_t i_last, const double v[4],
                                                 uint4 wl, uint4 wr, uint8_t *dst, FrameAcc &acc, OscCounter &osc)
 {
@@ -266,19 +272,21 @@ __device__ __forceinline__ void lean_frame_fast(const DevChain &ch, DevStream &s
     double o[4];
     rotate(c, sl, d0, d1, o[0], o[1]);
     rotate(c, sr, d2, d3, o[2], o[3]);
-    // master (:485-507)
-    d0 = (0.0 + o[0]) * ms.l_gain; d1 = (0.0 + o[1]) * ms.l_gain;
-    d2 = (0.0 + o[2]) * ms.r_gain; d3 = (0.0 + o[3]) * ms.r_gain;
-    const double lo = div_const(d0 + (ms.l_tout == ICW_OUT_SUB_REIM ? -d1 : d1), ICW_KC[KC_SQRT2], ICW_KC[KC_RSQRT2]);
-    const double ro = div_const(d2 + (ms.r_tout == ICW_OUT_SUB_REIM ? -d3 : d3), ICW_KC[KC_SQRT2], ICW_KC[KC_RSQRT2]);
-    const double dl = lean_dither<RT>(wl, acc.redraws);
-    const double dr = lean_dither<RT>(wr, acc.redraws);
-    const RenderOut a = render_one(rq, lo, dl);
-    const RenderOut b = render_one(rq, ro, dr);
-    acc.clips_l += a.clipped; acc.clips_r += b.clipped;
-    acc.peak_l = fmax(acc.peak_l, a.level); acc.peak_r = fmax(acc.peak_r, b.level);
-    store_frame_pcm(dst + i * 6, a.val, b.val, 3);
-    if (i == i_last) {
+    if (LAST != FRAME_LAST_ONLY) {
+        // master (:485-507)
+        d0 = (0.0 + o[0]) * ms.l_gain; d1 = (0.0 + o[1]) * ms.l_gain;
+        d2 = (0.0 + o[2]) * ms.r_gain; d3 = (0.0 + o[3]) * ms.r_gain;
+        const double lo = div_const(d0 + (ms.l_tout == ICW_OUT_SUB_REIM ? -d1 : d1), ICW_KC[KC_SQRT2], ICW_KC[KC_RSQRT2]);
+        const double ro = div_const(d2 + (ms.r_tout == ICW_OUT_SUB_REIM ? -d3 : d3), ICW_KC[KC_SQRT2], ICW_KC[KC_RSQRT2]);
+        const double dl = lean_dither<RT>(wl, acc.redraws);
+        const double dr = lean_dither<RT>(wr, acc.redraws);
+        const RenderOut a = render_one(rq, lo, dl);
+        const RenderOut b = render_one(rq, ro, dr);
+        acc.clips_l += a.clipped; acc.clips_r += b.clipped;
+        acc.peak_l = fmax(acc.peak_l, a.level); acc.peak_r = fmax(acc.peak_r, b.level);
+        store_frame_pcm(dst + i * 6, a.val, b.val, 3);
+    }
+    if (LAST == FRAME_LAST_ONLY || (LAST == FRAME_CHECK_LAST && i == i_last)) {
         st.bus[0][0] = v[0]; st.bus[0][1] = v[1]; st.bus[0][2] = v[2]; st.bus[0][3] = v[3];
         const int k = sh.n_out;
         st.bus[k][0] = o[0]; st.bus[k][1] = o[1]; st.bus[k][2] = o[2]; st.bus[k][3] = o[3];

@@ -51,4 +51,18 @@ __device__ __forceinline__ void mt_words_block(const uint32_t *__restrict__ old,
     }
 }
 
+// ---- the stream in windows -----------------------------------------------------------------------------------
+// u[j+624] = u[j+397] ^ twist(u[j], u[j+1]) reaches back 227 words at the nearest, so ANY window of up to 227
+// consecutive words can be made at once from what precedes it -- the windows need not be the reference's 624-word
+// blocks.  With the stream laid out LINEARLY in shared memory (624 words of history, then the tile's new words) a
+// thread makes word q from three loads at fixed offsets of one pointer: 3 LDS + 5 logic/multiply + 1 STS, every lane
+// busy, against ~28 issue slots a word for the block-shaped version above (227 of 256 lanes, then 170).  The words
+// stay UNTEMPERED in the buffer (the recurrence needs them so); whoever draws from them tempers at use.
+__device__ __forceinline__ uint32_t mt_window_word(uint32_t *__restrict__ u /* -> position of the new word */)
+{
+    const uint32_t n = u[-227] ^ mt_twist(u[-624], u[-623]);
+    u[0] = n;
+    return n;
+}
+
 }  // namespace icw

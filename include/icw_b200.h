@@ -257,7 +257,8 @@ int  icw_host_hb_convert(int filter_no, int to_basis, const double *in, double *
 /* ---- measurement: per-kernel device time from CUDA events on the launching stream ---------- */
 /* HILBERT: the exact recurrences (fused with the chain unless ICW_UNFUSED); SCAN_LOCAL / SCAN_APPLY: passes 1+2 and
  * pass 3 of the time-parallel converter; CHAIN: the pointwise kernel; MT: dither word generation incl. jump-ahead */
-enum { ICW_K_HILBERT = 0, ICW_K_CHAIN = 1, ICW_K_MT = 2, ICW_K_MISC = 3, ICW_K_SCAN_LOCAL = 4, ICW_K_SCAN_APPLY = 5, ICW_K_COUNT = 6 };
+enum { ICW_K_HILBERT = 0, ICW_K_CHAIN = 1, ICW_K_MT = 2, ICW_K_MISC = 3, ICW_K_SCAN_LOCAL = 4, ICW_K_SCAN_APPLY = 5,
+       ICW_K_SCAN_FUSED = 6 /* scan mode, whole chain in one kernel (icw_sfused.cu) */, ICW_K_COUNT = 7 };
 typedef struct icw_profile {
     double   ms[ICW_K_COUNT];       /* summed device time per kernel class since the last reset */
     uint64_t launches[ICW_K_COUNT];
