@@ -21,7 +21,8 @@
 //                         range's MT19937 words for both channels' generators (icw_mtdev.cuh, window form).
 //
 // Slices are handed over with named barriers (bar.arrive / bar.sync, one FULL and one EMPTY barrier per ring slot);
-// the register file is split with setmaxnreg (scan warps 152, pointwise warps 64).  A unit's filter state at its
+// the register file is split with setmaxnreg (scan warps 144, pointwise warps 64: the pool is what the CTA's own
+// warps give back, so the two must add up to the 640 x 96 registers of the launch).  A unit's filter state at its
 // first frame comes from a WARM-UP: the LOCAL pass alone over the frames before it (the filters forget: |p|^warm is
 // below 1e-19; the same fact the multi-GPU hand-off uses) -- so there is no pass 1 / pass 2 over the whole stream,
 // no carry arrays in HBM and no second read of the input.
@@ -156,7 +157,7 @@ scan_fused_kernel(const __grid_constant__ ModalCoef mc, const __grid_constant__ 
 
     if (tid < SF_SCAN_THREADS) {
         // ==========================================================================================================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");     // 256 x 144 + 384 x 64 = 640 x 96: exactly what the CTA was given at launch
         const int filt = tid & 1, chan = (tid >> 1) & 1, cf = tid & 3, c = tid >> 2;
         const double (*ksh)[SCAN_NMAX] = reinterpret_cast<const double (*)[SCAN_NMAX]>(sf_smem + SfSmem::KSH);
         double *carry = reinterpret_cast<double *>(sf_smem + SfSmem::CARRY);
@@ -323,19 +324,22 @@ scan_fused_kernel(const __grid_constant__ ModalCoef mc, const __grid_constant__ 
                         nb_sync(NB_EMPTY + ((gslice + k + 1) % SF_NSLOT), SF_THREADS);   // the odd filter's last value lands in the next slice
                     if (f < lc) {
                         const double xin = xp[(size_t)(k * (SF_SL / 2) + j) * 4];
-                        double y1 = direct ? d0x2 * xin : 0.0, y2 = 0.0;
+                        // four interleaved partial sums per output: with two scan warps per scheduler a 20-term chain of
+                        // dependent DFMAs (8 cycles each) is what the warp would otherwise spend its time waiting on
+                        double a1[4] = { direct ? d0x2 * xin : 0.0, 0.0, 0.0, 0.0 }, a2[4] = { 0.0, 0.0, 0.0, 0.0 };
 #pragma unroll
                         for (int m = 0; m < NM; ++m) {
                             if (RL && m == NM - 1) {                        // the real pole: im == 0 and its weights are 0
-                                y1 = fma(kcpr[m], S[m].re, y1);
+                                a1[m & 3] = fma(kcpr[m], S[m].re, a1[m & 3]);
                                 re_step(S[m], kpr[m], -xin);
-                                y2 = fma(kcr[m], S[m].re, y2);
+                                a2[m & 3] = fma(kcr[m], S[m].re, a2[m & 3]);
                             } else {
-                                y1 = fma(kcpr[m], S[m].re, fma(kcpi[m], S[m].im, y1));
+                                a1[m & 3] = fma(kcpr[m], S[m].re, fma(kcpi[m], S[m].im, a1[m & 3]));
                                 cx_step(S[m], kpr[m], kpi[m], -xin);
-                                y2 = fma(kcr[m], S[m].re, fma(kci[m], S[m].im, y2));
+                                a2[m & 3] = fma(kcr[m], S[m].re, fma(kci[m], S[m].im, a2[m & 3]));
                             }
                         }
+                        const double y1 = (a1[0] + a1[1]) + (a1[2] + a1[3]), y2 = (a2[0] + a2[1]) + (a2[2] + a2[3]);
                         *reinterpret_cast<double *>(sl + (2 * j + off) * 16) = y1;                       // re of its own frame
                         if (f + 1 < lc) {                                                               // im of the frame after it
                             if (2 * j + off + 1 < SF_SL) *reinterpret_cast<double *>(sl + (2 * j + off + 1) * 16 + 8) = y2;
