@@ -90,6 +90,8 @@ struct icw_engine {
     Scratch crc_partial;                // per-tile CRC registers + the result word
     Scratch ns_pre;                     // noise shaping: (value, dither) pairs between chain_kernel and ns_render_kernel
     struct ScanPlan { bool ready = false; ModalCoef mc; double *d_pw = nullptr; };
+    struct SfPlan { bool ready = false; SfTab tb; int64_t warm = 0; };
+    SfPlan sf[ICW_HB_NTYPES][2];        // [filter_no][baseline]: the one-kernel scan path's chunk tables (icw_sfused.h)
     ScanPlan scan[ICW_HB_NTYPES][2][4]; // [filter_no][baseline][chunk length: 256, 1024, 2048 (or the forced one); 3 = the one-kernel path's]
     int sfused = -1;                    // ICW_SFUSED: 1 = the one-kernel scan path wherever it applies, 0 = never, unset = where it pays
     MtJump mt;                          // MT19937 checkpoint service (icw_mt.cu)
@@ -780,25 +782,36 @@ static int get_scan_plan(icw_engine *e, int filter_no, bool baseline, double d0,
 // `pre`: dither words generated once for the whole call (pointing at this group's first frame), or NULL
 // `fuse_mt`: no word buffers at all -- chain_mt_kernel regenerates the dither inside the pointwise pass
 // scan mode, one long stream: the whole chain in one kernel (icw_sfused.cu)
+static icw_engine::SfPlan &get_sf_plan(icw_engine *e, int filter_no, bool baseline, double d0)
+{
+    icw_engine::SfPlan &p = e->sf[filter_no][baseline ? 1 : 0];
+    if (!p.ready) {
+        sfused_make_tables(filter_no, baseline, d0, p.tb);
+        p.warm = sfused_warm_frames(p.tb);
+        p.ready = true;
+    }
+    return p;
+}
+
 static int process_sfused(icw_session *s, int64_t n_frames, const uint8_t *d_in, uint8_t *d_out, cudaStream_t st)
 {
     icw_engine *e = s->e;
     const DevChain &ch = s->ch;
-    icw_engine::ScanPlan *plp;
-    int rc = get_scan_plan(e, s->spec.filter_no, !s->spec.is_kahan, s->coef.d0, SF_LC, &plp);
-    if (rc) return rc;
+    const icw_engine::SfPlan &sp = get_sf_plan(e, s->spec.filter_no, !s->spec.is_kahan, s->coef.d0);
     const int wps = ch.render.words_per_sample;
+    const int slots = e->sm_count * SF_CTAS_PER_SM;         // one wave of units
     MtPlan pl[2];
+    int rc;
     if (wps) {
         ProfSpan ps(s, st, ICW_K_MT);
         const uint32_t seeds[2] = { s->mt_seed[0][0], s->mt_seed[1][0] };
-        rc = e->mt.plan_pair(seeds, s->mt_drawn[0][0], n_frames * wps, e->sm_count, e->sm_count, st, &s->launches, pl);
+        rc = e->mt.plan_pair(seeds, s->mt_drawn[0][0], n_frames * wps, slots, e->sm_count, st, &s->launches, pl);
         if (rc) return fail(rc, "%s", e->mt.error());
     }
     {
         ProfSpan ps(s, st, ICW_K_SCAN_FUSED);
-        CK(launch_scan_fused(plp->mc, ch, s->d_streams, n_frames, d_in, d_out, wps ? &pl[0] : nullptr, wps ? &pl[1] : nullptr,
-                             e->sm_count, sfused_warm_frames(plp->mc), st));
+        CK(launch_scan_fused(sp.tb, ch, s->d_streams, n_frames, d_in, d_out, wps ? &pl[0] : nullptr, wps ? &pl[1] : nullptr,
+                             slots, sp.warm, st));
     }
     s->launches++;
     {
@@ -993,12 +1006,7 @@ static int call_begin(icw_session *s, int64_t n_total, cudaStream_t st, CallCtx 
         sfused_supports(ch, K, s->d_tap_bus || s->d_tap_lr) &&
         (!wps || (s->mt_drawn[0][0] == s->mt_drawn[1][0] && s->mt_drawn[0][0] % (uint64_t)wps == 0))) {
         bool go = e->sfused == 1;
-        if (!go) {
-            icw_engine::ScanPlan *plp;
-            int rc = get_scan_plan(e, s->spec.filter_no, !s->spec.is_kahan, s->coef.d0, SF_LC, &plp);
-            if (rc) return rc;
-            go = n_total / e->sm_count >= 4 * sfused_warm_frames(plp->mc);
-        }
+        if (!go) go = n_total / (e->sm_count * SF_CTAS_PER_SM) >= 2 * get_sf_plan(e, s->spec.filter_no, !s->spec.is_kahan, s->coef.d0).warm;
         if (go) { cx.sfused = true; cx.step = n_total; return ICW_OK; }
     }
     // the fused exact kernel reads word buffers; everything else that ends in chain_kernel can make its own

@@ -245,19 +245,14 @@ __host__ __device__ inline bool lean_fast_ok(const DevChain &ch)
     return lt && rt;
 }
 
+// n_value: the reference's scaled frame counter at frame i (adv_modulator.c:611-625), kept by the caller
 template <int RT, int LAST = FRAME_CHECK_LAST>
-__device__ __forceinline__ void lean_frame_fast(const DevChain &ch, DevStream &st, int64_t i, int64_t i_last, const double v[4],
-                                                uint4 wl, uint4 wr, uint8_t *dst, FrameAcc &acc, OscCounter &osc)
+__device__ __forceinline__ void lean_frame_fast_at(const DevChain &ch, DevStream &st, int64_t i, int64_t i_last, uint64_t n_value,
+                                                   const double v[4], uint4 wl, uint4 wr, uint8_t *dst, FrameAcc &acc)
 {
     const DevRender &rq = ch.render;
     const DevNode &sh = ch.nodes[0], &ms = ch.nodes[1];
-    // oscillator, scaled counter (adv_modulator.c:611-625)
-    uint64_t d = (uint64_t)(i - osc.frame);
-    osc.frame = i;
-    if (d >= ch.scale_sr) d %= ch.scale_sr;
-    osc.value += d;
-    if (osc.value >= ch.scale_sr) osc.value -= ch.scale_sr;
-    const double omega = norm_omega(ch, osc.value);
+    const double omega = norm_omega(ch, n_value);
     // shift node: mix from +0.0, gain, one phase for both channels (:519-550)
     double d0 = (0.0 + v[0]) * sh.l_gain, d1 = (0.0 + v[1]) * sh.l_gain;
     double d2 = (0.0 + v[2]) * sh.r_gain, d3 = (0.0 + v[3]) * sh.r_gain;
@@ -291,6 +286,19 @@ __device__ __forceinline__ void lean_frame_fast(const DevChain &ch, DevStream &s
         const int k = sh.n_out;
         st.bus[k][0] = o[0]; st.bus[k][1] = o[1]; st.bus[k][2] = o[2]; st.bus[k][3] = o[3];
     }
+}
+
+template <int RT, int LAST = FRAME_CHECK_LAST>
+__device__ __forceinline__ void lean_frame_fast(const DevChain &ch, DevStream &st, int64_t i, int64_t i_last, const double v[4],
+                                                uint4 wl, uint4 wr, uint8_t *dst, FrameAcc &acc, OscCounter &osc)
+{
+    // oscillator, scaled counter (adv_modulator.c:611-625)
+    uint64_t d = (uint64_t)(i - osc.frame);
+    osc.frame = i;
+    if (d >= ch.scale_sr) d %= ch.scale_sr;
+    osc.value += d;
+    if (osc.value >= ch.scale_sr) osc.value -= ch.scale_sr;
+    lean_frame_fast_at<RT, LAST>(ch, st, i, i_last, osc.value, v, wl, wr, dst, acc);
 }
 
 // plugs nobody writes keep whatever the context held (normally 0.0)

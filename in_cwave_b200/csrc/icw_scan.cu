@@ -26,6 +26,7 @@
 #include "icw_kernels.h"
 #include "icw_scan.h"
 #include "icw_scan_dev.cuh"
+#include "icw_sfused.h"
 #include "icw_hb_modal.inc"
 
 // 384 threads at 168 registers (12 warps per SM, ~100 B of spill per thread outside the sample loop's
@@ -124,6 +125,56 @@ void scan_make_coef(int filter_no, bool baseline, double d0, int L, ModalCoef &m
         }
         for (int r = nm; r <= SCAN_NMAX; ++r) mc.join[r] = L / 2;
     }
+}
+
+// The one-kernel path's chunk tables (icw_sfused.h: SfTab): every power of q = -p^2 a 16-frame chunk needs, the
+// functionals of the two outputs applied to them, and the chunk's own impulse-response taps -- long double from the
+// double-double poles and residues, rounded once.
+void sfused_make_tables(int filter_no, bool baseline, double d0, SfTab &tb)
+{
+    memset(&tb, 0, sizeof tb);
+    const int nm = ICW_HB_NMODES[filter_no];
+    tb.nm = nm;
+    tb.real_last = ICW_HB_MODES[filter_no][nm - 1].is_real;
+    tb.d0x2 = baseline ? 2.0 * d0 : 0.0;
+    ld ha[SF_NI], hb[SF_NI];
+    for (int k = 0; k < SF_NI; ++k) ha[k] = hb[k] = 0.0L;
+    for (int m = 0; m < nm; ++m) {
+        const icw_hb_mode &md = ICW_HB_MODES[filter_no][m];
+        const cld p = { (ld)md.p_re[0] + (ld)md.p_re[1], (ld)md.p_im[0] + (ld)md.p_im[1] };
+        const cld r = { (ld)md.r_re[0] + (ld)md.r_re[1], (ld)md.r_im[0] + (ld)md.r_im[1] };
+        const ld w = md.is_real ? 1.0L : 2.0L;
+        cld q = cmul(p, p);
+        q.re = -q.re; q.im = -q.im;
+        const cld rp = cmul(r, p);
+        const ld n2 = p.re * p.re + p.im * p.im;
+        // out1 = k4 S.re + k5 S.im (2 c p), out2 = k2 S.re + k3 S.im (-2 c): the constants of scan_make_coef, unrounded
+        const ld k4 = 2.0L * w * rp.re, k5 = -2.0L * w * rp.im, k2 = -2.0L * w * r.re, k3 = 2.0L * w * r.im;
+        cld qpow[SF_NI + 1];
+        cld g = { 1.0L, 0.0L };
+        for (int k = 0; k <= SF_NI; ++k) { qpow[k] = g; g = cmul(g, q); }
+        for (int j = 0; j < SF_NI; ++j) {
+            tb.q[j][m][0] = (double)-qpow[SF_NI - 1 - j].re;
+            tb.q[j][m][1] = (double)-qpow[SF_NI - 1 - j].im;
+        }
+        tb.q8[m][0] = (double)qpow[SF_NI].re; tb.q8[m][1] = (double)qpow[SF_NI].im;
+        tb.qt[m][0] = (double)q.re;           tb.qt[m][1] = (double)q.im;
+        tb.p[m][0] = (double)p.re;            tb.p[m][1] = (double)p.im;
+        tb.pinv[m][0] = (double)(p.re / n2);  tb.pinv[m][1] = (double)(-p.im / n2);
+        for (int i = 0; i < SF_NI; ++i) {
+            tb.ca[i][m][0] = (double)(k4 * qpow[i].re + k5 * qpow[i].im);
+            tb.ca[i][m][1] = (double)(-k4 * qpow[i].im + k5 * qpow[i].re);
+        }
+        for (int k = 0; k <= SF_NI; ++k) {
+            tb.cb[k][m][0] = (double)(k2 * qpow[k].re + k3 * qpow[k].im);
+            tb.cb[k][m][1] = (double)(-k2 * qpow[k].im + k3 * qpow[k].re);
+        }
+        for (int k = 0; k < SF_NI; ++k) {
+            ha[k] -= k4 * qpow[k].re + k5 * qpow[k].im;
+            hb[k] -= k2 * qpow[k].re + k3 * qpow[k].im;
+        }
+    }
+    for (int k = 0; k < SF_NI; ++k) { tb.ha[k] = (double)ha[k]; tb.hb[k] = (double)hb[k]; }
 }
 
 // ---------------------------------------------------------------------------------------------
