@@ -218,15 +218,18 @@ __device__ __forceinline__ void sf_level2_a(const SfTab &tb, const double (&x)[S
     // the start states, mode by mode: a LOOP whose counter only indexes the constants (so it lives in a uniform register and
     // the constants still arrive as LDCU / uniform operands) -- unrolled, the two halves of level 2 alone were 30 KB of
     // straight-line code, and the SM's instruction caches are 6 KB (L0) and 32 KB (L1.5) for everything the CTAs run
+    double2 sx = *tx, sy = *ty;
 #pragma unroll 1
-    for (int m = 0; m < NM; ++m, tx += SF_ESLOTS, ty += SF_ESLOTS) {
-        const double2 sx = *tx, sy = *ty;
+    for (int m = 0; m < NM; ++m) {
+        tx += SF_ESLOTS; ty += SF_ESLOTS;
+        const double2 nx = *tx, ny = *ty;               // the next mode's states, a trip ahead (behind the last mode: shared memory that is there, unused)
 #pragma unroll
         for (int i = 0; i < SF_NI; ++i) {
             const double2 k = *reinterpret_cast<const double2 *>(&tb.ca[i][m][0]);      // the real pole's imaginary weight is 0, and so is its state's
             ax[i] = fma(k.x, sx.x, fma(k.y, sx.y, ax[i]));
             ay[i] = fma(k.x, sy.x, fma(k.y, sy.y, ay[i]));
         }
+        sx = nx; sy = ny;
     }
 }
 
@@ -244,15 +247,18 @@ __device__ __forceinline__ void sf_level2_b(const SfTab &tb, const double (&x)[S
 #pragma unroll
         for (int j = 0; j < k; ++j) by[k] = fma(tb.hb[k - 1 - j], x[2 * j + 1], by[k]);
     }
+    double2 sx = *tx, sy = *ty;
 #pragma unroll 1
-    for (int m = 0; m < NM; ++m, tx += SF_ESLOTS, ty += SF_ESLOTS) {
-        const double2 sx = *tx, sy = *ty;
+    for (int m = 0; m < NM; ++m) {
+        tx += SF_ESLOTS; ty += SF_ESLOTS;
+        const double2 nx = *tx, ny = *ty;
 #pragma unroll
         for (int k = 0; k < SF_NI; ++k) {
             const double2 k1 = *reinterpret_cast<const double2 *>(&tb.cb[k + 1][m][0]), k0 = *reinterpret_cast<const double2 *>(&tb.cb[k][m][0]);
             bx[k] = fma(k1.x, sx.x, fma(k1.y, sx.y, bx[k]));
             by[k] = fma(k0.x, sy.x, fma(k0.y, sy.y, by[k]));
         }
+        sx = nx; sy = ny;
     }
 }
 
