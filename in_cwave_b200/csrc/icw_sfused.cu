@@ -53,6 +53,10 @@ constexpr int SF_PW_THREADS = SF_R / 4;                         // 128: four fra
 constexpr int SF_THREADS = SF_SCAN_THREADS + SF_GEN_THREADS + SF_PW_THREADS;
 constexpr int SF_PW0 = SF_SCAN_THREADS + SF_GEN_THREADS;        // first pointwise thread
 constexpr int SF_FPT = SF_R / SF_PW_THREADS;                    // frames per pointwise thread and range
+#ifndef ICW_SF_PW_TRIP
+#define ICW_SF_PW_TRIP 1
+#endif
+constexpr int SF_PW_TRIP = ICW_SF_PW_TRIP;                      // of which side by side in one loop trip (1, 2 or 4)
 constexpr int SF_APITCH = SF_LC * 16 + 16;                      // bytes per chunk of one channel's analytic plane (16 x (re, im), padded: banks)
 constexpr int SF_PLANE = SF_CH * SF_APITCH + 64;                // the two planes sit 16 banks apart
 constexpr int SF_ABUF = 2 * SF_PLANE;                           // one analytic buffer
@@ -599,15 +603,16 @@ scan_fused_kernel(const __grid_constant__ SfTab tb, const __grid_constant__ DevC
                 // chain of dependent FP64 operations
                 uint64_t nvc = osc.at(ch, F + t);
 #pragma unroll 1
-                for (int k2 = 0; k2 < SF_FPT; k2 += 2) {                    // two frames a trip: a loop the instruction cache can hold
-                    uint64_t nv[2];
-                    nv[0] = nvc;
-                    nv[1] = nvc + SF_PW_THREADS;                            // scaled counter (lean_fast_ok): wraps at scale_sr > SF_PW_THREADS
-                    if (nv[1] >= ch.scale_sr) nv[1] -= ch.scale_sr;
-                    nvc = nv[1] + SF_PW_THREADS;
-                    if (nvc >= ch.scale_sr) nvc -= ch.scale_sr;
+                for (int k2 = 0; k2 < SF_FPT; k2 += SF_PW_TRIP) {           // SF_PW_TRIP frames a trip: a loop the instruction cache can hold
+                    uint64_t nv[SF_PW_TRIP];
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) {
+                    for (int k = 0; k < SF_PW_TRIP; ++k) {
+                        nv[k] = nvc;
+                        nvc += SF_PW_THREADS;                               // scaled counter (lean_fast_ok): wraps at scale_sr > SF_PW_THREADS
+                        if (nvc >= ch.scale_sr) nvc -= ch.scale_sr;
+                    }
+#pragma unroll
+                    for (int k = 0; k < SF_PW_TRIP; ++k) {
                         const int f = t + (k2 + k) * SF_PW_THREADS;
                         const uint8_t *pa = an + (f >> 4) * SF_APITCH + (f & 15) * 16;
                         const double2 a0 = *reinterpret_cast<const double2 *>(pa), a1 = *reinterpret_cast<const double2 *>(pa + SF_PLANE);
