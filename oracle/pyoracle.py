@@ -118,6 +118,7 @@ def build(ref: bool = True) -> None:
     subprocess.run(["make", "-s", "-C", str(HERE), "port"], check=True)
     if ref:
         subprocess.run(["make", "-s", "-C", str(HERE), "ref"], check=True)
+        subprocess.run(["make", "-s", "-C", str(HERE), "ref_gpu"], check=True)     # needs libicw_b200.so: a no-op without it
 
 
 _port = None
@@ -169,41 +170,67 @@ def have_ref() -> bool:
     return (HERE / "_ref" / "libicw_ref.so").exists()
 
 
+def _bind_ref(L):
+    L.icwref_default_cfg.argtypes = [_p(RefCfg)]
+    L.icwref_reset.argtypes = [_p(RefCfg)]
+    L.icwref_set_graph.argtypes = [_p(Node), C.c_int, C.c_int]
+    L.icwref_set_graph.restype = C.c_int
+    L.icwref_process_file.argtypes = [C.c_char_p, C.c_uint, C.c_char_p, C.c_int64, _dbl_p,
+                                      _p(C.c_int), C.c_int]
+    L.icwref_process_file.restype = C.c_int64
+    L.icwref_transcode_file.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int64, _p(C.c_int)]
+    L.icwref_transcode_file.restype = C.c_int64
+    L.icwref_get_stats.argtypes = [_p(RefStats), C.c_int]
+    L.icwref_hilbert.argtypes = [C.c_uint, C.c_int, C.c_int, _dbl_p, C.c_int64, _dbl_p, _dbl_p]
+    L.icwref_hilbert.restype = C.c_uint64
+    L.icwref_iir.argtypes = [C.c_uint, C.c_int, C.c_int, _dbl_p, C.c_int64, _dbl_p]
+    L.icwref_render.argtypes = [_p(RefCfg), C.c_uint32, _dbl_p, C.c_int64, C.c_char_p,
+                                _p(C.c_uint), _dbl_p]
+    L.icwref_render.restype = C.c_int64
+    L.icwref_mt_words.argtypes = [C.c_uint32, C.c_int64, C.c_int64, _p(C.c_uint32)]
+    L.icwref_mt_words_key.argtypes = [_p(C.c_uint32), C.c_uint32, C.c_int64, _p(C.c_uint32)]
+    L.icwref_mt_dsopen.argtypes = [C.c_uint32, C.c_int64, _dbl_p]
+    L.icwref_reset_from_file.argtypes = [C.c_char_p]
+    L.icwref_reset_from_file.restype = C.c_int
+    L.icwref_save_config.argtypes = [C.c_char_p]
+    L.icwref_save_config.restype = C.c_int
+    L.icwref_get_cfg.argtypes = [_p(RefCfg)]
+    L.icwref_get_graph.argtypes = [_p(Node), C.c_int]
+    L.icwref_get_graph.restype = C.c_int
+    L.icwref_set_render_live.argtypes = [_p(RefCfg)]
+    L.icwref_reset_live.argtypes = [C.c_int, C.c_int]
+    return L
+
+
 def ref():
     global _ref
     if _ref is None:
         so = HERE / "_ref" / "libicw_ref.so"
         if not so.exists():
             raise FileNotFoundError(f"{so} not built (needs /root/reference; run make -C oracle ref)")
-        L = C.CDLL(str(so))
-        L.icwref_default_cfg.argtypes = [_p(RefCfg)]
-        L.icwref_reset.argtypes = [_p(RefCfg)]
-        L.icwref_set_graph.argtypes = [_p(Node), C.c_int, C.c_int]
-        L.icwref_set_graph.restype = C.c_int
-        L.icwref_process_file.argtypes = [C.c_char_p, C.c_uint, C.c_char_p, C.c_int64, _dbl_p,
-                                          _p(C.c_int), C.c_int]
-        L.icwref_process_file.restype = C.c_int64
-        L.icwref_transcode_file.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int64, _p(C.c_int)]
-        L.icwref_transcode_file.restype = C.c_int64
-        L.icwref_get_stats.argtypes = [_p(RefStats), C.c_int]
-        L.icwref_hilbert.argtypes = [C.c_uint, C.c_int, C.c_int, _dbl_p, C.c_int64, _dbl_p, _dbl_p]
-        L.icwref_hilbert.restype = C.c_uint64
-        L.icwref_iir.argtypes = [C.c_uint, C.c_int, C.c_int, _dbl_p, C.c_int64, _dbl_p]
-        L.icwref_render.argtypes = [_p(RefCfg), C.c_uint32, _dbl_p, C.c_int64, C.c_char_p,
-                                    _p(C.c_uint), _dbl_p]
-        L.icwref_render.restype = C.c_int64
-        L.icwref_mt_words.argtypes = [C.c_uint32, C.c_int64, C.c_int64, _p(C.c_uint32)]
-        L.icwref_mt_words_key.argtypes = [_p(C.c_uint32), C.c_uint32, C.c_int64, _p(C.c_uint32)]
-        L.icwref_mt_dsopen.argtypes = [C.c_uint32, C.c_int64, _dbl_p]
-        L.icwref_reset_from_file.argtypes = [C.c_char_p]
-        L.icwref_reset_from_file.restype = C.c_int
-        L.icwref_save_config.argtypes = [C.c_char_p]
-        L.icwref_save_config.restype = C.c_int
-        L.icwref_get_cfg.argtypes = [_p(RefCfg)]
-        L.icwref_get_graph.argtypes = [_p(Node), C.c_int]
-        L.icwref_get_graph.restype = C.c_int
-        _ref = L
+        _ref = _bind_ref(C.CDLL(str(so)))
     return _ref
+
+
+_ref_gpu = None
+
+
+def have_ref_gpu() -> bool:
+    return (HERE / "_ref_gpu" / "libicw_ref_gpu.so").exists()
+
+
+def ref_gpu():
+    """The SAME reference sources with amod_process_samples' frame loop running on the GPU
+    (in_cwave_b200/host/adv_modulator_gpu.c over libicw_b200.so; `make -C oracle ref_gpu`)."""
+    global _ref_gpu
+    if _ref_gpu is None:
+        so = HERE / "_ref_gpu" / "libicw_ref_gpu.so"
+        if not so.exists():
+            raise FileNotFoundError(f"{so} not built (needs /root/reference and libicw_b200.so; run make -C oracle ref_gpu)")
+        L = _bind_ref(C.CDLL(str(so)))
+        L.amod_gpu_last_error.restype = C.c_char_p
+        _ref_gpu = L
+    return _ref_gpu
 
 
 # ---------------------------------------------------------------------------------------------
@@ -344,9 +371,9 @@ def cwave_bytes(d: dict, raw: np.ndarray, version: int = 2, crc: int = 0) -> byt
 
 
 def ref_process(d: dict, raw: np.ndarray, taps: list[int] | None = None, read_quant: int = 4096,
-                reset: bool = True, tmpdir: str | None = None):
-    """Run the compiled reference over the same bytes (written to a temp file)."""
-    L = ref()
+                reset: bool = True, tmpdir: str | None = None, lib=None):
+    """Run the compiled reference over the same bytes (written to a temp file).  lib: ref() (default) or ref_gpu()."""
+    L = lib if lib is not None else ref()
     if reset:
         cfg = make_refcfg(d)
         # ms-based fades in the reference config; specs carry frames -> convert when exact

@@ -109,10 +109,15 @@ void icwref_default_cfg(icwref_cfg *c)
 }
 
 /* fresh plugin state == one independent stream ("checkpoint/resume") */
+/* present only in the build whose frame loop runs on the GPU (in_cwave_b200/host/adv_modulator_gpu.c): a fresh plugin
+   instance re-seeds the dither generators, so the sessions that hold their positions go too */
+void amod_gpu_reset(void) __attribute__((weak));
+
 void icwref_reset(const icwref_cfg *c)
 {
     g_cfg = *c;
     (void)winampGetInModule2();
+    if (amod_gpu_reset) amod_gpu_reset();
 }
 
 /* fresh plugin state configured by the reference's own parser from a config file; returns load_config()'s verdict */
@@ -121,6 +126,7 @@ int icwref_reset_from_file(const char *path)
     g_cfg_path = path;
     g_cfg_loaded = 0;
     (void)winampGetInModule2();
+    if (amod_gpu_reset) amod_gpu_reset();
     g_cfg_path = NULL;
     return g_cfg_loaded;
 }
@@ -156,6 +162,27 @@ int icwref_save_config(const char *path)
 {
     the.cfg.dsp_list = amod_cleanup(TRUE);
     return save_config(path);
+}
+
+/* a renderer-parameter change on the LIVE plugin, as the GUI thread does it (src/amod_gui_control.c:1555-1602):
+   no re-initialisation, both contexts keep their state; takes effect at the next block */
+void icwref_set_render_live(const icwref_cfg *c)
+{
+    SR_VCONFIG v;
+    v.dth_bits = c->dth_bits;
+    v.quantz_type = c->quantz_type;
+    v.render_type = c->render_type;
+    v.nshape_type = c->nshape_type;
+    v.sign_bits16 = c->sign_bits16;
+    v.sign_bits24 = c->sign_bits24;
+    srenders_set_vcfg(&v);
+}
+
+/* mod_context_reset_hilbert / _reset_framecnt on the transcode context (src/in_cwave.c:162,287) */
+void icwref_reset_live(int hilbert, int framecnt)
+{
+    if (hilbert) mod_context_reset_hilbert(&the.mc_transcode);
+    if (framecnt) mod_context_reset_framecnt(&the.mc_transcode);
 }
 
 /* flat description of one DSP-list node, in EXECUTION order (master last) */
