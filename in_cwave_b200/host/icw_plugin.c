@@ -619,3 +619,60 @@ void winampGetExtendedRead_close(intptr_t handle)
     P.open = 0;
     P.pcm_have = P.pcm_taken = 0;
 }
+
+/* ---- the input-module table (reference src/in_cwave.c:551-572, src/playback.c: get_playback_iface) -------------------------- */
+static int g_last_length_ms;
+
+static void im_config(void *w) { (void)w; }
+static void im_about(void *w) { (void)w; }
+static int  im_init(void) { ensure_defaults(); return 0; }          /* IN_INIT_SUCCESS */
+static void im_quit(void) { icwp_reset(); }
+static void im_getfileinfo(const char *file, char *title, int *length_in_ms)
+{
+    icwp_fileinfo fi;
+    if (title) title[0] = 0;
+    if (length_in_ms) *length_in_ms = -1000;                         /* the reference's "unknown" (src/playback.c) */
+    if (!file || !*file) {                                           /* NULL / "": the file last asked about */
+        if (length_in_ms && g_last_length_ms) *length_in_ms = g_last_length_ms;
+        return;
+    }
+    ensure_defaults();
+    if (!icwp_probe(file, &P.opt, &fi)) {
+        if (title) snprintf(title, 2048, "-CAN'T OPEN-");                /* src/playback.c:getfileinfo */
+        return;
+    }
+    if (title) {
+        const char *b = strrchr(file, '/');
+        const char *b2 = strrchr(file, '\\');
+        if (b2 && (!b || b2 > b)) b = b2;
+        snprintf(title, 2048, "%s", b ? b + 1 : file);               /* GETFILEINFO_TITLE_LENGTH */
+    }
+    g_last_length_ms = (int)(((fi.n_samples + fi.n_tail) * 1000) / (fi.sample_rate ? fi.sample_rate : 1));
+    if (length_in_ms) *length_in_ms = g_last_length_ms;
+}
+static int  im_infobox(const char *f, void *w) { (void)f; (void)w; return 1; }   /* INFOBOX_UNCHANGED */
+static int  im_isourfile(const char *fn) { (void)fn; return 0; }                  /* by extension only, like the reference */
+static int  im_play(const char *fn) { (void)fn; return ICWP_PLAY_UNSUPPORTED; }
+static void im_void(void) { }
+static int  im_zero(void) { return 0; }
+static int  im_getlength(void) { return g_last_length_ms; }
+static void im_int(int a) { (void)a; }
+
+static icwp_in_module g_in_module = {
+    ICWP_IN_VER,
+    (char *)"in_cwave on B200 (transcode entry points; playback out of scope)",
+    0, 0,
+    (char *)"cwave\0CWAVE analytic signal (*.cwave)\0wav\0WAV / RWAVE (*.wav)\0",
+    1, 1,
+    im_config, im_about, im_init, im_quit, im_getfileinfo, im_infobox, im_isourfile,
+    im_play, im_void, im_void, im_zero, im_void,
+    im_getlength, im_zero, im_int, im_int, im_int,
+    0, 0, 0, 0, 0, 0, 0, 0, 0,          /* visualisation feeds: filled in by the host */
+    0, 0, 0, 0, 0, 0
+};
+
+icwp_in_module *winampGetInModule2(void)
+{
+    ensure_defaults();
+    return &g_in_module;
+}

@@ -11,7 +11,7 @@ from . import _abi, spec as _spec
 PLUGIN_PATH = Path(__file__).resolve().parent / "libicw_plugin.so"
 EXPORTS = ["winampGetExtendedRead_open", "winampGetExtendedRead_getData", "winampGetExtendedRead_setTime",
            "winampGetExtendedRead_close", "icwp_configure", "icwp_reset", "icwp_stats", "icwp_probe",
-           "icwp_load_config", "icwp_save_config", "icwp_check_cwave", "icwp_io_stats"]
+           "icwp_load_config", "icwp_save_config", "icwp_check_cwave", "icwp_io_stats", "winampGetInModule2"]
 
 
 class Options(C.Structure):

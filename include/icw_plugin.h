@@ -97,6 +97,59 @@ int  icwp_load_config(const char *path, icw_chain_spec *chain, icwp_options *opt
 /* writes a file the reference's load_config() accepts (doubles as bit patterns, like save_config) */
 int  icwp_save_config(const char *path, const icw_chain_spec *chain, const icwp_options *opt);
 
+/* ---- the input-module table (reference Winamp/IN2.H:56-154, returned by winampGetInModule2, src/in_cwave.c:551-572) ----
+ * Same member order and meaning as the SDK's In_Module for the narrow-character build (IN_VER 0x101); window and
+ * module handles, the output module and the service pointer are opaque here.  What this library serves of it:
+ * the description and extension list, Init / Quit (plugin-wide state like the reference's one-time init),
+ * GetFileInfo (title = file name, length from the header incl. the sec_align tail, src/playback.c), IsOurFile,
+ * GetLength.  The PLAYBACK half (Play / Pause / Stop / seek, the decode thread, visualisation feeds, src/playback.c)
+ * is out of scope: those members are present and callable, Play returns ICWP_PLAY_UNSUPPORTED (a non-zero,
+ * non -1 value: "other error" in the SDK's convention) and the rest do nothing. */
+#define ICWP_IN_VER 0x101
+#define ICWP_PLAY_UNSUPPORTED 2
+typedef struct icwp_in_module {
+    int version;
+    char *description;
+    void *hMainWindow, *hDllInstance;
+    char *FileExtensions;
+    int is_seekable;
+    int UsesOutputPlug;
+    void (*Config)(void *hwndParent);
+    void (*About)(void *hwndParent);
+    int  (*Init)(void);
+    void (*Quit)(void);
+    void (*GetFileInfo)(const char *file, char *title, int *length_in_ms);
+    int  (*InfoBox)(const char *file, void *hwndParent);
+    int  (*IsOurFile)(const char *fn);
+    int  (*Play)(const char *fn);
+    void (*Pause)(void);
+    void (*UnPause)(void);
+    int  (*IsPaused)(void);
+    void (*Stop)(void);
+    int  (*GetLength)(void);
+    int  (*GetOutputTime)(void);
+    void (*SetOutputTime)(int time_in_ms);
+    void (*SetVolume)(int volume);
+    void (*SetPan)(int pan);
+    void (*SAVSAInit)(int maxlatency_in_ms, int srate);
+    void (*SAVSADeInit)(void);
+    void (*SAAddPCMData)(void *PCMData, int nch, int bps, int timestamp);
+    int  (*SAGetMode)(void);
+    int  (*SAAdd)(void *data, int timestamp, int csa);
+    void (*VSAAddPCMData)(void *PCMData, int nch, int bps, int timestamp);
+    int  (*VSAGetMode)(int *specNch, int *waveNch);
+    int  (*VSAAdd)(void *data, int timestamp);
+    void (*VSASetInfo)(int srate, int nch);
+    int  (*dsp_isactive)(void);
+    int  (*dsp_dosamples)(short int *samples, int numsamples, int bps, int nch, int srate);
+    void (*EQSet)(int on, char data[10], int preamp);
+    void (*SetInfo)(int bitrate, int srate, int stereo, int synched);
+    void *outMod;
+    void *service;
+} icwp_in_module;
+/* reference src/in_cwave.c:551: one-time plugin init (defaults, fresh contexts) + the table */
+icwp_in_module *winampGetInModule2(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -103,6 +103,43 @@ def test_plugin_exports_the_reference_symbols():
         assert hasattr(L, name)
 
 
+def test_input_module_table(tmp_path):
+    """winampGetInModule2 (reference src/in_cwave.c:551-572): the SDK's In_Module layout (Winamp/IN2.H:56-154) with the
+    members this library serves -- extension list, Init/Quit, GetFileInfo (length incl. the sec_align tail, like
+    src/playback.c:getfileinfo), GetLength -- and the playback half present but refusing."""
+    L = plugin.lib()
+    V = C.c_void_p
+    fn = lambda res, *a: C.CFUNCTYPE(res, *a)
+
+    class InModule(C.Structure):
+        _fields_ = [("version", C.c_int), ("description", C.c_char_p), ("hMainWindow", V), ("hDllInstance", V),
+                    ("FileExtensions", V), ("is_seekable", C.c_int), ("UsesOutputPlug", C.c_int),
+                    ("Config", fn(None, V)), ("About", fn(None, V)), ("Init", fn(C.c_int)), ("Quit", fn(None)),
+                    ("GetFileInfo", fn(None, C.c_char_p, C.c_char_p, C.POINTER(C.c_int))),
+                    ("InfoBox", fn(C.c_int, C.c_char_p, V)), ("IsOurFile", fn(C.c_int, C.c_char_p)),
+                    ("Play", fn(C.c_int, C.c_char_p)), ("Pause", fn(None)), ("UnPause", fn(None)), ("IsPaused", fn(C.c_int)),
+                    ("Stop", fn(None)), ("GetLength", fn(C.c_int)), ("GetOutputTime", fn(C.c_int)),
+                    ("SetOutputTime", fn(None, C.c_int)), ("SetVolume", fn(None, C.c_int)), ("SetPan", fn(None, C.c_int))]
+    L.winampGetInModule2.restype = C.POINTER(InModule)
+    m = L.winampGetInModule2().contents
+    assert m.version == 0x101 and m.is_seekable == 1 and m.UsesOutputPlug == 1
+    ext = C.string_at(m.FileExtensions, 80)
+    assert ext.startswith(b"cwave\0") and b"\0wav\0" in ext
+    assert m.Init() == 0
+    d = dict(fmt="wav_i16", n_channels=2, sample_rate=8000)
+    f = tmp_path / "len.wav"
+    f.write_bytes(po.wav_bytes(d, np.zeros(12345 * 4, dtype=np.uint8)))
+    title = C.create_string_buffer(2048)
+    ms = C.c_int(0)
+    m.GetFileInfo(str(f).encode(), title, C.byref(ms))
+    assert title.value == b"len.wav" and ms.value == 12345 * 1000 // 8000
+    assert m.GetLength() == ms.value
+    m.GetFileInfo(str(tmp_path / "missing.wav").encode(), title, C.byref(ms))
+    assert ms.value == -1000 and title.value == b"-CAN'T OPEN-"
+    assert m.Play(str(f).encode()) == 2 and m.IsPaused() == 0
+    m.Stop(); m.Pause(); m.SetVolume(10); m.Quit()
+
+
 @pytest.mark.gpu
 @pytest.mark.skipif(not po.have_ref(), reason="oracle/_ref/libicw_ref.so not built")
 def test_a_reference_config_file_drives_both_plugins_to_the_same_bytes(tmp_path):
