@@ -16,7 +16,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libicw_b200.so"
-SOURCES = ["icw_api.cu", "icw_kernels.cu", "icw_fused.cu", "icw_scan.cu", "icw_mt.cu", "icw_crc.cu", "icw_chainmt.cu", "icw_comm.cu", "icw_sfused.cu"]
+SOURCES = ["icw_api.cu", "icw_kernels.cu", "icw_fused.cu", "icw_split.cu", "icw_scan.cu", "icw_mt.cu", "icw_crc.cu", "icw_chainmt.cu", "icw_comm.cu", "icw_sfused.cu"]
 HOST_SOURCES = ["icw_hbconv.cpp"]      # plain g++ (binary128 arithmetic: nvcc's front end does not take __float128)
 NVCC_FLAGS = [
     "-O3", "-std=c++17",

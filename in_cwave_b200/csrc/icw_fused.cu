@@ -14,6 +14,7 @@
 // The FP64 pipe is the bound: 4 chain warps need ~2*281 issue cycles per sample each, the
 // latency of the serial state sum is ~76*8 cycles per sample, and the helpers' ~120 op/frame
 // fit in the slack.
+#include <cstdlib>
 #include "icw_dev.cuh"
 #include "icw_kernels.h"
 #include "icw_hb.cuh"
@@ -214,6 +215,15 @@ cudaError_t launch_hb_fused(const HbCoef &coef, const DevChain &ch, DevStream *s
                             const uint32_t *mtw_l, const uint32_t *mtw_r, size_t mt_stream_stride,
                             uint8_t *out, size_t out_stride, double *tap_bus, double *tap_lr, cudaStream_t s)
 {
+    // Kahan summation (the reference's default): the split-warp kernel (icw_split.cu); ICW_FUSED_ONE_WARP=1 keeps the
+    // one-instruction-stream form below for A/B runs.  Baseline summation is two short sums and stays here.
+    static const bool one_warp = [] { const char *v = getenv("ICW_FUSED_ONE_WARP"); return v && *v == '1'; }();
+    if (ch.is_kahan && !one_warp) {
+        const int fast = !tap_bus && !tap_lr && ch.render.render_type == ICW_RENDER_ROUND && lean_fast_ok(ch) &&
+                         ((size_t)(uintptr_t)out & 3u) == 0 && (n_streams == 1 || (out_stride & 3u) == 0);
+        return launch_hb_split(coef, ch, streams, n_streams, n_frames, in, in_stride, mtw_l, mtw_r, mt_stream_stride,
+                               out, out_stride, tap_bus, tap_lr, fast, s);
+    }
 #define ICW_FUSED_CASE(O) \
     case O: return launch_fused_ord<O>(ch.is_kahan, coef, ch, streams, n_streams, n_frames, in, in_stride, \
                                        mtw_l, mtw_r, mt_stream_stride, out, out_stride, tap_bus, tap_lr, s)
