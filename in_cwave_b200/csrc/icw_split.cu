@@ -51,7 +51,10 @@ constexpr int SP_NS = ICW_SPLIT_NS;             // streams per CTA (<= 32: one l
 constexpr int SP_NCH = SP_NS * 4;               // recurrences per CTA = doubles per row of W / YS
 constexpr int SP_T = ICW_SPLIT_T;               // frames per tile
 #ifndef ICW_SPLIT_PRELOAD
-#define ICW_SPLIT_PRELOAD 1
+#define ICW_SPLIT_PRELOAD 0
+#endif
+#ifndef ICW_SPLIT_OPIPE
+#define ICW_SPLIT_OPIPE 0
 #endif
 #ifndef ICW_SPLIT_K
 #define ICW_SPLIT_K 1
@@ -300,6 +303,27 @@ hb_split_kernel(const __grid_constant__ HbCoef coef, const __grid_constant__ Dev
 #pragma unroll
                     for (int k = 0; k < K; ++k) x[k] = __dmul_rn(__dmul_rn(r[K - 1 - k], coef.fb[0]), coef.d0);
                     comp_add_k<K>(o, x);
+#if ICW_SPLIT_OPIPE
+                    // the two addends of term i+1 are formed before term i is added (program order is what an in-order
+                    // issue port sees: a product formed right in front of its addition puts two DMUL latencies into the
+                    // chain of additions)
+                    double xa[K], xb[K];
+#pragma unroll
+                    for (int k = 0; k < K; ++k) { xa[k] = __dmul_rn(r[K - k], coef.ff[1]); xb[k] = __dmul_rn(__dmul_rn(r[K - k], coef.fb[1]), coef.d0); }
+#pragma unroll
+                    for (int i = 1; i < ORD; ++i) {
+                        double na[K], nb[K];
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            na[k] = i + 1 < ORD ? __dmul_rn(r[K - 1 - k + (i + 1 < ORD ? i + 1 : i)], coef.ff[i + 1 < ORD ? i + 1 : i]) : 0.0;
+                            nb[k] = i + 1 < ORD ? __dmul_rn(__dmul_rn(r[K - 1 - k + (i + 1 < ORD ? i + 1 : i)], coef.fb[i + 1 < ORD ? i + 1 : i]), coef.d0) : 0.0;
+                        }
+                        comp_add_k<K>(o, xa);
+                        comp_add_k<K>(o, xb);
+#pragma unroll
+                        for (int k = 0; k < K; ++k) { xa[k] = na[k]; xb[k] = nb[k]; }
+                    }
+#else
 #pragma unroll
                     for (int i = 1; i < ORD; ++i) {
 #pragma unroll
@@ -309,6 +333,7 @@ hb_split_kernel(const __grid_constant__ HbCoef coef, const __grid_constant__ Dev
                         for (int k = 0; k < K; ++k) x[k] = __dmul_rn(__dmul_rn(r[K - 1 - k + i], coef.fb[i]), coef.d0);
                         comp_add_k<K>(o, x);
                     }
+#endif
 #pragma unroll
                     for (int k = 0; k < K; ++k)
                         if (t + k < len) yp[(t + k) * SP_NCH] = o[k].s;     // no d0*x term: bug-for-bug (hblpf.c:1056)

@@ -77,6 +77,62 @@ __global__ void thr3_kernel(double *out, long long *cyc, int iters, const double
     if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
 }
 
+// DADD with TWO vector-register operands (the compensated sums of the exact mode: every addend is a register):
+// x[k] = x[k] + y[k]; and the compensated addition itself (4 dependent DADDs, all operands registers), ILP chains
+template <int ILP>
+__global__ void thr2_kernel(double *out, long long *cyc, int iters, const double *seed)
+{
+    double x[ILP], y[ILP];
+#pragma unroll
+    for (int k = 0; k < ILP; ++k) { x[k] = seed[threadIdx.x + k]; y[k] = seed[threadIdx.x + k + 64]; }
+    __syncthreads();
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+#pragma unroll
+            for (int k = 0; k < ILP; ++k) x[k] = __dadd_rn(x[k], y[k]);
+        }
+    }
+    __syncthreads();
+    long long t1 = clock64();
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < ILP; ++k) s += x[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+}
+template <int ILP>
+__global__ void kahan_kernel(double *out, long long *cyc, int iters, const double *seed)
+{
+    double s_[ILP], c_[ILP], x[ILP];
+#pragma unroll
+    for (int k = 0; k < ILP; ++k) { s_[k] = seed[threadIdx.x + k]; c_[k] = seed[threadIdx.x + k + 64]; x[k] = seed[threadIdx.x + k + 128]; }
+    __syncthreads();
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double y[ILP], t[ILP], d[ILP];
+#pragma unroll
+            for (int k = 0; k < ILP; ++k) y[k] = __dsub_rn(x[k], c_[k]);
+#pragma unroll
+            for (int k = 0; k < ILP; ++k) t[k] = __dadd_rn(s_[k], y[k]);
+#pragma unroll
+            for (int k = 0; k < ILP; ++k) d[k] = __dsub_rn(t[k], s_[k]);
+#pragma unroll
+            for (int k = 0; k < ILP; ++k) { c_[k] = __dsub_rn(d[k], y[k]); s_[k] = t[k]; }
+        }
+    }
+    __syncthreads();
+    long long t1 = clock64();
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < ILP; ++k) s += s_[k] + c_[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+}
+
 int main()
 {
     double *out; long long *cyc, h;
@@ -118,6 +174,33 @@ int main()
             double ops = (double)iters * 16 * 8 * warps * 32;
             printf("DFMA 3 vector operands, %2d warps/SM x ILP8: %.2f lanes/clk/SM (%.1f cycles per warp-instruction per SMSP)\n",
                    warps, ops / h, (double)h / ((double)iters * 16 * 8 * ((warps + 3) / 4)));
+        }
+    }
+    {
+        double *seed; cudaMalloc(&seed, 4096 * 8); cudaMemset(seed, 0, 4096 * 8);
+        for (int warps = 1; warps <= 32; warps *= 2) {
+            for (int rep = 0; rep < 2; ++rep) {
+                thr2_kernel<4><<<p.multiProcessorCount, warps * 32>>>(out, cyc, iters, seed);
+                cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+            }
+            printf("DADD 2 vector operands, %2d warps/SM x ILP4: %.2f lanes/clk/SM (%.2f cycles per warp-instruction per SMSP)\n",
+                   warps, (double)iters * 16 * 4 * warps * 32 / h, (double)h / ((double)iters * 16 * 4 * ((warps + 3) / 4)));
+        }
+        for (int warps = 1; warps <= 32; warps *= 2) {
+            for (int rep = 0; rep < 2; ++rep) {
+                kahan_kernel<1><<<p.multiProcessorCount, warps * 32>>>(out, cyc, iters, seed);
+                cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+            }
+            printf("compensated addition (4 dependent DADD, registers), %2d warps/SM x ILP1: %.2f cycles per DADD per warp, %.2f pipe cycles per warp-instruction per SMSP\n",
+                   warps, (double)h / ((double)iters * 16), (double)h / ((double)iters * 16 * ((warps + 3) / 4)));
+        }
+        for (int warps = 1; warps <= 16; warps *= 2) {
+            for (int rep = 0; rep < 2; ++rep) {
+                kahan_kernel<4><<<p.multiProcessorCount, warps * 32>>>(out, cyc, iters, seed);
+                cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+            }
+            printf("compensated addition, %2d warps/SM x ILP4: %.2f pipe cycles per warp-instruction per SMSP\n",
+                   warps, (double)h / ((double)iters * 16 * 4 * ((warps + 3) / 4)));
         }
     }
     // wall-clock rate for the whole chip (DADD, 16 warps/SM, ILP4)
