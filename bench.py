@@ -47,7 +47,7 @@ def workload(name: str) -> dict:
     if name == "c4":
         # 4096 independent 48 kHz stereo f32 streams, 10 s each; C1 graph; reference-exact Hilbert
         return dict(name="c4", desc="4096 x 48 kHz stereo f32 WAV, 10 s each: Hilbert(T1,Kahan,reject) + 100 Hz shift + 24-bit render, no dither",
-                    spec=S.config_c1(hilbert_mode="exact"), streams=4096, frames=480_000, chunk=16_384,
+                    spec=S.config_c1(hilbert_mode="exact"), streams=4096, frames=480_000, chunk=480_000,
                     bytes_per_frame=14, hilbert="exact")
     if name == "c4ns":
         # C4 with a noise shaper: the quantiser's error feedback is serial per channel
