@@ -108,6 +108,7 @@ struct icw_session {
     std::vector<uint32_t> mt_seed[2];
     std::vector<uint64_t> mt_drawn[2];
     uint64_t launches = 0;
+    unsigned long long redraws_seen = 0;    // sum of the streams' mt_redraws already reported (ICW_E_MT_REDRAW)
     cudaStream_t last_stream = nullptr; // the stream of the most recent process call (NULL: none yet / engine stream)
     int hb_basis = 0;                   // basis of the Hilbert state on the device
     bool hb_live = false;               // that state is not all-zero / has been used
@@ -534,10 +535,32 @@ static int quiesce(icw_session *s)
     return ICW_OK;
 }
 
+// The streams are idle (quiesce / a synchronised host call): did any dither draw run into the reference's rejection loop
+// since the last look?  The draw index is a closed form of the frame index here, so the draws after such an event are two
+// words early -- not the reference's output, and said so rather than passed on.
+static int check_redraws(icw_session *s)
+{
+    if (!s->ch.render.words_per_sample) return ICW_OK;
+    std::vector<unsigned long long> cnt((size_t)s->n_streams);
+    CK(cudaMemcpy2D(cnt.data(), sizeof(unsigned long long), &s->d_streams[0].mt_redraws, sizeof(DevStream), sizeof(unsigned long long),
+                    (size_t)s->n_streams, cudaMemcpyDeviceToHost));
+    unsigned long long tot = 0;
+    for (auto c : cnt) tot += c;
+    if (tot < s->redraws_seen) s->redraws_seen = tot;           // the counters were reset
+    if (tot != s->redraws_seen) {
+        const unsigned long long d = tot - s->redraws_seen;
+        s->redraws_seen = tot;
+        return fail(ICW_E_MT_REDRAW, "%llu dither draw(s) hit the generator's rejection loop (mt_jrnd.c:249-253): the output after the first "
+                                     "of them is not the reference's; replay the stream from a state before the event in smaller calls", d);
+    }
+    return ICW_OK;
+}
+
 extern "C" int icw_session_sync(icw_session *s)
 {
     if (!s) return fail(ICW_E_ARG, "NULL session");
-    return quiesce(s);
+    int rc = quiesce(s);
+    return rc ? rc : check_redraws(s);
 }
 
 extern "C" int icw_session_get_state(icw_session *s, int k, icw_stream_state *out)
@@ -1168,7 +1191,7 @@ extern "C" int icw_session_process_host(icw_session *s, int64_t n_frames, const 
     CK(cudaStreamSynchronize(e->d2h));
     CK(cudaStreamSynchronize(st));
     call_end(s, cx, st);
-    return ICW_OK;
+    return check_redraws(s);
 }
 
 extern "C" int icw_session_profile(icw_session *s, int on)
@@ -1336,6 +1359,20 @@ extern "C" int icw_debug_sincos_device(icw_engine *e, int64_t n, const double *d
     CK(cudaSetDevice(e->device));
     CK(launch_sincos_leaf(n, d_x, d_out, e->stream));
     CK(cudaStreamSynchronize(e->stream));
+    return ICW_OK;
+}
+
+// test hook for the ICW_E_MT_REDRAW report: the event itself has probability 2^-53 a draw and no seed is known that
+// produces it, so the test raises the stream's counter the way the kernels' commit would
+extern "C" int icw_debug_note_redraw(icw_session *s, int k, uint64_t n)
+{
+    if (!s || k < 0 || k >= s->n_streams) return fail(ICW_E_ARG, "bad stream index");
+    int rc = quiesce(s);
+    if (rc) return rc;
+    unsigned long long v = 0;
+    CK(cudaMemcpy(&v, &s->d_streams[k].mt_redraws, sizeof v, cudaMemcpyDeviceToHost));
+    v += n;
+    CK(cudaMemcpy(&s->d_streams[k].mt_redraws, &v, sizeof v, cudaMemcpyHostToDevice));
     return ICW_OK;
 }
 

@@ -40,7 +40,12 @@ enum {
     ICW_E_ARG = -1,             /* malformed argument / spec */
     ICW_E_CUDA = -2,            /* CUDA runtime failure (message has the detail) */
     ICW_E_UNSUPPORTED = -3,     /* valid in the reference but not modelled on the GPU (says which) */
-    ICW_E_NOMEM = -4
+    ICW_E_NOMEM = -4,
+    ICW_E_MT_REDRAW = -5        /* a dither draw hit the reference's rejection loop (src/mersene_twister/mt_jrnd.c:249-253:
+                                 * probability 2^-53 a draw); the frames before the event are the reference's, the
+                                 * later ones drew their words two places early.  Reported by the call that ran into it
+                                 * (host entry point) or by the next icw_session_sync / state accessor (device entry
+                                 * point) -- once; icw_stats.mt_redraws keeps the count */
 };
 
 /* input sample encodings.  0..4 = reference HRW_FMT_* (src/in_cwave.h:326-330, unpackers
@@ -279,6 +284,8 @@ int  icw_debug_phase_device(icw_engine *e, const icw_chain_spec *spec, uint64_t 
 /* trig leaf: out[i] = { s, c, sin(x[i]), cos(x[i]) } with (s, c) from the modulator's own sincos for
  * phases in [0, 2*pi) (icw_dev.cuh sincos_2pi) and the other two from CUDA's libdevice */
 int  icw_debug_sincos_device(icw_engine *e, int64_t n, const double *d_x, double *d_out);
+/* test hook: count n more dsopen re-draws on stream k, as a kernel that met one would (see ICW_E_MT_REDRAW) */
+int  icw_debug_note_redraw(icw_session *s, int k, uint64_t n);
 /* host-only checks of the MT19937 jump-ahead mathematics (no GPU is touched):
  * characteristic polynomial found by Berlekamp-Massey; the state array after `blocks` block
  * regenerations computed sequentially, through x^J mod phi, and through the x^(624*2^k) family */
