@@ -329,9 +329,7 @@ static int fold_spec(const icw_chain_spec &sp, DevChain &ch, HbCoef &coef)
             uint32_t later = 0;
             for (int j = i; j < sp.n_nodes; ++j)
                 if (sp.nodes[j].mode != ICW_MODE_MASTER) later |= 1u << sp.nodes[j].n_out;
-            if (s.inputs_mask & later & ~written)
-                return fail(ICW_E_UNSUPPORTED, "node %d reads a plug that is written later in the list: feedback "
-                                               "graphs are serial in time and are not run on the GPU", i);
+            if (s.inputs_mask & later & ~written) ch.feedback = 1;  // run frame by frame, one thread a stream (chain_serial_kernel)
         }
         d.mode = s.mode;
         d.inputs_mask = s.inputs_mask;
@@ -362,7 +360,7 @@ static int fold_spec(const icw_chain_spec &sp, DevChain &ch, HbCoef &coef)
     {
         auto plain = [](const DevNode &d) { return d.xch_mode == ICW_XCH_NORMAL && !d.l_iq_invert && !d.r_iq_invert; };
         const DevNode &last = ch.nodes[ch.n_nodes - 1];
-        if (!ch.bypass && plain(last)) {
+        if (!ch.bypass && !ch.feedback && plain(last)) {
             if (ch.n_nodes == 1 && last.inputs_mask == 1u) ch.shape = ICW_SHAPE_MASTER;
             if (ch.n_nodes == 2 && ch.nodes[0].mode == ICW_MODE_SHIFT && plain(ch.nodes[0]) && ch.nodes[0].inputs_mask == 1u &&
                 last.inputs_mask == (1u << ch.nodes[0].n_out))
@@ -867,7 +865,7 @@ static int process_group(icw_session *s, int64_t n_frames, const uint8_t *d_in, 
     const size_t mt_shared = dw.stream_stride;      // words between consecutive streams' dither (0 = shared)
     const bool scan = !ch.is_complex && s->spec.hilbert_mode == ICW_HILBERT_SCAN;
     const bool shaped = ch.render.ns_kind != 0;     // error feedback through the quantiser: serial per channel
-    if (!ch.is_complex && !scan && !e->unfused && !shaped && !ch.fp_check) {
+    if (!ch.is_complex && !scan && !e->unfused && !shaped && !ch.fp_check && !ch.feedback) {
         // real input, reference-exact Hilbert: the whole chain in one kernel
         if (dw.join) CK(cudaStreamWaitEvent(st, dw.join, 0));
         ProfSpan ps(s, st, ICW_K_HILBERT);
@@ -1016,7 +1014,7 @@ static int call_begin(icw_session *s, int64_t n_total, cudaStream_t st, CallCtx 
     // per-frame scratch: the analytic signal (real input unless the fused exact kernel runs) and, with a noise
     // shaper, the (value, dither) pairs between the pointwise pass and the serial quantiser -- 32 B/frame each
     const bool shaped = ch.render.ns_kind != 0;
-    const bool scratchy = (cx.real_in && (cx.mode == ICW_HILBERT_SCAN || e->unfused || ch.fp_check || shaped)) || shaped;
+    const bool scratchy = (cx.real_in && (cx.mode == ICW_HILBERT_SCAN || e->unfused || ch.fp_check || ch.feedback || shaped)) || shaped;
     // one stream: groups as long as the scratch may grow -- long groups let the scan use long chunks
     // (scan_chunk_len); many streams: 2^25 frames over ALL of them, never less than one scan tile per stream
     const int64_t seg = !scratchy ? n_total
@@ -1025,7 +1023,7 @@ static int call_begin(icw_session *s, int64_t n_total, cudaStream_t st, CallCtx 
     const int wps = ch.render.words_per_sample;
     // scan mode, one stream, straight-line list: everything in one kernel.  A unit (one CTA) first runs the filters over
     // `warm` frames before its own: that only pays on streams long enough to give every SM a unit many times that long
-    if (cx.real_in && cx.mode == ICW_HILBERT_SCAN && one_range && e->sfused != 0 && !e->unfused &&
+    if (cx.real_in && cx.mode == ICW_HILBERT_SCAN && one_range && e->sfused != 0 && !e->unfused && !ch.feedback &&
         sfused_supports(ch, K, s->d_tap_bus || s->d_tap_lr) &&
         (!wps || (s->mt_drawn[0][0] == s->mt_drawn[1][0] && s->mt_drawn[0][0] % (uint64_t)wps == 0))) {
         bool go = e->sfused == 1;
@@ -1033,8 +1031,8 @@ static int call_begin(icw_session *s, int64_t n_total, cudaStream_t st, CallCtx 
         if (go) { cx.sfused = true; cx.step = n_total; return ICW_OK; }
     }
     // the fused exact kernel reads word buffers; everything else that ends in chain_kernel can make its own
-    const bool hb_fused = cx.real_in && cx.mode == ICW_HILBERT_EXACT && !e->unfused && ch.render.ns_kind == 0 && !ch.fp_check;
-    if (wps && one_range && !hb_fused && !e->no_fuse_mt && K == 1 && chain_mt_supports(ch) &&
+    const bool hb_fused = cx.real_in && cx.mode == ICW_HILBERT_EXACT && !e->unfused && ch.render.ns_kind == 0 && !ch.fp_check && !ch.feedback;
+    if (wps && one_range && !hb_fused && !e->no_fuse_mt && !ch.feedback && K == 1 && chain_mt_supports(ch) &&
         s->mt_drawn[0][0] == s->mt_drawn[1][0] && s->mt_drawn[0][0] % (uint64_t)wps == 0) {
         cx.fuse_mt = true;
         if (scratchy) cx.step = n_total < FUSE_MT_GROUP ? (n_total < cx.step ? cx.step : n_total) : FUSE_MT_GROUP;

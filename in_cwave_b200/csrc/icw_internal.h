@@ -57,7 +57,9 @@ struct DevChain {
     int32_t  bypass, n_nodes;
     int32_t  shape;                     // ICW_SHAPE_*: DSP lists common enough to get straight-line code
     int32_t  filter_no, hb_ord, is_kahan, reject_flag;
-    int32_t  fp_check, pad_fp;          // the FP-exception-checked twins (reference src/fp_check.c:52-99)
+    int32_t  fp_check;                  // the FP-exception-checked twins (reference src/fp_check.c:52-99)
+    int32_t  feedback;                  // a node reads a plug written later in the list: the previous frame's value,
+                                        // so the DSP list is serial in time (reference src/adv_modulator.c:634-751)
     int64_t  n_samples, n_fade_in, n_fade_out;
     uint64_t scale_sr;                  // sample_rate * 1000 (scaled) or 0
     double   osc_div, osc_rdiv;         // divisor of the oscillator phase and RN(1/divisor)

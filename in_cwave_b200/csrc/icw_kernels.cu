@@ -289,6 +289,53 @@ chain_kernel(const __grid_constant__ DevChain ch, DevStream *__restrict__ stream
     commit_acc(&st, acc, 32);
 }
 
+// Feedback lists (a node reads a plug that a LATER node of the list writes, or its own output): the value read is the
+// previous frame's (the bus persists in the context, reference src/adv_modulator.c:634-751), so the frames of a stream
+// are serial.  One thread per stream walks them in order with its bus in local memory -- the same frame path, the bus
+// simply never reloaded; parallel only across streams (like the noise shapers).
+__global__ void __launch_bounds__(32)
+chain_serial_kernel(const __grid_constant__ DevChain ch, DevStream *__restrict__ streams, int n_streams, int64_t n_frames,
+                    const uint8_t *__restrict__ in, size_t in_stride, int from_analytic,
+                    const uint32_t *__restrict__ mtw_l, const uint32_t *__restrict__ mtw_r, size_t mt_stream_stride,
+                    uint8_t *__restrict__ out, size_t out_stride, double *__restrict__ tap_bus, double *__restrict__ tap_lr,
+                    double *__restrict__ pre)
+{
+    const int stream = blockIdx.x * blockDim.x + threadIdx.x;
+    if (stream >= n_streams) return;
+    DevStream &st = streams[stream];
+    const uint8_t *src = in + (size_t)stream * in_stride;
+    const size_t mt_off = (size_t)stream * mt_stream_stride;
+    FrameIO io;
+    io.mtw_l = mtw_l ? mtw_l + mt_off : nullptr;
+    io.mtw_r = mtw_r ? mtw_r + mt_off : nullptr;
+    io.dst = out + (size_t)stream * out_stride;
+    io.dst_aligned = ((size_t)(uintptr_t)io.dst & 3u) == 0;
+    io.tap_bus = tap_bus ? tap_bus + (size_t)stream * n_frames * (ICW_N_PLUGS * 4) : nullptr;
+    io.tap_lr = tap_lr ? tap_lr + (size_t)stream * n_frames * 2 : nullptr;
+    io.pre = pre ? pre + (size_t)stream * n_frames * 4 : nullptr;
+    FrameAcc acc;
+    double bus[ICW_N_PLUGS][4];
+    load_bus(st, bus);
+    bus[0][0] = st.bus[0][0]; bus[0][1] = st.bus[0][1]; bus[0][2] = st.bus[0][2]; bus[0][3] = st.bus[0][3];
+    OscCounter osc;
+    osc.init(ch, st.n_frame, 0);
+    for (int64_t i = 0; i < n_frames; ++i) {
+        double v[4];
+        if (from_analytic) {
+            const double *a = reinterpret_cast<const double *>(src) + i * 4;
+            v[0] = a[0]; v[1] = a[1]; v[2] = a[2]; v[3] = a[3];
+        } else {
+            unpack_frame(ch, src + i * ch.frame_bytes, st.pos + i, v);
+        }
+        finish_frame<DITHER_LATE>(ch, st, i, n_frames, v, bus, io, acc, osc);
+    }
+    if (acc.clips_l) atomicAdd(&st.clips[0], acc.clips_l);
+    if (acc.clips_r) atomicAdd(&st.clips[1], acc.clips_r);
+    if (acc.redraws) atomicAdd(&st.mt_redraws, (unsigned long long)acc.redraws);
+    atomicMax(reinterpret_cast<unsigned long long *>(&st.peak[0]), (unsigned long long)__double_as_longlong(acc.peak_l));
+    atomicMax(reinterpret_cast<unsigned long long *>(&st.peak[1]), (unsigned long long)__double_as_longlong(acc.peak_r));
+}
+
 // The same pass for the straight-line lists with plain PCM output and no dither or a 2-/4-word one:
 // list shape and dither type fixed at compile time (lean_frame, icw_frame.cuh), no thread-private bus.
 template <int SHAPE, int RT>
@@ -342,6 +389,11 @@ cudaError_t launch_chain(const DevChain &ch, DevStream *streams, int n_streams, 
     if (per_stream > cap) per_stream = cap;
     dim3 grid(per_stream, n_streams);
     const int rt = ch.render.render_type;
+    if (ch.feedback) {
+        chain_serial_kernel<<<(n_streams + 31) / 32, 32, 0, s>>>(ch, streams, n_streams, n_frames, in, in_stride, from_analytic, mtw_l, mtw_r,
+                                                                 mt_stream_stride, out, out_stride, tap_bus, tap_lr, pre);
+        return cudaGetLastError();
+    }
     if (!tap_bus && !tap_lr && !pre && !ch.bypass && !ch.fp_check && (ch.shape == ICW_SHAPE_MASTER || ch.shape == ICW_SHAPE_SHIFT_MASTER) &&
         (rt == ICW_RENDER_ROUND || rt == ICW_RENDER_RPDF || rt == ICW_RENDER_TPDF)) {
 #define ICW_LEAN(SH, RT) chain_lean_kernel<SH, RT><<<grid, threads, 0, s>>>(ch, streams, n_frames, in, in_stride, from_analytic, \

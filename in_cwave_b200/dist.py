@@ -94,6 +94,22 @@ def free_comm(comm) -> None:
         _abi.check(_abi.lib().icw_comm_destroy(comm))
 
 
+def graph_has_feedback(spec: dict) -> bool:
+    """The host's test (fold_spec, csrc/icw_api.cu): some node reads a plug that only a later node -- or the node itself
+    -- writes in the same frame, i.e. the previous frame's value."""
+    if spec.get("bypass"):
+        return False
+    nodes = spec["nodes"]
+    written = {0}
+    for i, nd in enumerate(nodes):
+        later = {m["out"] for m in nodes[i:] if m["mode"] != "master"}
+        if any(k in later and k not in written for k in nd.get("inputs", [0])):
+            return True
+        if nd["mode"] != "master":
+            written.add(nd["out"])
+    return False
+
+
 class CudaBackend:
     """The CUDA session as the compute engine of a time shard (scan mode).
 
@@ -108,6 +124,9 @@ class CudaBackend:
             raise ValueError("time sharding needs hilbert_mode='scan': the exact recurrences are serial in time")
         if int(spec.get("nshape_type", 0)):
             raise ValueError("time sharding needs FLAT noise shaping: the error feedback is serial in time (SURVEY.md 8e)")
+        if graph_has_feedback(spec):
+            raise ValueError("time sharding needs a feed-forward DSP list: a plug read before it is written carries the bus "
+                             "from frame to frame (reference src/adv_modulator.c:634-751), which is serial in time")
         self.engine, self.spec = engine, dict(spec)
         self.ses = engine.session(spec, 1)
         self.comm = comm

@@ -134,3 +134,12 @@ def test_time_shards_filter_state_handoff_gloo(oracle):
     pcm, _ = _run_world(spec, n)
     ref = oracle.port_process(spec, synth.stream_bytes(spec, n, stream_id=77))
     assert np.array_equal(pcm, ref["pcm"])
+
+
+def test_feedback_lists_are_not_time_sharded():
+    """A list that reads a plug before it is written carries the bus from frame to frame: no closed form at a cut."""
+    from in_cwave_b200 import dist as D, spec as S
+    from test_oracle_vs_ref import FEEDBACK_NODES
+    assert D.graph_has_feedback(S.default_spec(nodes=FEEDBACK_NODES))
+    assert not D.graph_has_feedback(S.config_c3()) and not D.graph_has_feedback(S.config_c2())
+    assert not D.graph_has_feedback(dict(S.default_spec(nodes=FEEDBACK_NODES), bypass=1))

@@ -240,3 +240,27 @@ def test_fp_checked_twins_port_equals_reference(oracle, case):
     # and with the check off the same input is processed unchecked: no counters move
     off = oracle.port_process(dict(spec, is_fp_check=0), raw)
     assert all(v == 0 for r in off["state"].fp_cnt for v in r)
+
+
+FEEDBACK_NODES = [
+    dict(mode="mix", inputs=[0, 7], out=1, l_gain=0.6, r_gain=0.6),            # plug 7 is written by the NEXT node: last frame's value
+    dict(mode="shift", inputs=[1], out=7, l_p=[3.5], r_p=[-2.25], l_gain=0.5, r_gain=0.5),
+    dict(mode="pm", inputs=[7, 9], out=9, l_p=[2.0, 0.0, 0.25, 0.0], r_p=[2.0, 0.5, 0.25, 0.0], l_gain=0.4, r_gain=0.4),   # reads its own output
+    dict(mode="master", inputs=[7, 9], l_gain=0.7, r_gain=0.7),
+]
+
+
+@pytest.mark.parametrize("fmt", ["wav_f32", "cw_f32"])
+def test_feedback_graph_port_equals_reference(fmt):
+    """A DSP list may read a plug that a later node (or the node itself) writes: the bus persists in MOD_CONTEXT, so the
+    value read is the previous frame's (src/adv_modulator.c:634-751).  The port must carry the bus the same way, also
+    across calls and files."""
+    spec = S.default_spec(fmt=fmt, sample_rate=48000, render_type=2, nodes=FEEDBACK_NODES)
+    n = 6000
+    raw = synth.stream_bytes(spec, n, stream_id=31)
+    plugs = [0, 1, 7, 9]
+    r = po.ref_process(spec, raw, read_quant=1111, taps=plugs)
+    p = po.port_process(spec, raw, taps=plugs)
+    assert np.array_equal(r["pcm"], p["pcm"])
+    assert np.array_equal(r["bus"], p["bus"])
+    assert np.any(r["bus"][1:, 2, :] != 0.0)
