@@ -54,9 +54,10 @@ def launches(path):
         a["n"] += 1
         a["ms"] += v
         a["shape"].add((r[ix["Grid Size"]], r[ix["Block Size"]]))
-    ours = {k: a for k, a in agg.items() if k.startswith("icw::")}
+    own = re.compile(r"^(icw::)?(mt_|advance_streams|hb_|chain_|scan_|ns_render|crc_|sincos_leaf|phase_leaf|modal_)")
+    ours = {k: a for k, a in agg.items() if own.match(k)}
     tot = sum(a["ms"] for a in ours.values())
-    lib = {k: a for k, a in agg.items() if not k.startswith("icw::")}
+    lib = {k: a for k, a in agg.items() if not own.match(k)}
     print(f"launches of icw:: kernels {sum(a['n'] for a in ours.values())}, total {tot:.3f} ms (cold-cache, serialised: compare shares)")
     for k, a in sorted(ours.items(), key=lambda kv: -kv[1]["ms"]):
         print(f"{k:<58} n={a['n']:4d} total={a['ms']:9.3f} ms avg={a['ms'] / a['n']:8.3f} share={a['ms'] / tot:.3f} grid/block={sorted(a['shape'])[:3]}")
