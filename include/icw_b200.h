@@ -199,7 +199,7 @@ typedef struct icw_stats {
     uint64_t clips[2];
     double   peak_db[2];
     uint64_t hb_rejects;
-    uint64_t mt_redraws;        /* dsopen re-draws seen (src/mt_jrnd.c:249-253); !=0 => resync needed */
+    uint64_t mt_redraws;        /* dsopen re-draws seen (src/mt_jrnd.c:249-253); each reported once as ICW_E_MT_REDRAW */
     uint64_t kernel_launches;   /* our kernels launched by this session so far */
 } icw_stats;
 int  icw_session_stats(icw_session *s, icw_stats *out);
