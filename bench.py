@@ -514,10 +514,34 @@ def measure(ctx, name: str, steps: int, warmup: int, want_e2e: bool, want_parity
             if world > 1:
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             same = bool(torch.equal(h_out[0, : min(N, 1 << 16) * ob].to(dev), d_out[0, : min(N, 1 << 16) * ob]))
+            # the ceiling of that number on this host: the same bytes over the same pinned buffers with NO kernels, H2D and
+            # D2H at once on two streams, every rank at the same time (name the end-to-end limiter)
+            s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+            copy_s = []
+            for _ in range(2):
+                barrier()
+                t0 = time.perf_counter()
+                with torch.cuda.stream(s_in):
+                    d_in[:, : N * fb].copy_(h_in, non_blocking=True)
+                with torch.cuda.stream(s_out):
+                    h_out.copy_(d_out[:, : N * ob], non_blocking=True)
+                s_in.synchronize()
+                s_out.synchronize()
+                barrier()
+                copy_s.append(time.perf_counter() - t0)
+            tc = torch.tensor([min(copy_s)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+            copy_ms = float(tc.item()) * 1e3
             res["e2e"] = dict(value=frames_step / float(tt.item()) / 1e6, unit=UNIT, h2d_bytes_per_step=K * N * fb,
                               d2h_bytes_per_step=K * N * ob, ms_per_step=float(tt.item()) * 1e3, steps=reps,
                               how="icw_session_process_host on pinned host buffers; H2D + kernels + D2H inside the timed region",
-                              host_affinity=ctx["numa_note"], same_bytes_as_resident_run=same)
+                              host_affinity=ctx["numa_note"], same_bytes_as_resident_run=same,
+                              copy_only=dict(ms=copy_ms, h2d_gbs_per_rank=K * N * fb / copy_ms / 1e6, d2h_gbs_per_rank=K * N * ob / copy_ms / 1e6,
+                                             aggregate_gbs_each_way=world * K * N * max(fb, ob) / copy_ms / 1e6,
+                                             e2e_over_copy_only=float(tt.item()) * 1e3 / copy_ms,
+                                             how="the step's bytes, pinned <-> device, both directions at once, no kernels, all ranks "
+                                                 "together: what the host's PCIe / memory path gives this many ranks"))
             del h_in, h_out
         except RuntimeError as ex:
             res["e2e"] = dict(value=None, unit=UNIT, error=str(ex)[:200])

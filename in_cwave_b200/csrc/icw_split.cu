@@ -28,6 +28,7 @@
 // W holds the states w[n] as rows of 4 NS doubles, three tile buffers, each preceded by the last HIST rows of the tile
 // before it (written twice by the state warp), so that both consumers read w[n-1-i] at compile-time offsets from one
 // row pointer: no circular-buffer arithmetic, no register moves (the z[] shift costs icw_fused.cu 40 MOVs a sample).
+#include <cstdlib>
 #include "icw_dev.cuh"
 #include "icw_kernels.h"
 #include "icw_hb.cuh"
@@ -38,70 +39,58 @@ namespace icw {
 #ifndef ICW_SPLIT_T
 #define ICW_SPLIT_T 32
 #endif
-// timing experiments only (wrong results): leave one role's work out
-#ifndef ICW_SPLIT_SKIP
-#define ICW_SPLIT_SKIP 0
-#endif
-constexpr bool SP_DEBUG_SKIP_STATE = (ICW_SPLIT_SKIP & 1) != 0, SP_DEBUG_SKIP_OUT = (ICW_SPLIT_SKIP & 2) != 0,
-               SP_DEBUG_SKIP_UNPACK = (ICW_SPLIT_SKIP & 4) != 0, SP_DEBUG_SKIP_RENDER = (ICW_SPLIT_SKIP & 8) != 0;
-#ifndef ICW_SPLIT_NS
-#define ICW_SPLIT_NS 28
-#endif
-constexpr int SP_NS = ICW_SPLIT_NS;             // streams per CTA (<= 32: one lane per recurrence in four state warps); 28: 4096 streams = 147 CTAs
-constexpr int SP_NCH = SP_NS * 4;               // recurrences per CTA = doubles per row of W / YS
-constexpr int SP_T = ICW_SPLIT_T;               // frames per tile
-#ifndef ICW_SPLIT_PRELOAD
-#define ICW_SPLIT_PRELOAD 0
-#endif
-#ifndef ICW_SPLIT_OPIPE
-#define ICW_SPLIT_OPIPE 0
-#endif
 #ifndef ICW_SPLIT_K
 #define ICW_SPLIT_K 1
 #endif
 #ifndef ICW_SPLIT_PH
 #define ICW_SPLIT_PH 2
 #endif
-constexpr int SP_K = ICW_SPLIT_K;               // samples of a recurrence whose output sums one thread advances in lock step
-constexpr int SP_PH = ICW_SPLIT_PH;             // output warps per recurrence: each takes every PH-th group of K samples
 #ifndef ICW_SPLIT_HPS
 #define ICW_SPLIT_HPS 8
 #endif
-#ifndef ICW_SPLIT_STATE_SUBS
-#define ICW_SPLIT_STATE_SUBS 4
+// timing experiments only (wrong results): leave one role's work out
+#ifndef ICW_SPLIT_SKIP
+#define ICW_SPLIT_SKIP 0
 #endif
+constexpr bool SP_DEBUG_SKIP_STATE = (ICW_SPLIT_SKIP & 1) != 0, SP_DEBUG_SKIP_OUT = (ICW_SPLIT_SKIP & 2) != 0,
+               SP_DEBUG_SKIP_UNPACK = (ICW_SPLIT_SKIP & 4) != 0, SP_DEBUG_SKIP_RENDER = (ICW_SPLIT_SKIP & 8) != 0;
+constexpr int SP_T = ICW_SPLIT_T;               // frames per tile
+constexpr int SP_K = ICW_SPLIT_K;               // samples of a recurrence whose output sums one thread advances in lock step (1: see DESIGN.md 5.1)
+constexpr int SP_PH = ICW_SPLIT_PH;             // output lanes per recurrence: each takes every PH-th group of K samples
 constexpr int SP_HPS = ICW_SPLIT_HPS;           // helper threads per stream: a frame is ~3000 cycles of dependent work
-constexpr int SP_HELP_WARPS = (SP_NS * SP_HPS + 31) / 32;
-constexpr int SP_OUT_WARPS = (SP_NCH * SP_PH + 31) / 32;   // output tasks (recurrence, phase) packed into full warps
-constexpr int SP_STATE_SUBS = ICW_SPLIT_STATE_SUBS;     // sub-partitions that carry the four state warps (1, 2 or 4)
 constexpr int SP_HIST = 20;                     // rows of history in front of a tile (>= the highest order)
 constexpr int SP_WROWS = SP_HIST + SP_T;
-constexpr int SP_ROWS1 = (SP_OUT_WARPS + SP_HELP_WARPS + 2) / 3 > 4 ? (SP_OUT_WARPS + SP_HELP_WARPS + 2) / 3 : 4;    // warp ranks when sub-partition 0 is the state warps' alone
-constexpr int SP_THREADS = 32 * (SP_STATE_SUBS == 1 ? 4 * SP_ROWS1 : 4 + SP_OUT_WARPS + SP_HELP_WARPS);   // see split_role()
 static_assert(SP_T >= SP_HIST && SP_HIST >= ICW_MAX_ORD && SP_T % (SP_K * SP_PH) == 0 && SP_T % SP_HPS == 0,
               "a tile must cover the history it hands on and divide among the output and helper warps");
 
-constexpr size_t SP_XS_BYTES = sizeof(double) * 2 * SP_T * SP_NS * 2;
-constexpr size_t SP_W_BYTES = sizeof(double) * 3 * SP_WROWS * SP_NCH;
-constexpr size_t SP_YS_BYTES = sizeof(double) * 2 * SP_T * SP_NCH;
-constexpr size_t SP_SMEM = SP_XS_BYTES + SP_W_BYTES + SP_YS_BYTES;
-static_assert(SP_SMEM <= 227 * 1024, "tile buffers exceed the shared memory of an SM");
+// Streams per CTA are a launch-time choice: 28 fills 147 SMs with 4096 streams; a smaller batch takes 14 / 7 / 4 so that
+// it still covers the machine -- the FP64 pipe of a sub-partition then carries half / a quarter of the throughput work
+// next to its state warp, and the state sum (the run time) loses fewer arbitrations.
+template <int NS_>
+struct SplitGeom {
+    static constexpr int NS = NS_;                      // streams per CTA (<= 32: one lane per recurrence in <= 4 state warps)
+    static constexpr int NCH = NS * 4;                  // recurrences per CTA = doubles per row of W / YS
+    static constexpr int STATE_WARPS = (NCH + 31) / 32; // warp ids 0 .. : one per sub-partition
+    static constexpr int OUT_WARPS = (NCH * SP_PH + 31) / 32;   // output tasks (recurrence, phase) packed into full warps
+    static constexpr int HELP_WARPS = (NS * SP_HPS + 31) / 32;
+    static constexpr int THREADS = 32 * (STATE_WARPS + OUT_WARPS + HELP_WARPS);
+    static constexpr size_t XS_BYTES = sizeof(double) * 2 * SP_T * NS * 2;
+    static constexpr size_t W_BYTES = sizeof(double) * 3 * SP_WROWS * NCH;
+    static constexpr size_t YS_BYTES = sizeof(double) * 2 * SP_T * NCH;
+    static constexpr size_t SMEM = XS_BYTES + W_BYTES + YS_BYTES;
+    static_assert(NS <= 32 && SMEM <= 227 * 1024, "tile buffers exceed the shared memory of an SM");
+};
 
-// kind 0 state, 1 output, 2 helper, 3 idle; index = which warp of that kind.  The state warps take the lowest ranks of
-// the first SP_STATE_SUBS sub-partitions (a warp runs on sub-partition id mod 4); every other warp slot, in warp order,
-// is an output warp until there are SP_OUT_WARPS, then a helper.
+// kind 0 state, 1 output, 2 helper; index = which warp of that kind (a warp runs on sub-partition id mod 4: the state
+// warps, ids 0.., sit on different ones)
 struct SplitRole { int kind, index; };
+template <class G>
 __device__ __forceinline__ SplitRole split_role(int warp)
 {
-    const int sub = warp & 3, k = warp >> 2;
-    if (sub < SP_STATE_SUBS && k < 4 / SP_STATE_SUBS) return SplitRole{0, k * SP_STATE_SUBS + sub};
-    // rank of this warp among the non-state warps
-    int n = 0;
-    for (int v = 0; v < warp; ++v) n += !((v & 3) < SP_STATE_SUBS && (v >> 2) < 4 / SP_STATE_SUBS);
-    if (n < SP_OUT_WARPS) return SplitRole{1, n};
-    n -= SP_OUT_WARPS;
-    if (n < SP_HELP_WARPS) return SplitRole{2, n};
-    return SplitRole{3, 0};
+    if (warp < G::STATE_WARPS) return SplitRole{0, warp};
+    warp -= G::STATE_WARPS;
+    if (warp < G::OUT_WARPS) return SplitRole{1, warp};
+    return SplitRole{2, warp - G::OUT_WARPS};
 }
 
 // a helper thread's counters into its stream (commit_acc, icw_frame.cuh, without the shuffle tree: 3 threads a stream)
@@ -129,8 +118,8 @@ __device__ __forceinline__ void comp_add_k(Comp (&o)[K], const double (&x)[K])
     for (int k = 0; k < K; ++k) { o[k].c = __dsub_rn(d[k], y[k]); o[k].s = t[k]; }
 }
 
-template <int ORD>
-__global__ void __launch_bounds__(SP_THREADS, 1)
+template <int ORD, int NS>
+__global__ void __launch_bounds__(SplitGeom<NS>::THREADS, 1)
 hb_split_kernel(const __grid_constant__ HbCoef coef, const __grid_constant__ DevChain ch,
                 DevStream *__restrict__ streams, int n_streams, int64_t n_frames,
                 const uint8_t *__restrict__ in, size_t in_stride,
@@ -138,19 +127,20 @@ hb_split_kernel(const __grid_constant__ HbCoef coef, const __grid_constant__ Dev
                 uint8_t *__restrict__ out, size_t out_stride,
                 double *__restrict__ tap_bus, double *__restrict__ tap_lr, int fast)
 {
+    using G = SplitGeom<NS>;
     extern __shared__ __align__(16) unsigned char split_smem[];
-    double (*xs)[SP_T][SP_NS * 2] = reinterpret_cast<double (*)[SP_T][SP_NS * 2]>(split_smem);
-    double (*wb)[SP_WROWS][SP_NCH] = reinterpret_cast<double (*)[SP_WROWS][SP_NCH]>(split_smem + SP_XS_BYTES);
-    double (*ys)[SP_T][SP_NCH] = reinterpret_cast<double (*)[SP_T][SP_NCH]>(split_smem + SP_XS_BYTES + SP_W_BYTES);
+    double (*xs)[SP_T][G::NS * 2] = reinterpret_cast<double (*)[SP_T][G::NS * 2]>(split_smem);
+    double (*wb)[SP_WROWS][G::NCH] = reinterpret_cast<double (*)[SP_WROWS][G::NCH]>(split_smem + G::XS_BYTES);
+    double (*ys)[SP_T][G::NCH] = reinterpret_cast<double (*)[SP_T][G::NCH]>(split_smem + G::XS_BYTES + G::W_BYTES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const SplitRole role = split_role(warp);
-    const int stream0 = blockIdx.x * SP_NS;
+    const SplitRole role = split_role<G>(warp);
+    const int stream0 = blockIdx.x * G::NS;
     const int64_t n_tiles = (n_frames + SP_T - 1) / SP_T;
 
     // ---- state-warp set-up: lane = one recurrence ---------------------------------------------------------------
     const int c_local = role.index * 32 + lane;                 // state warps: recurrence index inside the CTA
-    const bool is_state = role.kind == 0 && c_local < SP_NCH;
+    const bool is_state = role.kind == 0 && c_local < G::NCH;
     const int c_iq = c_local & 1, c_chan = (c_local >> 1) & 1, c_sl = c_local >> 2;
     const bool c_live = is_state && stream0 + c_sl < n_streams;
     unsigned long long rejects = 0;
@@ -172,13 +162,13 @@ hb_split_kernel(const __grid_constant__ HbCoef coef, const __grid_constant__ Dev
 
     // ---- output-warp set-up: lane = (recurrence, phase): every PH-th group of K samples of that recurrence ----------
     const int o_task = role.index * 32 + lane;
-    const bool is_out = role.kind == 1 && o_task < SP_NCH * SP_PH;
-    const int o_chain = o_task % SP_NCH, o_phase = o_task / SP_NCH;
+    const bool is_out = role.kind == 1 && o_task < G::NCH * SP_PH;
+    const int o_chain = o_task % G::NCH, o_phase = o_task / G::NCH;
 
     // ---- helper-warp set-up ------------------------------------------------------------------------------------------
     const int h = role.index * 32 + lane;
     const int h_sl = h / SP_HPS, h_part = h % SP_HPS;
-    const bool h_live = role.kind == 2 && h_sl < SP_NS && stream0 + h_sl < n_streams;
+    const bool h_live = role.kind == 2 && h_sl < G::NS && stream0 + h_sl < n_streams;
     FrameAcc acc;
     FrameIO io;
     io.mtw_l = io.mtw_r = nullptr; io.dst = nullptr; io.dst_aligned = 0; io.tap_bus = io.tap_lr = nullptr; io.pre = nullptr;
@@ -220,12 +210,12 @@ hb_split_kernel(const __grid_constant__ HbCoef coef, const __grid_constant__ Dev
                 const int col = c_sl * 2 + c_chan;
                 const double *xp = &xs[xb][0][col];
                 double *wr = &wb[wbi][SP_HIST][c_local];                // row of the tile's first sample
-                double *wn = &wb[wbn][0][c_local] + (SP_HIST - SP_T) * SP_NCH;   // the same rows seen from the next buffer's history
+                double *wn = &wb[wbn][0][c_local] + (SP_HIST - SP_T) * G::NCH;   // the same rows seen from the next buffer's history
                 // products of the states the first sample reads, except the newest (its product heads the serial chain)
                 double q[ORD];
-                double w_prev = wr[-1 * SP_NCH];
+                double w_prev = wr[-1 * G::NCH];
 #pragma unroll
-                for (int i = 1; i < ORD; ++i) q[i] = __dmul_rn(wr[(-1 - i) * SP_NCH], coef.fb[i]);
+                for (int i = 1; i < ORD; ++i) q[i] = __dmul_rn(wr[(-1 - i) * G::NCH], coef.fb[i]);
                 // fs/4 down-mix without branches (lpf_hilbert_quad.c:132-153): the I filter takes +x on phase 0 and -x on
                 // phase 2, the Q filter -x on phase 1 and +x on phase 3, zero otherwise
                 const unsigned ph_pos = c_iq ? 3u : 0u, ph_neg = c_iq ? 1u : 2u;
@@ -234,7 +224,7 @@ hb_split_kernel(const __grid_constant__ HbCoef coef, const __grid_constant__ Dev
                 x = qd == ph_pos ? x : (qd == ph_neg ? -x : 0.0);
                 for (int t = 0; t < len; ++t) {
                     const int tn = t + 1 < len ? t + 1 : t;
-                    const double xraw = xp[tn * (SP_NS * 2)];           // the next input, a sample ahead
+                    const double xraw = xp[tn * (G::NS * 2)];           // the next input, a sample ahead
                     // first compensated addition: y = p - 0 is p itself for every p (also -0 and NaN)
                     Comp a;
                     {
@@ -243,31 +233,18 @@ hb_split_kernel(const __grid_constant__ HbCoef coef, const __grid_constant__ Dev
                         a.c = __dsub_rn(__dsub_rn(t0, x), y);
                         a.s = t0;
                     }
-#if ICW_SPLIT_PRELOAD
-                    // the states the NEXT sample's terms read are already there (rows t - i): fetched before the sum
-                    // starts, multiplied after it, so that neither the loads' latency nor their issue slots sit between
-                    // two samples' sums (in-order issue: what follows the sum in program order delays the next one)
-                    double zr[ORD];
-#pragma unroll
-                    for (int i = 1; i < ORD; ++i) zr[i] = wr[(t - i) * SP_NCH];
-#pragma unroll
-                    for (int i = 1; i < ORD; ++i) comp_add(a, q[i]);
-#pragma unroll
-                    for (int i = 1; i < ORD; ++i) q[i] = __dmul_rn(zr[i], coef.fb[i]);
-#else
 #pragma unroll
                     for (int i = 1; i < ORD; ++i) {
                         comp_add(a, q[i]);
                         // the same term of the NEXT sample: its state is already there (row t - i)
-                        q[i] = __dmul_rn(wr[(t - i) * SP_NCH], coef.fb[i]);
+                        q[i] = __dmul_rn(wr[(t - i) * G::NCH], coef.fb[i]);
                     }
-#endif
                     double w = a.s;
                     const bool rj = (ch.reject_flag != 0) & (fabs(w) < thr);    // |w| < flag value: bug-for-bug (hblpf.c:1046)
                     w = rj ? 0.0 : w;
                     rejects += rj ? 1ull : 0ull;
-                    wr[t * SP_NCH] = w;
-                    if (t >= SP_T - SP_HIST) wn[t * SP_NCH] = w;
+                    wr[t * G::NCH] = w;
+                    if (t >= SP_T - SP_HIST) wn[t * G::NCH] = w;
                     w_prev = w;
                     qd = (qd + 1u) & 3u;
                     x = qd == ph_pos ? xraw : (qd == ph_neg ? -xraw : 0.0);
@@ -275,7 +252,7 @@ hb_split_kernel(const __grid_constant__ HbCoef coef, const __grid_constant__ Dev
                 if (ts == n_tiles - 1 && c_live) {
                     DevStream &st = streams[stream0 + c_sl];
 #pragma unroll
-                    for (int i = 0; i < ORD; ++i) st.hb[c_chan][c_iq][i] = wr[(len - 1 - i) * SP_NCH];
+                    for (int i = 0; i < ORD; ++i) st.hb[c_chan][c_iq][i] = wr[(len - 1 - i) * G::NCH];
                     st.hb_rejects[c_chan][c_iq] = rejects;
                 }
             }
@@ -295,7 +272,7 @@ hb_split_kernel(const __grid_constant__ HbCoef coef, const __grid_constant__ Dev
                     constexpr int K = SP_K;
                     double r[ORD + K - 1];
 #pragma unroll
-                    for (int j = 0; j < ORD + K - 1; ++j) r[j] = wr[(t + K - 2 - j) * SP_NCH];
+                    for (int j = 0; j < ORD + K - 1; ++j) r[j] = wr[(t + K - 2 - j) * G::NCH];
                     Comp o[K];
                     double x[K];
 #pragma unroll
@@ -303,27 +280,6 @@ hb_split_kernel(const __grid_constant__ HbCoef coef, const __grid_constant__ Dev
 #pragma unroll
                     for (int k = 0; k < K; ++k) x[k] = __dmul_rn(__dmul_rn(r[K - 1 - k], coef.fb[0]), coef.d0);
                     comp_add_k<K>(o, x);
-#if ICW_SPLIT_OPIPE
-                    // the two addends of term i+1 are formed before term i is added (program order is what an in-order
-                    // issue port sees: a product formed right in front of its addition puts two DMUL latencies into the
-                    // chain of additions)
-                    double xa[K], xb[K];
-#pragma unroll
-                    for (int k = 0; k < K; ++k) { xa[k] = __dmul_rn(r[K - k], coef.ff[1]); xb[k] = __dmul_rn(__dmul_rn(r[K - k], coef.fb[1]), coef.d0); }
-#pragma unroll
-                    for (int i = 1; i < ORD; ++i) {
-                        double na[K], nb[K];
-#pragma unroll
-                        for (int k = 0; k < K; ++k) {
-                            na[k] = i + 1 < ORD ? __dmul_rn(r[K - 1 - k + (i + 1 < ORD ? i + 1 : i)], coef.ff[i + 1 < ORD ? i + 1 : i]) : 0.0;
-                            nb[k] = i + 1 < ORD ? __dmul_rn(__dmul_rn(r[K - 1 - k + (i + 1 < ORD ? i + 1 : i)], coef.fb[i + 1 < ORD ? i + 1 : i]), coef.d0) : 0.0;
-                        }
-                        comp_add_k<K>(o, xa);
-                        comp_add_k<K>(o, xb);
-#pragma unroll
-                        for (int k = 0; k < K; ++k) { xa[k] = na[k]; xb[k] = nb[k]; }
-                    }
-#else
 #pragma unroll
                     for (int i = 1; i < ORD; ++i) {
 #pragma unroll
@@ -333,10 +289,9 @@ hb_split_kernel(const __grid_constant__ HbCoef coef, const __grid_constant__ Dev
                         for (int k = 0; k < K; ++k) x[k] = __dmul_rn(__dmul_rn(r[K - 1 - k + i], coef.fb[i]), coef.d0);
                         comp_add_k<K>(o, x);
                     }
-#endif
 #pragma unroll
                     for (int k = 0; k < K; ++k)
-                        if (t + k < len) yp[(t + k) * SP_NCH] = o[k].s;     // no d0*x term: bug-for-bug (hblpf.c:1056)
+                        if (t + k < len) yp[(t + k) * G::NCH] = o[k].s;     // no d0*x term: bug-for-bug (hblpf.c:1056)
                 }
             }
             __syncthreads();
@@ -388,9 +343,34 @@ hb_split_kernel(const __grid_constant__ HbCoef coef, const __grid_constant__ Dev
             __syncthreads();
         }
         if (h_live) commit_acc_one(streams[stream0 + h_sl], acc);
-    } else {
-        for (int64_t s = 0; s < n_steps; ++s) __syncthreads();
     }
+}
+
+template <int ORD, int NS>
+static cudaError_t launch_split_geom(const HbCoef &coef, const DevChain &ch, DevStream *streams, int n_streams, int64_t n_frames,
+                                     const uint8_t *in, size_t in_stride, const uint32_t *mtw_l, const uint32_t *mtw_r,
+                                     size_t mt_stream_stride, uint8_t *out, size_t out_stride, double *tap_bus, double *tap_lr,
+                                     int fast, cudaStream_t s)
+{
+    using G = SplitGeom<NS>;
+    const int blocks = (n_streams + NS - 1) / NS;
+    cudaError_t e1 = cudaFuncSetAttribute(hb_split_kernel<ORD, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
+    if (e1 != cudaSuccess) return e1;
+    hb_split_kernel<ORD, NS><<<blocks, G::THREADS, G::SMEM, s>>>(coef, ch, streams, n_streams, n_frames, in, in_stride, mtw_l, mtw_r,
+                                                                 mt_stream_stride, out, out_stride, tap_bus, tap_lr, fast);
+    return cudaGetLastError();
+}
+
+// streams per CTA: the largest of 28 / 14 / 7 / 4 that still gives every SM a CTA (ICW_SPLIT_NS forces one)
+static int split_streams_per_cta(int n_streams)
+{
+    static const int forced = [] { const char *v = getenv("ICW_SPLIT_NS"); return v ? atoi(v) : 0; }();
+    if (forced == 28 || forced == 14 || forced == 7 || forced == 4) return forced;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    for (int ns : { 28, 14, 7 })
+        if ((n_streams + ns - 1) / ns >= sms - 1) return ns;
+    return 4;
 }
 
 template <int ORD>
@@ -399,12 +379,17 @@ static cudaError_t launch_split_ord(const HbCoef &coef, const DevChain &ch, DevS
                                     size_t mt_stream_stride, uint8_t *out, size_t out_stride, double *tap_bus, double *tap_lr,
                                     int fast, cudaStream_t s)
 {
-    const int blocks = (n_streams + SP_NS - 1) / SP_NS;
-    cudaError_t e1 = cudaFuncSetAttribute(hb_split_kernel<ORD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SMEM);
-    if (e1 != cudaSuccess) return e1;
-    hb_split_kernel<ORD><<<blocks, SP_THREADS, SP_SMEM, s>>>(coef, ch, streams, n_streams, n_frames, in, in_stride, mtw_l, mtw_r,
-                                                            mt_stream_stride, out, out_stride, tap_bus, tap_lr, fast);
-    return cudaGetLastError();
+#define ICW_SPLIT_GEOM(N) \
+    case N: return launch_split_geom<ORD, N>(coef, ch, streams, n_streams, n_frames, in, in_stride, mtw_l, mtw_r, mt_stream_stride, \
+                                             out, out_stride, tap_bus, tap_lr, fast, s)
+    switch (split_streams_per_cta(n_streams)) {
+        ICW_SPLIT_GEOM(28);
+        ICW_SPLIT_GEOM(14);
+        ICW_SPLIT_GEOM(7);
+    default:
+        ICW_SPLIT_GEOM(4);
+    }
+#undef ICW_SPLIT_GEOM
 }
 
 cudaError_t launch_hb_split(const HbCoef &coef, const DevChain &ch, DevStream *streams, int n_streams, int64_t n_frames,
