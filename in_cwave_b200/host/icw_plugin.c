@@ -27,7 +27,8 @@ typedef struct reader {
 
 /* One read-ahead block: `to_read` frames from the file at byte offset `file_off`, then `to_fill` frames of
  * virtual silence, in a page-locked buffer (so the H2D copy of icw_session_process_host is a real
- * asynchronous DMA).  Two of them: while the GPU renders one, the reader thread fills the other. */
+ * asynchronous DMA).  Three of them: while the host drains the PCM of one in its 4-64 KB getData calls, the render
+ * thread has the next on the GPU and the reader thread reads the one after that from the file. */
 typedef struct block {
     unsigned char *buf;
     size_t         cap;
@@ -35,6 +36,11 @@ typedef struct block {
     int64_t        to_read, to_fill;
     int64_t        file_off;
     int            ok;                       /* the file gave every byte asked for */
+    /* the block rendered: its PCM (page-locked), and the stream state its first frame started from */
+    unsigned char *pcm;
+    size_t         pcm_cap;
+    int            rendered;
+    icw_stream_state snap;
 } block;
 
 static struct {
@@ -46,23 +52,19 @@ static struct {
     reader          rd;
     int             open;
     int             out_frame_bytes;
-    /* read-ahead.  The DSP state on the device stands at the END of the rendered block; `snap` is the state
-     * at its START, so that a seek or an early close can put the stream back to exactly the frames the host
+    /* read-ahead.  The DSP state on the device stands at the END of the last rendered block; a block's `snap` is the
+     * state at its START, so that a seek or an early close can put the stream back to exactly the frames the host
      * took (the reference advances its MOD_CONTEXT only by what each getData asked for, src/transcode.c:82-100) */
-    block           blk[2];
+    block           blk[3];                  /* cur: served; cur+1: rendered ahead; cur+2: read ahead (indices mod 3) */
     int             cur;                     /* block whose PCM is being served */
-    int             pf_valid;                /* blk[cur ^ 1] holds (or is receiving) the block after `cur` */
-    unsigned char  *pcm_buf;
-    size_t          pcm_cap;
-    int64_t         pcm_have, pcm_taken;     /* bytes */
+    int             pf_valid;                /* blk[cur + 1] holds (or is receiving) the rendered block after `cur` */
+    int             rd_for;                  /* block index the reader thread was given last (-1: none) */
+    int64_t         want;                    /* frames per block */
+    int64_t         pcm_have, pcm_taken;     /* bytes of blk[cur].pcm */
     int64_t         blk_frames;              /* frames rendered from blk[cur] */
-    icw_stream_state snap;
-    /* reader thread */
-    pthread_t       th;
-    int             th_up, th_quit;
+    /* two worker threads: file reads, and rendering (read k+2 || render k+1 || host drains k) */
     pthread_mutex_t mu;
     pthread_cond_t  cv_req, cv_done;
-    int             req_pending, req_blk, req_fd;
     icwp_iostats    io;
 } P = { .mu = PTHREAD_MUTEX_INITIALIZER, .cv_req = PTHREAD_COND_INITIALIZER, .cv_done = PTHREAD_COND_INITIALIZER };
 
@@ -302,6 +304,7 @@ int icwp_configure(const icw_chain_spec *chain, const icwp_options *opt)
 }
 
 static void reader_stop(void);
+static void reader_wait(void);
 static void settle(void);
 
 void icwp_reset(void)
@@ -309,8 +312,10 @@ void icwp_reset(void)
     if (P.open) winampGetExtendedRead_close((intptr_t)&P);
     if (P.session) { icw_session_destroy(P.session); P.session = NULL; }
     reader_stop();
-    for (int i = 0; i < 2; ++i) { icw_pinned_free(P.blk[i].buf); P.blk[i].buf = NULL; P.blk[i].cap = 0; }
-    icw_pinned_free(P.pcm_buf); P.pcm_buf = NULL; P.pcm_cap = 0;
+    for (int i = 0; i < 3; ++i) {
+        icw_pinned_free(P.blk[i].buf); P.blk[i].buf = NULL; P.blk[i].cap = 0;
+        icw_pinned_free(P.blk[i].pcm); P.blk[i].pcm = NULL; P.blk[i].pcm_cap = 0;
+    }
 }
 
 int icwp_io_stats(icwp_iostats *out, int reset)
@@ -323,6 +328,7 @@ int icwp_io_stats(icwp_iostats *out, int reset)
 int icwp_stats(icw_stats *out)
 {
     if (!P.session) return ICW_E_ARG;
+    reader_wait();                                  /* the worker may be rendering the next block on this session */
     return icw_session_stats(P.session, out);
 }
 
@@ -359,7 +365,7 @@ intptr_t winampGetExtendedRead_open(const char *filename, int *size, int *bps, i
     if (icw_session_reset(P.session, reset) != ICW_OK) goto fail;
     P.rd.pos_samples = P.rd.pos_tail = 0;
     P.pcm_have = P.pcm_taken = 0;
-    P.pf_valid = 0; P.cur = 0; P.blk_frames = 0;
+    P.pf_valid = 0; P.cur = 0; P.blk_frames = 0; P.rd_for = -1;
     P.open = 1;
     *nch = 2;
     *srate = (int)P.rd.fi.sample_rate;
@@ -396,47 +402,131 @@ static int fill_block(block *b, int fd, int silence_byte, int frame_bytes)
     return 1;
 }
 
-static void *reader_main(void *arg)
+/* render blk[i] (already filled) into its PCM buffer, remembering the state it started from */
+static int render_block(block *b, int64_t n)
 {
-    (void)arg;
+    size_t need_out = (size_t)n * P.out_frame_bytes;
+    double t0;
+    b->rendered = 0;
+    if (need_out > b->pcm_cap) {
+        icw_pinned_free(b->pcm);
+        b->pcm = NULL; b->pcm_cap = 0;
+        if (icw_pinned_alloc(need_out, (void **)&b->pcm) != ICW_OK) return 0;
+        b->pcm_cap = need_out;
+    }
+    if (icw_session_get_state(P.session, 0, &b->snap) != ICW_OK) return 0;
+    t0 = now_s();
+    if (icw_session_process_host(P.session, n, b->buf, 0, b->pcm, 0) != ICW_OK) return 0;
+    pthread_mutex_lock(&P.mu);
+    P.io.gpu_s += now_s() - t0;
+    P.io.frames += (uint64_t)n;
+    pthread_mutex_unlock(&P.mu);
+    b->rendered = 1;
+    return 1;
+}
+
+typedef struct worker {
+    pthread_t th;
+    int       up, quit, pending, arg;
+    void    (*fn)(int);
+} worker;
+
+static void *worker_main(void *arg)
+{
+    worker *w = (worker *)arg;
     pthread_mutex_lock(&P.mu);
     for (;;) {
-        while (!P.req_pending && !P.th_quit) pthread_cond_wait(&P.cv_req, &P.mu);
-        if (P.th_quit) break;
-        block *b = &P.blk[P.req_blk];
-        int fd = P.req_fd, sil = P.rd.fi.fmt == ICW_FMT_WAV_U8 ? 0x80 : 0, fb = P.rd.frame_bytes;
+        while (!w->pending && !w->quit) pthread_cond_wait(&P.cv_req, &P.mu);
+        if (w->quit) break;
+        int a = w->arg;
         pthread_mutex_unlock(&P.mu);
-        double t0 = now_s();
-        int ok = fill_block(b, fd, sil, fb);
-        double dt = now_s() - t0;
+        w->fn(a);
         pthread_mutex_lock(&P.mu);
-        b->ok = ok;
-        P.io.read_s += dt;
-        P.io.read_bytes += (uint64_t)b->to_read * (uint64_t)fb;
-        P.req_pending = 0;
+        w->pending = 0;
         pthread_cond_broadcast(&P.cv_done);
     }
     pthread_mutex_unlock(&P.mu);
     return NULL;
 }
 
-static void reader_wait(void)
+static void worker_wait(worker *w)
 {
     pthread_mutex_lock(&P.mu);
-    while (P.req_pending) pthread_cond_wait(&P.cv_done, &P.mu);
+    while (w->pending) pthread_cond_wait(&P.cv_done, &P.mu);
     pthread_mutex_unlock(&P.mu);
+}
+
+static int worker_submit(worker *w, int arg)
+{
+    if (!w->up) {
+        if (pthread_create(&w->th, NULL, worker_main, w)) return 0;
+        w->up = 1;
+    }
+    pthread_mutex_lock(&P.mu);
+    w->arg = arg; w->pending = 1;
+    pthread_cond_broadcast(&P.cv_req);
+    pthread_mutex_unlock(&P.mu);
+    return 1;
+}
+
+static void worker_stop(worker *w)
+{
+    if (!w->up) return;
+    worker_wait(w);
+    pthread_mutex_lock(&P.mu);
+    w->quit = 1;
+    pthread_cond_broadcast(&P.cv_req);
+    pthread_mutex_unlock(&P.mu);
+    pthread_join(w->th, NULL);
+    w->up = 0; w->quit = 0;
+}
+
+static int64_t plan_block(block *b, int64_t ps, int64_t pt, int64_t want);
+static int block_reserve(block *b, size_t need);
+
+/* reader thread: the file bytes (and the silence tail) of blk[i] */
+static void do_read(int i)
+{
+    block *b = &P.blk[i];
+    const int sil = P.rd.fi.fmt == ICW_FMT_WAV_U8 ? 0x80 : 0, fb = P.rd.frame_bytes;
+    double t0 = now_s();
+    int ok = fill_block(b, b->to_read > 0 ? fileno(P.rd.fp) : -1, sil, fb);
+    double dt = now_s() - t0;
+    pthread_mutex_lock(&P.mu);
+    b->ok = ok;
+    P.io.read_s += dt;
+    P.io.read_bytes += (uint64_t)b->to_read * (uint64_t)fb;
+    pthread_mutex_unlock(&P.mu);
+}
+static worker W_read = { .fn = do_read };
+
+/* render thread: blk[i] (planned by whoever asked) -> its PCM.  The session is this thread's until the request is done:
+ * every other user of the session waits for that first (workers_wait). */
+static void do_render(int i)
+{
+    block *b = &P.blk[i], *nb = &P.blk[(i + 1) % 3];
+    int64_t n_next;
+    if (P.rd_for == i) worker_wait(&W_read);        /* read while the block before this one was on the GPU */
+    else do_read(i);
+    /* the block after this one: off to the reader thread before the GPU gets this one */
+    n_next = plan_block(nb, b->pos_samples + b->to_read, b->pos_tail + b->to_fill, P.want);
+    nb->rendered = 0;
+    if (n_next > 0 && block_reserve(nb, (size_t)n_next * P.rd.frame_bytes) && worker_submit(&W_read, (i + 1) % 3)) P.rd_for = (i + 1) % 3;
+    else P.rd_for = -1;
+    if (b->ok) render_block(b, b->to_read + b->to_fill);
+}
+static worker W_render = { .fn = do_render };
+
+static void reader_wait(void)                       /* both workers idle: the session and every block are the caller's */
+{
+    worker_wait(&W_render);
+    worker_wait(&W_read);
 }
 
 static void reader_stop(void)
 {
-    if (!P.th_up) return;
-    reader_wait();
-    pthread_mutex_lock(&P.mu);
-    P.th_quit = 1;
-    pthread_cond_broadcast(&P.cv_req);
-    pthread_mutex_unlock(&P.mu);
-    pthread_join(P.th, NULL);
-    P.th_up = 0; P.th_quit = 0;
+    worker_stop(&W_render);
+    worker_stop(&W_read);
 }
 
 /* what xwave_read_samples would take next from position (ps, pt): frames from the file, then silence */
@@ -469,77 +559,57 @@ static int block_reserve(block *b, size_t need)
     return 1;
 }
 
-/* hand blk[i] to the reader thread (started on first use) */
-static int reader_submit(int i)
-{
-    if (!P.th_up) {
-        if (pthread_create(&P.th, NULL, reader_main, NULL)) return 0;
-        P.th_up = 1;
-    }
-    pthread_mutex_lock(&P.mu);
-    P.req_blk = i; P.req_fd = fileno(P.rd.fp); P.req_pending = 1;
-    pthread_cond_broadcast(&P.cv_req);
-    pthread_mutex_unlock(&P.mu);
-    return 1;
-}
-
-/* render the next block of up to `want` frames from the reader position; returns frames rendered */
+/* make the next block of up to `want` frames from the reader position the current one; returns its frames */
 static int64_t refill(int64_t want)
 {
     reader *r = &P.rd;
     block *b;
     int64_t n, n_next;
-    size_t need_out;
+    const int next = (P.cur + 1) % 3;
     double t0;
 
-    if (P.pf_valid && P.blk[P.cur ^ 1].pos_samples == r->pos_samples && P.blk[P.cur ^ 1].pos_tail == r->pos_tail) {
+    P.want = want;
+    if (P.pf_valid && P.blk[next].pos_samples == r->pos_samples && P.blk[next].pos_tail == r->pos_tail) {
         t0 = now_s();
-        reader_wait();                              /* usually done long ago */
+        worker_wait(&W_render);                     /* read and rendered while the host drained the block before it */
         P.io.wait_s += now_s() - t0;
-        P.cur ^= 1;
+        P.cur = next;
         b = &P.blk[P.cur];
         n = b->to_read + b->to_fill;
+        P.pf_valid = 0;
+        if (n <= 0 || !b->ok || !b->rendered) return 0;
         P.io.blocks_prefetched++;
     } else {
-        reader_wait();                              /* a prefetch for another position (seek): let it finish, drop it */
+        reader_wait();                              /* (settle() has already dropped blocks made for another position) */
+        P.pf_valid = 0; P.rd_for = -1;
         b = &P.blk[P.cur];
         n = plan_block(b, r->pos_samples, r->pos_tail, want);
-        if (n <= 0) { P.pf_valid = 0; return 0; }
+        if (n <= 0) return 0;
         if (!block_reserve(b, (size_t)n * r->frame_bytes)) return 0;
         t0 = now_s();
         b->ok = fill_block(b, fileno(r->fp), r->fi.fmt == ICW_FMT_WAV_U8 ? 0x80 : 0, r->frame_bytes);
         P.io.read_s += now_s() - t0;
         P.io.read_bytes += (uint64_t)b->to_read * (uint64_t)r->frame_bytes;
         P.io.blocks_sync++;
+        if (!b->ok || !render_block(b, n)) return 0;
     }
-    P.pf_valid = 0;
-    if (n <= 0 || !b->ok) return 0;
-    /* the block after this one goes to the reader thread before the GPU gets this one */
-    {
-        block *nb = &P.blk[P.cur ^ 1];
-        n_next = plan_block(nb, b->pos_samples + b->to_read, b->pos_tail + b->to_fill, want);
-        if (n_next > 0 && nb->to_read > 0 && block_reserve(nb, (size_t)n_next * r->frame_bytes) && reader_submit(P.cur ^ 1))
-            P.pf_valid = 1;
-        else if (n_next > 0 && nb->to_read == 0 && block_reserve(nb, (size_t)n_next * r->frame_bytes)) {
-            nb->ok = fill_block(nb, -1, r->fi.fmt == ICW_FMT_WAV_U8 ? 0x80 : 0, r->frame_bytes);   /* silence only */
-            P.pf_valid = 1;
-        }
-    }
-    need_out = (size_t)n * P.out_frame_bytes;
-    if (need_out > P.pcm_cap) {
-        icw_pinned_free(P.pcm_buf);
-        P.pcm_buf = NULL; P.pcm_cap = 0;
-        if (icw_pinned_alloc(need_out, (void **)&P.pcm_buf) != ICW_OK) return 0;
-        P.pcm_cap = need_out;
-    }
-    if (icw_session_get_state(P.session, 0, &P.snap) != ICW_OK) return 0;
-    t0 = now_s();
-    if (icw_session_process_host(P.session, n, b->buf, 0, P.pcm_buf, 0) != ICW_OK) return 0;
-    P.io.gpu_s += now_s() - t0;
-    P.io.frames += (uint64_t)n;
     r->pos_samples += b->to_read;
     r->pos_tail += b->to_fill;
     P.blk_frames = n;
+    /* the block after this one goes to the render thread (its bytes are usually there already: the render thread put the
+     * reader thread on them before it rendered this block) */
+    {
+        const int nn = (P.cur + 1) % 3;
+        block *nb = &P.blk[nn];
+        if (P.rd_for != nn) {
+            n_next = plan_block(nb, r->pos_samples, r->pos_tail, want);
+            if (n_next > 0 && !block_reserve(nb, (size_t)n_next * r->frame_bytes)) n_next = 0;
+        } else {
+            n_next = nb->to_read + nb->to_fill;
+        }
+        nb->rendered = 0;
+        if (n_next > 0 && worker_submit(&W_render, nn)) P.pf_valid = 1;
+    }
     return n;
 }
 
@@ -550,13 +620,24 @@ static int64_t refill(int64_t want)
 static void settle(void)
 {
     int64_t served;
-    if (!P.session || P.pcm_taken >= P.pcm_have) { P.pcm_have = P.pcm_taken = 0; return; }
+    block *b = &P.blk[P.cur];
+    int next_rendered;
+    if (!P.session) { P.pcm_have = P.pcm_taken = 0; return; }
+    reader_wait();                                  /* the worker may be in the middle of the block after this one */
+    next_rendered = P.pf_valid && P.blk[(P.cur + 1) % 3].ok && P.blk[(P.cur + 1) % 3].rendered;
+    P.pf_valid = 0; P.rd_for = -1;
+    if (P.pcm_taken >= P.pcm_have) {
+        /* everything rendered from this block was handed out; a block rendered ahead of it is un-done by going back to
+         * the state it started from (= the state after this block) */
+        if (next_rendered) { icw_session_set_state(P.session, 0, &P.blk[(P.cur + 1) % 3].snap); P.io.resettles++; }
+        P.pcm_have = P.pcm_taken = 0;
+        return;
+    }
     served = P.pcm_taken / P.out_frame_bytes;
-    if (icw_session_set_state(P.session, 0, &P.snap) == ICW_OK && served > 0)
-        icw_session_process_host(P.session, served, P.blk[P.cur].buf, 0, P.pcm_buf, 0);
+    if (icw_session_set_state(P.session, 0, &b->snap) == ICW_OK && served > 0)
+        icw_session_process_host(P.session, served, b->buf, 0, b->pcm, 0);
     /* the reader stands after the served frames too */
     {
-        const block *b = &P.blk[P.cur];
         int64_t from_file = served < b->to_read ? served : b->to_read;
         P.rd.pos_samples = b->pos_samples + from_file;
         P.rd.pos_tail = b->pos_tail + (served - from_file);
@@ -581,7 +662,7 @@ intptr_t winampGetExtendedRead_getData(intptr_t handle, char *dest, int len, int
             avail = P.pcm_have;
         }
         take = want_bytes - done < avail ? want_bytes - done : avail;
-        memcpy(dest + done, P.pcm_buf + P.pcm_taken, (size_t)take);
+        memcpy(dest + done, P.blk[P.cur].pcm + P.pcm_taken, (size_t)take);
         P.pcm_taken += take;
         done += take;
     }
