@@ -616,6 +616,10 @@ extern "C" int icw_session_reset(icw_session *s, unsigned what)
 {
     if (!s) return fail(ICW_E_ARG, "NULL session");
     if (what & ICW_RESET_HILBERT) s->hb_live = false;
+    if (what & ICW_RESET_RENDER) {
+        for (int c = 0; c < 2; ++c) std::fill(s->mt_drawn[c].begin(), s->mt_drawn[c].end(), (uint64_t)0);
+        s->redraws_seen = 0;
+    }
     return rewrite_states(s, [](DevStream &d, void *a) {
         unsigned w = *(unsigned *)a;
         if (w & ICW_RESET_HILBERT) {            // hq_rp_reset, reference src/lpf_hilbert_quad.c:160-165
@@ -629,6 +633,14 @@ extern "C" int icw_session_reset(icw_session *s, unsigned what)
             memset(d.fp_cnt, 0, sizeof d.fp_cnt);               // except_stats_reset, reference src/fp_check.c:37-47
         }
         if (w & ICW_RESET_FILEPOS) d.pos = 0;
+        if (w & ICW_RESET_RENDER) {             // what a fresh context holds (winampGetInModule2, src/in_cwave.c:46-80,551-572)
+            d.mt_drawn[0] = d.mt_drawn[1] = 0;  // mtrnd_init_seed: the generators back at their seeds' first draw
+            d.prev_rnd[0] = d.prev_rnd[1] = 0.0; d.prev_rnd_next[0] = d.prev_rnd_next[1] = 0.0;
+            memset(d.ns_e, 0, sizeof d.ns_e); memset(d.ns_o, 0, sizeof d.ns_o);
+            d.ns_prev_err[0] = d.ns_prev_err[1] = 0.0;
+            memset(d.bus, 0, sizeof d.bus);
+            d.mt_redraws = 0;
+        }
     }, &what);
 }
 
@@ -865,13 +877,27 @@ static int process_group(icw_session *s, int64_t n_frames, const uint8_t *d_in, 
     const size_t mt_shared = dw.stream_stride;      // words between consecutive streams' dither (0 = shared)
     const bool scan = !ch.is_complex && s->spec.hilbert_mode == ICW_HILBERT_SCAN;
     const bool shaped = ch.render.ns_kind != 0;     // error feedback through the quantiser: serial per channel
-    if (!ch.is_complex && !scan && !e->unfused && !shaped && !ch.fp_check && !ch.feedback) {
-        // real input, reference-exact Hilbert: the whole chain in one kernel
+    if (!ch.is_complex && !scan && !e->unfused && !ch.fp_check && !ch.feedback) {
+        // real input, reference-exact Hilbert: the whole chain in one kernel; with a noise shaper on it stops in front of
+        // the quantiser ((value, dither) pairs in `pre`, 32 B/frame) and the serial quantiser follows
         if (dw.join) CK(cudaStreamWaitEvent(st, dw.join, 0));
-        ProfSpan ps(s, st, ICW_K_HILBERT);
-        CK(launch_hb_fused(s->coef, ch, s->d_streams, K, n_frames, d_in, in_stride, wl, wr, mt_shared,
-                           d_out, out_stride, s->d_tap_bus, s->d_tap_lr, st));
-        s->launches++;
+        double *pre = nullptr;
+        if (shaped) {
+            rc = e->ns_pre.reserve((size_t)n_frames * 4 * sizeof(double) * (size_t)K);
+            if (rc) return rc;
+            pre = (double *)e->ns_pre.p;
+        }
+        {
+            ProfSpan ps(s, st, ICW_K_HILBERT);
+            CK(launch_hb_fused(s->coef, ch, s->d_streams, K, n_frames, d_in, in_stride, wl, wr, mt_shared,
+                               d_out, out_stride, s->d_tap_bus, s->d_tap_lr, pre, st));
+            s->launches++;
+        }
+        if (shaped) {
+            ProfSpan ps(s, st, ICW_K_CHAIN);
+            CK(launch_ns_render(ch, s->d_streams, K, n_frames, pre, d_out, out_stride, st));
+            s->launches++;
+        }
     } else {
         const uint8_t *src = d_in;
         size_t src_stride = in_stride;
@@ -1031,7 +1057,7 @@ static int call_begin(icw_session *s, int64_t n_total, cudaStream_t st, CallCtx 
         if (go) { cx.sfused = true; cx.step = n_total; return ICW_OK; }
     }
     // the fused exact kernel reads word buffers; everything else that ends in chain_kernel can make its own
-    const bool hb_fused = cx.real_in && cx.mode == ICW_HILBERT_EXACT && !e->unfused && ch.render.ns_kind == 0 && !ch.fp_check && !ch.feedback;
+    const bool hb_fused = cx.real_in && cx.mode == ICW_HILBERT_EXACT && !e->unfused && !ch.fp_check && !ch.feedback;
     if (wps && one_range && !hb_fused && !e->no_fuse_mt && !ch.feedback && K == 1 && chain_mt_supports(ch) &&
         s->mt_drawn[0][0] == s->mt_drawn[1][0] && s->mt_drawn[0][0] % (uint64_t)wps == 0) {
         cx.fuse_mt = true;

@@ -38,7 +38,7 @@ hb_fused_kernel(const __grid_constant__ HbCoef coef, const __grid_constant__ Dev
                 const uint8_t *__restrict__ in, size_t in_stride,
                 const uint32_t *__restrict__ mtw_l, const uint32_t *__restrict__ mtw_r, size_t mt_stream_stride,
                 uint8_t *__restrict__ out, size_t out_stride,
-                double *__restrict__ tap_bus, double *__restrict__ tap_lr,
+                double *__restrict__ tap_bus, double *__restrict__ tap_lr, double *__restrict__ pre,
                 int fast /* Shift -> Master, no dither, no taps, aligned rows: lean_frame_fast (icw_frame.cuh) */)
 {
     using Chain = typename ChainSel<ORD, KAHAN>::type;
@@ -97,6 +97,7 @@ hb_fused_kernel(const __grid_constant__ HbCoef coef, const __grid_constant__ Dev
         io.dst_aligned = ((size_t)(uintptr_t)io.dst & 3u) == 0;
         io.tap_bus = tap_bus ? tap_bus + (size_t)stream * n_frames * (ICW_N_PLUGS * 4) : nullptr;
         io.tap_lr = tap_lr ? tap_lr + (size_t)stream * n_frames * 2 : nullptr;
+        io.pre = pre ? pre + (size_t)stream * n_frames * 4 : nullptr;
         h_src = in + (size_t)stream * in_stride;
         h_pos0 = st.pos;
         h_q0[0] = st.quad[0]; h_q0[1] = st.quad[1];
@@ -191,10 +192,10 @@ template <int ORD>
 static cudaError_t launch_fused_ord(bool kahan, const HbCoef &coef, const DevChain &ch, DevStream *streams,
                                     int n_streams, int64_t n_frames, const uint8_t *in, size_t in_stride,
                                     const uint32_t *mtw_l, const uint32_t *mtw_r, size_t mt_stream_stride,
-                                    uint8_t *out, size_t out_stride, double *tap_bus, double *tap_lr, cudaStream_t s)
+                                    uint8_t *out, size_t out_stride, double *tap_bus, double *tap_lr, double *pre, cudaStream_t s)
 {
     const int blocks = (n_streams + FUSED_STREAMS - 1) / FUSED_STREAMS;
-    const int fast = !tap_bus && !tap_lr && ch.render.render_type == ICW_RENDER_ROUND && lean_fast_ok(ch) &&
+    const int fast = !tap_bus && !tap_lr && !pre && ch.render.render_type == ICW_RENDER_ROUND && lean_fast_ok(ch) &&
                      ((size_t)(uintptr_t)out & 3u) == 0 && (n_streams == 1 || (out_stride & 3u) == 0);
     {   // per device, not per process: set on every launch rather than cached in a static
         cudaError_t e1 = kahan ? cudaFuncSetAttribute(hb_fused_kernel<ORD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUSED_SMEM)
@@ -203,30 +204,30 @@ static cudaError_t launch_fused_ord(bool kahan, const HbCoef &coef, const DevCha
     }
     if (kahan)
         hb_fused_kernel<ORD, true><<<blocks, FUSED_THREADS, FUSED_SMEM, s>>>(coef, ch, streams, n_streams, n_frames, in, in_stride,
-                                                          mtw_l, mtw_r, mt_stream_stride, out, out_stride, tap_bus, tap_lr, fast);
+                                                          mtw_l, mtw_r, mt_stream_stride, out, out_stride, tap_bus, tap_lr, pre, fast);
     else
         hb_fused_kernel<ORD, false><<<blocks, FUSED_THREADS, FUSED_SMEM, s>>>(coef, ch, streams, n_streams, n_frames, in, in_stride,
-                                                           mtw_l, mtw_r, mt_stream_stride, out, out_stride, tap_bus, tap_lr, fast);
+                                                           mtw_l, mtw_r, mt_stream_stride, out, out_stride, tap_bus, tap_lr, pre, fast);
     return cudaGetLastError();
 }
 
 cudaError_t launch_hb_fused(const HbCoef &coef, const DevChain &ch, DevStream *streams, int n_streams,
                             int64_t n_frames, const uint8_t *in, size_t in_stride,
                             const uint32_t *mtw_l, const uint32_t *mtw_r, size_t mt_stream_stride,
-                            uint8_t *out, size_t out_stride, double *tap_bus, double *tap_lr, cudaStream_t s)
+                            uint8_t *out, size_t out_stride, double *tap_bus, double *tap_lr, double *pre, cudaStream_t s)
 {
     // Kahan summation (the reference's default): the split-warp kernel (icw_split.cu); ICW_FUSED_ONE_WARP=1 keeps the
     // one-instruction-stream form below for A/B runs.  Baseline summation is two short sums and stays here.
     static const bool one_warp = [] { const char *v = getenv("ICW_FUSED_ONE_WARP"); return v && *v == '1'; }();
     if (ch.is_kahan && !one_warp) {
-        const int fast = !tap_bus && !tap_lr && ch.render.render_type == ICW_RENDER_ROUND && lean_fast_ok(ch) &&
+        const int fast = !tap_bus && !tap_lr && !pre && ch.render.render_type == ICW_RENDER_ROUND && lean_fast_ok(ch) &&
                          ((size_t)(uintptr_t)out & 3u) == 0 && (n_streams == 1 || (out_stride & 3u) == 0);
         return launch_hb_split(coef, ch, streams, n_streams, n_frames, in, in_stride, mtw_l, mtw_r, mt_stream_stride,
-                               out, out_stride, tap_bus, tap_lr, fast, s);
+                               out, out_stride, tap_bus, tap_lr, pre, fast, s);
     }
 #define ICW_FUSED_CASE(O) \
     case O: return launch_fused_ord<O>(ch.is_kahan, coef, ch, streams, n_streams, n_frames, in, in_stride, \
-                                       mtw_l, mtw_r, mt_stream_stride, out, out_stride, tap_bus, tap_lr, s)
+                                       mtw_l, mtw_r, mt_stream_stride, out, out_stride, tap_bus, tap_lr, pre, s)
     switch (ch.hb_ord) {
         ICW_FUSED_CASE(15);
         ICW_FUSED_CASE(18);

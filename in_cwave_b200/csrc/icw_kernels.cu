@@ -451,9 +451,23 @@ ns_render_kernel(const __grid_constant__ DevChain ch, DevStream *__restrict__ st
     double peak = 0.0;
     const double2 *src = reinterpret_cast<const double2 *>(pre + (size_t)stream * n_frames * 4) + c;
     uint8_t *dst = out + (size_t)stream * out_stride + c * q.bytes;
-    double2 cur = n_frames > 0 ? src[0] : make_double2(0.0, 0.0);
-    for (int64_t i = 0; i < n_frames; ++i) {
-        const double2 nxt = src[2 * (i + 1 < n_frames ? i + 1 : i)];       // (value, dither) of the next frame
+    // (value, dither) pairs are fetched a group of NS_AHEAD frames ahead: one thread per channel means one or two warps
+    // per SM sub-partition, nothing else hides the DRAM latency of a load, and a sample is only ~250 cycles of work
+    constexpr int NS_AHEAD = 8;
+    double2 grp[NS_AHEAD], ngrp[NS_AHEAD];
+#pragma unroll
+    for (int j = 0; j < NS_AHEAD; ++j) grp[j] = n_frames > 0 ? src[2 * (j < n_frames ? j : n_frames - 1)] : make_double2(0.0, 0.0);
+    for (int64_t i0 = 0; i0 < n_frames; i0 += NS_AHEAD) {
+#pragma unroll
+        for (int j = 0; j < NS_AHEAD; ++j) {
+            const int64_t f = i0 + NS_AHEAD + j;
+            ngrp[j] = src[2 * (f < n_frames ? f : n_frames - 1)];
+        }
+#pragma unroll
+        for (int j = 0; j < NS_AHEAD; ++j) {
+        const int64_t i = i0 + j;
+        if (i >= n_frames) break;
+        const double2 cur = grp[j];
         // CHECK: the FP-exception-checked twins (src/sound_render.c:846-897, :415-441, :458-489)
         uint32_t *cnt = st.fp_cnt[2 + c];
         auto F = [&](double x) { return CHECK ? fc(x, cnt) : x; };
@@ -485,7 +499,9 @@ ns_render_kernel(const __grid_constant__ DevChain ch, DevStream *__restrict__ st
         prev_err = res;
         val = (int)((unsigned)val << q.shift);
         store_pcm(dst + i * ch.out_frame_bytes, val, q.bytes);
-        cur = nxt;
+        }
+#pragma unroll
+        for (int j = 0; j < NS_AHEAD; ++j) grp[j] = ngrp[j];
     }
 #pragma unroll
     for (int i = 0; i < ORD; ++i) st.ns_e[c][i] = e[i];

@@ -26,15 +26,16 @@ struct HbLeafState {
 cudaError_t launch_hb_exact(const HbCoef &coef, const DevChain &ch, DevStream *streams, int n_streams,
                             int64_t n_frames, const uint8_t *in, size_t in_stride, double *analytic,
                             cudaStream_t s);
+// pre != NULL (noise shaping on): (value, dither) pairs [stream][frame][4] for ns_render_kernel instead of PCM
 cudaError_t launch_hb_fused(const HbCoef &coef, const DevChain &ch, DevStream *streams, int n_streams,
                             int64_t n_frames, const uint8_t *in, size_t in_stride,
                             const uint32_t *mtw_l, const uint32_t *mtw_r, size_t mt_stream_stride,
-                            uint8_t *out, size_t out_stride, double *tap_bus, double *tap_lr, cudaStream_t s);
+                            uint8_t *out, size_t out_stride, double *tap_bus, double *tap_lr, double *pre, cudaStream_t s);
 // Kahan summation only: the state sum and the output sum of the recurrence on different warps (icw_split.cu)
 cudaError_t launch_hb_split(const HbCoef &coef, const DevChain &ch, DevStream *streams, int n_streams, int64_t n_frames,
                             const uint8_t *in, size_t in_stride, const uint32_t *mtw_l, const uint32_t *mtw_r,
                             size_t mt_stream_stride, uint8_t *out, size_t out_stride, double *tap_bus, double *tap_lr,
-                            int fast, cudaStream_t s);
+                            double *pre, int fast, cudaStream_t s);
 cudaError_t launch_hb_leaf(const HbCoef &coef, int ord, bool kahan, int reject, int n_chan, int64_t n,
                            const double *x, double *out, HbLeafState *st, cudaStream_t s);
 cudaError_t launch_mt_words(const uint32_t *ckpt, int n_cta, int blocks_per_cta, int64_t first_word,

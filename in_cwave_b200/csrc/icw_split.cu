@@ -132,7 +132,7 @@ hb_split_kernel(const __grid_constant__ HbCoef coef, const __grid_constant__ Dev
                 const uint8_t *__restrict__ in, size_t in_stride,
                 const uint32_t *__restrict__ mtw_l, const uint32_t *__restrict__ mtw_r, size_t mt_stream_stride,
                 uint8_t *__restrict__ out, size_t out_stride,
-                double *__restrict__ tap_bus, double *__restrict__ tap_lr, int fast)
+                double *__restrict__ tap_bus, double *__restrict__ tap_lr, double *__restrict__ pre, int fast)
 {
     using G = SplitGeom<NS>;
     extern __shared__ __align__(16) unsigned char split_smem[];
@@ -195,6 +195,7 @@ hb_split_kernel(const __grid_constant__ HbCoef coef, const __grid_constant__ Dev
         io.dst_aligned = ((size_t)(uintptr_t)io.dst & 3u) == 0;
         io.tap_bus = tap_bus ? tap_bus + (size_t)stream * n_frames * (ICW_N_PLUGS * 4) : nullptr;
         io.tap_lr = tap_lr ? tap_lr + (size_t)stream * n_frames * 2 : nullptr;
+        io.pre = pre ? pre + (size_t)stream * n_frames * 4 : nullptr;
         h_src = in + (size_t)stream * in_stride;
         h_pos0 = st.pos;
         h_q0[0] = st.quad[0]; h_q0[1] = st.quad[1];
@@ -359,14 +360,14 @@ template <int ORD, int NS>
 static cudaError_t launch_split_geom(const HbCoef &coef, const DevChain &ch, DevStream *streams, int n_streams, int64_t n_frames,
                                      const uint8_t *in, size_t in_stride, const uint32_t *mtw_l, const uint32_t *mtw_r,
                                      size_t mt_stream_stride, uint8_t *out, size_t out_stride, double *tap_bus, double *tap_lr,
-                                     int fast, cudaStream_t s)
+                                     double *pre, int fast, cudaStream_t s)
 {
     using G = SplitGeom<NS>;
     const int blocks = (n_streams + NS - 1) / NS;
     cudaError_t e1 = cudaFuncSetAttribute(hb_split_kernel<ORD, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
     if (e1 != cudaSuccess) return e1;
     hb_split_kernel<ORD, NS><<<blocks, G::THREADS, G::SMEM, s>>>(coef, ch, streams, n_streams, n_frames, in, in_stride, mtw_l, mtw_r,
-                                                                 mt_stream_stride, out, out_stride, tap_bus, tap_lr, fast);
+                                                                 mt_stream_stride, out, out_stride, tap_bus, tap_lr, pre, fast);
     return cudaGetLastError();
 }
 
@@ -386,11 +387,11 @@ template <int ORD>
 static cudaError_t launch_split_ord(const HbCoef &coef, const DevChain &ch, DevStream *streams, int n_streams, int64_t n_frames,
                                     const uint8_t *in, size_t in_stride, const uint32_t *mtw_l, const uint32_t *mtw_r,
                                     size_t mt_stream_stride, uint8_t *out, size_t out_stride, double *tap_bus, double *tap_lr,
-                                    int fast, cudaStream_t s)
+                                    double *pre, int fast, cudaStream_t s)
 {
 #define ICW_SPLIT_GEOM(N) \
     case N: return launch_split_geom<ORD, N>(coef, ch, streams, n_streams, n_frames, in, in_stride, mtw_l, mtw_r, mt_stream_stride, \
-                                             out, out_stride, tap_bus, tap_lr, fast, s)
+                                             out, out_stride, tap_bus, tap_lr, pre, fast, s)
     switch (split_streams_per_cta(n_streams)) {
         ICW_SPLIT_GEOM(28);
         ICW_SPLIT_GEOM(14);
@@ -404,11 +405,11 @@ static cudaError_t launch_split_ord(const HbCoef &coef, const DevChain &ch, DevS
 cudaError_t launch_hb_split(const HbCoef &coef, const DevChain &ch, DevStream *streams, int n_streams, int64_t n_frames,
                             const uint8_t *in, size_t in_stride, const uint32_t *mtw_l, const uint32_t *mtw_r,
                             size_t mt_stream_stride, uint8_t *out, size_t out_stride, double *tap_bus, double *tap_lr,
-                            int fast, cudaStream_t s)
+                            double *pre, int fast, cudaStream_t s)
 {
 #define ICW_SPLIT_CASE(O) \
     case O: return launch_split_ord<O>(coef, ch, streams, n_streams, n_frames, in, in_stride, mtw_l, mtw_r, mt_stream_stride, \
-                                       out, out_stride, tap_bus, tap_lr, fast, s)
+                                       out, out_stride, tap_bus, tap_lr, pre, fast, s)
     switch (ch.hb_ord) {
         ICW_SPLIT_CASE(15);
         ICW_SPLIT_CASE(18);

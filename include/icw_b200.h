@@ -179,6 +179,8 @@ int  icw_session_set_state(icw_session *s, int stream, const icw_stream_state *i
 /* mod_context_reset_hilbert / _reset_framecnt (src/in_cwave.c:161,287), counters
  * (amod_get_clips_peaks isReset, src/adv_modulator.c:445), new file position */
 enum { ICW_RESET_HILBERT = 1, ICW_RESET_FRAMECNT = 2, ICW_RESET_COUNTERS = 4, ICW_RESET_FILEPOS = 8,
+       ICW_RESET_RENDER = 16,   /* dither generators back at their seeds, prev_rnd, shaper memory and bus cleared: with the
+                                 * other four, the state of a fresh context (winampGetInModule2, src/in_cwave.c:551-572) */
        ICW_RESET_ALL = 255 };
 int  icw_session_reset(icw_session *s, unsigned what);
 
