@@ -340,7 +340,10 @@ def parity_check(wl: dict, d_in, d_out, K: int, N: int) -> dict:
 # ---------------------------------------------------------------------------------------------
 # one workload on this rank: resident timing, per-kernel roofline, e2e, parity
 # ---------------------------------------------------------------------------------------------
-FP64_OPS = {"c2": 164 + 82 + 105, "c5": 164 + 82 + 70, "c1": 164 + 82 + 70, "c4": 1124 + 70, "c4ns": 1124 + 200, "c3": 300}
+# FP64 instructions per stereo frame the kernels that run these workloads actually issue: the one-kernel
+# scan path 2 x 73 DFMA per frame (c2, c5: icw_sfused.cu) or the three-pass scan 164 + 82 (c1), the exact Kahan recurrences
+# 4 x 281 (c4), plus the frame path (oscillator, DSP list, dither, quantiser)
+FP64_OPS = {"c2": 146 + 105, "c5": 146 + 70, "c1": 164 + 82 + 70, "c4": 1124 + 70, "c4ns": 1124 + 200, "c3": 300}
 
 
 def measure(ctx, name: str, steps: int, warmup: int, want_e2e: bool, want_parity: bool, args=None) -> dict:
@@ -641,7 +644,7 @@ def main():
     # graph, and -- where there is more than one GPU -- the time-sharded stream with its NCCL hand-off timed ------------
     others = {}
     if not args.no_workloads and args.workload == "c2" and not args.streams and not args.frames:
-        for name in ["c4", "c3"] + (["c5"] if world > 1 else []):
+        for name in ["c4", "c3", "c4ns"] + (["c5"] if world > 1 else []):
             try:
                 r = measure(ctx, name, max(3, min(args.steps, 10)), 3, want_e2e=not args.no_e2e, want_parity=not args.no_parity)
                 r.pop("_spec", None)
