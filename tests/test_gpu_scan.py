@@ -201,18 +201,20 @@ def test_mode_switch_on_live_stream(engine, oracle, ft, first):
         assert e0 <= 30.0 * REF_NOISE_RMS[ft] + 1e-12
 
 
-def test_time_sharding_stitches_on_one_gpu(engine, oracle):
+@pytest.mark.parametrize("ft,warm,n", [(0, 40_000, 120_000), (5, 1 << 19, 2 * (1 << 19) + 30_000)])
+def test_time_sharding_stitches_on_one_gpu(engine, oracle, ft, warm, n):
     """The multi-GPU time split, emulated on one GPU: shard 1 starts from closed-form scalars and a
-    filter state obtained by a warm-up over the tail of shard 0 (what rank 0 would send over NCCL)."""
+    filter state obtained by a warm-up over the tail of shard 0 (what rank 0 would send over NCCL).  Type 0 forgets
+    fastest (0.99832^40000 ~ 1e-29); type 5 is the slowest design (pole radius 0.99986) and gets the hand-off's own
+    warm-up length, dist.WARMUP_FRAMES = 2^19 (0.99986^(2^19) ~ 1e-32)."""
     from in_cwave_b200 import dist as D
-    spec = S.config_c2(hilbert_mode="scan", filter_no=0)       # type 0 forgets fastest: short warm-up suffices
+    assert warm <= D.WARMUP_FRAMES
+    spec = S.config_c2(hilbert_mode="scan", filter_no=ft)
     fb = S.frame_bytes(spec)
-    n = 120_000
     raw = rand_bytes(spec, n, 61)
     whole = engine.session(spec, 1).process_host(raw)[0]
     a1, _ = D.shard_time(n, 1, 2)
     be0, be1 = D.CudaBackend(engine, spec), D.CudaBackend(engine, spec)
-    warm = 40_000                                               # 0.99832^40000 ~ 1e-29
     tail = raw[(a1 - warm) * fb: a1 * fb]
     state = be0.hilbert_state_after(tail, D.closed_form_state(spec, a1 - warm).quad)
     be0.start_at(D.closed_form_state(spec, 0), np.zeros(D.STATE_DOUBLES))
