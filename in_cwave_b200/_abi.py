@@ -84,7 +84,7 @@ EXPORTS = [
     "icw_session_create", "icw_session_destroy", "icw_session_set_spec", "icw_session_get_state",
     "icw_session_set_state", "icw_session_reset", "icw_session_process_host",
     "icw_session_process_device", "icw_session_sync", "icw_session_stats", "icw_session_fp_stats", "icw_hilbert_device",
-    "icw_mt_words_device", "icw_session_set_taps", "icw_debug_phase_device", "icw_debug_sincos_device", "icw_debug_note_redraw", "icw_mt_host_charpoly",
+    "icw_mt_words_device", "icw_session_set_taps", "icw_debug_phase_device", "icw_debug_sincos_device", "icw_debug_note_redraw", "icw_debug_patch_mt_word", "icw_mt_host_charpoly",
     "icw_mt_host_seq_state", "icw_mt_host_jump_state", "icw_mt_host_jump_state_family", "icw_mt_host_jump_state_product", "icw_mt_host_unit_blocks", "icw_host_scan_chunk_len",
     "icw_session_profile", "icw_session_profile_read", "icw_kernel_class_name", "icw_crc32_device", "icw_crc32_host", "icw_crc32_combine",
     "icw_pinned_alloc", "icw_pinned_free",
@@ -149,6 +149,7 @@ def lib() -> C.CDLL:
     L.icw_debug_phase_device.argtypes = [vp, P(ChainSpecC), u64, i64, C.c_double, vp]
     L.icw_debug_sincos_device.argtypes = [vp, i64, vp, vp]
     L.icw_debug_note_redraw.argtypes = [vp, C.c_int, C.c_uint64]
+    L.icw_debug_patch_mt_word.argtypes = [vp, C.c_int, C.c_uint64, C.c_uint32]
     L.icw_mt_host_charpoly.argtypes = [P(C.c_int), P(C.c_int)]
     L.icw_mt_host_seq_state.argtypes = [C.c_uint32, u64, P(C.c_uint32)]
     L.icw_mt_host_seq_state.restype = None

@@ -2,6 +2,7 @@
 // stream state, and the per-call launch sequence.  Host side only; kernels live in icw_kernels.cu.
 #include <algorithm>
 #include <cmath>
+#include <climits>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -109,6 +110,10 @@ struct icw_session {
     std::vector<uint64_t> mt_drawn[2];
     uint64_t launches = 0;
     unsigned long long redraws_seen = 0;    // sum of the streams' mt_redraws already reported (ICW_E_MT_REDRAW)
+    uint64_t redraws_handled = 0;           // dither draws that met the rejection loop and were replayed the reference's way
+    DevStream *d_snap = nullptr;            // the streams as they stood when the current host call began (replay)
+    struct MtPatch { int chan; uint64_t idx; uint32_t value; };
+    std::vector<MtPatch> mt_patches;        // test hook: icw_debug_patch_mt_word
     cudaStream_t last_stream = nullptr; // the stream of the most recent process call (NULL: none yet / engine stream)
     int hb_basis = 0;                   // basis of the Hilbert state on the device
     bool hb_live = false;               // that state is not all-zero / has been used
@@ -516,6 +521,7 @@ extern "C" void icw_session_destroy(icw_session *s)
     if (!s) return;
     quiesce(s);
     if (s->d_streams) cudaFree(s->d_streams);
+    if (s->d_snap) cudaFree(s->d_snap);
     for (auto &sp : s->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto ev : s->ev_pool) cudaEventDestroy(ev);
     icw_engine *e = s->e;
@@ -754,6 +760,18 @@ extern "C" int icw_session_set_taps(icw_session *s, double *d_tap_bus, double *d
 // ---------------------------------------------------------------------------------------------
 struct DitherWords { const uint32_t *l = nullptr, *r = nullptr; size_t stream_stride = 0; cudaEvent_t join = nullptr; };
 
+// words [first, first + n) of channel c's generator (seeded with `seed`) into dst
+static int generate_words(icw_session *s, int c, uint32_t seed, uint64_t first, int64_t n, uint32_t *dst, cudaStream_t st)
+{
+    icw_engine *e = s->e;
+    int rc = e->mt.generate(seed, first, n, dst, e->sm_count, st, &s->launches);
+    if (rc) return fail(rc, "%s", e->mt.error());
+    for (const auto &pt : s->mt_patches)        // test hook: one word of the stream replaced (icw_debug_patch_mt_word)
+        if (pt.chan == c && pt.idx >= first && pt.idx < first + (uint64_t)n)
+            CK(cudaMemcpyAsync(dst + (pt.idx - first), &pt.value, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    return ICW_OK;
+}
+
 static int make_dither_words(icw_session *s, int64_t n_frames, cudaStream_t st, DitherWords &dw)
 {
     int mt_shared;
@@ -769,19 +787,19 @@ static int make_dither_words(icw_session *s, int64_t n_frames, cudaStream_t st, 
             if (s->mt_seed[c][k] != s->mt_seed[c][0] || s->mt_drawn[c][k] != s->mt_drawn[c][0]) mt_shared = 0;
     for (int c = 0; c < 2; ++c)
         for (int k = 0; k < K; ++k)
-            if (s->mt_drawn[c][k] % (uint64_t)wps)
-                return fail(ICW_E_UNSUPPORTED, "stream %d channel %d: generator offset %llu is not a multiple of the %d words "
-                                               "one sample draws (left by another dither type or a rejected draw)", k, c,
-                            (unsigned long long)s->mt_drawn[c][k], wps);
-    const int64_t words = n_frames * wps;
+            if (s->mt_drawn[c][k] % 2u)
+                return fail(ICW_E_UNSUPPORTED, "stream %d channel %d: generator offset %llu is odd (every draw takes two words)", k, c,
+                            (unsigned long long)s->mt_drawn[c][k]);
+    // a frame replayed with the reference's rejection loop may take more words than its share: room for 32 rejected pairs
+    const int64_t words = n_frames * wps + ((s->ch.feedback & 2) ? 64 : 0);
     const int groups = mt_shared ? 1 : K;
     for (int c = 0; c < 2; ++c) {
         int rc = e->mtw[c].reserve((size_t)groups * (size_t)words * sizeof(uint32_t));
         if (rc) return rc;
         for (int g = 0; g < groups; ++g) {
             uint32_t *dst = (uint32_t *)e->mtw[c].p + (size_t)g * (size_t)words;
-            rc = e->mt.generate(s->mt_seed[c][g], s->mt_drawn[c][g], words, dst, e->sm_count, st, &s->launches);
-            if (rc) return fail(rc, "%s", e->mt.error());
+            rc = generate_words(s, c, s->mt_seed[c][g], s->mt_drawn[c][g], words, dst, st);
+            if (rc) return rc;
         }
     }
     wl = (const uint32_t *)e->mtw[0].p;
@@ -1151,11 +1169,8 @@ extern "C" int icw_session_process_device(icw_session *s, int64_t n_frames, cons
 // double-buffered device staging, so that on a long call the PCIe transfers of neighbouring
 // segments hide behind the kernels.  Works from pageable memory too (the copies then stage
 // through the driver and overlap less).
-extern "C" int icw_session_process_host(icw_session *s, int64_t n_frames, const void *in, size_t in_stride,
-                                        void *out, size_t out_stride)
+static int host_run(icw_session *s, int64_t n_frames, const void *in, size_t in_stride, void *out, size_t out_stride)
 {
-    if (!s || !in || !out) return fail(ICW_E_ARG, "NULL argument");
-    if (n_frames <= 0) return n_frames ? fail(ICW_E_ARG, "negative frame count") : ICW_OK;
     icw_engine *e = s->e;
     const DevChain &ch = s->ch;
     const int K = s->n_streams;
@@ -1215,7 +1230,128 @@ extern "C" int icw_session_process_host(icw_session *s, int64_t n_frames, const 
     CK(cudaStreamSynchronize(e->d2h));
     CK(cudaStreamSynchronize(st));
     call_end(s, cx, st);
-    return check_redraws(s);
+    return ICW_OK;
+}
+
+// The streams are idle and some kernel of the call that just ran has counted a dither draw that met the generator's
+// rejection loop.  Which frame of the call was the first?  The kernels keep a count and nothing else, so the answer is
+// looked up in the generators' own words: every stream whose count moved has the words its channels drew in this call
+// made again (in pieces of 2^24) and searched for the first pair the reference would throw away.  Streams that stand at
+// the same place of the same generator share the answer.  *frame = LLONG_MAX if nothing was counted.
+static int first_redraw_frame(icw_session *s, const std::vector<unsigned long long> &cnt0, const std::vector<uint64_t> (&drawn0)[2],
+                              int64_t n_frames, int64_t *frame)
+{
+    icw_engine *e = s->e;
+    const int K = s->n_streams, wps = s->ch.render.words_per_sample;
+    std::vector<unsigned long long> cnt((size_t)K);
+    CK(cudaMemcpy2D(cnt.data(), sizeof(unsigned long long), &s->d_streams[0].mt_redraws, sizeof(DevStream), sizeof(unsigned long long),
+                    (size_t)K, cudaMemcpyDeviceToHost));
+    *frame = LLONG_MAX;
+    std::map<std::pair<uint32_t, uint64_t>, long long> seen;       // (seed, first word) -> first rejected word or LLONG_MAX
+    long long *d_first = nullptr;
+    const int64_t piece = (int64_t)1 << 24;
+    for (int k = 0; k < K; ++k) {
+        if (cnt[(size_t)k] == cnt0[(size_t)k]) continue;
+        for (int c = 0; c < 2; ++c) {
+            const uint32_t seed = s->mt_seed[c][(size_t)k];
+            const uint64_t w0 = drawn0[c][(size_t)k];
+            auto key = std::make_pair(seed, w0);
+            auto it = seen.find(key);
+            long long first = LLONG_MAX;
+            if (it != seen.end()) first = it->second;
+            else {
+                if (!d_first && cudaMalloc(&d_first, sizeof(long long)) != cudaSuccess) { cudaGetLastError(); return fail(ICW_E_NOMEM, "cudaMalloc failed"); }
+                int rc = e->mtw[c].reserve((size_t)piece * sizeof(uint32_t));
+                if (rc) { cudaFree(d_first); return rc; }
+                const int64_t total = n_frames * wps;
+                for (int64_t off = 0; off < total && first == LLONG_MAX; off += piece) {
+                    const int64_t nw = total - off < piece ? total - off : piece;
+                    const long long init = LLONG_MAX;
+                    CK(cudaMemcpyAsync(d_first, &init, sizeof init, cudaMemcpyHostToDevice, e->stream));
+                    rc = generate_words(s, c, seed, w0 + (uint64_t)off, nw, (uint32_t *)e->mtw[c].p, e->stream);
+                    if (rc) { cudaFree(d_first); return rc; }
+                    CK(launch_mt_find_reject((const uint32_t *)e->mtw[c].p, nw / 2, (long long)((w0 + (uint64_t)off) / 2), d_first, e->sm_count, e->stream));
+                    CK(cudaMemcpyAsync(&first, d_first, sizeof first, cudaMemcpyDeviceToHost, e->stream));
+                    CK(cudaStreamSynchronize(e->stream));
+                    if (first != LLONG_MAX) first *= 2;             // pair number -> word number
+                }
+                seen[key] = first;
+            }
+            if (first != LLONG_MAX) *frame = std::min<int64_t>(*frame, (int64_t)(((uint64_t)first - w0) / (uint64_t)wps));
+        }
+    }
+    if (d_first) cudaFree(d_first);
+    return ICW_OK;
+}
+
+// Host entry point.  The kernels draw the dither by frame index (draw j of a channel = words 2j, 2j+1 of its generator);
+// the reference draws word after word and throws a pair away when it maps to -1 (mtrnd_gen_dsopen,
+// src/mersene_twister/mt_jrnd.c:245-256; probability 2^-53 a draw).  A call whose kernels met such a pair is REPLAYED: the
+// streams go back to where they stood when the call began, the frames before the event run again as they did, the one frame
+// with the event runs through the frame-serial route with the reference's own loop (its generator ends two words further
+// on), and the rest of the call follows from there -- the output is the reference's for every frame.  The input is still in
+// the caller's buffer, which is why this is the host entry point's privilege (the device entry point reports the event).
+extern "C" int icw_session_process_host(icw_session *s, int64_t n_frames, const void *in, size_t in_stride,
+                                        void *out, size_t out_stride)
+{
+    if (!s || !in || !out) return fail(ICW_E_ARG, "NULL argument");
+    if (n_frames <= 0) return n_frames ? fail(ICW_E_ARG, "negative frame count") : ICW_OK;
+    const int K = s->n_streams;
+    const DevChain &ch = s->ch;
+    if (!ch.render.words_per_sample) return host_run(s, n_frames, in, in_stride, out, out_stride);
+    const size_t in_row = (size_t)n_frames * ch.frame_bytes, out_row = (size_t)n_frames * ch.out_frame_bytes;
+    if (K > 1 && (in_stride < in_row || out_stride < out_row)) return fail(ICW_E_ARG, "stream strides too short");
+    // a sub-range of the call keeps the caller's row strides (one stream: the rows are the whole buffers)
+    const size_t hs_in = K > 1 ? in_stride : in_row, hs_out = K > 1 ? out_stride : out_row;
+    CK(cudaSetDevice(s->e->device));
+    int rc = quiesce(s);
+    if (rc) return rc;
+    if (!s->d_snap && cudaMalloc(&s->d_snap, sizeof(DevStream) * (size_t)K) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ICW_E_NOMEM, "cudaMalloc(state snapshot) failed");
+    }
+    auto sub = [&](int64_t f0, int64_t n) {
+        // rows of K > 1 streams keep their stride; a single stream's sub-range is contiguous
+        return host_run(s, n, (const uint8_t *)in + (size_t)f0 * ch.frame_bytes, K > 1 ? hs_in : 0,
+                        (uint8_t *)out + (size_t)f0 * ch.out_frame_bytes, K > 1 ? hs_out : 0);
+    };
+    int64_t done = 0;
+    for (int guard = 0; done < n_frames; ++guard) {
+        // where the streams stand now
+        CK(cudaMemcpy(s->d_snap, s->d_streams, sizeof(DevStream) * (size_t)K, cudaMemcpyDeviceToDevice));
+        std::vector<unsigned long long> cnt0((size_t)K);
+        CK(cudaMemcpy2D(cnt0.data(), sizeof(unsigned long long), &s->d_streams[0].mt_redraws, sizeof(DevStream), sizeof(unsigned long long),
+                        (size_t)K, cudaMemcpyDeviceToHost));
+        const std::vector<uint64_t> drawn0[2] = { s->mt_drawn[0], s->mt_drawn[1] };
+        const int basis0 = s->hb_basis;
+        const bool live0 = s->hb_live;
+        rc = sub(done, n_frames - done);
+        if (rc) return rc;
+        int64_t f;
+        rc = first_redraw_frame(s, cnt0, drawn0, n_frames - done, &f);
+        if (rc) return rc;
+        if (f == LLONG_MAX) return ICW_OK;
+        if (guard >= 64) return fail(ICW_E_MT_REDRAW, "more than 64 rejected dither draws in one call");
+        // back to the start of this stretch, then: the frames before the event as before, the event's frame the reference's way
+        CK(cudaMemcpy(s->d_streams, s->d_snap, sizeof(DevStream) * (size_t)K, cudaMemcpyDeviceToDevice));
+        s->mt_drawn[0] = drawn0[0]; s->mt_drawn[1] = drawn0[1];
+        s->hb_basis = basis0; s->hb_live = live0;
+        if (f > 0) {
+            rc = sub(done, f);
+            if (rc) return rc;
+        }
+        s->ch.feedback |= 2;
+        rc = sub(done + f, 1);
+        s->ch.feedback &= ~2;
+        if (rc) return rc;
+        // the generators stand where the serial draws left them
+        for (int c = 0; c < 2; ++c)
+            CK(cudaMemcpy2D(s->mt_drawn[c].data(), sizeof(uint64_t), &s->d_streams[0].mt_drawn[c], sizeof(DevStream), sizeof(uint64_t),
+                            (size_t)K, cudaMemcpyDeviceToHost));
+        ++s->redraws_handled;
+        done += f + 1;
+    }
+    return ICW_OK;
 }
 
 extern "C" int icw_session_profile(icw_session *s, int on)
@@ -1265,6 +1401,7 @@ extern "C" int icw_session_stats(icw_session *s, icw_stats *out)
         }
         out->mt_redraws += d.mt_redraws;
     }
+    out->mt_redraws += s->redraws_handled;
     out->peak_db[0] = icw_peak_db(pk[0]);
     out->peak_db[1] = icw_peak_db(pk[1]);
     out->kernel_launches = s->launches;
@@ -1397,6 +1534,21 @@ extern "C" int icw_debug_note_redraw(icw_session *s, int k, uint64_t n)
     CK(cudaMemcpy(&v, &s->d_streams[k].mt_redraws, sizeof v, cudaMemcpyDeviceToHost));
     v += n;
     CK(cudaMemcpy(&s->d_streams[k].mt_redraws, &v, sizeof v, cudaMemcpyHostToDevice));
+    return ICW_OK;
+}
+
+// test hook for the replay of a rejected dither draw: word number `idx` (counted from the seeding) of channel `chan`'s
+// generator comes out as `value` wherever the dither words go through a buffer (every route but the two that make them
+// inside the pointwise kernel: exact mode, batches, interpreted lists, noise shaping, sloped TPDF, Gauss all do).
+// n_patches < 0 clears the list.
+extern "C" int icw_debug_patch_mt_word(icw_session *s, int chan, uint64_t idx, uint32_t value)
+{
+    if (!s) return fail(ICW_E_ARG, "NULL session");
+    if (chan < 0) { s->mt_patches.clear(); return ICW_OK; }
+    if (chan > 1) return fail(ICW_E_ARG, "channel 0 or 1");
+    int rc = quiesce(s);
+    if (rc) return rc;
+    s->mt_patches.push_back({ chan, idx, value });
     return ICW_OK;
 }
 

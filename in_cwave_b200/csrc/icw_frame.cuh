@@ -93,6 +93,45 @@ struct FrameAcc {
     unsigned clips_l = 0, clips_r = 0, redraws = 0;
     double peak_l = 0.0, peak_r = 0.0;
 };
+// The reference's own way to draw (mtrnd_gen_dsopen, src/mersene_twister/mt_jrnd.c:218-226,245-256): words taken one after
+// the other, a pair that maps to -1 thrown away and the next pair taken.  Used for the one frame of a call that met such a
+// pair (the closed form "draw j = words 2j, 2j+1" ends there); `cur` = next word of the channel's buffer.
+__device__ __forceinline__ double serial_dsopen(const uint32_t *w, unsigned &cur)
+{
+    for (;;) {
+        bool rd;
+        const double v = mt_dsopen(w[cur], w[cur + 1], rd);
+        cur += 2;
+        if (!rd) return v;
+    }
+}
+__device__ __forceinline__ double serial_dither(const DevRender &r, const uint32_t *w, unsigned &cur, double prev_tr, double &first)
+{
+    switch (r.render_type) {
+    case ICW_RENDER_RPDF:
+        first = serial_dsopen(w, cur);
+        return div_const_finite(first, ICW_KC[KC_SQRT2], ICW_KC[KC_RSQRT2]);
+    case ICW_RENDER_TPDF: {
+        first = serial_dsopen(w, cur);
+        double v = first;
+        v += serial_dsopen(w, cur);
+        return v * 0.5;
+    }
+    case ICW_RENDER_STPDF:
+        first = serial_dsopen(w, cur);
+        return (first - prev_tr) * 0.5;
+    case ICW_RENDER_GAUSS: {
+        first = serial_dsopen(w, cur);
+        double v = first;
+        for (int j = 1; j < 12; ++j) v += serial_dsopen(w, cur);
+        const double d = 2.0 * ICW_SQRT6;
+        return div_const_finite(v, d, 1.0 / d);
+    }
+    default:
+        first = 0.0;
+        return 0.0;
+    }
+}
 
 struct FrameIO {
     const uint32_t *mtw_l, *mtw_r;  // tempered MT words of this stream's call range (or NULL)
@@ -107,7 +146,8 @@ struct FrameIO {
 // DITHER_AT: where the dither words of the 2- and 4-word types come from -- fetched before the DSP
 // list (8 more live registers), fetched at their use, or handed in by the caller (chain_mt_kernel
 // makes them in shared memory; Gauss and sloped TPDF never take that route).
-enum { DITHER_EARLY = 1, DITHER_LATE = 0, DITHER_GIVEN = 2 };
+enum { DITHER_EARLY = 1, DITHER_LATE = 0, DITHER_GIVEN = 2,
+       DITHER_SERIAL = 3 /* a one-frame call replayed with the reference's rejection loop (chain_serial_kernel only) */ };
 template <int DITHER_AT = DITHER_EARLY>
 __device__ __forceinline__ void finish_frame(const DevChain &ch, DevStream &st, int64_t i, int64_t n_frames,
                                              const double v[4], double (*bus)[4], const FrameIO &io, FrameAcc &acc,
@@ -144,9 +184,19 @@ __device__ __forceinline__ void finish_frame(const DevChain &ch, DevStream &st, 
             if (i == 0) { prev_l = st.prev_rnd[0]; prev_r = st.prev_rnd[1]; }
             else { prev_l = first_draw(io.mtw_l, i - 1); prev_r = first_draw(io.mtw_r, i - 1); }
         }
-        if (DITHER_AT == DITHER_LATE) { wl = dither_fetch(wps, io.mtw_l, i); wr = dither_fetch(wps, io.mtw_r, i); }
-        dl = dither_sample(rq, wl, io.mtw_l, i, prev_l, acc.redraws);
-        dr = dither_sample(rq, wr, io.mtw_r, i, prev_r, acc.redraws);
+        if (DITHER_AT == DITHER_SERIAL) {
+            // replay of a frame that met the rejection loop: a one-frame call (i == 0), the channel's words in order
+            unsigned cl = 0, cr = 0;
+            double fl, fr;
+            dl = serial_dither(rq, io.mtw_l, cl, st.prev_rnd[0], fl);
+            dr = serial_dither(rq, io.mtw_r, cr, st.prev_rnd[1], fr);
+            st.serial_used[0] = cl; st.serial_used[1] = cr;
+            if (rq.render_type == ICW_RENDER_STPDF) { st.prev_rnd_next[0] = fl; st.prev_rnd_next[1] = fr; }
+        } else {
+            if (DITHER_AT == DITHER_LATE) { wl = dither_fetch(wps, io.mtw_l, i); wr = dither_fetch(wps, io.mtw_r, i); }
+            dl = dither_sample(rq, wl, io.mtw_l, i, prev_l, acc.redraws);
+            dr = dither_sample(rq, wr, io.mtw_r, i, prev_r, acc.redraws);
+        }
     }
     if (io.pre) {
         double4 *q = reinterpret_cast<double4 *>(io.pre) + i;
@@ -169,7 +219,7 @@ __device__ __forceinline__ void finish_frame(const DevChain &ch, DevStream &st, 
     if (i == n_frames - 1) {
         // the context's bus after the call == the last frame's values (adv_modulator.c:634-751)
         for (int k = 0; k < ICW_N_PLUGS; ++k) { st.bus[k][0] = bus[k][0]; st.bus[k][1] = bus[k][1]; st.bus[k][2] = bus[k][2]; st.bus[k][3] = bus[k][3]; }
-        if (DITHER_AT != DITHER_GIVEN && rq.render_type == ICW_RENDER_STPDF) {
+        if (DITHER_AT != DITHER_GIVEN && DITHER_AT != DITHER_SERIAL && rq.render_type == ICW_RENDER_STPDF) {
             // frame 0 of this call may still be reading prev_rnd in another CTA: write the shadow copy
             st.prev_rnd_next[0] = first_draw(io.mtw_l, i);
             st.prev_rnd_next[1] = first_draw(io.mtw_r, i);

@@ -58,8 +58,10 @@ struct DevChain {
     int32_t  shape;                     // ICW_SHAPE_*: DSP lists common enough to get straight-line code
     int32_t  filter_no, hb_ord, is_kahan, reject_flag;
     int32_t  fp_check;                  // the FP-exception-checked twins (reference src/fp_check.c:52-99)
-    int32_t  feedback;                  // a node reads a plug written later in the list: the previous frame's value,
-                                        // so the DSP list is serial in time (reference src/adv_modulator.c:634-751)
+    int32_t  feedback;                  // bit 0: a node reads a plug written later in the list: the previous frame's value,
+                                        // so the DSP list is serial in time (reference src/adv_modulator.c:634-751);
+                                        // bit 1 (per call): the dither draws of this call are taken one after the other with the
+                                        // reference's rejection loop (replay of a frame that met it, icw_api.cu)
     int64_t  n_samples, n_fade_in, n_fade_out;
     uint64_t scale_sr;                  // sample_rate * 1000 (scaled) or 0
     double   osc_div, osc_rdiv;         // divisor of the oscillator phase and RN(1/divisor)
@@ -89,7 +91,10 @@ struct DevStream {
     double   ns_e[2][ICW_NS_MAX_TAPS], ns_o[2][ICW_NS_MAX_TAPS], ns_prev_err[2];   // age-ordered shaper memory
     // FP_EXCEPT_STATS x 4: [hilbert L, hilbert R, render L, render R][total, snan, qnan, ninf, nden, pden, pinf]
     uint32_t fp_cnt[4][7];
-    uint32_t pad_fp[4];
+    // the frame-serial replay of a frame whose dither draw ran into the generator's rejection loop (mt_jrnd.c:249-253): the words
+    // each channel's generator consumed
+    uint32_t serial_used[2];
+    uint32_t pad_fp[2];
 };
 
 }  // namespace icw

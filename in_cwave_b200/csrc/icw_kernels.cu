@@ -327,7 +327,8 @@ chain_serial_kernel(const __grid_constant__ DevChain ch, DevStream *__restrict__
         } else {
             unpack_frame(ch, src + i * ch.frame_bytes, st.pos + i, v);
         }
-        finish_frame<DITHER_LATE>(ch, st, i, n_frames, v, bus, io, acc, osc);
+        if (ch.feedback & 2) finish_frame<DITHER_SERIAL>(ch, st, i, n_frames, v, bus, io, acc, osc);      // replay of a rejected draw's frame
+        else finish_frame<DITHER_LATE>(ch, st, i, n_frames, v, bus, io, acc, osc);
     }
     if (acc.clips_l) atomicAdd(&st.clips[0], acc.clips_l);
     if (acc.clips_r) atomicAdd(&st.clips[1], acc.clips_r);
@@ -540,6 +541,25 @@ cudaError_t launch_ns_render(const DevChain &ch, DevStream *streams, int n_strea
     return cudaGetLastError();
 }
 
+// Where in a stretch of a generator's words is the first pair that mtrnd_gen_dsopen would throw away (both halves zero after
+// their shifts: u == 0, the draw maps to -1; src/mersene_twister/mt_jrnd.c:218-226,245-256)?  Only run after a kernel has
+// counted such a draw: the hot kernels keep a count and nothing else (the event has probability 2^-53).
+__global__ void mt_find_reject_kernel(const uint32_t *__restrict__ w, int64_t n_pairs, long long base_pair, long long *first)
+{
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += (int64_t)gridDim.x * blockDim.x)
+        if (((w[2 * p] >> 5) | (w[2 * p + 1] >> 6)) == 0u) atomicMin(first, base_pair + (long long)p);
+}
+
+cudaError_t launch_mt_find_reject(const uint32_t *w, int64_t n_pairs, long long base_pair, long long *d_first, int sm_count, cudaStream_t s)
+{
+    const int threads = 256;
+    int64_t blocks = (n_pairs + threads - 1) / threads;
+    if (blocks > (int64_t)sm_count * 16) blocks = (int64_t)sm_count * 16;
+    if (blocks < 1) blocks = 1;
+    mt_find_reject_kernel<<<(int)blocks, threads, 0, s>>>(w, n_pairs, base_pair, d_first);
+    return cudaGetLastError();
+}
+
 // after a process call: advance the per-stream scalars that are closed forms of the frame count
 __global__ void advance_streams_kernel(const __grid_constant__ DevChain ch, DevStream *streams, int n_streams,
                                        int64_t n_frames, int advance_quad)
@@ -556,8 +576,9 @@ __global__ void advance_streams_kernel(const __grid_constant__ DevChain ch, DevS
     }
     if (ch.render.render_type == ICW_RENDER_STPDF) { st.prev_rnd[0] = st.prev_rnd_next[0]; st.prev_rnd[1] = st.prev_rnd_next[1]; }
     uint64_t words = (uint64_t)n_frames * (uint64_t)ch.render.words_per_sample;
-    st.mt_drawn[0] += words;
-    st.mt_drawn[1] += words;
+    const bool serial = (ch.feedback & 2) != 0 && ch.render.words_per_sample != 0;     // the draws were taken one by one
+    st.mt_drawn[0] += serial ? (uint64_t)st.serial_used[0] : words;
+    st.mt_drawn[1] += serial ? (uint64_t)st.serial_used[1] : words;
 }
 
 cudaError_t launch_advance(const DevChain &ch, DevStream *streams, int n_streams, int64_t n_frames,

@@ -56,6 +56,8 @@ cudaError_t launch_chain_mt(const DevChain &ch, DevStream *streams, int64_t n_fr
 // noise shaping on: chain_kernel leaves (value, dither) pairs in `pre`; one thread per (stream, channel) quantises
 cudaError_t launch_ns_render(const DevChain &ch, DevStream *streams, int n_streams, int64_t n_frames,
                              const double *pre, uint8_t *out, size_t out_stride, cudaStream_t s);
+// first pair of a stretch of generator words that the reference's dsopen would reject (atomicMin into *d_first)
+cudaError_t launch_mt_find_reject(const uint32_t *w, int64_t n_pairs, long long base_pair, long long *d_first, int sm_count, cudaStream_t s);
 cudaError_t launch_advance(const DevChain &ch, DevStream *streams, int n_streams, int64_t n_frames,
                            int advance_quad, cudaStream_t s);
 cudaError_t launch_sincos_leaf(int64_t n, const double *x, double *out, cudaStream_t s);

@@ -57,7 +57,9 @@ constexpr bool SP_DEBUG_SKIP_STATE = (ICW_SPLIT_SKIP & 1) != 0, SP_DEBUG_SKIP_OU
 constexpr int SP_T = ICW_SPLIT_T;               // frames per tile
 constexpr int SP_K = ICW_SPLIT_K;               // samples of a recurrence whose output sums one thread advances in lock step (1: see DESIGN.md 5.1)
 constexpr int SP_PH = ICW_SPLIT_PH;             // output lanes per recurrence: each takes every PH-th group of K samples
-constexpr int SP_HPS = ICW_SPLIT_HPS;           // helper threads per stream: a frame is ~3000 cycles of dependent work
+constexpr int SP_HPS = ICW_SPLIT_HPS;           // helper threads per stream: a frame is ~3000 cycles of dependent work (more with dither and a
+                                                // noise shaper's hand-off: 4 a stream is enough for C4 and costs c4ns 25 %).  18 warps at 28
+                                                // streams; the SM allots registers to warps in fours, so 96 a thread is the ceiling
 constexpr int SP_HIST = 20;                     // rows of history in front of a tile (>= the highest order)
 constexpr int SP_WROWS = SP_HIST + SP_T;
 static_assert(SP_T >= SP_HIST && SP_HIST >= ICW_MAX_ORD && SP_T % (SP_K * SP_PH) == 0 && SP_T % SP_HPS == 0,

@@ -42,10 +42,11 @@ enum {
     ICW_E_UNSUPPORTED = -3,     /* valid in the reference but not modelled on the GPU (says which) */
     ICW_E_NOMEM = -4,
     ICW_E_MT_REDRAW = -5        /* a dither draw hit the reference's rejection loop (src/mersene_twister/mt_jrnd.c:249-253:
-                                 * probability 2^-53 a draw); the frames before the event are the reference's, the
-                                 * later ones drew their words two places early.  Reported by the call that ran into it
-                                 * (host entry point) or by the next icw_session_sync / state accessor (device entry
-                                 * point) -- once; icw_stats.mt_redraws keeps the count */
+                                 * probability 2^-53 a draw).  The HOST entry point replays such a call the reference's way
+                                 * (icw_session_process_host) and never returns this; the DEVICE entry point cannot (the
+                                 * input may be gone): the frames before the event are the reference's, the later ones drew
+                                 * their words two places early, and the next icw_session_sync says so -- once;
+                                 * icw_stats.mt_redraws counts both kinds */
 };
 
 /* input sample encodings.  0..4 = reference HRW_FMT_* (src/in_cwave.h:326-330, unpackers
@@ -288,6 +289,9 @@ int  icw_debug_phase_device(icw_engine *e, const icw_chain_spec *spec, uint64_t 
 int  icw_debug_sincos_device(icw_engine *e, int64_t n, const double *d_x, double *d_out);
 /* test hook: count n more dsopen re-draws on stream k, as a kernel that met one would (see ICW_E_MT_REDRAW) */
 int  icw_debug_note_redraw(icw_session *s, int k, uint64_t n);
+/* test hook: word `idx` (counted from the seeding) of channel chan's generator is handed out as `value` wherever the dither
+ * words pass through a buffer; chan < 0 clears the patches.  Two patched words (0, 0) make a pair the reference rejects. */
+int  icw_debug_patch_mt_word(icw_session *s, int chan, uint64_t idx, uint32_t value);
 /* host-only checks of the MT19937 jump-ahead mathematics (no GPU is touched):
  * characteristic polynomial found by Berlekamp-Massey; the state array after `blocks` block
  * regenerations computed sequentially, through x^J mod phi, and through the x^(624*2^k) family */

@@ -77,6 +77,18 @@ static void mt_regenerate(uint32_t *w)
     }
 }
 
+/* Test hook: a draw lands on the rejection loop of mtrnd_gen_dsopen (mt_jrnd.c:249-253) with probability 2^-53, and no
+ * seed is known that gets there.  A patch replaces ONE output word of a generator's stream: word number `idx` (counted
+ * from the seeding), if it comes out as `match` (which tells the two channels' generators apart), is handed out as
+ * `value` instead.  Two patched words (0, 0) make a pair that the loop below rejects.  tests/ only. */
+static struct { uint64_t idx; uint32_t match, value; } g_patch[16];
+static int g_npatch;
+void icwo_debug_patch_word(uint64_t idx, uint32_t match, uint32_t value)
+{
+    if (g_npatch < 16) { g_patch[g_npatch].idx = idx; g_patch[g_npatch].match = match; g_patch[g_npatch].value = value; ++g_npatch; }
+}
+void icwo_debug_clear_patches(void) { g_npatch = 0; }
+
 uint32_t icwo_mt_u32(icwo_mt *mt)
 {
     if (mt->pos >= ICWO_MT_N) {
@@ -90,6 +102,8 @@ uint32_t icwo_mt_u32(icwo_mt *mt)
     y ^= (y << 7) & 0x9D2C5680u;
     y ^= (y << 15) & 0xEFC60000u;
     y ^= y >> 18;
+    for (int k = 0; k < g_npatch; ++k)
+        if (g_patch[k].idx == mt->drawn - 1 && g_patch[k].match == y) return g_patch[k].value;
     return y;
 }
 

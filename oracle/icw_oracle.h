@@ -85,6 +85,9 @@ typedef struct icwo_mt {
     int      pos;               /* next word to hand out; ICWO_MT_N = regenerate first */
     uint64_t drawn;             /* words consumed so far */
 } icwo_mt;
+/* test hook (tests/ only): replace word `idx` of a generator's stream, if it comes out as `match`, by `value` */
+void icwo_debug_patch_word(uint64_t idx, uint32_t match, uint32_t value);
+void icwo_debug_clear_patches(void);
 
 /* everything that persists from frame to frame (reference MOD_CONTEXT, src/in_cwave.h:410-424) */
 /* noise-shaper memory of one channel (reference NS_SHAPER, src/sound_render.h:113-139), ordered by AGE:
