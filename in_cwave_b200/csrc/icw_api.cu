@@ -1071,7 +1071,10 @@ static int call_begin(icw_session *s, int64_t n_total, cudaStream_t st, CallCtx 
         sfused_supports(ch, K, s->d_tap_bus || s->d_tap_lr) &&
         (!wps || (s->mt_drawn[0][0] == s->mt_drawn[1][0] && s->mt_drawn[0][0] % (uint64_t)wps == 0))) {
         bool go = e->sfused == 1;
-        if (!go) go = n_total / (e->sm_count * SF_CTAS_PER_SM) >= 2 * get_sf_plan(e, s->spec.filter_no, !s->spec.is_kahan, s->coef.d0).warm;
+        // ... and on streams with dither: without it the generator warps idle and two scan warps a CTA are all the SM gets for
+        // the filters -- the three-kernel path, analytic round trip and all, is then the faster one (C5 shape, 400 M frames of
+        // f32 without dither: 11.4 ms against 16.2; C2, i24 with TPDF: 30.8 against 26.1)
+        if (!go) go = wps != 0 && n_total / (e->sm_count * SF_CTAS_PER_SM) >= 2 * get_sf_plan(e, s->spec.filter_no, !s->spec.is_kahan, s->coef.d0).warm;
         if (go) { cx.sfused = true; cx.step = n_total; return ICW_OK; }
     }
     // the fused exact kernel reads word buffers; everything else that ends in chain_kernel can make its own
