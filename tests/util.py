@@ -49,3 +49,66 @@ def port_state_to_dict(st) -> dict:
         rejects=sum(int(st.lpf[c][f].rejects) for c in range(2) for f in range(2)),
         drawn=(int(st.mt[0].drawn), int(st.mt[1].drawn)),
     )
+
+
+# ---------------------------------------------------------------------------------------------
+# randomised specs for the differential tests (tests/test_fuzz.py): every knob of the path the reference
+# exposes (src/config.c:118-207 bounds), DSP lists of any shape incl. one-frame feedback loops
+# ---------------------------------------------------------------------------------------------
+FUZZ_FORMATS = ["wav_u8", "wav_i16", "wav_i24", "wav_i32", "wav_f32", "cw_f64", "cw_i16", "cw_i16f32", "cw_f32"]
+
+
+def random_nodes(rng, feedback: bool) -> list:
+    n_mid = int(rng.integers(0, 6))
+    outs = sorted(int(p) for p in rng.choice(np.arange(1, 27), size=max(n_mid, 1), replace=bool(rng.integers(0, 2))))[:n_mid]
+    rng.shuffle(outs)
+    nodes, written = [], [0]
+
+    def pick_inputs(pool):
+        k = int(rng.integers(1, min(3, len(pool)) + 1))
+        return sorted(int(p) for p in rng.choice(pool, size=k, replace=False))
+
+    # A feedback loop with gain above one is chaotic: the reference itself answers a one-ulp change of a gain with thousands of
+    # different samples, so the <= 2 ulp between glibc's and libdevice's sin/cos cannot be held to an LSB there.  Feedback lists are
+    # therefore drawn either without sin/cos (any gains, also unstable ones: both sides do the same IEEE operations -> equal bytes,
+    # through Inf and NaN) or contractive (at most three inputs a node, every gain <= 0.3).
+    trig_ok = not feedback or rng.random() < 0.6
+    if feedback and trig_ok:
+        gain = lambda: float(rng.choice([0.3, 0.25, 0.1, round(float(rng.uniform(0.02, 0.3)), 3)]))
+    else:
+        gain = lambda: float(rng.choice([1.0, 0.8, 0.5, round(float(rng.uniform(0.05, 1.2)), 3)]))
+    for i, out in enumerate(outs):
+        mode = str(rng.choice(["shift", "pm", "mix"])) if trig_ok else "mix"
+        pool = sorted(set(written) | (set(outs) if feedback else set()))
+        nd = dict(mode=mode, inputs=pick_inputs(pool), out=out, xch=int(rng.integers(0, 5)),
+                  l_iq_invert=int(rng.integers(0, 2)), r_iq_invert=int(rng.integers(0, 2)), l_gain=gain(), r_gain=gain(),
+                  l_on=int(rng.random() < 0.85), r_on=int(rng.random() < 0.85))
+        if mode == "shift":
+            nd["l_p"] = [round(float(rng.uniform(-60, 60)), 3)]
+            nd["r_p"] = [round(float(rng.uniform(-60, 60)), 3)]
+        elif mode == "pm":
+            nd["l_p"] = [round(float(rng.uniform(0, 30)), 3), round(float(rng.uniform(-1, 1)), 3), round(float(rng.uniform(0, 2)), 3), round(float(rng.uniform(-1, 1)), 3)]
+            nd["r_p"] = [round(float(rng.uniform(0, 30)), 3), round(float(rng.uniform(-1, 1)), 3), round(float(rng.uniform(0, 2)), 3), round(float(rng.uniform(-1, 1)), 3)]
+        nodes.append(nd)
+        written.append(out)
+    pool = sorted(set(written))
+    nodes.append(dict(mode="master", inputs=pick_inputs(pool), xch=int(rng.integers(0, 5)) if rng.random() < 0.3 else 0,
+                      l_iq_invert=int(rng.random() < 0.2), r_iq_invert=int(rng.random() < 0.2),
+                      l_gain=gain(), r_gain=gain(), l_tout=int(rng.integers(0, 4)), r_tout=int(rng.integers(0, 4))))
+    return nodes
+
+
+def random_spec(rng, hilbert_mode: str = "exact", allow_feedback: bool = True, allow_shaping: bool = True) -> dict:
+    fmt = str(rng.choice(FUZZ_FORMATS))
+    need24 = int(rng.integers(0, 2))
+    feedback = bool(allow_feedback and rng.random() < 0.2)
+    d = dict(
+        fmt=fmt, n_channels=int(rng.integers(1, 3)), sample_rate=int(rng.choice([8000, 22050, 44100, 48000, 96000, 192000, 384000])),
+        filter_no=int(rng.integers(0, 6)), is_kahan=int(rng.integers(0, 2)), is_subnorm_reject=int(rng.integers(0, 2)),
+        hilbert_mode=hilbert_mode, is_frmod_scaled=int(rng.random() < 0.7), need24bits=need24,
+        dth_bits=float(rng.choice([1.0, 0.5, 2.0, 3.25])), quantz_type=int(rng.integers(0, 2)), render_type=int(rng.integers(0, 5)),
+        nshape_type=int(rng.integers(1, 18)) if (allow_shaping and rng.random() < 0.25) else 0,
+        sign_bits16=int(rng.choice([16, 16, 12, 8, 2])), sign_bits24=int(rng.choice([24, 24, 20, 17, 9, 2])),
+        bypass=int(rng.random() < 0.1), nodes=random_nodes(rng, feedback),
+    )
+    return S.default_spec(**d)
