@@ -341,9 +341,9 @@ def parity_check(wl: dict, d_in, d_out, K: int, N: int) -> dict:
 # one workload on this rank: resident timing, per-kernel roofline, e2e, parity
 # ---------------------------------------------------------------------------------------------
 # FP64 instructions per stereo frame the kernels that run these workloads actually issue: the one-kernel
-# scan path 2 x 73 DFMA per frame (c2, c5: icw_sfused.cu) or the three-pass scan 164 + 82 (c1), the exact Kahan recurrences
+# scan path 2 x 73 DFMA per frame (c2: icw_sfused.cu) or the three-pass scan 164 + 82 (c1, and c5: no dither), the exact Kahan recurrences
 # 4 x 281 (c4), plus the frame path (oscillator, DSP list, dither, quantiser)
-FP64_OPS = {"c2": 146 + 105, "c5": 146 + 70, "c1": 164 + 82 + 70, "c4": 1124 + 70, "c4ns": 1124 + 200, "c3": 300}
+FP64_OPS = {"c2": 146 + 105, "c5": 164 + 82 + 70, "c1": 164 + 82 + 70, "c4": 1124 + 70, "c4ns": 1124 + 200, "c3": 300}
 
 
 def measure(ctx, name: str, steps: int, warmup: int, want_e2e: bool, want_parity: bool, args=None) -> dict:
