@@ -357,6 +357,29 @@ static int fold_spec(const icw_chain_spec &sp, DevChain &ch, HbCoef &coef)
             d.l_angle = s.l_p[3];           d.r_angle = s.r_p[3];
         }
         if (s.mode != ICW_MODE_MASTER) written |= 1u << s.n_out;
+        d.n_in = 0; d.pad_ = 0;
+        memset(d.in_off, 0, sizeof d.in_off);
+        {
+            int idx[3] = { 0, 0, 0 }, n_in = 0;
+            for (int k = 0; k < ICW_N_PLUGS; ++k)
+                if (s.inputs_mask >> k & 1u) { if (n_in < 3) idx[n_in] = k; ++n_in; }
+            int m[4] = { 0, 1, 2, 3 };
+            bool ok = n_in >= 1 && n_in <= 3;
+            switch (s.xch_mode) {                               // reference src/adv_modulator.c:668-722: XCH, then I/Q inversion
+            case ICW_XCH_NORMAL: break;
+            case ICW_XCH_SWAP:      m[0] = 2; m[1] = 3; m[2] = 0; m[3] = 1; break;
+            case ICW_XCH_LEFTONLY:  m[2] = 0; m[3] = 1; break;
+            case ICW_XCH_RIGHTONLY: m[0] = 2; m[1] = 3; break;
+            default: ok = false; break;                         // (L+R)/2 is arithmetic, not a move
+            }
+            if (d.l_iq_invert) { const int t = m[0]; m[0] = m[1]; m[1] = t; }
+            if (d.r_iq_invert) { const int t = m[2]; m[2] = m[3]; m[3] = t; }
+            if (ok) {
+                d.n_in = n_in;
+                for (int i = 0; i < n_in; ++i)
+                    for (int j = 0; j < 4; ++j) d.in_off[i][j] = (idx[i] * 4 + m[j]) * (int)sizeof(double);
+            }
+        }
     }
     if (!ch.is_complex && sp.hilbert_mode != ICW_HILBERT_EXACT && sp.hilbert_mode != ICW_HILBERT_SCAN)
         return fail(ICW_E_ARG, "hilbert_mode out of range");

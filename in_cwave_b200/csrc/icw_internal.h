@@ -36,6 +36,13 @@ struct DevNode {
     double   l_ph0, r_ph0;          // pm: phase * PI          (:572)
     double   l_lvlpi, r_lvlpi;      // pm: level * PI          (:572)
     double   l_angle, r_angle;      // pm: angle
+    // the interpreter's short cut (run_graph): a node with 1..3 inputs whose exchange mode is not (L+R)/2 takes its four
+    // values straight out of the bus in the order XCH and the I/Q inversions would leave them -- the sums are per component,
+    // so moving the components before or after the sum is the same arithmetic
+    int32_t  n_in;                  // number of inputs when the short cut applies (1..3), else 0
+    int32_t  pad_;
+    int32_t  in_off[3][4];          // [input][value j]: byte offset into the thread's bus[ICW_N_PLUGS][4] of the component that
+                                    // ends up as value j (plugs in ascending order)
 };
 
 // quantiser constants (reference sound_render_recalc, src/sound_render.c:499-551)

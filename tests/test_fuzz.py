@@ -44,6 +44,31 @@ def _has_trig(spec):
     return not spec["bypass"] and any(nd["mode"] in ("shift", "pm") and (nd.get("l_on", 1) or nd.get("r_on", 1)) for nd in spec["nodes"])
 
 
+def _explain_flips(eng, spec, raw, pcm, want, label):
+    """More flipped LSBs than one in 10^5: a list can make its output a difference of nearly equal numbers (a plug mixed with its
+    own I/Q-swapped copy, master I-Q: seed 3140), whose sign -- the quantiser's step at zero -- then hangs on the last bit of a
+    sin/cos.  Then, and only then: the same bytes again with the master output tapped; that output within 1e-12 of the bus
+    scale of the restatement's; bytes differ ONLY where the tapped doubles differ."""
+    from util import pcm_to_int
+    ses = eng.session(spec, 1)
+    try:
+        n = raw.size // S.frame_bytes(spec)
+        _, lr = ses.enable_taps(n)
+        again = ses.process_host(raw)[0]
+        assert np.array_equal(again, pcm), label
+        plugs = sorted({0} | {nd["out"] for nd in spec["nodes"] if nd["mode"] != "master"})
+        ref = po.port_process(spec, raw, taps=plugs, want_lr=True)
+        got = lr.cpu().numpy()[0]
+        scale = max(float(np.max(np.abs(ref["bus"]))), 1e-300)
+        assert float(np.max(np.abs(got - ref["lr"]))) <= 1e-12 * scale, label
+        bps = _bps(spec)
+        flipped = (pcm_to_int(pcm, bps) != pcm_to_int(want, bps)).reshape(-1, 2)
+        same_in = got == ref["lr"]
+        assert not np.any(flipped & same_in), label
+    finally:
+        ses.close()
+
+
 def run_cuda_case(seed, eng, n_max=30000, k_choices=(1, 1, 2, 5)):
     """One random configuration through the C ABI (K streams, the call cut at random places) against the reference."""
     rng = np.random.default_rng(5000 + seed)
@@ -67,7 +92,9 @@ def run_cuda_case(seed, eng, n_max=30000, k_choices=(1, 1, 2, 5)):
             if _has_trig(spec):
                 # a quantiser with few significant bits turns one flipped rounding into 2^(shift) output steps
                 step = 1 << ((24 - spec["sign_bits24"]) if spec["need24bits"] else (16 - spec["sign_bits16"]))
-                assert rep["max_lsb"] <= step and rep["mismatches"] <= max(1, rep["samples"] // 100000), (seed, k, rep, spec)
+                assert rep["max_lsb"] <= step, (seed, k, rep, spec)
+                if rep["mismatches"] > max(1, rep["samples"] // 100000):
+                    _explain_flips(eng, spec, raws[k], pcm[k], ref["pcm"], (seed, k, rep))
             else:
                 assert rep["mismatches"] == 0, (seed, k, rep, spec)
             p = port["state"]
