@@ -1163,8 +1163,10 @@ static void call_end(icw_session *s, const CallCtx &cx, cudaStream_t st)
 static void note_alignment(icw_session *s, const void *d_in, size_t in_stride)
 {
     // typed loads are only legal when every sample sits on its natural alignment
+    // (a complex format's unit is its (I, Q) pair: one 32- or 64-bit word, or two doubles; the 6-byte i16 + f32 pair never is)
     const int cb = s->ch.chan_bytes;
-    const size_t a = (cb == 2 || cb == 4) ? (size_t)cb : 0;
+    size_t a = (cb == 2 || cb == 4) ? (size_t)cb : 0;
+    if (s->ch.is_complex) a = s->ch.fmt == ICW_FMT_CW_I16 ? 4 : (s->ch.fmt == ICW_FMT_CW_F32 || s->ch.fmt == ICW_FMT_CW_F64) ? 8 : 0;
     s->ch.aligned = a && ((size_t)(uintptr_t)d_in % a == 0) && (s->n_streams == 1 || in_stride % a == 0);
 }
 
