@@ -357,7 +357,8 @@ static int fold_spec(const icw_chain_spec &sp, DevChain &ch, HbCoef &coef)
             d.l_angle = s.l_p[3];           d.r_angle = s.r_p[3];
         }
         if (s.mode != ICW_MODE_MASTER) written |= 1u << s.n_out;
-        d.n_in = 0; d.pad_ = 0;
+        d.n_in = 0;
+        memset(d.pad_, 0, sizeof d.pad_);
         memset(d.in_off, 0, sizeof d.in_off);
         {
             int idx[3] = { 0, 0, 0 }, n_in = 0;
@@ -376,8 +377,10 @@ static int fold_spec(const icw_chain_spec &sp, DevChain &ch, HbCoef &coef)
             if (d.r_iq_invert) { const int t = m[2]; m[2] = m[3]; m[3] = t; }
             if (ok) {
                 d.n_in = n_in;
-                for (int i = 0; i < n_in; ++i)
-                    for (int j = 0; j < 4; ++j) d.in_off[i][j] = (idx[i] * 4 + m[j]) * (int)sizeof(double);
+                for (int i = 0; i < n_in; ++i) {
+                    auto off = [&](int j) { return (idx[i] * 4 + m[j]) * (int)sizeof(double); };
+                    d.in_off[i] = make_int4(off(0), off(1), off(2), off(3));
+                }
             }
         }
     }

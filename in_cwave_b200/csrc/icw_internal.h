@@ -40,9 +40,9 @@ struct DevNode {
     // values straight out of the bus in the order XCH and the I/Q inversions would leave them -- the sums are per component,
     // so moving the components before or after the sum is the same arithmetic
     int32_t  n_in;                  // number of inputs when the short cut applies (1..3), else 0
-    int32_t  pad_;
-    int32_t  in_off[3][4];          // [input][value j]: byte offset into the thread's bus[ICW_N_PLUGS][4] of the component that
-                                    // ends up as value j (plugs in ascending order)
+    int32_t  pad_[3];
+    int4     in_off[3];             // [input] .x .y .z .w: byte offset into the thread's bus[ICW_N_PLUGS][4] of the component that
+                                    // ends up as value 0..3 (plugs in ascending order); one 128-bit constant load an input
 };
 
 // quantiser constants (reference sound_render_recalc, src/sound_render.c:499-551)

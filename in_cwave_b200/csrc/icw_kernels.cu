@@ -248,7 +248,12 @@ cudaError_t launch_mt_words(const uint32_t *ckpt, int n_units, int blocks_per_un
 #define ICW_CHAIN_THREADS 256
 #define ICW_CHAIN_CTAS 4
 #endif
-__global__ void __launch_bounds__(ICW_CHAIN_THREADS, ICW_CHAIN_CTAS)
+// the interpreter's own launch shape (A/B: profiles/r2_ab_interpreter.txt)
+#ifndef ICW_GCHAIN_THREADS
+#define ICW_GCHAIN_THREADS 256
+#define ICW_GCHAIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(ICW_GCHAIN_THREADS, ICW_GCHAIN_CTAS)
 chain_kernel(const __grid_constant__ DevChain ch, DevStream *__restrict__ streams, int64_t n_frames,
              const uint8_t *__restrict__ in, size_t in_stride, int from_analytic,
              const uint32_t *__restrict__ mtw_l, const uint32_t *__restrict__ mtw_r, size_t mt_stream_stride,
@@ -278,6 +283,15 @@ chain_kernel(const __grid_constant__ DevChain ch, DevStream *__restrict__ stream
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_frames;
          i += (int64_t)gridDim.x * blockDim.x) {
         double v[4];
+        {
+            // the thread's next frame is a grid stride away: asked for now, it is in L1 when its turn comes (the load at the top
+            // of a trip was 8 % of the kernel's stall samples on C3)
+            const int64_t nx = i + (int64_t)gridDim.x * blockDim.x;
+            if (nx < n_frames) {
+                const uint8_t *pn = from_analytic ? src + nx * 32 : src + nx * ch.frame_bytes;
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(pn));
+            }
+        }
         if (from_analytic) {
             const double *a = reinterpret_cast<const double *>(src) + i * 4;
             v[0] = a[0]; v[1] = a[1]; v[2] = a[2]; v[3] = a[3];
@@ -417,8 +431,16 @@ cudaError_t launch_chain(const DevChain &ch, DevStream *streams, int n_streams, 
 #undef ICW_LEAN
         return cudaGetLastError();
     }
-    chain_kernel<<<grid, threads, 0, s>>>(ch, streams, n_frames, in, in_stride, from_analytic, mtw_l, mtw_r,
-                                          mt_stream_stride, out, out_stride, tap_bus, tap_lr, pre);
+    {
+        const int gthreads = ICW_GCHAIN_THREADS;
+        const int64_t gneed = (n_frames + gthreads - 1) / gthreads;
+        int gper = (int)(gneed < 1 ? 1 : gneed);
+        int gcap = (sm_count * 2 * ICW_GCHAIN_CTAS + n_streams - 1) / n_streams;
+        if (gcap < 1) gcap = 1;
+        if (gper > gcap) gper = gcap;
+        chain_kernel<<<dim3(gper, n_streams), gthreads, 0, s>>>(ch, streams, n_frames, in, in_stride, from_analytic, mtw_l, mtw_r,
+                                                                mt_stream_stride, out, out_stride, tap_bus, tap_lr, pre);
+    }
     return cudaGetLastError();
 }
 
