@@ -13,7 +13,7 @@ import pytest
 
 from in_cwave_b200 import spec as S, synth
 from oracle import pyoracle as po
-from util import pcm_report, random_spec
+from util import add_random_fades, pcm_report, random_spec
 
 N_CPU, N_GPU = 24, 48
 
@@ -33,7 +33,8 @@ def test_restatement_equals_the_compiled_reference_on_random_specs(seed):
         pytest.skip("oracle/_ref is not built")
     rng = np.random.default_rng(1000 + seed)
     spec = random_spec(rng)
-    n = int(rng.integers(1, 6000))
+    n = int(rng.integers(2, 6000))                 # MIN_FILE_SAMPLES (src/in_cwave.h:315): the reader refuses a shorter file
+    spec = add_random_fades(rng, spec, n)
     raw = _input(spec, rng, n)
     r = po.ref_process(spec, raw, read_quant=int(rng.choice([4096, 1111, 1, 64])) if n < 2000 else 4096)
     p = po.port_process(spec, raw)
@@ -74,7 +75,8 @@ def run_cuda_case(seed, eng, n_max=30000, k_choices=(1, 1, 2, 5)):
     rng = np.random.default_rng(5000 + seed)
     spec = random_spec(rng)
     K = int(rng.choice(k_choices))
-    n = int(rng.integers(1, n_max))
+    n = int(rng.integers(2, n_max))
+    spec = add_random_fades(rng, spec, n)
     fb = S.frame_bytes(spec)
     raws = [np.frombuffer(bytes(_input(spec, rng, n)), dtype=np.uint8) for _ in range(K)]
     raw = np.stack(raws)

@@ -112,3 +112,18 @@ def random_spec(rng, hilbert_mode: str = "exact", allow_feedback: bool = True, a
         bypass=int(rng.random() < 0.1), nodes=random_nodes(rng, feedback),
     )
     return S.default_spec(**d)
+
+
+def add_random_fades(rng, spec: dict, n: int) -> dict:
+    """Fade in / out (reference src/xwave_reader.c:707-723, 921-936) on a track of n frames: whole milliseconds (the reference's
+    unit) at a rate that makes them whole frames, short enough that its one-third cap does not apply."""
+    sr = spec["sample_rate"]
+    if sr % 1000 or n < 64 or rng.random() < 0.6:
+        return spec
+    per_ms = sr // 1000
+    most = (n - 1) // 2 // per_ms                       # n_fade_in + n_fade_out < n_samples
+    if most < 1:
+        return spec
+    fi = int(rng.integers(0, min(most, 40) + 1)) * per_ms
+    fo = int(rng.integers(0, min(most, 40) + 1)) * per_ms
+    return dict(spec, n_samples=n, n_fade_in=fi, n_fade_out=fo)
