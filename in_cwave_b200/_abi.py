@@ -21,7 +21,7 @@ FMT = {
 CHAN_BYTES = {0: 1, 1: 2, 2: 3, 3: 4, 4: 4, 16: 16, 17: 4, 18: 6, 19: 8}
 MODE = {"master": 0, "shift": 1, "pm": 2, "mix": 3}
 HILBERT = {"exact": 0, "scan": 1}
-RESET_HILBERT, RESET_FRAMECNT, RESET_COUNTERS, RESET_FILEPOS, RESET_RENDER, RESET_ALL = 1, 2, 4, 8, 16, 255
+RESET_HILBERT, RESET_FRAMECNT, RESET_COUNTERS, RESET_FILEPOS, RESET_RENDER, RESET_RENDER_MEMORY, RESET_ALL = 1, 2, 4, 8, 16, 32, 255
 
 
 class Node(C.Structure):

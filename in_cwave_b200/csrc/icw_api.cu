@@ -665,6 +665,11 @@ extern "C" int icw_session_reset(icw_session *s, unsigned what)
             memset(d.fp_cnt, 0, sizeof d.fp_cnt);               // except_stats_reset, reference src/fp_check.c:37-47
         }
         if (w & ICW_RESET_FILEPOS) d.pos = 0;
+        if (w & ICW_RESET_RENDER_MEMORY) {      // sound_render_recalc (src/sound_render.c:509,556-580)
+            d.prev_rnd[0] = d.prev_rnd[1] = 0.0; d.prev_rnd_next[0] = d.prev_rnd_next[1] = 0.0;
+            memset(d.ns_e, 0, sizeof d.ns_e); memset(d.ns_o, 0, sizeof d.ns_o);
+            d.ns_prev_err[0] = d.ns_prev_err[1] = 0.0;
+        }
         if (w & ICW_RESET_RENDER) {             // what a fresh context holds (winampGetInModule2, src/in_cwave.c:46-80,551-572)
             d.mt_drawn[0] = d.mt_drawn[1] = 0;  // mtrnd_init_seed: the generators back at their seeds' first draw
             d.prev_rnd[0] = d.prev_rnd[1] = 0.0; d.prev_rnd_next[0] = d.prev_rnd_next[1] = 0.0;

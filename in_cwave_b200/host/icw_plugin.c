@@ -337,7 +337,9 @@ intptr_t winampGetExtendedRead_open(const char *filename, int *size, int *bps, i
 {
     icw_chain_spec sp;
     int64_t total, sz;
-    unsigned reset = ICW_RESET_FILEPOS;
+    /* every mod_context_fopen re-runs sound_render_recalc on both renderers (src/in_cwave.c:231-234): sloped-TPDF memory and
+     * shaper memory start from zero in every file, the dither generators carry on */
+    unsigned reset = ICW_RESET_FILEPOS | ICW_RESET_RENDER_MEMORY;
 
     ensure_defaults();
     if (P.open) return 0;                           /* one transcode at a time, like &the.mc_transcode */

@@ -182,6 +182,9 @@ int  icw_session_set_state(icw_session *s, int stream, const icw_stream_state *i
 enum { ICW_RESET_HILBERT = 1, ICW_RESET_FRAMECNT = 2, ICW_RESET_COUNTERS = 4, ICW_RESET_FILEPOS = 8,
        ICW_RESET_RENDER = 16,   /* dither generators back at their seeds, prev_rnd, shaper memory and bus cleared: with the
                                  * other four, the state of a fresh context (winampGetInModule2, src/in_cwave.c:551-572) */
+       ICW_RESET_RENDER_MEMORY = 32,    /* what sound_render_recalc clears (src/sound_render.c:509,556-580): prev_rnd, the shaper's
+                                         * buffers and prev_ns_err -- run by EVERY mod_context_fopen through sound_render_set_outbits
+                                         * (src/in_cwave.c:231-234); the generators keep their place */
        ICW_RESET_ALL = 255 };
 int  icw_session_reset(icw_session *s, unsigned what);
 

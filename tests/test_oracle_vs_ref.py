@@ -150,6 +150,28 @@ def test_state_survives_files():
     assert np.array_equal(r1["pcm"], p1["pcm"]) and np.array_equal(r2["pcm"], p2["pcm"])
 
 
+@pytest.mark.parametrize("over", [dict(render_type=3, dth_bits=3.25), dict(render_type=2, nshape_type=6), dict(render_type=4, nshape_type=17)])
+def test_every_file_open_clears_the_render_memory(over):
+    """mod_context_fopen runs sound_render_set_outbits -> sound_render_recalc on both renderers for EVERY file
+    (src/in_cwave.c:231-234, src/sound_render.c:509,556-580): the sloped-TPDF memory and the shaper's buffers start from zero in
+    each file, while the generators (and everything else) carry on.  What include/icw_b200.h calls ICW_RESET_RENDER_MEMORY."""
+    d = S.config_c2(**over)
+    fb = S.frame_bytes(d)
+    raw = synth.stream_bytes(d, 3000, stream_id=12)
+    po.ref_process(d, raw[: 1000 * fb])
+    r2 = po.ref_process(d, raw[1000 * fb:], reset=False)
+    st = po.new_state()
+    po.port_process(d, raw[: 1000 * fb], state=st)
+    carried = po.port_process(d, raw[1000 * fb:], state=C.pointer(st).contents.__class__.from_buffer_copy(st))
+    st.pos = 0
+    for c in range(2):
+        st.prev_rnd[c] = 0.0
+        C.memset(C.byref(st.ns[c]), 0, C.sizeof(st.ns[c]))
+    p2 = po.port_process(d, raw[1000 * fb:], state=st)
+    assert np.array_equal(r2["pcm"], p2["pcm"])
+    assert not np.array_equal(r2["pcm"], carried["pcm"])        # ... and carrying that memory over is NOT what the reference does
+
+
 def test_frame_counter_wrap():
     """Scaled counter wraps at sample_rate*1000 frames (src/adv_modulator.c:614-617)."""
     d = S.default_spec(fmt="cw_i16", sample_rate=8, need24bits=0,

@@ -206,7 +206,7 @@ def test_transcode_entry_points_match_the_reference(tmp_path, case):
     arr = (po.Node * len(spec["nodes"]))()
     for i, nd in enumerate(spec["nodes"]):
         po.fill_node(arr[i], nd)
-    assert po.ref().icwref_set_graph(arr, len(spec["nodes"]), 0) == 0
+    assert po.ref().icwref_set_graph(arr, len(spec["nodes"]), int(spec.get("bypass", 0))) == 0
     cap = (n + 30000) * 6
     want = np.zeros(cap, dtype=np.uint8)
     info = (C.c_int * 4)()
@@ -318,7 +318,7 @@ def _both(spec, script, readahead, opts=None, over=None):
     arr = (po.Node * len(spec["nodes"]))()
     for i, nd in enumerate(spec["nodes"]):
         po.fill_node(arr[i], nd)
-    assert po.ref().icwref_set_graph(arr, len(spec["nodes"]), 0) == 0
+    assert po.ref().icwref_set_graph(arr, len(spec["nodes"]), int(spec.get("bypass", 0))) == 0
     want = _run_script(_bind_transcode(po.ref()), script)
     plugin.lib().icwp_reset()
     plugin.configure(spec, readahead_frames=readahead, **(opts or {}))
@@ -393,3 +393,45 @@ def test_overlapped_reader_prefetches_blocks(tmp_path):
     assert pcm.size == 200_000 * 6
     assert st["blocks_sync"] == 1 and st["blocks_prefetched"] == (200_000 + 32767) // 32768 - 1
     assert st["frames"] == 200_000 and st["read_bytes"] == raw.size and st["resettles"] == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not po.have_ref(), reason="oracle/_ref/libicw_ref.so not built")
+@pytest.mark.parametrize("seed", range(int(os.environ.get("ICW_PLUGIN_FUZZ", "16"))))     # a longer walk: ICW_PLUGIN_FUZZ=300
+def test_random_transcode_scripts(tmp_path, seed):
+    """Random configuration (tests/util.py::random_spec), two files, a random walk over the four entry points -- requests of any
+    byte count, seeks anywhere, a transcode cancelled half way and the next file opened on the surviving context -- through
+    libicw_plugin.so and through the compiled reference: the same bytes in the same order (src/transcode.c:40-118)."""
+    from util import random_spec
+    rng = np.random.default_rng(7000 + seed)
+    spec = random_spec(rng)
+    fb = S.frame_bytes(spec)
+    is_cw = spec["fmt"].startswith("cw_")
+    n = [int(rng.integers(3000, 40000)) for _ in range(2)]
+    raw = synth.stream_bytes(spec, n[0] + n[1], stream_id=int(rng.integers(1, 1 << 30)))
+    paths = []
+    for j, (a, b) in enumerate(((0, n[0]), (n[0], n[0] + n[1]))):
+        p = tmp_path / (f"f{j}.cwave" if is_cw else f"f{j}.wav")
+        p.write_bytes(po.cwave_bytes(spec, raw[a * fb:b * fb]) if is_cw else po.wav_bytes(spec, raw[a * fb:b * fb]))
+        paths.append(p)
+    script = []
+    for j, p in enumerate(paths):
+        script.append(("open", p))
+        dur_ms = n[j] * 1000 // spec["sample_rate"]
+        for _ in range(int(rng.integers(1, 7))):
+            if rng.random() < 0.3 and dur_ms > 1:
+                script.append(("seek", int(rng.integers(0, dur_ms))))
+            else:
+                script.append(("get", int(rng.integers(6, 9000)), int(rng.integers(1, 7))))
+        if j == 1 or rng.random() < 0.5:
+            script.append(("drain", int(rng.integers(600, 70000))))
+        script.append(("close",))
+    readahead = int(rng.choice([0, 1, 777, 7001, 1 << 20]))
+    rep, _ = _both(spec, script, readahead)
+    print(f"[random script {seed} ra={readahead}] {rep} {[op[:1] + op[2:] if op[0] == 'open' else op for op in script]}")
+    trig = not spec["bypass"] and any(nd["mode"] in ("shift", "pm") for nd in spec["nodes"])
+    if trig:
+        step = 1 << ((24 - spec["sign_bits24"]) if spec["need24bits"] else (16 - spec["sign_bits16"]))
+        assert rep["max_lsb"] <= step and rep["mismatches"] <= max(2, rep["samples"] // 50000), (seed, rep)
+    else:
+        assert rep["mismatches"] == 0, (seed, rep)
