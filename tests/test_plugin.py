@@ -395,13 +395,8 @@ def test_overlapped_reader_prefetches_blocks(tmp_path):
     assert st["frames"] == 200_000 and st["read_bytes"] == raw.size and st["resettles"] == 0
 
 
-@pytest.mark.gpu
-@pytest.mark.skipif(not po.have_ref(), reason="oracle/_ref/libicw_ref.so not built")
-@pytest.mark.parametrize("seed", range(int(os.environ.get("ICW_PLUGIN_FUZZ", "16"))))     # a longer walk: ICW_PLUGIN_FUZZ=300
-def test_random_transcode_scripts(tmp_path, seed):
-    """Random configuration (tests/util.py::random_spec), two files, a random walk over the four entry points -- requests of any
-    byte count, seeks anywhere, a transcode cancelled half way and the next file opened on the surviving context -- through
-    libicw_plugin.so and through the compiled reference: the same bytes in the same order (src/transcode.c:40-118)."""
+def random_transcode_script(tmp_path, seed):
+    """A random configuration, two files of it on disk and a random walk over the four entry points."""
     from util import random_spec
     rng = np.random.default_rng(7000 + seed)
     spec = random_spec(rng)
@@ -426,6 +421,17 @@ def test_random_transcode_scripts(tmp_path, seed):
         if j == 1 or rng.random() < 0.5:
             script.append(("drain", int(rng.integers(600, 70000))))
         script.append(("close",))
+    return spec, script, rng
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not po.have_ref(), reason="oracle/_ref/libicw_ref.so not built")
+@pytest.mark.parametrize("seed", range(int(os.environ.get("ICW_PLUGIN_FUZZ", "16"))))     # a longer walk: ICW_PLUGIN_FUZZ=300
+def test_random_transcode_scripts(tmp_path, seed):
+    """Random configuration (tests/util.py::random_spec), two files, a random walk over the four entry points -- requests of any
+    byte count, seeks anywhere, a transcode cancelled half way and the next file opened on the surviving context -- through
+    libicw_plugin.so and through the compiled reference: the same bytes in the same order (src/transcode.c:40-118)."""
+    spec, script, rng = random_transcode_script(tmp_path, seed)
     readahead = int(rng.choice([0, 1, 777, 7001, 1 << 20]))
     rep, _ = _both(spec, script, readahead)
     print(f"[random script {seed} ra={readahead}] {rep} {[op[:1] + op[2:] if op[0] == 'open' else op for op in script]}")

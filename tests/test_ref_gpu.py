@@ -10,7 +10,7 @@ import pytest
 
 from in_cwave_b200 import spec as S, synth
 from oracle import pyoracle as po
-from test_plugin import _bind_transcode, _run_script
+from test_plugin import _bind_transcode, _run_script, random_transcode_script
 from util import pcm_report
 
 pytestmark = [pytest.mark.gpu,
@@ -149,3 +149,28 @@ def test_clip_and_peak_counters_through_the_replaced_getter(tmp_path):
     assert sr[0] > 0 and sr[:2] == sg[:2]
     assert abs(sr[2] - sg[2]) < 1e-9 and abs(sr[3] - sg[3]) < 1e-9
     assert np.array_equal(pr, pg)
+
+
+@pytest.mark.parametrize("seed", range(100, 112))
+def test_random_transcode_scripts_through_the_seam(tmp_path, seed):
+    """The random walk of tests/test_plugin.py::test_random_transcode_scripts over the reference's own reader and entry
+    points with the frame loop on the GPU (adv_modulator_gpu.c) against the pure reference."""
+    spec, script, _ = random_transcode_script(tmp_path, seed)
+    out = []
+    for L in (po.ref(), po.ref_gpu()):
+        cfg = po.make_refcfg(spec)
+        L.icwref_reset(C.byref(cfg))
+        arr = (po.Node * len(spec["nodes"]))()
+        for i, nd in enumerate(spec["nodes"]):
+            po.fill_node(arr[i], nd)
+        assert L.icwref_set_graph(arr, len(spec["nodes"]), int(spec.get("bypass", 0))) == 0
+        out.append(_run_script(_bind_transcode(L), script))
+    want, got = out
+    assert got.size == want.size and got.size > 0
+    rep = pcm_report(got, want, 3 if spec["need24bits"] else 2)
+    trig = not spec["bypass"] and any(nd["mode"] in ("shift", "pm") for nd in spec["nodes"])
+    if trig:
+        step = 1 << ((24 - spec["sign_bits24"]) if spec["need24bits"] else (16 - spec["sign_bits16"]))
+        assert rep["max_lsb"] <= step and rep["mismatches"] <= max(2, rep["samples"] // 50000), (seed, rep)
+    else:
+        assert rep["mismatches"] == 0, (seed, rep)
