@@ -162,3 +162,86 @@ def test_list_without_a_leading_master_is_dropped_but_the_file_is_accepted(tmp_p
 def test_missing_file(tmp_path):
     ok, sp, o, nodes = plugin.load_config(tmp_path / "nope.cfg")
     assert not ok and sp.n_nodes == 1 and sp.filter_no == 1
+
+
+# ---- randomised: files of random specs, and random damage to them, through both loaders -----------------------------------
+def _mutate(rng, lines):
+    """One random edit of a configuration file: the kind of damage a hand-edited or truncated file carries."""
+    import numpy as np
+    lines = list(lines)
+    k = int(rng.integers(0, len(lines)))
+    kind = int(rng.integers(0, 10))
+    toks = lines[k].split(" ")
+    if kind == 0:
+        del lines[k]
+    elif kind == 1:
+        lines.insert(k, lines[int(rng.integers(0, len(lines)))])                    # a line twice / out of place
+    elif kind == 2 and len(toks) > 1:
+        j = int(rng.integers(1, len(toks)))
+        toks[j] = str(rng.choice(["-1", "0", "1", "2", "7", "99", "1e9", "-0.0", "0.5", "nan", "inf", "x", "", "0x3FF0000000000000",
+                                  "0x7FF8000000000000", "4294967296", "-2147483649", "1.5e-320"]))
+        lines[k] = " ".join(toks)
+    elif kind == 3 and len(toks) > 2:
+        lines[k] = " ".join(toks[: int(rng.integers(1, len(toks)))])                # truncated line
+    elif kind == 4:
+        lines[k] = lines[k] + " " + " ".join(str(int(v)) for v in rng.integers(0, 3, size=int(rng.integers(1, 5))))   # extra fields
+    elif kind == 5 and "=" in lines[k]:
+        key, val = lines[k].split("=", 1)
+        lines[k] = str(rng.choice([key.lower(), key.title(), " " + key, key + " ", key[:-1], key + "X"])) + "=" + val
+    elif kind == 6:
+        lines[k] = lines[k].replace("=", str(rng.choice(["", "==", " = ", ":"])), 1)
+    elif kind == 7:
+        lines.insert(k, str(rng.choice(["", "   ", "\t", "# comment", "; comment", "[section]", "NODE_DSP=", "NODE_DSP=Master",
+                                        "VER_CONFIG=10", "VER_CONFIG=11"])))
+    elif kind == 8 and len(toks) > 3:
+        a, b = (int(v) for v in rng.integers(1, len(toks), size=2))
+        toks[a], toks[b] = toks[b], toks[a]
+        lines[k] = " ".join(toks)
+    else:
+        lines[k] = lines[k].replace("Master", str(rng.choice(["master", "Mast%er", "M%%", "Shift-1", "%"])), 1)
+    return lines
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_specs_and_random_damage_through_both_loaders(tmp_path, seed):
+    """A random chain written by the reference's save_config parses to the same chain in both loaders -- and so does the
+    same file after one to three random edits (lines dropped, doubled, truncated, fields replaced by junk, keys re-cased,
+    separators broken): same accept / reject verdict, same values, same DSP list, bit for bit (src/config.c:562-975)."""
+    import numpy as np
+    sys.path.insert(0, str(ROOT / "tests"))
+    from util import random_spec
+    rng = np.random.default_rng(4000 + seed)
+    d = random_spec(rng)
+    f = tmp_path / "ref.cfg"
+    assert po.ref_save_config(d, f)
+    ok_r, cfg_r, nodes_r = po.ref_load_config(f)
+    ok_o, sp, o, nodes_o = plugin.load_config(f)
+    assert ok_r and ok_o and _cfg_tuple_ours(sp, o) == _cfg_tuple_ref(cfg_r) and nodes_o == nodes_r
+    base = f.read_text().split("\n")
+    while base and base[-1] == "":
+        base.pop()
+    for trial in range(25):
+        lines = base
+        for _ in range(int(rng.integers(1, 4))):
+            lines = _mutate(rng, lines)
+        g = tmp_path / "damaged.cfg"
+        g.write_text("\n".join(lines) + "\n")
+        ok_r, cfg_r, nodes_r = po.ref_load_config(g)
+        ok_o, sp, o, nodes_o = plugin.load_config(g)
+        ctx = (seed, trial, "\n".join(lines))
+        assert ok_o == ok_r, ctx
+        assert _cfg_tuple_ours(sp, o) == _cfg_tuple_ref(cfg_r), ctx
+        assert _same_nodes(nodes_o, nodes_r), ctx
+
+
+def _same_nodes(a, b):
+    """Node tuples equal, NaN equal to NaN (a damaged file can carry one)."""
+    import math
+
+    def eq(x, y):
+        if isinstance(x, tuple):
+            return isinstance(y, tuple) and len(x) == len(y) and all(eq(p, q) for p, q in zip(x, y))
+        if isinstance(x, float) and isinstance(y, float) and math.isnan(x) and math.isnan(y):
+            return True
+        return x == y
+    return len(a) == len(b) and all(eq(p, q) for p, q in zip(a, b))
