@@ -441,3 +441,62 @@ def test_random_transcode_scripts(tmp_path, seed):
         assert rep["max_lsb"] <= step and rep["mismatches"] <= max(2, rep["samples"] // 50000), (seed, rep)
     else:
         assert rep["mismatches"] == 0, (seed, rep)
+
+
+def _damage_header(rng, blob, is_cw):
+    """One to three random edits inside (or at the end of) a file's header: a byte replaced, a 16/32-bit field set to an edge
+    value, bytes dropped or inserted, the file cut short."""
+    b = bytearray(blob)
+    for _ in range(int(rng.integers(1, 4))):
+        hdr = min(len(b), 48 if is_cw else 80)
+        if hdr < 12:
+            break
+        kind = int(rng.integers(0, 6))
+        if kind == 0:
+            b[int(rng.integers(0, hdr))] = int(rng.integers(0, 256))
+        elif kind == 1:
+            at = int(rng.integers(0, hdr - 4))
+            b[at:at + 4] = struct.pack("<I", int(rng.choice([0, 1, 2, 3, 7, 8, 16, 24, 32, 48, 0xFFFF, 0x10000, 0x7FFFFFFF, 0x80000000, 0xFFFFFFFF,
+                                                             len(b), max(len(b) - 44, 0), max(len(b) - 8, 0), 2_000_000, 2_000_001])))
+        elif kind == 2:
+            at = int(rng.integers(0, hdr - 2))
+            b[at:at + 2] = struct.pack("<H", int(rng.choice([0, 1, 2, 3, 4, 6, 8, 16, 24, 32, 64, 0xFFFE, 0xFFFF])))
+        elif kind == 3:
+            at = int(rng.integers(0, hdr))
+            del b[at:at + int(rng.integers(1, 9))]
+        elif kind == 4:
+            at = int(rng.integers(0, hdr))
+            b[at:at] = bytes(int(v) for v in rng.integers(0, 256, size=int(rng.integers(1, 9))))
+        else:
+            del b[int(rng.integers(8, len(b))):]
+    return bytes(b)
+
+
+@pytest.mark.skipif(not po.have_ref(), reason="oracle/_ref/libicw_ref.so not built")
+@pytest.mark.parametrize("seed", range(12))
+def test_damaged_headers_get_the_reference_readers_verdict(tmp_path, seed):
+    """Random damage to WAV (plain and extensible) and CWAVE (V1, V2) headers: icwp_probe accepts exactly the files the
+    reference's reader accepts (src/xwave_reader.c:243-585), with the same length, rate and output size."""
+    rng = np.random.default_rng(600 + seed)
+    agree = accepted = 0
+    for trial in range(60):
+        is_cw = bool(rng.integers(0, 2))
+        if is_cw:
+            d = dict(fmt=str(rng.choice(["cw_f64", "cw_i16", "cw_i16f32", "cw_f32"])), n_channels=int(rng.integers(1, 3)), sample_rate=96000)
+            raw = rng.integers(0, 256, size=int(rng.integers(2, 400)) * S.frame_bytes(d), dtype=np.uint8)
+            blob = po.cwave_bytes(d, raw, version=int(rng.integers(1, 3)))
+        else:
+            d = dict(fmt=str(rng.choice(["wav_u8", "wav_i16", "wav_i24", "wav_i32", "wav_f32"])), n_channels=int(rng.integers(1, 3)), sample_rate=44100)
+            raw = rng.integers(0, 256, size=int(rng.integers(2, 400)) * S.frame_bytes(d), dtype=np.uint8)
+            blob = po.wav_bytes(d, raw, extensible=bool(rng.integers(0, 2)))
+        p = tmp_path / ("d.cwave" if is_cw else "d.wav")
+        p.write_bytes(_damage_header(rng, blob, is_cw))
+        ref = _ref_open(p)
+        fi = plugin.probe(p)
+        assert (ref is None) == (fi is None), (seed, trial, "reference " + ("rejects" if ref is None else "accepts"), p.read_bytes()[:96].hex())
+        agree += 1
+        if ref is not None:
+            accepted += 1
+            size, bps, nch, srate = ref
+            assert (fi.n_samples + fi.n_tail) * 6 == size and fi.sample_rate == srate, (seed, trial, p.read_bytes()[:96].hex())
+    assert agree == 60 and accepted > 0
