@@ -8,12 +8,14 @@ exchange modes, I/Q inversions, gains, switched-off channels, several inputs, by
 Bars: reference against restatement -- equal bytes.  CUDA path in exact mode -- equal bytes unless the list holds a
 sin/cos (libdevice against glibc, <= 2 ulp: one LSB on at most 1 sample in 10^5, counted); clip counters, reject
 counters and generator positions equal."""
+import os
+
 import numpy as np
 import pytest
 
 from in_cwave_b200 import spec as S, synth
 from oracle import pyoracle as po
-from util import add_random_fades, pcm_report, random_spec
+from util import add_exceptional_samples, add_random_fades, pcm_report, random_spec
 
 N_CPU, N_GPU = 24, 48
 
@@ -24,7 +26,8 @@ def _bps(spec):
 
 def _input(spec, rng, n):
     lvl = float(rng.choice([0.25, 0.9, 1.6]))                 # the last one clips
-    return synth.stream_bytes(spec, n, stream_id=int(rng.integers(1, 1 << 30)), level=lvl)
+    raw = synth.stream_bytes(spec, n, stream_id=int(rng.integers(1, 1 << 30)), level=lvl)
+    return add_exceptional_samples(rng, spec, np.frombuffer(bytes(raw), dtype=np.uint8), p=float(os.environ.get("ICW_FUZZ_EXC", "0.15")))
 
 
 @pytest.mark.parametrize("seed", range(N_CPU))
@@ -103,6 +106,9 @@ def run_cuda_case(seed, eng, n_max=30000, k_choices=(1, 1, 2, 5)):
             st = ses.get_state(k)
             assert st.n_frame == p.n_frame
             assert (st.mt_drawn[0], st.mt_drawn[1]) == (p.mt[0].drawn, p.mt[1].drawn), (seed, k)
+            if spec["is_fp_check"] and not _has_trig(spec):
+                # FP_EXCEPT_STATS of the four checked stages (src/fp_check.c:48-99): [stage][total, snan, qnan, -inf, -den, +den, +inf]
+                assert ses.fp_stats(k) == [list(r) for r in p.fp_cnt], (seed, k, spec)
             clips[0] += p.clips[0]; clips[1] += p.clips[1]
         if not _has_trig(spec):
             assert tuple(stats["clips"]) == tuple(clips), (seed, stats["clips"], clips)
@@ -127,6 +133,7 @@ def run_scan_case(seed, eng, n_max=40000):
     rng = np.random.default_rng(9000 + seed)
     spec = random_spec(rng, hilbert_mode="scan")
     spec["fmt"] = str(rng.choice(REAL_FORMATS))
+    spec["is_fp_check"] = 0
     spec["is_subnorm_reject"] = 0                   # scan mode has no state zeroing (counted, not modelled)
     n = int(rng.integers(64, n_max))
     fb = S.frame_bytes(spec)

@@ -110,6 +110,7 @@ def random_spec(rng, hilbert_mode: str = "exact", allow_feedback: bool = True, a
         nshape_type=int(rng.integers(1, 18)) if (allow_shaping and rng.random() < 0.25) else 0,
         sign_bits16=int(rng.choice([16, 16, 12, 8, 2])), sign_bits24=int(rng.choice([24, 24, 20, 17, 9, 2])),
         bypass=int(rng.random() < 0.1), nodes=random_nodes(rng, feedback),
+        is_fp_check=int(hilbert_mode == "exact" and rng.random() < 0.15),      # the FP-exception-checked twins (scan mode refuses them)
     )
     return S.default_spec(**d)
 
@@ -127,3 +128,18 @@ def add_random_fades(rng, spec: dict, n: int) -> dict:
     fi = int(rng.integers(0, min(most, 40) + 1)) * per_ms
     fo = int(rng.integers(0, min(most, 40) + 1)) * per_ms
     return dict(spec, n_samples=n, n_fade_in=fi, n_fade_out=fo)
+
+
+def add_exceptional_samples(rng, spec: dict, raw: np.ndarray, p: float = 0.15) -> np.ndarray:
+    """Floating-point formats, now and then: NaN, +-Inf, denormals and huge values scattered through the input (what the
+    reference's FP_CHECK twins count, src/fp_check.c:48-99, and what must clip / propagate the same way without them)."""
+    fmt = spec["fmt"]
+    if fmt not in ("wav_f32", "cw_f32", "cw_f64") or rng.random() >= p:
+        return raw
+    f64 = fmt == "cw_f64"
+    f = np.frombuffer(bytes(raw), dtype=np.float64 if f64 else np.float32).copy()
+    k = int(min(f.size, rng.integers(1, 40)))
+    vals = [np.nan, np.inf, -np.inf, 3e-312 if f64 else 1e-42, -2e-311 if f64 else -1e-43, 1e300 if f64 else 3e38, -0.0]
+    for i in rng.choice(f.size, k, replace=False):
+        f[i] = vals[int(rng.integers(0, len(vals)))]
+    return f.view(np.uint8)
