@@ -49,6 +49,13 @@ def workload(name: str) -> dict:
         return dict(name="c4", desc="4096 x 48 kHz stereo f32 WAV, 10 s each: Hilbert(T1,Kahan,reject) + 100 Hz shift + 24-bit render, no dither",
                     spec=S.config_c1(hilbert_mode="exact"), streams=4096, frames=480_000, chunk=480_000,
                     bytes_per_frame=14, hilbert="exact")
+    if name == "c4w":
+        # the same batch on EVERY rank (N x 4096 streams in all): the exact kernel's run time is set by the 480 000 serial samples of a
+        # stream, not by the stream count, so c4 cut by stream does not speed up with N -- this line shows what N GPUs carry in that time
+        w = workload("c4")
+        w.update(name="c4w", weak_batch=True,
+                 desc="4096 x 48 kHz stereo f32 WAV per GPU, 10 s each (the c4 batch on every rank): Hilbert(T1,Kahan,reject) + 100 Hz shift + 24-bit render, no dither")
+        return w
     if name == "c4ns":
         # C4 with a noise shaper: the quantiser's error feedback is serial per channel
         return dict(name="c4ns", desc="4096 x 44.1 kHz stereo f32 WAV, 10 s each: Hilbert(T1,Kahan,reject) + 100 Hz shift + TPDF + "
@@ -343,7 +350,7 @@ def parity_check(wl: dict, d_in, d_out, K: int, N: int) -> dict:
 # FP64 instructions per stereo frame the kernels that run these workloads actually issue: the one-kernel
 # scan path 2 x 73 DFMA per frame (c2: icw_sfused.cu) or the three-pass scan 164 + 82 (c1, and c5: no dither), the exact Kahan recurrences
 # 4 x 281 (c4), plus the frame path (oscillator, DSP list, dither, quantiser)
-FP64_OPS = {"c2": 146 + 105, "c5": 164 + 82 + 70, "c1": 164 + 82 + 70, "c4": 1124 + 70, "c4ns": 1124 + 200, "c3": 300}
+FP64_OPS = {"c2": 146 + 105, "c5": 164 + 82 + 70, "c1": 164 + 82 + 70, "c4": 1124 + 70, "c4w": 1124 + 70, "c4ns": 1124 + 200, "c3": 300}
 
 
 def measure(ctx, name: str, steps: int, warmup: int, want_e2e: bool, want_parity: bool, args=None) -> dict:
@@ -360,7 +367,7 @@ def measure(ctx, name: str, steps: int, warmup: int, want_e2e: bool, want_parity
     K_all = wl["streams"]
     # how the workload spreads over the ranks: a batch is cut by stream (fixed total: strong scaling);
     # one long stream is cut in time (c5) or, having nothing to cut, replicated (weak scaling, no collective)
-    if K_all > 1 and world > 1:
+    if K_all > 1 and world > 1 and not wl.get("weak_batch"):
         lo, hi = D.shard_streams(K_all, rank, world)
         K, scaling, sharding = hi - lo, "strong", f"by stream: {K_all} streams / {world} ranks, no collective"
         frames_step = K_all * N
@@ -370,7 +377,8 @@ def measure(ctx, name: str, steps: int, warmup: int, want_e2e: bool, want_parity
         frames_step = N * world
     else:
         K, scaling = K_all, "weak"
-        sharding = "replicas: one independent stream per rank, no collective" if world > 1 else "single GPU"
+        sharding = ("single GPU" if world == 1 else f"by stream: {K_all} streams on every rank, {K_all * world} in all, no collective" if K_all > 1
+                    else "replicas: one independent stream per rank, no collective")
         frames_step = K * N * world
     fb, ob = S.frame_bytes(spec), S.out_frame_bytes(spec)
     ses = eng.session(spec, K)
@@ -447,7 +455,7 @@ def measure(ctx, name: str, steps: int, warmup: int, want_e2e: bool, want_parity
     for tf in ("r2_traffic.json", "r1_traffic.json"):        # dram bytes per frame from the ncu --set full captures
         tfile = ROOT / "profiles" / tf
         if tfile.exists():
-            tt = json.loads(tfile.read_text()).get(wl["name"], {}).get(dom)
+            tt = json.loads(tfile.read_text()).get("c4" if wl["name"] == "c4w" else wl["name"], {}).get(dom)
             if tt:
                 traffic = tt["dram_bytes_per_frame"] * units_per_launch
                 break
@@ -644,9 +652,9 @@ def main():
     # graph, and -- where there is more than one GPU -- the time-sharded stream with its NCCL hand-off timed ------------
     others = {}
     if not args.no_workloads and args.workload == "c2" and not args.streams and not args.frames:
-        for name in ["c4", "c3", "c4ns"] + (["c5"] if world > 1 else []):
+        for name in ["c4", "c3", "c4ns"] + (["c5", "c4w"] if world > 1 else []):
             try:
-                r = measure(ctx, name, max(3, min(args.steps, 10)), 3, want_e2e=not args.no_e2e, want_parity=not args.no_parity)
+                r = measure(ctx, name, max(3, min(args.steps, 10)), 3, want_e2e=not args.no_e2e and name != "c4w", want_parity=not args.no_parity)
                 r.pop("_spec", None)
                 others[name] = r
             except Exception as ex:
