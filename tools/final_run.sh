@@ -1,3 +1,7 @@
+#!/bin/bash
+# final_run.sh -- the round-end sequence on one GPU box (gpurun -- 'bash tools/final_run.sh'): GPU tests, smoke, the default bench line,
+# the reference arm, the ncu launch list of the bench command and one --set full capture of the interpreter kernel; everything lands in
+# gpurun_out/final_*, from where the summaries under profiles/ are made (tools/ncu_summary.py, tools/ncu_sass_regions.py)
 set -x
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/final_tests.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/final_smoke.log 2>&1
