@@ -73,17 +73,23 @@ def _explain_flips(eng, spec, raw, pcm, want, label):
         ses.close()
 
 
-def run_cuda_case(seed, eng, n_max=30000, k_choices=(1, 1, 2, 5)):
-    """One random configuration through the C ABI (K streams, the call cut at random places) against the reference."""
+def make_case(seed, n_max=30000, k_choices=(1, 1, 2, 5)):
+    """The random configuration, stream count, inputs and call cuts of case `seed` (tools/fuzz_one.py replays one of them)."""
     rng = np.random.default_rng(5000 + seed)
     spec = random_spec(rng)
     K = int(rng.choice(k_choices))
     n = int(rng.integers(2, n_max))
     spec = add_random_fades(rng, spec, n)
-    fb = S.frame_bytes(spec)
     raws = [np.frombuffer(bytes(_input(spec, rng, n)), dtype=np.uint8) for _ in range(K)]
-    raw = np.stack(raws)
     cuts = sorted({0, n} | {int(c) for c in rng.integers(0, n + 1, size=int(rng.integers(0, 4)))})
+    return rng, spec, K, n, raws, cuts
+
+
+def run_cuda_case(seed, eng, n_max=30000, k_choices=(1, 1, 2, 5)):
+    """One random configuration through the C ABI (K streams, the call cut at random places) against the reference."""
+    rng, spec, K, n, raws, cuts = make_case(seed, n_max, k_choices)
+    fb = S.frame_bytes(spec)
+    raw = np.stack(raws)
     ses = eng.session(spec, K)
     try:
         parts = []
