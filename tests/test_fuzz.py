@@ -144,9 +144,9 @@ REAL_FORMATS = ["wav_u8", "wav_i16", "wav_i24", "wav_i32", "wav_f32"]
 
 
 def run_scan_case(seed, eng, n_max=40000):
-    """Scan mode on a random configuration: the analytic signal against the binary128 evaluation of the reference's filter
-    (1e-12 of its RMS, tests/test_gpu_scan.py), and everything behind the converter against the restatement FED that analytic
-    signal (the same bar as exact mode)."""
+    """Scan mode on a random configuration, one to three streams, the call cut at random places: the analytic signal against the
+    binary128 evaluation of the reference's filter (1e-12 of its RMS, tests/test_gpu_scan.py), and everything behind the
+    converter against the restatement FED that analytic signal (the same bar as exact mode)."""
     import ctypes as C
     rng = np.random.default_rng(9000 + seed)
     spec = random_spec(rng, hilbert_mode="scan")
@@ -154,37 +154,40 @@ def run_scan_case(seed, eng, n_max=40000):
     spec["is_fp_check"] = 0
     spec["is_subnorm_reject"] = 0                   # scan mode has no state zeroing (counted, not modelled)
     n = int(rng.integers(64, n_max))
+    K = int(rng.choice([1, 1, 3]))
     fb = S.frame_bytes(spec)
-    raw = np.frombuffer(bytes(synth.stream_bytes(spec, n, stream_id=int(rng.integers(1, 1 << 30)), level=0.25)), dtype=np.uint8)
+    raws = [np.frombuffer(bytes(synth.stream_bytes(spec, n, stream_id=int(rng.integers(1, 1 << 30)), level=0.25)), dtype=np.uint8) for _ in range(K)]
+    raw = np.stack(raws)
     cuts = sorted({0, n} | {int(c) for c in rng.integers(0, n + 1, size=int(rng.integers(0, 3)))})
-    ses = eng.session(spec, 1)
+    ses = eng.session(spec, K)
     try:
         bus, lr = ses.enable_taps(n)
         parts, anas = [], []
         for a, b in zip(cuts[:-1], cuts[1:]):
             if b == a:
                 continue
-            parts.append(ses.process_host(np.ascontiguousarray(raw[a * fb:b * fb]))[0])
-            # the tap buffer is packed per call: [frames of this call][plug][4]
-            anas.append(bus.reshape(-1)[: (b - a) * bus.shape[2] * 4].reshape(b - a, bus.shape[2], 4)[:, 0, :].cpu().numpy().copy())
-        pcm, ana = np.concatenate(parts), np.ascontiguousarray(np.concatenate(anas))
+            parts.append(ses.process_host(np.ascontiguousarray(raw[:, a * fb:b * fb])))
+            # the tap buffer is packed per call: [stream][frames of this call][plug][4]
+            anas.append(bus.reshape(-1)[: K * (b - a) * bus.shape[2] * 4].reshape(K, b - a, bus.shape[2], 4)[:, :, 0, :].cpu().numpy().copy())
+        pcm, ana = np.concatenate(parts, axis=1), np.ascontiguousarray(np.concatenate(anas, axis=1))
         nch = spec["n_channels"]
-        un = np.zeros((n, 4))
-        po.port().icwo_unpack(po.FMT[spec["fmt"]], nch, raw.ctypes.data_as(C.POINTER(C.c_uint8)), n, un.ctypes.data_as(C.POINTER(C.c_double)))
-        for ch in range(2):
-            ti, tq = po.hilbert_truth(np.ascontiguousarray(un[:, 2 * ch]), spec["filter_no"], 1 if spec["is_kahan"] else 0, 0)
-            scale = max(float(np.sqrt(np.mean(ti ** 2 + tq ** 2))), 1e-300)
-            err = max(np.max(np.abs(ana[:, 2 * ch] - ti)), np.max(np.abs(ana[:, 2 * ch + 1] - tq))) / scale
-            assert err <= 1e-12, (seed, ch, err, spec)
-        ref = po.port_process(dict(spec, fmt="cw_f64", n_channels=2), ana.view(np.uint8).ravel())
-        rep = pcm_report(pcm, ref["pcm"], _bps(spec))
-        if _has_trig(spec):
-            step = 1 << ((24 - spec["sign_bits24"]) if spec["need24bits"] else (16 - spec["sign_bits16"]))
-            assert rep["max_lsb"] <= step and rep["mismatches"] <= max(1, rep["samples"] // 100000), (seed, rep, spec)
-        else:
-            assert rep["mismatches"] == 0, (seed, rep, spec)
-        st = ses.get_state(0)
-        assert st.n_frame == n and st.hb_basis == 1
+        for k in range(K):
+            un = np.zeros((n, 4))
+            po.port().icwo_unpack(po.FMT[spec["fmt"]], nch, raws[k].ctypes.data_as(C.POINTER(C.c_uint8)), n, un.ctypes.data_as(C.POINTER(C.c_double)))
+            for ch in range(2):
+                ti, tq = po.hilbert_truth(np.ascontiguousarray(un[:, 2 * ch]), spec["filter_no"], 1 if spec["is_kahan"] else 0, 0)
+                scale = max(float(np.sqrt(np.mean(ti ** 2 + tq ** 2))), 1e-300)
+                err = max(np.max(np.abs(ana[k, :, 2 * ch] - ti)), np.max(np.abs(ana[k, :, 2 * ch + 1] - tq))) / scale
+                assert err <= 1e-12, (seed, k, ch, err, spec)
+            ref = po.port_process(dict(spec, fmt="cw_f64", n_channels=2), np.ascontiguousarray(ana[k]).view(np.uint8).ravel())
+            rep = pcm_report(pcm[k], ref["pcm"], _bps(spec))
+            if _has_trig(spec):
+                step = 1 << ((24 - spec["sign_bits24"]) if spec["need24bits"] else (16 - spec["sign_bits16"]))
+                assert rep["max_lsb"] <= step and rep["mismatches"] <= max(1, rep["samples"] // 100000), (seed, k, rep, spec)
+            else:
+                assert rep["mismatches"] == 0, (seed, k, rep, spec)
+            st = ses.get_state(k)
+            assert st.n_frame == n and st.hb_basis == 1
     finally:
         ses.close()
 
