@@ -63,3 +63,27 @@ def test_missing_gpu_fails_loudly():
     rc = _abi.lib().icw_engine_create(0, C.byref(h))
     assert rc != 0 and not h.value
     assert _abi.lib().icw_last_error()
+
+
+def test_enum_values_match_the_python_mirror():
+    """The constants the ctypes layer carries are the header's (compiled, not parsed: a C program prints them)."""
+    import os
+    import subprocess
+    import tempfile
+    names = ["ICW_RESET_HILBERT", "ICW_RESET_FRAMECNT", "ICW_RESET_COUNTERS", "ICW_RESET_FILEPOS", "ICW_RESET_RENDER",
+             "ICW_RESET_RENDER_MEMORY", "ICW_RESET_ALL", "ICW_HILBERT_EXACT", "ICW_HILBERT_SCAN", "ICW_MODE_MASTER", "ICW_MODE_SHIFT",
+             "ICW_MODE_PM", "ICW_MODE_MIX", "ICW_N_PLUGS", "ICW_MAX_NODES"]
+    src = '#include <stdio.h>\n#include "icw_b200.h"\nint main(void){' + "".join(f'printf("%d\\n",(int){n});' for n in names) + "return 0;}\n"
+    with tempfile.TemporaryDirectory() as td:
+        c = os.path.join(td, "e.c")
+        open(c, "w").write(src)
+        exe = os.path.join(td, "e")
+        subprocess.run(["gcc", "-std=c99", "-I", str(ROOT / "include"), c, "-o", exe], check=True)
+        vals = dict(zip(names, (int(v) for v in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split())))
+    assert (vals["ICW_RESET_HILBERT"], vals["ICW_RESET_FRAMECNT"], vals["ICW_RESET_COUNTERS"], vals["ICW_RESET_FILEPOS"], vals["ICW_RESET_RENDER"],
+            vals["ICW_RESET_RENDER_MEMORY"], vals["ICW_RESET_ALL"]) == (_abi.RESET_HILBERT, _abi.RESET_FRAMECNT, _abi.RESET_COUNTERS,
+                                                                        _abi.RESET_FILEPOS, _abi.RESET_RENDER, _abi.RESET_RENDER_MEMORY, _abi.RESET_ALL)
+    assert (vals["ICW_HILBERT_EXACT"], vals["ICW_HILBERT_SCAN"]) == (_abi.HILBERT["exact"], _abi.HILBERT["scan"])
+    assert [vals[f"ICW_MODE_{m.upper()}"] for m in ("master", "shift", "pm", "mix")] == [_abi.MODE[m] for m in ("master", "shift", "pm", "mix")]
+    assert vals["ICW_N_PLUGS"] == _abi.N_PLUGS
+    assert vals["ICW_RESET_ALL"] & vals["ICW_RESET_RENDER_MEMORY"]          # a full reset includes what a file open clears
