@@ -500,3 +500,22 @@ def test_damaged_headers_get_the_reference_readers_verdict(tmp_path, seed):
             size, bps, nch, srate = ref
             assert (fi.n_samples + fi.n_tail) * 6 == size and fi.sample_rate == srate, (seed, trial, p.read_bytes()[:96].hex())
     assert agree == 60 and accepted > 0
+
+
+@pytest.mark.skipif(not po.have_ref(), reason="oracle/_ref/libicw_ref.so not built")
+def test_random_track_geometry_against_the_reference(tmp_path):
+    """Silence tail up to a whole number of SEC_ALIGN seconds (src/xwave_reader.c:693-703): the output size the reference's
+    open reports for random lengths, rates and alignments is the one icwp_probe computes."""
+    rng = np.random.default_rng(77)
+    for trial in range(120):
+        sr = int(rng.choice([8000, 11025, 22050, 44100, 48000, 96000]))
+        d = dict(fmt=str(rng.choice(["wav_u8", "wav_i16", "wav_i24"])), n_channels=int(rng.integers(1, 3)), sample_rate=sr)
+        n = int(rng.choice([2, 3, sr - 1, sr, sr + 1, int(rng.integers(2, 4 * sr))]))
+        align = int(rng.integers(0, 21))
+        p = tmp_path / "g.wav"
+        p.write_bytes(po.wav_bytes(d, np.zeros(n * S.frame_bytes(d), dtype=np.uint8)))
+        ref = _ref_open(p, dict(sec_align=align))
+        fi = plugin.probe(p, sec_align=align, fade_in_ms=int(rng.integers(0, 300)), fade_out_ms=int(rng.integers(0, 300)))
+        assert ref is not None and fi is not None, (trial, d, n, align)
+        assert (fi.n_samples, (fi.n_samples + fi.n_tail) * 6) == (n, ref[0]), (trial, d, n, align, fi.n_tail, ref)
+        assert fi.n_fade_in + fi.n_fade_out < max(n, 1) or (fi.n_fade_in, fi.n_fade_out) == (0, 0)
