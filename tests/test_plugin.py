@@ -421,7 +421,11 @@ def random_transcode_script(tmp_path, seed):
         if j == 1 or rng.random() < 0.5:
             script.append(("drain", int(rng.integers(600, 70000))))
         script.append(("close",))
-    return spec, script, rng
+    # four walks in ten also get the reader's options: a silence tail up to whole seconds and fades (src/xwave_reader.c:693-723)
+    geo = {}
+    if rng.random() < 0.4:
+        geo = dict(sec_align=int(rng.integers(1, 4)), fade_in=int(rng.integers(0, 400)), fade_out=int(rng.integers(0, 400)))
+    return spec, script, rng, geo
 
 
 @pytest.mark.gpu
@@ -431,9 +435,10 @@ def test_random_transcode_scripts(tmp_path, seed):
     """Random configuration (tests/util.py::random_spec), two files, a random walk over the four entry points -- requests of any
     byte count, seeks anywhere, a transcode cancelled half way and the next file opened on the surviving context -- through
     libicw_plugin.so and through the compiled reference: the same bytes in the same order (src/transcode.c:40-118)."""
-    spec, script, rng = random_transcode_script(tmp_path, seed)
+    spec, script, rng, geo = random_transcode_script(tmp_path, seed)
     readahead = int(rng.choice([0, 1, 777, 7001, 1 << 20]))
-    rep, _ = _both(spec, script, readahead)
+    opts = dict(sec_align=geo["sec_align"], fade_in_ms=geo["fade_in"], fade_out_ms=geo["fade_out"]) if geo else None
+    rep, _ = _both(spec, script, readahead, opts, geo or None)
     print(f"[random script {seed} ra={readahead}] {rep} {[op[:1] + op[2:] if op[0] == 'open' else op for op in script]}")
     trig = not spec["bypass"] and any(nd["mode"] in ("shift", "pm") for nd in spec["nodes"])
     if trig:

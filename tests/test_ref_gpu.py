@@ -155,10 +155,10 @@ def test_clip_and_peak_counters_through_the_replaced_getter(tmp_path):
 def test_random_transcode_scripts_through_the_seam(tmp_path, seed):
     """The random walk of tests/test_plugin.py::test_random_transcode_scripts over the reference's own reader and entry
     points with the frame loop on the GPU (adv_modulator_gpu.c) against the pure reference."""
-    spec, script, _ = random_transcode_script(tmp_path, seed)
+    spec, script, _, geo = random_transcode_script(tmp_path, seed)
     out = []
     for L in (po.ref(), po.ref_gpu()):
-        cfg = po.make_refcfg(spec)
+        cfg = po.make_refcfg(dict(spec, **geo))
         L.icwref_reset(C.byref(cfg))
         arr = (po.Node * len(spec["nodes"]))()
         for i, nd in enumerate(spec["nodes"]):
