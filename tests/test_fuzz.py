@@ -17,7 +17,7 @@ from in_cwave_b200 import spec as S, synth
 from oracle import pyoracle as po
 from util import add_exceptional_samples, add_random_fades, pcm_report, random_spec
 
-N_CPU, N_GPU = 24, 48
+N_CPU, N_GPU = 48, 48
 
 
 def _bps(spec):
